@@ -1,0 +1,242 @@
+/*
+ * dungeon_maps_b200 — C ABI of the B200-native depth → top-down hot path.
+ *
+ * Every entry point below is what the reference's Python layer would bind
+ * (ctypes) in place of the body of one of its own functions.  The reference
+ * interface each one replaces is cited as /root/reference file:line.
+ *
+ * Conventions
+ *   - plain pointers + sizes only, no torch types; all `const float*` etc. are
+ *     DEVICE pointers unless the function name ends in `_host`.
+ *   - all tensors are dense, C-contiguous, float32 / uint8 (bool) / int64.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *   - return value: 0 on success, a positive cudaError_t value on a CUDA
+ *     failure, a negative DM_E* code on a usage error.  Nothing is printed.
+ *   - arithmetic follows the reference's float32 op order exactly (one IEEE
+ *     rounding per torch op, FMA only where the reference's sgemm used it);
+ *     see DESIGN.md "Numerics".
+ */
+#ifndef DUNGEON_MAPS_B200_H_
+#define DUNGEON_MAPS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DM_ABI_VERSION 1
+
+#define DM_OK 0
+#define DM_EINVAL (-1)     /* bad argument (null pointer, non-positive size, ...) */
+#define DM_EWORKSPACE (-2) /* workspace too small */
+#define DM_ETIMEOUT (-3)   /* device-side dependency wait timed out (bug guard) */
+
+/* One rigid step of the reference's space transforms.
+ *   kind 1 (ROT_THEN_ADD): p' = rot(R, p) + t      camera_to_local_space  maps.py:753-800
+ *                                                  local_to_global_space  maps.py:850-895
+ *   kind 2 (ADD_THEN_ROT): p' = rot(R, p + t)      local_to_camera_space  maps.py:802-848
+ *                                                  global_to_local_space  maps.py:897-942
+ *   kind 0: identity (step skipped)
+ * rot(R, p)_i, utils.py:329 (einsum 'bji,b...j->b...i' → at::bmm), depends on how many
+ * points n the reference rotates in one call, because ATen switches kernels:
+ *   fused = 1 (9*n >= 400, MKL sgemm):   fma(R[2][i], p2, fma(R[1][i], p1, R[0][i]*p0))
+ *   fused = 0 (9*n <  400, naive loop):  (R[0][i]*p0 + R[1][i]*p1) + R[2][i]*p2, each op rounded
+ * R is the Rodrigues matrix built on the host exactly as utils.py:303-327 does.
+ */
+#define DM_STEP_NONE 0
+#define DM_STEP_ROT_THEN_ADD 1
+#define DM_STEP_ADD_THEN_ROT 2
+
+typedef struct DmStep {
+  float R[9]; /* row-major R[j][i] = R[3*j+i] */
+  float t[3];
+  int32_t kind;
+  int32_t fused;
+  int32_t _pad[2];
+} DmStep; /* 64 bytes */
+
+/* Per-sample parameters of orth_project (maps.py:127-351). */
+typedef struct DmProjSample {
+  DmStep to_local;  /* pitch about x, + (0, cam_height, 0) */
+  DmStep to_global; /* yaw about y, + (x, 0, z); kind 0 when to_global is False */
+  float width_offset;
+  float height_offset;
+  float _pad[14];
+} DmProjSample; /* 192 bytes */
+
+/* Batch-wide configuration of orth_project. */
+typedef struct DmProjCfg {
+  int32_t H, W;      /* depth frame */
+  int32_t C;         /* value channels; 0: the heights are the values (value_map None) */
+  int32_t Mh, Mw;    /* map_height, map_width */
+  float fx, fy, cx, cy;
+  float map_res;
+  float trunc_depth_min, trunc_depth_max, trunc_height_max;
+  int32_t has_trunc_depth_min, has_trunc_depth_max, has_trunc_height_max;
+  int32_t clip_border;
+  int32_t flip_h;
+  float fill_value;  /* effective initial canvas value: fill_value, or 0 when None (utils.py:472-473) */
+  int32_t want_height; /* C>0 only: also produce the 1-channel height map (maps.py:335-349) */
+  int32_t reduction;   /* 0 = max (Reduction.max / None), 1 = min */
+  int32_t _pad[4];
+} DmProjCfg;
+
+/* Fused orthographic projection.  Replaces the body of orth_project
+ * (maps.py:259-351): depth_map_to_point_cloud, _mask_borders,
+ * camera_to_local_space, height truncation, local_to_global_space,
+ * map_quantize, project/scatter_tensor (utils.py:389-492) and the second
+ * height scatter — without materialising the point cloud.
+ *
+ *   depth   (b, 1, H, W) f32
+ *   values  (b, C, H, W) f32 or NULL when cfg->C == 0
+ *   valid   (b, 1, H, W) u8  or NULL
+ *   samples b entries
+ *   topdown (b, max(C,1), Mh, Mw) f32   out
+ *   mask    (b, max(C,1), Mh, Mw) u8    out   "cell changed" mask (utils.py:489-491)
+ *   height  (b, 1, Mh, Mw) f32          out, may be NULL unless cfg->want_height
+ *   workspace: device scratch of at least dm_orth_project_workspace_bytes();
+ *     it must be zero-filled before its first use and may be reused across
+ *     calls (every call leaves it zero-filled again).
+ */
+size_t dm_orth_project_workspace_bytes(const DmProjCfg* cfg, int32_t b);
+int dm_orth_project_f32(const float* depth, const float* values, const uint8_t* valid,
+                        const DmProjSample* samples, const DmProjCfg* cfg, int32_t b,
+                        float* topdown, uint8_t* mask, float* height,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same call with HOST buffers: copies inputs host→device, runs
+ * dm_orth_project_f32, copies the outputs back.  `samples` and `cfg` are host
+ * structs in both variants' cfg; here `samples` is a host array too.  Device
+ * scratch is owned by the library (grown on demand, released by
+ * dm_release_scratch).  Pinned host memory makes the copies asynchronous. */
+int dm_orth_project_host_f32(const float* depth, const float* values, const uint8_t* valid,
+                             const DmProjSample* samples, const DmProjCfg* cfg, int32_t b,
+                             float* topdown, uint8_t* mask, float* height, int32_t device);
+void dm_release_scratch(void);
+
+/* Per-sample parameters of camera_affine_grid (maps.py:353-460). */
+typedef struct DmFlowSample {
+  DmStep to_local;   /* pitch, +cam_height                    maps.py:428-433 */
+  DmStep transition; /* yaw delta about y, + (dx, 0, dz)      maps.py:435-439 */
+  DmStep to_camera;  /* + (0,-cam_height,0) then rot(-pitch)  maps.py:441-446 */
+} DmFlowSample; /* 192 bytes */
+
+typedef struct DmFlowCfg {
+  int32_t H, W;
+  int32_t channels; /* depth channels per sample (grid is (b, channels, H, W, 2)) */
+  float fx, fy, cx, cy;
+  int32_t flip_h;
+  int32_t emit_flow; /* 0: grid (camera_affine_grid). 1: ego flow of the demo helper
+                        compute_ego_flow (demos/ego_flow/run.py:75-90):
+                        (x - gx, -(y - gy)) */
+  int32_t _pad[6];
+} DmFlowCfg;
+
+/* Fused unproject → transform → reproject.  Replaces the body of
+ * camera_affine_grid (maps.py:414-460).
+ *   depth (b, channels, H, W) f32 ; grid (b, channels, H, W, 2) f32 out */
+int dm_affine_grid_f32(const float* depth, const DmFlowSample* samples, const DmFlowCfg* cfg,
+                       int32_t b, float* grid, void* stream);
+
+/* ---- MapBuilder merge: fuse_topdown_maps (maps.py:2181-2287) ---------------- */
+
+/* One source map of a fusion, all samples sharing its geometry. */
+typedef struct DmFuseSource {
+  const float* height;   /* (b, C, h, w) f32; channel stride may be 0 (stride-0 expand, maps.py:349) */
+  const float* values;   /* (b, C, h, w) f32 or NULL for a height map */
+  const uint8_t* mask;   /* (b, C, h, w) u8 */
+  int64_t height_bstride, height_cstride; /* in elements */
+  int32_t h, w;          /* this map's map_height, map_width */
+  int32_t flip_h;
+  float map_res;
+  const float* width_offset;  /* (b,) device */
+  const float* height_offset; /* (b,) device */
+  const DmStep* steps;   /* (b, 2) device: [source local→global or none, global→target local or none]
+                            _flattened_topdown_map maps.py:2059-2060, _merge_point_clouds maps.py:2116-2117 */
+} DmFuseSource;
+
+/* Pass 1: bounding box of every valid point of every source in bins of the
+ * target resolution with zero offsets and no flip
+ * (_compute_new_shape_and_offsets, maps.py:2146-2179).
+ * out (device, 5×int64): min_x, max_x, min_z, max_z, n_valid.  The caller
+ * initialises nothing; the call overwrites all five. */
+int dm_fuse_bbox_i64(const DmFuseSource* sources, int32_t n_sources, int32_t b, int32_t C,
+                     float target_res, int64_t* out, void* stream);
+
+/* Pass 2: re-quantise every valid point with the new offsets and scatter-max
+ * it into the freshly sized canvases (maps.py:2232-2272).
+ *   topdown (b, C, Mh, Mw) f32 out; mask (b, C, Mh, Mw) u8 out;
+ *   height  (b, C, Mh, Mw) f32 out, NULL for height maps (then topdown is the height map). */
+typedef struct DmFuseTarget {
+  int32_t Mh, Mw;
+  int32_t flip_h;
+  float map_res;
+  float width_offset, height_offset; /* scalars: one bbox over the whole batch */
+  float fill_value;
+  int32_t reduction;
+} DmFuseTarget;
+int dm_fuse_scatter_f32(const DmFuseSource* sources, int32_t n_sources, int32_t b, int32_t C,
+                        const DmFuseTarget* target, float* topdown, uint8_t* mask, float* height,
+                        void* stream);
+
+/* ---- materialising primitives (the reference's public L0/L1 functions) ------ */
+
+/* points (b, n, 3) f32 → out (b, n, 3): applies steps[b][n_steps] in order.
+ * utils.rotate utils.py:261-330, utils.translate utils.py:229-259 and the four
+ * space transforms maps.py:753-942. */
+int dm_transform_points_f32(const float* points, const DmStep* steps, int32_t n_steps,
+                            int32_t b, int64_t n, float* out, void* stream);
+
+/* image_to_camera_space maps.py:616-682 (to_image = 0) and
+ * camera_to_image_space maps.py:684-751 (to_image = 1) on (n, 3) points. */
+int dm_image_camera_f32(const float* points, int64_t n, float fx, float fy, float cx, float cy,
+                        int32_t flip_h, int32_t height, int32_t to_image, float* out, void* stream);
+
+/* depth_map_to_point_cloud maps.py:462-545: depth (b*c, H, W) → points (b*c, H, W, 3) and
+ * valid (b*c, H, W) u8. valid_in may be NULL. */
+int dm_depth_to_points_f32(const float* depth, const uint8_t* valid_in, int64_t frames, int32_t H,
+                           int32_t W, float fx, float fy, float cx, float cy, int32_t flip_h,
+                           int32_t has_tmin, float tmin, int32_t has_tmax, float tmax,
+                           float* points, uint8_t* valid_out, void* stream);
+
+/* map_quantize maps.py:944-1019: x, z (b, n) f32 + offsets (b,) → bins (b, n) int64. */
+int dm_map_quantize_f32(const float* x, const float* z, const float* width_offset,
+                        const float* height_offset, int32_t b, int64_t n, float map_res,
+                        int32_t map_height, int32_t flip_h, int64_t* x_bin, int64_t* z_bin,
+                        void* stream);
+/* map_dequantize maps.py:1021-1087. */
+int dm_map_dequantize_f32(const float* x_bin, const float* z_bin, const float* width_offset,
+                          const float* height_offset, int32_t b, int64_t n, float map_res,
+                          int32_t map_height, int32_t flip_h, float* x, float* z, void* stream);
+
+/* scatter_tensor utils.py:389-492 / project maps.py:1089-1173 for 2-D canvases:
+ * values (B, N) f32, coords (B, N, 2) int64 [row, col], valid (B, N) u8 or NULL,
+ * canvas (B, Mh, Mw) f32 in/out (pre-filled by the call when has_fill),
+ * mask (B, Mh, Mw) u8 out.  reduction 0 max, 1 min. */
+int dm_scatter_f32(const float* values, const int64_t* coords, const uint8_t* valid, int64_t B,
+                   int64_t N, int32_t Mh, int32_t Mw, int32_t has_fill, float fill_value,
+                   int32_t reduction, float* canvas, uint8_t* mask, void* stream);
+
+/* crop_topdown_map maps.py:1959-2037 = generate_crop_grid utils.py:571-611 +
+ * image_sample utils.py:613-652 (pad 1, grid_sample nearest, align_corners).
+ * image (b, c, h, w) f32 → out (b, c, crop_h, crop_w); center (b, 2) f32 device.
+ * border = 1: padding_mode 'border' with pad value `fill` (fill_value given);
+ * border = 0: zeros. */
+int dm_crop_nearest_f32(const float* image, const float* center, int32_t b, int32_t c, int32_t h,
+                        int32_t w, int32_t crop_h, int32_t crop_w, int32_t border, float fill,
+                        float* out, void* stream);
+int dm_crop_nearest_u8(const uint8_t* image, const float* center, int32_t b, int32_t c, int32_t h,
+                       int32_t w, int32_t crop_h, int32_t crop_w, uint8_t* out, void* stream);
+
+/* Library/ABI introspection. */
+int dm_abi_version(void);
+const char* dm_build_info(void);
+/* Number of kernel launches issued by this library since load (bench "gpu_launches"). */
+int64_t dm_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DUNGEON_MAPS_B200_H_ */

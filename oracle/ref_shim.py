@@ -1,0 +1,58 @@
+"""ORACLE — test infrastructure only.  Imports the UNMODIFIED reference from
+/root/reference in the authoring container (it does not exist on the GPU box;
+nothing that runs there may import this module).
+
+The reference imports `torch_scatter` at module top (utils.py:16), which is not
+installed.  A stand-in is registered first: scatter_{max,min,add,mul} with an
+`out=` tensor are `out.scatter_reduce_(dim, index.expand_as(src), src, reduce,
+include_self=True)`, which for max/min is semantically identical to
+torch_scatter (the existing `out` participates, the result is order-independent).
+scatter_mean is not equivalent and raises.
+"""
+import sys
+import types
+
+import torch
+
+REFERENCE_ROOT = "/root/reference"
+
+
+def _make(reduce: str):
+  def scatter(src, index, dim=-1, out=None, dim_size=None):
+    assert out is not None, "the reference always passes out="
+    out.scatter_reduce_(dim, index.expand_as(src), src, reduce=reduce, include_self=True)
+    return out, None
+  return scatter
+
+
+def _mean(*args, **kwargs):
+  raise NotImplementedError("scatter_mean has no faithful stand-in (SURVEY.md §8c)")
+
+
+def load_reference():
+  """Returns the reference package `dungeon_maps` (v0.0.3a1)."""
+  if "torch_scatter" not in sys.modules:
+    ts = types.ModuleType("torch_scatter")
+    ts.scatter_max = _make("amax")
+    ts.scatter_min = _make("amin")
+    ts.scatter_add = _make("sum")
+    ts.scatter_mul = _make("prod")
+    ts.scatter_mean = _mean
+    sys.modules["torch_scatter"] = ts
+  if REFERENCE_ROOT not in sys.path:
+    sys.path.insert(0, REFERENCE_ROOT)
+  import dungeon_maps  # noqa: E402
+  return dungeon_maps
+
+
+def per_sample(fn, batch: int, batched_args: dict, shared_args: dict):
+  """The reference raises for batch > 1 (utils.py:311-316 stacks a (batch,) zeros
+  tensor with (1,) axis components).  Batched semantics are therefore defined as
+  the reference applied to each sample alone, outputs concatenated."""
+  outs = []
+  for i in range(batch):
+    args = {k: (None if v is None else v[i:i + 1]) for k, v in batched_args.items()}
+    out = fn(**args, **shared_args)
+    outs.append(out if isinstance(out, tuple) else (out,))
+  cat = tuple(torch.cat([o[j] for o in outs], dim=0) for j in range(len(outs[0])))
+  return cat if len(cat) > 1 else cat[0]
