@@ -1,0 +1,163 @@
+"""ctypes binding of libdungeon_maps_b200.so (the C ABI in include/dungeon_maps_b200.h).
+
+There is no CPU fallback: if the library is missing it is built with nvcc when
+a toolchain is present, otherwise loading fails loudly; every compute entry
+point requires a CUDA device.
+"""
+import ctypes
+import os
+from ctypes import POINTER, c_float, c_int32, c_int64, c_size_t, c_void_p
+
+import torch
+
+from . import build as _build
+
+ABI_VERSION = 1
+
+
+class NativeError(RuntimeError):
+  pass
+
+
+class DmStep(ctypes.Structure):
+  _fields_ = [("R", c_float * 9), ("t", c_float * 3), ("kind", c_int32), ("fused", c_int32),
+              ("_pad", c_int32 * 2)]
+
+
+class DmProjCfg(ctypes.Structure):
+  _fields_ = [
+    ("H", c_int32), ("W", c_int32), ("C", c_int32), ("Mh", c_int32), ("Mw", c_int32),
+    ("fx", c_float), ("fy", c_float), ("cx", c_float), ("cy", c_float), ("map_res", c_float),
+    ("trunc_depth_min", c_float), ("trunc_depth_max", c_float), ("trunc_height_max", c_float),
+    ("has_trunc_depth_min", c_int32), ("has_trunc_depth_max", c_int32), ("has_trunc_height_max", c_int32),
+    ("clip_border", c_int32), ("flip_h", c_int32), ("fill_value", c_float), ("want_height", c_int32),
+    ("reduction", c_int32), ("_pad", c_int32 * 4),
+  ]
+
+
+class DmFlowCfg(ctypes.Structure):
+  _fields_ = [
+    ("H", c_int32), ("W", c_int32), ("channels", c_int32),
+    ("fx", c_float), ("fy", c_float), ("cx", c_float), ("cy", c_float),
+    ("flip_h", c_int32), ("emit_flow", c_int32), ("_pad", c_int32 * 6),
+  ]
+
+
+class DmFuseSource(ctypes.Structure):
+  _fields_ = [
+    ("height", c_void_p), ("values", c_void_p), ("mask", c_void_p),
+    ("height_bstride", c_int64), ("height_cstride", c_int64),
+    ("h", c_int32), ("w", c_int32), ("flip_h", c_int32), ("map_res", c_float),
+    ("width_offset", c_void_p), ("height_offset", c_void_p), ("steps", c_void_p),
+  ]
+
+
+class DmFuseTarget(ctypes.Structure):
+  _fields_ = [
+    ("Mh", c_int32), ("Mw", c_int32), ("flip_h", c_int32), ("map_res", c_float),
+    ("width_offset", c_float), ("height_offset", c_float), ("fill_value", c_float),
+    ("reduction", c_int32),
+  ]
+
+
+STEP_WORDS = ctypes.sizeof(DmStep) // 4          # 16
+PROJ_SAMPLE_WORDS = 48                           # DmProjSample: 2 steps + 2 offsets + pad
+FLOW_SAMPLE_WORDS = 48                           # DmFlowSample: 3 steps
+
+_SIGNATURES = {
+  "dm_abi_version": (ctypes.c_int, []),
+  "dm_build_info": (ctypes.c_char_p, []),
+  "dm_launch_count": (c_int64, []),
+  "dm_release_scratch": (None, []),
+  "dm_orth_project_workspace_bytes": (c_size_t, [POINTER(DmProjCfg), c_int32]),
+  "dm_orth_project_f32": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(DmProjCfg), c_int32,
+                                         c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+  "dm_orth_project_host_f32": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(DmProjCfg), c_int32,
+                                              c_void_p, c_void_p, c_void_p, c_int32]),
+  "dm_affine_grid_f32": (ctypes.c_int, [c_void_p, c_void_p, POINTER(DmFlowCfg), c_int32, c_void_p, c_void_p]),
+  "dm_fuse_bbox_i64": (ctypes.c_int, [POINTER(DmFuseSource), c_int32, c_int32, c_int32, c_float, c_void_p, c_void_p]),
+  "dm_fuse_scatter_f32": (ctypes.c_int, [POINTER(DmFuseSource), c_int32, c_int32, c_int32, POINTER(DmFuseTarget),
+                                         c_void_p, c_void_p, c_void_p, c_void_p]),
+  "dm_transform_points_f32": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int64, c_void_p, c_void_p]),
+  "dm_image_camera_f32": (ctypes.c_int, [c_void_p, c_int64, c_float, c_float, c_float, c_float, c_int32, c_int32,
+                                         c_int32, c_void_p, c_void_p]),
+  "dm_depth_to_points_f32": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_float, c_float,
+                                            c_float, c_float, c_int32, c_int32, c_float, c_int32, c_float,
+                                            c_void_p, c_void_p, c_void_p]),
+  "dm_map_quantize_f32": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_float,
+                                         c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+  "dm_map_dequantize_f32": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_float,
+                                           c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+  "dm_scatter_f32": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32, c_int32,
+                                    c_float, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+  "dm_crop_nearest_f32": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                         c_int32, c_float, c_void_p, c_void_p]),
+  "dm_crop_nearest_u8": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                        c_void_p, c_void_p]),
+}
+EXPORTS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def library_path() -> str:
+  return _build.LIB
+
+
+def lib() -> ctypes.CDLL:
+  """Loads (building if needed and possible) the native library.  Never falls back."""
+  global _lib
+  if _lib is not None:
+    return _lib
+  path = _build.LIB
+  if not os.path.exists(path):
+    try:
+      _build.build()
+    except Exception as e:  # no nvcc on this machine
+      raise NativeError(
+        f"{path} is missing and could not be built ({e}); run `python -m dungeon_maps_b200.build` "
+        "on a machine with nvcc. dungeon_maps_b200 has no CPU fallback.") from e
+  handle = ctypes.CDLL(path)
+  for name, (res, args) in _SIGNATURES.items():
+    fn = getattr(handle, name)  # AttributeError if the .so does not export a declared symbol
+    fn.restype = res
+    fn.argtypes = args
+  if handle.dm_abi_version() != ABI_VERSION:
+    raise NativeError(f"ABI mismatch: library {handle.dm_abi_version()} != binding {ABI_VERSION}")
+  _lib = handle
+  return _lib
+
+
+def check(rc: int, what: str) -> None:
+  if rc == 0:
+    return
+  if rc > 0:
+    raise NativeError(f"{what}: CUDA error {rc}")
+  names = {-1: "invalid argument", -2: "workspace too small", -3: "device-side wait timed out"}
+  raise NativeError(f"{what}: {names.get(rc, rc)}")
+
+
+def require_cuda(device=None) -> torch.device:
+  """The device the kernels will run on.  Raises if there is no CUDA device."""
+  if not torch.cuda.is_available():
+    raise NativeError("dungeon_maps_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+  if device is None:
+    return torch.device("cuda", torch.cuda.current_device())
+  device = torch.device(device)
+  if device.type != "cuda":
+    raise NativeError(f"dungeon_maps_b200 runs on CUDA devices only, got device={device}")
+  if device.index is None:
+    device = torch.device("cuda", torch.cuda.current_device())
+  return device
+
+
+def ptr(t) -> int:
+  return 0 if t is None else t.data_ptr()
+
+
+def stream_ptr(device: torch.device) -> int:
+  return torch.cuda.current_stream(device).cuda_stream
+
+
+def launch_count() -> int:
+  return int(lib().dm_launch_count())

@@ -1,0 +1,141 @@
+"""Host-side parameter blocks for the kernels.
+
+The per-sample quantities (poses, pitch, camera height, map offsets) are a few
+floats; everything derived from them — the Rodrigues matrices in particular —
+is computed here on the CPU with the same torch ops in the same order as the
+reference (utils.py:303-327), because sin/cos differ in the last ulp between
+CPU and GPU libm and the matrices feed bit-exact bin arithmetic.  The result is
+packed as DmStep / DmProjSample / DmFlowSample records (include/dungeon_maps_b200.h)
+and uploaded once per distinct parameter set (small LRU cache).
+"""
+from collections import OrderedDict
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+ANGLE_EPS = 0.001
+
+STEP_NONE, STEP_ROT_THEN_ADD, STEP_ADD_THEN_ROT, STEP_ADD, STEP_ROT = 0, 1, 2, 3, 4
+STEP_WORDS = 16
+
+
+def host_f32(x, shape_tail=()) -> torch.Tensor:
+  """Any scalar / list / ndarray / tensor (any device) → float32 CPU tensor (-1, *shape_tail)."""
+  if torch.is_tensor(x):
+    t = x.detach().to(device="cpu", dtype=torch.float32)
+  else:
+    t = torch.as_tensor(np.asarray(x, dtype=np.float32))
+  return t.reshape((-1,) + tuple(shape_tail))
+
+
+def per_sample(x, b: int, shape_tail=(), what: str = "argument") -> torch.Tensor:
+  t = host_f32(x, shape_tail)
+  if t.shape[0] == b:
+    return t
+  if t.shape[0] == 1:
+    return t.expand((b,) + tuple(shape_tail))
+  raise ValueError(f"{what}: expected 1 or {b} entries, got {t.shape[0]}")
+
+
+def fused_for(n_points: int) -> bool:
+  """at::bmm (behind utils.py:329) switches from its naive loop to MKL sgemm at 9*n >= 400;
+  the two accumulate differently (see DmStep in the public header)."""
+  return 9 * int(n_points) >= 400
+
+
+def rotation_matrices(axis: Sequence[float], angle: torch.Tensor, angle_eps: float = ANGLE_EPS) -> torch.Tensor:
+  """(b, 9) float32, R = I + sin(a) S + (1 - cos(a)) S², |a| <= eps → identity (utils.py:303-327)."""
+  angle = angle.reshape(-1, 1).to(torch.float32)
+  b = angle.shape[0]
+  ax = host_f32(axis, (3,))
+  ax = ax / torch.linalg.norm(ax, dim=-1, keepdim=True)
+  if ax.shape[0] != b:
+    ax = ax.expand(b, 3)
+  zero = torch.zeros((b,), dtype=torch.float32)
+  skew = torch.stack((zero, -ax[:, 2], ax[:, 1], ax[:, 2], zero, -ax[:, 0], -ax[:, 1], ax[:, 0], zero), dim=-1)
+  skew3 = skew.view(b, 3, 3)
+  skew_sq = torch.einsum("bij,bjk->bik", skew3, skew3).reshape(b, 9)
+  eye = torch.eye(3, dtype=torch.float32).view(1, 9)
+  angle = torch.where(torch.abs(angle) > angle_eps, angle, torch.tensor(0.0))
+  return eye + torch.sin(angle) * skew + (1 - torch.cos(angle)) * skew_sq
+
+
+def pack_steps(kind: int, R: Optional[torch.Tensor], t: Optional[torch.Tensor], b: int, n_points: int) -> torch.Tensor:
+  """(b, 16) float32 words laid out as DmStep."""
+  out = torch.zeros((b, STEP_WORDS), dtype=torch.float32)
+  if kind == STEP_NONE:
+    return out
+  if R is not None:
+    out[:, 0:9] = R
+  if t is not None:
+    out[:, 9:12] = t
+  ints = out.view(torch.int32)
+  ints[:, 12] = kind
+  ints[:, 13] = 1 if fused_for(n_points) else 0
+  return out
+
+
+def xyz(b: int, x=None, y=None, z=None) -> torch.Tensor:
+  t = torch.zeros((b, 3), dtype=torch.float32)
+  if x is not None: t[:, 0] = x
+  if y is not None: t[:, 1] = y
+  if z is not None: t[:, 2] = z
+  return t
+
+
+def camera_to_local(pitch: torch.Tensor, cam_h: torch.Tensor, n_points: int) -> torch.Tensor:
+  b = pitch.shape[0]  # maps.py:789-797
+  return pack_steps(STEP_ROT_THEN_ADD, rotation_matrices([1., 0., 0.], pitch), xyz(b, y=cam_h), b, n_points)
+
+
+def local_to_camera(pitch: torch.Tensor, cam_h: torch.Tensor, n_points: int) -> torch.Tensor:
+  b = pitch.shape[0]  # maps.py:838-845
+  return pack_steps(STEP_ADD_THEN_ROT, rotation_matrices([1., 0., 0.], -pitch), xyz(b, y=-cam_h), b, n_points)
+
+
+def local_to_global(pose: torch.Tensor, n_points: int) -> torch.Tensor:
+  b = pose.shape[0]  # maps.py:883-892
+  return pack_steps(STEP_ROT_THEN_ADD, rotation_matrices([0., 1., 0.], pose[:, 2]),
+                    xyz(b, x=pose[:, 0], z=pose[:, 1]), b, n_points)
+
+
+def global_to_local(pose: torch.Tensor, n_points: int) -> torch.Tensor:
+  b = pose.shape[0]  # maps.py:930-939: translate(-pos) then rotate(-yaw)
+  return pack_steps(STEP_ADD_THEN_ROT, rotation_matrices([0., 1., 0.], -pose[:, 2]),
+                    -xyz(b, x=pose[:, 0], z=pose[:, 1]), b, n_points)
+
+
+def identity(b: int) -> torch.Tensor:
+  return pack_steps(STEP_NONE, None, None, b, 0)
+
+
+class _DeviceCache:
+  """Small LRU of uploaded parameter blocks keyed by their bytes (MapProjector defaults
+  repeat call after call)."""
+
+  def __init__(self, capacity: int = 64):
+    self._d = OrderedDict()
+    self._cap = capacity
+
+  def get(self, host: torch.Tensor, device: torch.device) -> torch.Tensor:
+    host = host.contiguous()
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream, host.dtype, tuple(host.shape),
+           host.numpy().tobytes())
+    hit = self._d.get(key)
+    if hit is not None:
+      self._d.move_to_end(key)
+      return hit
+    dev = host.to(device)
+    self._d[key] = dev
+    if len(self._d) > self._cap:
+      self._d.popitem(last=False)
+    return dev
+
+
+_cache = _DeviceCache()
+
+
+def upload(host: torch.Tensor, device: torch.device) -> torch.Tensor:
+  """Device copy of a host parameter block, cached per (device, current stream, content)."""
+  return _cache.get(host, device)

@@ -1,0 +1,157 @@
+// Shared device-side pieces of the dungeon_maps_b200 kernels (sm_100a).
+//
+// Numerics contract (DESIGN.md "Numerics"): every reference torch op is one IEEE
+// float32 rounding.  All coordinate math below is written with the __f*_rn
+// intrinsics, which nvcc never contracts into FMAs (the files are additionally
+// compiled with --fmad=false); __fmaf_rn appears only where the reference's
+// sgemm fused (utils.py:329 → at::bmm → MKL, see DmStep in the public header).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/dungeon_maps_b200.h"
+
+namespace dm {
+
+// ---- launch accounting / error plumbing -------------------------------------
+extern int64_t g_launches;  // defined in dm_api.cu
+
+#define DM_CUDA_OK(expr)                                  \
+  do {                                                    \
+    cudaError_t _e = (expr);                              \
+    if (_e != cudaSuccess) return static_cast<int>(_e);   \
+  } while (0)
+
+#define DM_LAUNCHED()                                     \
+  do {                                                    \
+    ++::dm::g_launches;                                   \
+    cudaError_t _e = cudaPeekAtLastError();               \
+    if (_e != cudaSuccess) return static_cast<int>(_e);   \
+  } while (0)
+
+constexpr int kNumSMs = 148;  // B200
+
+// ---- reference arithmetic ------------------------------------------------------
+struct V3 {
+  float x, y, z;
+};
+
+// utils.py:329 (see DmStep: fused = MKL sgemm FMA chain, otherwise ATen's naive loop).
+__device__ __forceinline__ V3 rot(const float* __restrict__ R, V3 p, int fused) {
+  V3 o;
+  if (fused) {
+    o.x = __fmaf_rn(R[6], p.z, __fmaf_rn(R[3], p.y, __fmul_rn(R[0], p.x)));
+    o.y = __fmaf_rn(R[7], p.z, __fmaf_rn(R[4], p.y, __fmul_rn(R[1], p.x)));
+    o.z = __fmaf_rn(R[8], p.z, __fmaf_rn(R[5], p.y, __fmul_rn(R[2], p.x)));
+  } else {
+    o.x = __fadd_rn(__fadd_rn(__fmul_rn(R[0], p.x), __fmul_rn(R[3], p.y)), __fmul_rn(R[6], p.z));
+    o.y = __fadd_rn(__fadd_rn(__fmul_rn(R[1], p.x), __fmul_rn(R[4], p.y)), __fmul_rn(R[7], p.z));
+    o.z = __fadd_rn(__fadd_rn(__fmul_rn(R[2], p.x), __fmul_rn(R[5], p.y)), __fmul_rn(R[8], p.z));
+  }
+  return o;
+}
+
+// utils.py:229-259: all three components are added (the zeros too).
+__device__ __forceinline__ V3 add3(V3 p, const float* __restrict__ t) {
+  return V3{__fadd_rn(p.x, t[0]), __fadd_rn(p.y, t[1]), __fadd_rn(p.z, t[2])};
+}
+
+// maps.py:753-942.
+__device__ __forceinline__ V3 apply_step(const DmStep& s, V3 p) {
+  if (s.kind == DM_STEP_ROT_THEN_ADD) return add3(rot(s.R, p, s.fused), s.t);
+  if (s.kind == DM_STEP_ADD_THEN_ROT) return rot(s.R, add3(p, s.t), s.fused);
+  if (s.kind == DM_STEP_ADD) return add3(p, s.t);
+  if (s.kind == DM_STEP_ROT) return rot(s.R, p, s.fused);
+  return p;
+}
+
+// maps.py:667-679 image_to_camera_space for pixel (row r, col c).
+__device__ __forceinline__ V3 unproject(int r, int c, float z, int H, float fx, float fy, float cx,
+                                        float cy, int flip_h) {
+  const float yy = flip_h ? __fsub_rn((float)(H - 1), (float)r) : (float)r;
+  V3 p;
+  p.x = __fmul_rn(__fdiv_rn(__fsub_rn((float)c, cx), fx), z);
+  p.y = __fmul_rn(__fdiv_rn(__fsub_rn(yy, cy), fy), z);
+  p.z = z;
+  return p;
+}
+
+// maps.py:1004-1013 map_quantize, kept in float: floor(x + 0.5) as an integral float.  The
+// reference casts to int64 (NaN / out of range → INT64_MIN on x86) and bounds-checks after;
+// comparing the float against [0, size) gives the same verdict for every input.
+__device__ __forceinline__ void quantize_f(float x, float z, float woff, float hoff, float res,
+                                           int Mh, int flip_h, float* xf, float* zf) {
+  const float xb = __fadd_rn(__fdiv_rn(x, res), woff);
+  float zb = __fadd_rn(__fdiv_rn(z, res), hoff);
+  if (flip_h) zb = __fsub_rn((float)(Mh - 1), zb);
+  *xf = floorf(__fadd_rn(xb, 0.5f));
+  *zf = floorf(__fadd_rn(zb, 0.5f));
+}
+
+// Tensor.to(int64) on x86: cvttss2si semantics.
+__device__ __forceinline__ long long f2i64(float v) {
+  if (!(v >= -9223372036854775808.0f && v < 9223372036854775808.0f)) return (long long)0x8000000000000000ULL;
+  return (long long)v;
+}
+
+// ---- order-preserving keys ------------------------------------------------------
+// enc() maps float order onto unsigned order; key 0 is reserved for "cell untouched" and is
+// never produced for a value that passed the `better than fill` test.  A min-reduction
+// stores ~enc() so that one atomicMax serves both.
+__device__ __forceinline__ uint32_t enc(float v) {
+  const uint32_t b = __float_as_uint(v);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float dec(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+__device__ __forceinline__ uint32_t enc_red(float v, int is_min) { return is_min ? ~enc(v) : enc(v); }
+__device__ __forceinline__ float dec_red(uint32_t k, int is_min) { return dec(is_min ? ~k : k); }
+// torch_scatter semantics: `src > out` (max) / `src < out` (min); NaN never wins.
+__device__ __forceinline__ bool better(float v, float cur, int is_min) {
+  return is_min ? (v < cur) : (v > cur);
+}
+
+// Raw-float atomic max/min on a canvas holding plain floats (no key decode needed):
+// non-negative floats order like signed ints, negative floats order inversely as unsigned.
+__device__ __forceinline__ void atomic_max_f32(float* addr, float v) {
+  if (!(__float_as_uint(v) & 0x80000000u))
+    atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else
+    atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_min_f32(float* addr, float v) {
+  if (!(__float_as_uint(v) & 0x80000000u))
+    atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else
+    atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+// ---- streaming memory access ------------------------------------------------------
+// Inputs are read exactly once: bypass L1 allocation, mark evict-first in L2 so the
+// accumulation ring (re-used every frame) keeps its L2 residency.
+__device__ __forceinline__ float4 ld_stream_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ld_stream_f1(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_stream_f4(float* p, float4 v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void st_stream_f1(float* p, float v) {
+  asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_stream_u8(uint8_t* p, uint8_t v) {
+  asm volatile("st.global.cs.u8 [%0], %1;" ::"l"(p), "r"((uint32_t)v) : "memory");
+}
+
+}  // namespace dm

@@ -1,0 +1,310 @@
+// Materialising primitives: the reference's public L0/L1 functions for callers that ask for
+// the intermediate tensors (TopdownMap.get_coords/get_points, user code).  Each is one
+// element-wise (or scatter) kernel with the reference's float32 op order.
+//   utils.rotate / utils.translate          utils.py:229-330
+//   camera/local/global space transforms    maps.py:753-942
+//   image_to_camera_space / camera_to_image maps.py:616-751
+//   depth_map_to_point_cloud                maps.py:462-545
+//   map_quantize / map_dequantize           maps.py:944-1087
+//   scatter_tensor / project (2-D canvas)   utils.py:389-492, maps.py:1089-1173
+//   crop_topdown_map                        maps.py:1959-2037, utils.py:571-652
+#include "dm_common.cuh"
+
+namespace dm {
+
+constexpr int kThreads = 256;
+
+static unsigned grid_for(long long items) {
+  long long blocks = (items + kThreads - 1) / kThreads;
+  const long long cap = (long long)kNumSMs * 8 * 2;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+#define DM_GRID_STRIDE(i, n) \
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += (long long)gridDim.x * blockDim.x)
+
+__global__ void __launch_bounds__(kThreads)
+transform_points_kernel(const float* __restrict__ pts, const DmStep* __restrict__ steps, int n_steps,
+                        long long n, long long total, float* __restrict__ out) {
+  DM_GRID_STRIDE(i, total) {
+    const int s = (int)(i / n);
+    V3 p{pts[i * 3], pts[i * 3 + 1], pts[i * 3 + 2]};
+    for (int k = 0; k < n_steps; ++k) p = apply_step(steps[s * n_steps + k], p);
+    out[i * 3] = p.x; out[i * 3 + 1] = p.y; out[i * 3 + 2] = p.z;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+image_camera_kernel(const float* __restrict__ pts, long long n, float fx, float fy, float cx, float cy,
+                    int flip_h, int height, int to_image, float* __restrict__ out) {
+  DM_GRID_STRIDE(i, n) {
+    float x = pts[i * 3], y = pts[i * 3 + 1];
+    const float z = pts[i * 3 + 2];
+    if (!to_image) {  // maps.py:670-678
+      if (flip_h) y = __fsub_rn((float)(height - 1), y);
+      x = __fmul_rn(__fdiv_rn(__fsub_rn(x, cx), fx), z);
+      y = __fmul_rn(__fdiv_rn(__fsub_rn(y, cy), fy), z);
+    } else {  // maps.py:743-747
+      const float ze = __fadd_rn(z, 1e-7f);
+      x = __fadd_rn(__fmul_rn(__fdiv_rn(x, ze), fx), cx);
+      y = __fadd_rn(__fmul_rn(__fdiv_rn(y, ze), fy), cy);
+      if (flip_h) y = __fsub_rn((float)(height - 1), y);
+    }
+    out[i * 3] = x; out[i * 3 + 1] = y; out[i * 3 + 2] = z;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+depth_to_points_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ valid_in, long long total,
+                       int H, int W, float fx, float fy, float cx, float cy, int flip_h, int has_tmin,
+                       float tmin, int has_tmax, float tmax, float* __restrict__ pts,
+                       uint8_t* __restrict__ valid_out) {
+  const int N = H * W;
+  DM_GRID_STRIDE(i, total) {
+    const int n = (int)(i % N);
+    const int r = n / W, c = n - r * W;
+    const float z = depth[i];
+    const V3 p = unproject(r, c, z, H, fx, fy, cx, cy, flip_h);
+    pts[i * 3] = p.x; pts[i * 3 + 1] = p.y; pts[i * 3 + 2] = p.z;
+    bool ok = true;
+    if (has_tmax) ok = ok && (z <= tmax);
+    if (has_tmin) ok = ok && (z >= tmin);
+    if (valid_in) ok = ok && valid_in[i];
+    valid_out[i] = ok;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+quantize_kernel(const float* __restrict__ x, const float* __restrict__ z, const float* __restrict__ woff,
+                const float* __restrict__ hoff, long long n, long long total, float res, int Mh, int flip_h,
+                long long* __restrict__ xb, long long* __restrict__ zb) {
+  DM_GRID_STRIDE(i, total) {
+    const int s = (int)(i / n);
+    float xf, zf;
+    quantize_f(x[i], z[i], woff[s], hoff[s], res, Mh, flip_h, &xf, &zf);
+    xb[i] = f2i64(xf);
+    zb[i] = f2i64(zf);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+dequantize_kernel(const float* __restrict__ xb, const float* __restrict__ zb, const float* __restrict__ woff,
+                  const float* __restrict__ hoff, long long n, long long total, float res, int Mh, int flip_h,
+                  float* __restrict__ x, float* __restrict__ z) {
+  DM_GRID_STRIDE(i, total) {
+    const int s = (int)(i / n);
+    float zz = zb[i];
+    if (flip_h) zz = __fsub_rn((float)(Mh - 1), zz);  // maps.py:1081-1084
+    z[i] = __fmul_rn(__fsub_rn(zz, hoff[s]), res);
+    x[i] = __fmul_rn(__fsub_rn(xb[i], woff[s]), res);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+fill_kernel(float* __restrict__ a, long long n, float v) {
+  DM_GRID_STRIDE(i, n) a[i] = v;
+}
+
+__global__ void __launch_bounds__(kThreads)
+copy_kernel(const float* __restrict__ a, float* __restrict__ b, long long n) {
+  DM_GRID_STRIDE(i, n) b[i] = a[i];
+}
+
+__global__ void __launch_bounds__(kThreads)
+scatter_kernel(const float* __restrict__ values, const long long* __restrict__ coords,
+               const uint8_t* __restrict__ valid, long long N, long long total, int Mh, int Mw, int is_min,
+               float* __restrict__ canvas) {
+  const long long M = (long long)Mh * Mw;
+  DM_GRID_STRIDE(i, total) {
+    if (valid && !valid[i]) continue;
+    const long long r = coords[i * 2], c = coords[i * 2 + 1];
+    if (r < 0 || r >= Mh || c < 0 || c >= Mw) continue;  // utils.py:448-453
+    const float v = values[i];
+    if (v != v) continue;
+    float* dst = canvas + (i / N) * M + r * Mw + c;
+    if (is_min) atomic_min_f32(dst, v); else atomic_max_f32(dst, v);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+changed_fill_kernel(const float* __restrict__ now, float fill, long long n, uint8_t* __restrict__ mask) {
+  DM_GRID_STRIDE(i, n) {
+    float d = fabsf(__fsub_rn(now[i], fill));
+    if (d != d) d = 0.0f;
+    mask[i] = d != 0.0f;
+  }
+}
+
+// utils.py:489-491 with an arbitrary "before" canvas.
+__global__ void __launch_bounds__(kThreads)
+changed_kernel(const float* __restrict__ now, const float* __restrict__ before, long long n,
+               uint8_t* __restrict__ mask) {
+  DM_GRID_STRIDE(i, n) {
+    float d = fabsf(__fsub_rn(now[i], before[i]));
+    if (d != d) d = 0.0f;
+    mask[i] = d != 0.0f;
+  }
+}
+
+// generate_crop_grid (utils.py:597-609) + grid_sample(nearest, align_corners=True) on the image
+// padded by one ring of `fill` (utils.py:639-650).  Source index as ATen's CPU kernel computes it:
+// unnormalize(g) = (g + 1) * ((size - 1) / 2); border mode clamps before rounding; nearbyint.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+crop_kernel(const T* __restrict__ image, const float* __restrict__ center, int b, int c, int h, int w, int ch_,
+            int cw_, int border, T fill, T zero, T* __restrict__ out) {
+  const int ph = h + 2, pw = w + 2;
+  const long long per = (long long)ch_ * cw_;
+  const long long total = (long long)b * c * per;
+  const float half_pw = (float)(pw / 2.0), half_ph = (float)(ph / 2.0);
+  const float half_cw = (float)(cw_ / 2.0), half_ch = (float)(ch_ / 2.0);
+  DM_GRID_STRIDE(i, total) {
+    const long long sc = i / per;
+    const int o = (int)(i - sc * per);
+    const int s = (int)(sc / c);
+    const int oi = o / cw_, oj = o - oi * cw_;
+    const float center_x = __fsub_rn(__fadd_rn(center[s * 2 + 0], 1.0f), half_pw);
+    const float center_y = __fsub_rn(__fadd_rn(center[s * 2 + 1], 1.0f), half_ph);
+    const float gx = __fdiv_rn(__fadd_rn(__fsub_rn((float)oj, half_cw), center_x), half_pw);
+    const float gy = __fdiv_rn(__fadd_rn(__fsub_rn((float)oi, half_ch), center_y), half_ph);
+    float ix = __fmul_rn(__fadd_rn(gx, 1.0f), __fdiv_rn((float)(pw - 1), 2.0f));
+    float iy = __fmul_rn(__fadd_rn(gy, 1.0f), __fdiv_rn((float)(ph - 1), 2.0f));
+    if (border) {
+      ix = fminf((float)(pw - 1), fmaxf(ix, 0.0f));
+      iy = fminf((float)(ph - 1), fmaxf(iy, 0.0f));
+    }
+    const float rx = nearbyintf(ix), ry = nearbyintf(iy);
+    T v = zero;
+    if (rx >= 0.0f && rx < (float)pw && ry >= 0.0f && ry < (float)ph) {
+      const int X = (int)rx, Y = (int)ry;
+      v = (X >= 1 && X <= w && Y >= 1 && Y <= h) ? image[(sc * h + (Y - 1)) * w + (X - 1)] : fill;
+    }
+    out[i] = v;
+  }
+}
+
+}  // namespace dm
+
+using namespace dm;
+
+extern "C" int dm_transform_points_f32(const float* points, const DmStep* steps, int32_t n_steps, int32_t b,
+                                       int64_t n, float* out, void* stream) {
+  if (b < 0 || n < 0 || n_steps < 0) return DM_EINVAL;
+  const long long total = (long long)b * n;
+  if (total == 0) return DM_OK;
+  if (!points || !out || (n_steps > 0 && !steps)) return DM_EINVAL;
+  transform_points_kernel<<<grid_for(total), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      points, steps, n_steps, n, total, out);
+  DM_LAUNCHED();
+  return DM_OK;
+}
+
+extern "C" int dm_image_camera_f32(const float* points, int64_t n, float fx, float fy, float cx, float cy,
+                                   int32_t flip_h, int32_t height, int32_t to_image, float* out, void* stream) {
+  if (n < 0) return DM_EINVAL;
+  if (n == 0) return DM_OK;
+  if (!points || !out) return DM_EINVAL;
+  image_camera_kernel<<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      points, n, fx, fy, cx, cy, flip_h, height, to_image, out);
+  DM_LAUNCHED();
+  return DM_OK;
+}
+
+extern "C" int dm_depth_to_points_f32(const float* depth, const uint8_t* valid_in, int64_t frames, int32_t H,
+                                      int32_t W, float fx, float fy, float cx, float cy, int32_t flip_h,
+                                      int32_t has_tmin, float tmin, int32_t has_tmax, float tmax, float* points,
+                                      uint8_t* valid_out, void* stream) {
+  if (frames < 0 || H <= 0 || W <= 0) return DM_EINVAL;
+  const long long total = (long long)frames * H * W;
+  if (total == 0) return DM_OK;
+  if (!depth || !points || !valid_out) return DM_EINVAL;
+  depth_to_points_kernel<<<grid_for(total), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      depth, valid_in, total, H, W, fx, fy, cx, cy, flip_h, has_tmin, tmin, has_tmax, tmax, points, valid_out);
+  DM_LAUNCHED();
+  return DM_OK;
+}
+
+extern "C" int dm_map_quantize_f32(const float* x, const float* z, const float* width_offset,
+                                   const float* height_offset, int32_t b, int64_t n, float map_res,
+                                   int32_t map_height, int32_t flip_h, int64_t* x_bin, int64_t* z_bin,
+                                   void* stream) {
+  if (b < 0 || n < 0) return DM_EINVAL;
+  const long long total = (long long)b * n;
+  if (total == 0) return DM_OK;
+  if (!x || !z || !width_offset || !height_offset || !x_bin || !z_bin) return DM_EINVAL;
+  quantize_kernel<<<grid_for(total), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, z, width_offset, height_offset, n, total, map_res, map_height, flip_h,
+      reinterpret_cast<long long*>(x_bin), reinterpret_cast<long long*>(z_bin));
+  DM_LAUNCHED();
+  return DM_OK;
+}
+
+extern "C" int dm_map_dequantize_f32(const float* x_bin, const float* z_bin, const float* width_offset,
+                                     const float* height_offset, int32_t b, int64_t n, float map_res,
+                                     int32_t map_height, int32_t flip_h, float* x, float* z, void* stream) {
+  if (b < 0 || n < 0) return DM_EINVAL;
+  const long long total = (long long)b * n;
+  if (total == 0) return DM_OK;
+  if (!x || !z || !width_offset || !height_offset || !x_bin || !z_bin) return DM_EINVAL;
+  dequantize_kernel<<<grid_for(total), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      x_bin, z_bin, width_offset, height_offset, n, total, map_res, map_height, flip_h, x, z);
+  DM_LAUNCHED();
+  return DM_OK;
+}
+
+extern "C" int dm_scatter_f32(const float* values, const int64_t* coords, const uint8_t* valid, int64_t B,
+                              int64_t N, int32_t Mh, int32_t Mw, int32_t has_fill, float fill_value,
+                              int32_t reduction, const float* canvas_in, float* canvas_out, uint8_t* mask,
+                              void* stream_) {
+  if (B < 0 || N < 0 || Mh <= 0 || Mw <= 0 || (reduction != 0 && reduction != 1)) return DM_EINVAL;
+  if (B == 0) return DM_OK;
+  if (!canvas_out || !mask || (N > 0 && (!values || !coords))) return DM_EINVAL;
+  if (!has_fill && !canvas_in) return DM_EINVAL;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const long long n_out = (long long)B * Mh * Mw;
+  if (has_fill)  // utils.py:472-473
+    fill_kernel<<<grid_for(n_out), kThreads, 0, stream>>>(canvas_out, n_out, fill_value);
+  else           // utils.py:467: the scatter works on a copy of the caller's canvas
+    copy_kernel<<<grid_for(n_out), kThreads, 0, stream>>>(canvas_in, canvas_out, n_out);
+  DM_LAUNCHED();
+  const long long total = (long long)B * N;
+  if (total > 0) {
+    scatter_kernel<<<grid_for(total), kThreads, 0, stream>>>(values, reinterpret_cast<const long long*>(coords),
+                                                             valid, N, total, Mh, Mw, reduction, canvas_out);
+    DM_LAUNCHED();
+  }
+  if (has_fill)
+    changed_fill_kernel<<<grid_for(n_out), kThreads, 0, stream>>>(canvas_out, fill_value, n_out, mask);
+  else
+    changed_kernel<<<grid_for(n_out), kThreads, 0, stream>>>(canvas_out, canvas_in, n_out, mask);
+  DM_LAUNCHED();
+  return DM_OK;
+}
+
+extern "C" int dm_crop_nearest_f32(const float* image, const float* center, int32_t b, int32_t c, int32_t h,
+                                   int32_t w, int32_t crop_h, int32_t crop_w, int32_t border, float fill,
+                                   float* out, void* stream) {
+  if (b < 0 || c < 0 || h <= 0 || w <= 0 || crop_h < 0 || crop_w < 0) return DM_EINVAL;
+  const long long total = (long long)b * c * crop_h * crop_w;
+  if (total == 0) return DM_OK;
+  if (!image || !center || !out) return DM_EINVAL;
+  crop_kernel<float><<<grid_for(total), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      image, center, b, c, h, w, crop_h, crop_w, border, fill, 0.0f, out);
+  DM_LAUNCHED();
+  return DM_OK;
+}
+
+extern "C" int dm_crop_nearest_u8(const uint8_t* image, const float* center, int32_t b, int32_t c, int32_t h,
+                                  int32_t w, int32_t crop_h, int32_t crop_w, uint8_t* out, void* stream) {
+  if (b < 0 || c < 0 || h <= 0 || w <= 0 || crop_h < 0 || crop_w < 0) return DM_EINVAL;
+  const long long total = (long long)b * c * crop_h * crop_w;
+  if (total == 0) return DM_OK;
+  if (!image || !center || !out) return DM_EINVAL;
+  // the reference crops masks with fill_value=False → border mode over a ring of zeros
+  crop_kernel<uint8_t><<<grid_for(total), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      image, center, b, c, h, w, crop_h, crop_w, 1, (uint8_t)0, (uint8_t)0, out);
+  DM_LAUNCHED();
+  return DM_OK;
+}

@@ -1,0 +1,75 @@
+"""HOST-buffer entry of the projection: numpy / pinned CPU tensors in, numpy out, through
+`dm_orth_project_host_f32` (host→device copy, kernels, device→host copy pipelined over two
+streams inside the library).  This is what a non-torch host (or the reference's numpy-facing
+MapBuilder.step) would call, and what bench.py times as `e2e`.
+"""
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from . import _params as prm
+from . import utils
+
+
+def _host(a, dtype):
+  if a is None:
+    return None
+  if torch.is_tensor(a):
+    a = a.detach().cpu().numpy()
+  return np.ascontiguousarray(a, dtype=dtype)
+
+
+def orth_project_host(depth_map, value_map, valid_map, cam_pose, width_offset, height_offset, cam_pitch,
+                      cam_height, map_res, map_width, map_height, focal_x, focal_y, center_x, center_y,
+                      trunc_depth_min, trunc_depth_max, trunc_height_max, clip_border, to_global, flip_h=True,
+                      fill_value=None, reduction=None, get_height_map=False, device: int = 0, out=None):
+  """Same arguments as maps.orth_project with (b,1,H,W) / (b,C,H,W) HOST arrays; returns numpy
+  (topdown, mask[, height]).  `out` may carry preallocated (pinned) result arrays."""
+  nat.require_cuda(device)
+  depth = _host(depth_map, np.float32)
+  values = _host(value_map, np.float32)
+  valid = None if valid_map is None else _host(np.asarray(valid_map).astype(bool), np.uint8)
+  b, _, H, W = depth.shape
+  C = 0 if values is None else values.shape[1]
+  n_points = H * W
+  pose = prm.per_sample(cam_pose, b, (3,), "cam_pose")
+  pitch, camh = prm.per_sample(cam_pitch, b), prm.per_sample(cam_height, b)
+  samples = torch.zeros((b, nat.PROJ_SAMPLE_WORDS), dtype=torch.float32)
+  samples[:, 0:16] = prm.camera_to_local(pitch, camh, n_points)
+  samples[:, 16:32] = prm.local_to_global(pose, n_points) if to_global else prm.identity(b)
+  samples[:, 32] = prm.per_sample(width_offset, b)
+  samples[:, 33] = prm.per_sample(height_offset, b)
+  samples = samples.numpy()
+  cfg = nat.DmProjCfg()
+  cfg.H, cfg.W, cfg.C, cfg.Mh, cfg.Mw = H, W, C, int(map_height), int(map_width)
+  cfg.fx, cfg.fy, cfg.cx, cfg.cy = focal_x, focal_y, center_x, center_y
+  cfg.map_res = map_res
+  cfg.has_trunc_depth_min = trunc_depth_min is not None
+  cfg.has_trunc_depth_max = trunc_depth_max is not None
+  cfg.has_trunc_height_max = trunc_height_max is not None
+  cfg.trunc_depth_min = trunc_depth_min or 0.
+  cfg.trunc_depth_max = trunc_depth_max or 0.
+  cfg.trunc_height_max = trunc_height_max or 0.
+  cfg.clip_border = int(clip_border) if clip_border is not None else 0
+  cfg.flip_h = bool(flip_h)
+  cfg.fill_value = 0. if fill_value is None else fill_value
+  want_h = bool(get_height_map) and C > 0
+  cfg.want_height = want_h
+  cfg.reduction = utils._reduction_code(reduction)
+  Cv = max(C, 1)
+  if out is None:
+    top = np.empty((b, Cv, cfg.Mh, cfg.Mw), np.float32)
+    mask = np.empty((b, Cv, cfg.Mh, cfg.Mw), np.uint8)
+    hgt = np.empty((b, 1, cfg.Mh, cfg.Mw), np.float32) if want_h else None
+  else:
+    top, mask, hgt = out
+  p = lambda a: None if a is None else a.ctypes.data
+  rc = nat.lib().dm_orth_project_host_f32(p(depth), p(values), p(valid), p(samples), cfg, b, p(top), p(mask),
+                                          p(hgt), int(device))
+  nat.check(rc, "dm_orth_project_host_f32")
+  mask_b = mask.view(np.bool_)
+  if not get_height_map:
+    return top, mask_b
+  return top, mask_b, (top if C == 0 else hgt)

@@ -1,0 +1,923 @@
+"""Drop-in for `dungeon_maps.maps` (reference: /root/reference/dungeon_maps/maps.py).
+
+Same public functions and classes, same argument names / meaning / defaults;
+the bodies call the fused sm_100a kernels through the C ABI
+(include/dungeon_maps_b200.h) instead of chaining ~100 aten ops and
+torch_scatter.  Host code here only validates and reshapes arguments, builds
+the per-sample parameter blocks (_params.py) and allocates outputs.
+
+There is no CPU path: inputs that are not on a CUDA device are moved to one
+(`device=` or the current CUDA device); results live on that device.  Batch > 1
+is supported and defined as "the reference applied to every sample"
+(the reference itself raises for batch > 1, utils.py:311-316).
+"""
+import enum
+import inspect
+from typing import Any, Dict, List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from . import _params as prm
+from . import utils
+from .utils import CameraIntrinsics, Float3D, NINF, Reduction
+
+
+@enum.unique
+class CenterMode(str, enum.Enum):
+  """maps.py:26-39; CenterMode(None) is CenterMode.none."""
+  none = "none"
+  origin = "origin"
+  camera = "camera"
+
+  @classmethod
+  def _missing_(cls, value):
+    if value is None:
+      return cls.none
+
+
+__all__ = [
+  'CenterMode', 'get', 'orth_project', 'camera_affine_grid', 'compute_ego_flow', 'depth_map_to_point_cloud',
+  'height_map_to_point_cloud', 'image_to_camera_space', 'camera_to_image_space', 'camera_to_local_space',
+  'local_to_camera_space', 'local_to_global_space', 'global_to_local_space', 'map_quantize',
+  'map_dequantize', 'project', 'compute_center_offsets', 'MapProjector', 'TopdownMap', 'crop_topdown_map',
+  'fuse_topdown_maps', 'MapBuilder', 'Reduction', 'CameraIntrinsics', 'NINF', 'Float3D',
+]
+
+
+def get(*args: Any) -> Any:
+  """First argument that is not None (the last one if all are)."""
+  arg = None
+  for arg in args:
+    if arg is not None:
+      break
+  return arg
+
+
+# ---- internal plumbing ----------------------------------------------------------------------
+
+_workspaces: Dict[Tuple[int, int], torch.Tensor] = {}
+
+
+def _workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
+  """Zero-initialised accumulation ring, one per (device, stream); the kernels leave it zeroed."""
+  key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+  ws = _workspaces.get(key)
+  if ws is None or ws.numel() < nbytes:
+    ws = torch.zeros(max(nbytes, 16), dtype=torch.uint8, device=dev)
+    _workspaces[key] = ws
+  return ws
+
+
+def _pick_device(device, *tensors) -> torch.device:
+  if device is not None and not isinstance(device, bool):
+    return nat.require_cuda(device)
+  for t in tensors:
+    if torch.is_tensor(t) and t.is_cuda:
+      return t.device
+  return nat.require_cuda(None)
+
+
+def _image(x, dev: torch.device, dtype: torch.dtype) -> torch.Tensor:
+  """2/3/4-D image → contiguous (b, c, h, w) on `dev`."""
+  t = utils.to_tensor(x)
+  t = utils.to_4D_image(t)
+  return t.to(device=dev, dtype=dtype).contiguous()
+
+
+def _points(x, dev: torch.device) -> Tuple[torch.Tensor, torch.Size]:
+  """(..., 3) points → contiguous (b, n, 3) float32 on `dev` plus the original shape."""
+  t = utils.to_tensor(x).to(device=dev, dtype=torch.float32)
+  shape = t.shape
+  if t.dim() < 2:
+    t = t.view(-1, 3)
+  b = t.shape[0]
+  return t.reshape(b, -1, 3).contiguous(), shape
+
+
+def _run_steps(points, dev, host_steps: List[torch.Tensor]) -> torch.Tensor:
+  flat, shape = _points(points, dev)
+  steps = torch.cat(host_steps, dim=1)
+  return utils._apply_steps(flat, steps, len(host_steps)).reshape(shape)
+
+
+def _f32(x) -> float:
+  """Python float rounded to float32 (what torch does to a Python scalar in a float32 op)."""
+  return float(np.float32(x))
+
+
+# ======== Raw functional APIs (maps.py:121-1248) ==============================================
+
+def orth_project(
+  depth_map: torch.Tensor,
+  value_map: Optional[torch.Tensor],
+  valid_map: Optional[torch.Tensor],
+  cam_pose: torch.Tensor,
+  width_offset: torch.Tensor,
+  height_offset: torch.Tensor,
+  cam_pitch: torch.Tensor,
+  cam_height: torch.Tensor,
+  map_res: float,
+  map_width: int,
+  map_height: int,
+  focal_x: float,
+  focal_y: float,
+  center_x: float,
+  center_y: float,
+  trunc_depth_min: Optional[float],
+  trunc_depth_max: Optional[float],
+  trunc_height_max: Optional[float],
+  clip_border: Optional[int],
+  to_global: bool,
+  flip_h: bool = True,
+  fill_value: Optional[float] = None,
+  reduction: Optional[Reduction] = None,
+  get_height_map: bool = False,
+  device: Optional[torch.device] = None,
+  _validate_args: bool = True
+) -> Union[Tuple[torch.Tensor, torch.Tensor], Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
+  """Orthographic projection of UNNORMALIZED depth maps (and optional per-pixel value maps)
+  onto top-down maps: one fused kernel pass + one resolve pass (csrc/dm_project.cu) in place of
+  maps.py:259-351.  Arguments, defaults and return values are those of the reference:
+
+  Returns (topdown_map (b,C,mh,mw) f32, masks (b,C,mh,mw) bool[, height_map]); every value
+  channel is reduced independently (max unless `reduction` says min); cells nothing landed on
+  hold `fill_value` (0 when None) and are False in `masks`; `height_map` is the same tensor as
+  `topdown_map` when `value_map` is None, otherwise a stride-0 expand of the (b,1,mh,mw)
+  max-height map with -inf in empty cells.
+  """
+  red = utils._reduction_code(reduction)
+  dev = _pick_device(device, depth_map, value_map)
+  depth = _image(depth_map, dev, torch.float32)
+  b, dc, H, W = depth.shape
+  values = None if value_map is None else _image(value_map, dev, torch.float32)
+  valid = None if valid_map is None else _image(valid_map, dev, torch.bool)
+  if values is not None and values.shape[-2:] != depth.shape[-2:]:
+    raise RuntimeError(f"value_map {tuple(values.shape)} does not match depth_map {tuple(depth.shape)}")
+  # per-sample host parameters
+  pose = prm.per_sample(cam_pose, b, (3,), "cam_pose")
+  pitch = prm.per_sample(cam_pitch, b, (), "cam_pitch")
+  camh = prm.per_sample(cam_height, b, (), "cam_height")
+  woff = prm.per_sample(width_offset, b, (), "width_offset")
+  hoff = prm.per_sample(height_offset, b, (), "height_offset")
+  frames = b
+  C = 0 if values is None else values.shape[1]
+  if dc != 1:
+    # one index set per depth channel (maps.py:298-318 keeps the channel dim): fold it into the batch
+    if values is not None and values.shape[1] != dc:
+      raise RuntimeError(f"value_map has {values.shape[1]} channels, depth_map has {dc}")
+    if valid is not None and valid.shape[1] not in (1, dc):
+      raise RuntimeError(f"valid_map has {valid.shape[1]} channels, depth_map has {dc}")
+    frames = b * dc
+    depth = depth.reshape(frames, 1, H, W)
+    if values is not None:
+      values = values.reshape(frames, 1, H, W)
+      C = 1
+    if valid is not None:
+      valid = valid.expand(b, dc, H, W).reshape(frames, 1, H, W).contiguous()
+    rep = lambda t: t.repeat_interleave(dc, dim=0)
+    pose, pitch, camh, woff, hoff = rep(pose), rep(pitch), rep(camh), rep(woff), rep(hoff)
+  elif valid is not None and valid.shape[1] != 1:
+    raise RuntimeError(f"valid_map has {valid.shape[1]} channels, depth_map has 1")
+  n_points = dc * H * W  # points the reference rotates per sample in one bmm
+  samples = torch.zeros((frames, nat.PROJ_SAMPLE_WORDS), dtype=torch.float32)
+  samples[:, 0:16] = prm.camera_to_local(pitch, camh, n_points)
+  samples[:, 16:32] = prm.local_to_global(pose, n_points) if to_global else prm.identity(frames)
+  samples[:, 32] = woff
+  samples[:, 33] = hoff
+  samples_dev = prm.upload(samples, dev)
+
+  cfg = nat.DmProjCfg()
+  cfg.H, cfg.W, cfg.C, cfg.Mh, cfg.Mw = H, W, C, int(map_height), int(map_width)
+  cfg.fx, cfg.fy, cfg.cx, cfg.cy = focal_x, focal_y, center_x, center_y
+  cfg.map_res = map_res
+  cfg.has_trunc_depth_min = trunc_depth_min is not None
+  cfg.has_trunc_depth_max = trunc_depth_max is not None
+  cfg.has_trunc_height_max = trunc_height_max is not None
+  cfg.trunc_depth_min = trunc_depth_min or 0.
+  cfg.trunc_depth_max = trunc_depth_max or 0.
+  cfg.trunc_height_max = trunc_height_max or 0.
+  cfg.clip_border = int(clip_border) if clip_border is not None else 0
+  cfg.flip_h = bool(flip_h)
+  cfg.fill_value = 0. if fill_value is None else fill_value
+  want_height = bool(get_height_map) and C > 0
+  cfg.want_height = want_height
+  cfg.reduction = red
+  Cv = max(C, 1)
+  topdown = torch.empty((frames, Cv, cfg.Mh, cfg.Mw), dtype=torch.float32, device=dev)
+  masks = torch.empty((frames, Cv, cfg.Mh, cfg.Mw), dtype=torch.bool, device=dev)
+  height = torch.empty((frames, 1, cfg.Mh, cfg.Mw), dtype=torch.float32, device=dev) if want_height else None
+  lib = nat.lib()
+  with torch.cuda.device(dev):
+    ws = _workspace(dev, lib.dm_orth_project_workspace_bytes(cfg, frames))
+    rc = lib.dm_orth_project_f32(depth.data_ptr(), nat.ptr(values), nat.ptr(valid), samples_dev.data_ptr(),
+                                 cfg, frames, topdown.data_ptr(), masks.data_ptr(), nat.ptr(height),
+                                 ws.data_ptr(), ws.numel(), nat.stream_ptr(dev))
+  nat.check(rc, "dm_orth_project_f32")
+  if dc != 1:
+    topdown = topdown.reshape(b, dc, cfg.Mh, cfg.Mw)
+    masks = masks.reshape(b, dc, cfg.Mh, cfg.Mw)
+    if height is not None:
+      height = height.reshape(b, dc, cfg.Mh, cfg.Mw)
+  if not get_height_map:
+    return topdown, masks
+  if value_map is None:
+    return topdown, masks, topdown          # maps.py:333-334: the very same tensor
+  return topdown, masks, torch.broadcast_to(height, topdown.shape)  # maps.py:349
+
+
+def camera_affine_grid(
+  depth_map: torch.Tensor,
+  trans_pose: torch.Tensor,
+  cam_pitch: torch.Tensor,
+  cam_height: torch.Tensor,
+  focal_x: float,
+  focal_y: float,
+  center_x: float,
+  center_y: float,
+  flip_h: bool = True,
+  device: Optional[torch.device] = None,
+  _validate_args: bool = True,
+  _emit_flow: bool = False
+) -> torch.Tensor:
+  """Where every pixel of `depth_map` (time t) lands in the image after the camera moved by
+  `trans_pose` = [dx, dz, dyaw]: one fused element-wise kernel (csrc/dm_flow.cu) in place of
+  maps.py:414-460.  Returns the (b, ..., h, w, 2) float32 grid of image (x, y)."""
+  dev = _pick_device(device, depth_map)
+  depth = _image(depth_map, dev, torch.float32)
+  b, ch, H, W = depth.shape
+  pose = prm.per_sample(trans_pose, b, (3,), "trans_pose")
+  pitch = prm.per_sample(cam_pitch, b, (), "cam_pitch")
+  camh = prm.per_sample(cam_height, b, (), "cam_height")
+  n_points = ch * H * W
+  samples = torch.cat((prm.camera_to_local(pitch, camh, n_points), prm.local_to_global(pose, n_points),
+                       prm.local_to_camera(pitch, camh, n_points)), dim=1)
+  samples_dev = prm.upload(samples, dev)
+  cfg = nat.DmFlowCfg()
+  cfg.H, cfg.W, cfg.channels = H, W, ch
+  cfg.fx, cfg.fy, cfg.cx, cfg.cy = focal_x, focal_y, center_x, center_y
+  cfg.flip_h = bool(flip_h)
+  cfg.emit_flow = bool(_emit_flow)
+  grid = torch.empty((b, ch, H, W, 2), dtype=torch.float32, device=dev)
+  with torch.cuda.device(dev):
+    rc = nat.lib().dm_affine_grid_f32(depth.data_ptr(), samples_dev.data_ptr(), cfg, b, grid.data_ptr(),
+                                      nat.stream_ptr(dev))
+  nat.check(rc, "dm_affine_grid_f32")
+  return grid
+
+
+def compute_ego_flow(proj: "MapProjector", depth_map: torch.Tensor, trans_pose: torch.Tensor) -> torch.Tensor:
+  """Egocentric motion flow of the reference's demo helper (demos/ego_flow/run.py:75-90):
+  (x - grid_x, -(y - grid_y)) in pixels, fused into the same kernel.  depth_map (c, h, w) or
+  (b, c, h, w); returns the flow of the first sample / channel, (h, w, 2), like the demo."""
+  flow = camera_affine_grid(
+    depth_map=depth_map, trans_pose=trans_pose, cam_pitch=proj.cam_pitch, cam_height=proj.cam_height,
+    focal_x=proj.cam_params.fx, focal_y=proj.cam_params.fy, center_x=proj.cam_params.cx,
+    center_y=proj.cam_params.cy, flip_h=proj.flip_h, device=proj.device, _emit_flow=True)
+  return flow[0, 0]
+
+
+def depth_map_to_point_cloud(
+  depth_map: torch.Tensor,
+  valid_map: Optional[torch.Tensor],
+  focal_x: float,
+  focal_y: float,
+  center_x: float,
+  center_y: float,
+  trunc_depth_min: Optional[float],
+  trunc_depth_max: Optional[float],
+  flip_h: bool = True,
+  device: Optional[torch.device] = None,
+  _validate_args: bool = True
+) -> Tuple[torch.Tensor, torch.Tensor]:
+  """Camera-space points (b, c, h, w, 3) and the valid area (b, c, h, w) of a depth map
+  (maps.py:462-545); X right, Y up, Z forward."""
+  dev = _pick_device(device, depth_map)
+  depth = _image(depth_map, dev, torch.float32)
+  b, c, H, W = depth.shape
+  valid = None
+  if valid_map is not None:
+    valid = _image(valid_map, dev, torch.bool).expand(b, c, H, W).contiguous()
+  pts = torch.empty((b, c, H, W, 3), dtype=torch.float32, device=dev)
+  ok = torch.empty((b, c, H, W), dtype=torch.bool, device=dev)
+  with torch.cuda.device(dev):
+    rc = nat.lib().dm_depth_to_points_f32(
+      depth.data_ptr(), nat.ptr(valid), b * c, H, W, focal_x, focal_y, center_x, center_y, int(bool(flip_h)),
+      int(trunc_depth_min is not None), trunc_depth_min or 0., int(trunc_depth_max is not None),
+      trunc_depth_max or 0., pts.data_ptr(), ok.data_ptr(), nat.stream_ptr(dev))
+  nat.check(rc, "dm_depth_to_points_f32")
+  return pts, ok
+
+
+def height_map_to_point_cloud(
+  height_map: torch.Tensor,
+  width_offset: torch.Tensor,
+  height_offset: torch.Tensor,
+  map_res: float,
+  map_height: int,
+  flip_h: bool = True,
+  device: Optional[torch.device] = None,
+  _validate_args: bool = True
+) -> torch.Tensor:
+  """Every cell of a height map as a 3-D point (b, c, h, w, 3) (maps.py:547-612)."""
+  dev = _pick_device(device, height_map)
+  hm = _image(height_map, dev, torch.float32)
+  xb, zb = utils.generate_image_coords(hm.shape, dtype=torch.float32, device=dev)
+  x, z = map_dequantize(xb, zb, width_offset, height_offset, map_res, map_height, flip_h, device=dev)
+  return torch.stack((x, hm, z), dim=-1)
+
+
+def _image_camera(points, fx, fy, cx, cy, flip_h, height, to_image, device):
+  dev = _pick_device(device, points)
+  t = utils.to_tensor(points).to(device=dev, dtype=torch.float32)
+  if flip_h and height is None:
+    if t.dim() < 3:
+      raise RuntimeError("The rank of `points` must be at least 3D (..., h, w, 3) "
+                         "or `height` should be provided if `flip_h` is enabled.")
+    height = t.shape[-3]
+  flat = t.reshape(-1, 3).contiguous()
+  out = torch.empty_like(flat)
+  with torch.cuda.device(dev):
+    rc = nat.lib().dm_image_camera_f32(flat.data_ptr(), flat.shape[0], fx, fy, cx, cy, int(bool(flip_h)),
+                                       int(height or 0), int(to_image), out.data_ptr(), nat.stream_ptr(dev))
+  nat.check(rc, "dm_image_camera_f32")
+  return out.reshape(t.shape)
+
+
+def image_to_camera_space(points: torch.Tensor, focal_x: float, focal_y: float, center_x: float,
+                          center_y: float, flip_h: bool = True, height: Optional[int] = None,
+                          device: Optional[torch.device] = None, _validate_args: bool = True) -> torch.Tensor:
+  """(pixel x, pixel y, depth) → camera space (maps.py:616-682)."""
+  return _image_camera(points, focal_x, focal_y, center_x, center_y, flip_h, height, 0, device)
+
+
+def camera_to_image_space(points: torch.Tensor, focal_x: float, focal_y: float, center_x: float,
+                          center_y: float, flip_h: bool = True, height: Optional[int] = None,
+                          device: Optional[torch.device] = None, _validate_args: bool = True) -> torch.Tensor:
+  """Camera space → (pixel x, pixel y, depth) (maps.py:684-751)."""
+  return _image_camera(points, focal_x, focal_y, center_x, center_y, flip_h, height, 1, device)
+
+
+def _n_points(points) -> Tuple[int, int]:
+  t = utils.to_tensor(points)
+  if t.dim() < 2:
+    return 1, max(t.numel() // 3, 1)
+  b = t.shape[0]
+  return b, max(t.numel() // (3 * max(b, 1)), 1)
+
+
+def camera_to_local_space(points: torch.Tensor, cam_pitch: torch.Tensor, cam_height: torch.Tensor,
+                          device: Optional[torch.device] = None, _validate_args: bool = True) -> torch.Tensor:
+  """Rotate by the camera pitch about x, lift by the camera height (maps.py:753-800)."""
+  b, n = _n_points(points)
+  st = prm.camera_to_local(prm.per_sample(cam_pitch, b), prm.per_sample(cam_height, b), n)
+  return _run_steps(points, _pick_device(device, points), [st])
+
+
+def local_to_camera_space(points: torch.Tensor, cam_pitch: torch.Tensor, cam_height: torch.Tensor,
+                          device: Optional[torch.device] = None, _validate_args: bool = True) -> torch.Tensor:
+  """Inverse of camera_to_local_space (maps.py:802-848)."""
+  b, n = _n_points(points)
+  st = prm.local_to_camera(prm.per_sample(cam_pitch, b), prm.per_sample(cam_height, b), n)
+  return _run_steps(points, _pick_device(device, points), [st])
+
+
+def local_to_global_space(points: torch.Tensor, cam_pose: torch.Tensor,
+                          device: Optional[torch.device] = None, _validate_args: bool = True) -> torch.Tensor:
+  """Rotate by yaw about y, translate by (x, 0, z) (maps.py:850-895)."""
+  b, n = _n_points(points)
+  st = prm.local_to_global(prm.per_sample(cam_pose, b, (3,)), n)
+  return _run_steps(points, _pick_device(device, points), [st])
+
+
+def global_to_local_space(points: torch.Tensor, cam_pose: torch.Tensor,
+                          device: Optional[torch.device] = None, _validate_args: bool = True) -> torch.Tensor:
+  """Inverse of local_to_global_space (maps.py:897-942)."""
+  b, n = _n_points(points)
+  st = prm.global_to_local(prm.per_sample(cam_pose, b, (3,)), n)
+  return _run_steps(points, _pick_device(device, points), [st])
+
+
+def _coords_pair(x_coords, z_coords, dev):
+  x = utils.to_tensor(x_coords).to(device=dev, dtype=torch.float32)
+  z = utils.to_tensor(z_coords).to(device=dev, dtype=torch.float32)
+  x, z = torch.broadcast_tensors(x, z)
+  shape = x.shape
+  if x.dim() < 2:
+    x, z = x.reshape(1, -1), z.reshape(1, -1)
+  b = x.shape[0]
+  return x.reshape(b, -1).contiguous(), z.reshape(b, -1).contiguous(), shape, b
+
+
+def map_quantize(x_coords: torch.Tensor, z_coords: torch.Tensor, width_offset: torch.Tensor,
+                 height_offset: torch.Tensor, map_res: float, map_height: Optional[int] = None,
+                 flip_h: bool = True, device: Optional[torch.device] = None,
+                 _validate_args: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+  """World x, z → integer map bins, rounding half up (maps.py:944-1019)."""
+  dev = _pick_device(device, x_coords, z_coords)
+  x, z, shape, b = _coords_pair(x_coords, z_coords, dev)
+  if flip_h:
+    assert map_height is not None
+  woff = prm.upload(prm.per_sample(width_offset, b).contiguous(), dev)
+  hoff = prm.upload(prm.per_sample(height_offset, b).contiguous(), dev)
+  xb = torch.empty(x.shape, dtype=torch.int64, device=dev)
+  zb = torch.empty(x.shape, dtype=torch.int64, device=dev)
+  with torch.cuda.device(dev):
+    rc = nat.lib().dm_map_quantize_f32(x.data_ptr(), z.data_ptr(), woff.data_ptr(), hoff.data_ptr(), b,
+                                       x.shape[1], map_res, int(map_height or 0), int(bool(flip_h)),
+                                       xb.data_ptr(), zb.data_ptr(), nat.stream_ptr(dev))
+  nat.check(rc, "dm_map_quantize_f32")
+  out_shape = shape if len(shape) >= 2 else (1, xb.numel())
+  return xb.reshape(out_shape), zb.reshape(out_shape)
+
+
+def map_dequantize(x_coords: torch.Tensor, z_coords: torch.Tensor, width_offset: torch.Tensor,
+                   height_offset: torch.Tensor, map_res: float, map_height: Optional[int] = None,
+                   flip_h: bool = True, device: Optional[torch.device] = None,
+                   _validate_args: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+  """Inverse of map_quantize (maps.py:1021-1087)."""
+  dev = _pick_device(device, x_coords, z_coords)
+  xb, zb, shape, b = _coords_pair(x_coords, z_coords, dev)
+  if flip_h:
+    assert map_height is not None
+  woff = prm.upload(prm.per_sample(width_offset, b).contiguous(), dev)
+  hoff = prm.upload(prm.per_sample(height_offset, b).contiguous(), dev)
+  x = torch.empty_like(xb)
+  z = torch.empty_like(zb)
+  with torch.cuda.device(dev):
+    rc = nat.lib().dm_map_dequantize_f32(xb.data_ptr(), zb.data_ptr(), woff.data_ptr(), hoff.data_ptr(), b,
+                                         xb.shape[1], map_res, int(map_height or 0), int(bool(flip_h)),
+                                         x.data_ptr(), z.data_ptr(), nat.stream_ptr(dev))
+  nat.check(rc, "dm_map_dequantize_f32")
+  out_shape = shape if len(shape) >= 2 else (1, x.numel())
+  return x.reshape(out_shape), z.reshape(out_shape)
+
+
+def project(coords: torch.Tensor, values: torch.Tensor, masks: torch.Tensor, canvas: torch.Tensor,
+            canvas_masks: Optional[torch.Tensor] = None, fill_value: Optional[float] = None,
+            reduction: Optional[Reduction] = None, device: Optional[torch.device] = None,
+            _validate_args: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+  """Scatter `values` (b, ..., n) onto `canvas` (b, ..., mh, mw) at `coords` (b, ..., n, 2) =
+  [row, col]; out-of-range or masked points are dropped (maps.py:1089-1173)."""
+  dev = _pick_device(device, coords, values, canvas)
+  coords = utils.to_tensor(coords).to(device=dev, dtype=torch.int64)
+  if coords.dim() < 3:
+    coords = coords.view(1, -1, 2)
+  maps_, changed = utils.scatter_tensor(canvas=canvas, indices=coords, values=values, masks=masks,
+                                        fill_value=fill_value, reduction=reduction)
+  if canvas_masks is not None:
+    cm = utils.to_tensor(canvas_masks).to(device=dev, dtype=torch.bool)
+    changed = torch.logical_or(torch.broadcast_to(cm, changed.shape), changed)
+  return maps_, changed
+
+
+def compute_center_offsets(cam_pose: torch.Tensor, width_offset: torch.Tensor, height_offset: torch.Tensor,
+                           map_res: float, map_width: float, map_height: int, to_global: bool,
+                           center_mode: CenterMode = CenterMode.none, device: Optional[torch.device] = None,
+                           _validate_args: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+  """Map offsets that put the origin / the camera at the map centre (maps.py:1175-1248).
+  A handful of floats per sample: host arithmetic (float32, reference op order); the results
+  are host tensors that feed the kernels' parameter blocks."""
+  center_mode = CenterMode(center_mode)
+  pose = prm.host_f32(np.zeros(3, np.float32) if cam_pose is None else cam_pose)
+  woff = prm.host_f32(0. if width_offset is None else width_offset)
+  hoff = prm.host_f32(0. if height_offset is None else height_offset)
+  if center_mode is CenterMode.none:
+    return woff + 0., hoff + 0.
+  pose = pose.reshape(-1, 3)
+  center_x = torch.zeros(pose.shape[0])
+  center_z = torch.zeros(pose.shape[0])
+  if center_mode is CenterMode.camera and to_global:
+    # local_to_global_space of the origin: rot(0) + (x, 0, z)   (maps.py:1228-1233)
+    center_x = center_x + pose[:, 0]
+    center_z = center_z + pose[:, 1]
+  # map_quantize(width_offset=0., height_offset=0., flip_h=False)   (maps.py:1235-1243)
+  res = torch.tensor(map_res, dtype=torch.float32)
+  qx = torch.floor(center_x / res + 0. + 0.5).to(torch.int64).view(1, -1)
+  qz = torch.floor(center_z / res + 0. + 0.5).to(torch.int64).view(1, -1)
+  return woff + (map_width / 2. - qx), hoff + (map_height / 2. - qz)
+
+
+# ======== MapProjector (maps.py:1252-1749) ======================================================
+
+# name of a functional-API parameter → where MapProjector finds its default
+_INTRINSIC_DEFAULTS = {"focal_x": "fx", "focal_y": "fy", "center_x": "cx", "center_y": "cy"}
+_ATTR_DEFAULTS = (
+  "cam_pose", "width_offset", "height_offset", "cam_pitch", "cam_height", "map_res", "map_width",
+  "map_height", "trunc_depth_min", "trunc_depth_max", "trunc_height_max", "clip_border", "to_global",
+  "flip_h", "fill_value", "reduction", "device", "height",
+)
+_OPTIONAL_DATA = ("value_map", "valid_map")
+_CTOR_ARGS = (
+  "width", "height", "hfov", "vfov", "cam_pose", "width_offset", "height_offset", "cam_pitch", "cam_height",
+  "map_res", "map_width", "map_height", "trunc_depth_min", "trunc_depth_max", "trunc_height_max",
+  "clip_border", "to_global", "flip_h", "fill_value", "reduction", "device",
+)
+
+
+def _with_projector_defaults(fn):
+  """Method wrapper: every argument left at None falls back to the projector's stored default
+  (the reference spells this out per method as get(arg, self.arg), maps.py:1406-1749)."""
+  params = list(inspect.signature(fn).parameters.values())
+  names = [p.name for p in params]
+  own_defaults = {p.name: p.default for p in params if p.default is not inspect.Parameter.empty}
+  keep_own = {"get_height_map", "_validate_args", "center_mode", "canvas_masks", "_emit_flow"}
+
+  def method(self, *args, **kwargs):
+    if len(args) > len(names):
+      raise TypeError(f"{fn.__name__}() takes at most {len(names)} positional arguments")
+    call = dict(zip(names, args))
+    for k, v in kwargs.items():
+      if k not in names:
+        raise TypeError(f"{fn.__name__}() got an unexpected keyword argument '{k}'")
+      if k in call:
+        raise TypeError(f"{fn.__name__}() got multiple values for argument '{k}'")
+      call[k] = v
+    for name in names:
+      if name in keep_own:
+        call.setdefault(name, own_defaults[name])
+      elif call.get(name) is None:
+        if name in _INTRINSIC_DEFAULTS:
+          call[name] = getattr(self.cam_params, _INTRINSIC_DEFAULTS[name])
+        elif name in _ATTR_DEFAULTS:
+          call[name] = getattr(self, name)
+        elif name in _OPTIONAL_DATA:
+          call[name] = None
+        elif name not in call:
+          raise TypeError(f"{fn.__name__}() missing required argument: '{name}'")
+    return fn(**call)
+
+  method.__name__ = fn.__name__
+  method.__doc__ = fn.__doc__
+  return method
+
+
+class MapProjector():
+  """Stores the camera / map configuration once so the functional APIs can be called with only
+  the per-frame data; per-call keyword arguments override the stored values.  Constructor
+  arguments are those of the reference (maps.py:1253-1347): width, height, hfov, vfov, cam_pose
+  [x, z, yaw], width_offset, height_offset, cam_pitch, cam_height, map_res, map_width, map_height,
+  trunc_depth_min/max, trunc_height_max, clip_border, to_global, flip_h, fill_value (default
+  -inf), reduction, device."""
+
+  def __init__(
+    self,
+    width: int,
+    height: int,
+    hfov: float,
+    vfov: Optional[float] = None,
+    cam_pose: Optional[Float3D] = None,
+    width_offset: Optional[float] = None,
+    height_offset: Optional[float] = None,
+    cam_pitch: Optional[float] = None,
+    cam_height: Optional[float] = None,
+    map_res: Optional[float] = None,
+    map_width: Optional[int] = None,
+    map_height: Optional[int] = None,
+    trunc_depth_min: Optional[float] = None,
+    trunc_depth_max: Optional[float] = None,
+    trunc_height_max: Optional[float] = None,
+    clip_border: Optional[int] = None,
+    to_global: bool = False,
+    flip_h: bool = True,
+    fill_value: Optional[float] = NINF,
+    reduction: Optional[Reduction] = None,
+    device: Optional[torch.device] = None
+  ):
+    given = locals()
+    for name in _CTOR_ARGS:
+      setattr(self, name, given[name])
+    self.cam_params: CameraIntrinsics = utils.get_camera_intrinsics(
+      width=self.width, height=self.height, hfov=self.hfov, vfov=self.vfov)
+
+  def clone(self, **overrides) -> "MapProjector":
+    """Shallow copy with some constructor arguments replaced (None keeps the stored value),
+    maps.py:1349-1404."""
+    unknown = set(overrides) - set(_CTOR_ARGS)
+    if unknown:
+      raise TypeError(f"clone() got unexpected keyword arguments {sorted(unknown)}")
+    return MapProjector(**{name: get(overrides.get(name), getattr(self, name)) for name in _CTOR_ARGS})
+
+  orth_project = _with_projector_defaults(orth_project)
+  camera_affine_grid = _with_projector_defaults(camera_affine_grid)
+  depth_map_to_point_cloud = _with_projector_defaults(depth_map_to_point_cloud)
+  height_map_to_point_cloud = _with_projector_defaults(height_map_to_point_cloud)
+  image_to_camera_space = _with_projector_defaults(image_to_camera_space)
+  camera_to_image_space = _with_projector_defaults(camera_to_image_space)
+  camera_to_local_space = _with_projector_defaults(camera_to_local_space)
+  local_to_camera_space = _with_projector_defaults(local_to_camera_space)
+  local_to_global_space = _with_projector_defaults(local_to_global_space)
+  global_to_local_space = _with_projector_defaults(global_to_local_space)
+  map_quantize = _with_projector_defaults(map_quantize)
+  map_dequantize = _with_projector_defaults(map_dequantize)
+  project = _with_projector_defaults(project)
+  compute_center_offsets = _with_projector_defaults(compute_center_offsets)
+
+
+# ======== TopdownMap (maps.py:1753-1955) ========================================================
+
+class TopdownMap():
+  """A top-down map with its mask, height map and the projector that produced it."""
+
+  def __init__(self, topdown_map: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None,
+               height_map: Optional[torch.Tensor] = None, map_projector: Optional[MapProjector] = None,
+               is_height_map: Optional[bool] = None):
+    self._proj = map_projector
+    self._topdown_map = topdown_map
+    self._mask = mask
+    self._height_map = height_map
+    if is_height_map is None:  # same object ⇒ the map is its own height map (maps.py:1781-1783)
+      is_height_map = (topdown_map is not None) and (topdown_map is height_map)
+    self._is_height_map = is_height_map
+
+  @property
+  def is_empty(self) -> bool:
+    return self._topdown_map is None
+
+  @property
+  def is_height_map(self) -> bool:
+    return self._is_height_map
+
+  @property
+  def map(self) -> torch.Tensor:
+    return self._topdown_map
+
+  @property
+  def topdown_map(self) -> torch.Tensor:
+    return self._topdown_map
+
+  @property
+  def height_map(self) -> torch.Tensor:
+    return self._topdown_map if self._is_height_map else self._height_map
+
+  @property
+  def mask(self) -> torch.Tensor:
+    return self._mask
+
+  @property
+  def proj(self) -> MapProjector:
+    return self._proj
+
+  def get_camera(self) -> torch.Tensor:
+    """Map coordinates (b, 2) int64 of the camera, i.e. of the local origin (maps.py:1824-1839)."""
+    return self.get_coords(torch.zeros((3,), dtype=torch.float32), is_global=False).squeeze(dim=-2)
+
+  def get_origin(self) -> torch.Tensor:
+    """Map coordinates (b, 2) int64 of the global origin (maps.py:1841-1856)."""
+    return self.get_coords(torch.zeros((3,), dtype=torch.float32), is_global=True).squeeze(dim=-2)
+
+  def get_coords(self, points: torch.Tensor, is_global: bool = True) -> torch.Tensor:
+    """Map coordinates (b, n, 2) int64 [x_bin, z_bin] of 3-D points (maps.py:1858-1897)."""
+    points = utils.to_tensor(points)
+    if points.dim() < 3:
+      points = points.view(1, -1, 3)
+    if self.proj.to_global and not is_global:
+      points = self.proj.local_to_global_space(points=points)
+    elif (not self.proj.to_global) and is_global:
+      points = self.proj.global_to_local_space(points=points)
+    pos_x, pos_z = self.proj.map_quantize(x_coords=points[..., 0], z_coords=points[..., 2])
+    return torch.stack((pos_x, pos_z), dim=-1)
+
+  def get_points(self, coords: torch.Tensor) -> torch.Tensor:
+    """World (x, z) (b, n, 2) float32 of map coordinates (maps.py:1899-1921)."""
+    coords = utils.to_tensor(coords)
+    if coords.dim() < 3:
+      coords = coords.view(1, -1, 2)
+    pos_x, pos_z = self.proj.map_dequantize(x_coords=coords[..., 0], z_coords=coords[..., 1])
+    return torch.stack((pos_x, pos_z), dim=-1)
+
+  def select(self, center: torch.Tensor, crop_width: int, crop_height: int,
+             fill_value: Optional[float] = None) -> "TopdownMap":
+    """Crop (or pad) a crop_width × crop_height window around `center` (maps.py:1923-1949)."""
+    return crop_topdown_map(self, center=center, crop_width=crop_width, crop_height=crop_height,
+                            fill_value=fill_value, _validate_args=True)
+
+  def merge(self, *sources: List["TopdownMap"]) -> "TopdownMap":
+    raise NotImplementedError
+
+
+# ======== TopdownMap functional API ===============================================================
+
+def _crop(image: torch.Tensor, center_dev: torch.Tensor, crop_h: int, crop_w: int,
+          fill_value: Optional[float]) -> torch.Tensor:
+  b, c, h, w = image.shape
+  dev = image.device
+  lib = nat.lib()
+  with torch.cuda.device(dev):
+    if image.dtype == torch.bool:
+      out = torch.empty((b, c, crop_h, crop_w), dtype=torch.bool, device=dev)
+      rc = lib.dm_crop_nearest_u8(image.data_ptr(), center_dev.data_ptr(), b, c, h, w, crop_h, crop_w,
+                                  out.data_ptr(), nat.stream_ptr(dev))
+    else:
+      out = torch.empty((b, c, crop_h, crop_w), dtype=torch.float32, device=dev)
+      rc = lib.dm_crop_nearest_f32(image.data_ptr(), center_dev.data_ptr(), b, c, h, w, crop_h, crop_w,
+                                   int(fill_value is not None), 0. if fill_value is None else fill_value,
+                                   out.data_ptr(), nat.stream_ptr(dev))
+  nat.check(rc, "dm_crop_nearest")
+  return out
+
+
+def crop_topdown_map(source: TopdownMap, center: torch.Tensor, crop_width: int, crop_height: int,
+                     fill_value: Optional[float] = None, mode: str = 'nearest',
+                     _validate_args: bool = True) -> TopdownMap:
+  """Nearest-neighbour crop of map, mask and height map around `center` (b, 2) = [x, y] in map
+  pixels, exactly as the reference's pad + grid_sample formulation resamples it
+  (maps.py:1959-2037); one fused kernel per tensor (csrc/dm_points.cu crop_kernel).  Unlike the
+  reference, the caller's `center` tensor is not modified (maps.py:2021-2022 does, by aliasing)."""
+  if mode != 'nearest':
+    raise NotImplementedError("only mode='nearest' is implemented by the B200 kernels")
+  proj = source.proj
+  hm = source.height_map
+  dev = hm.device
+  center_host = prm.host_f32(center, (2,))
+  b = hm.shape[0]
+  center_dev = prm.upload(prm.per_sample(center_host, b, (2,), "center").contiguous(), dev)
+  base = hm[:, :1] if (hm.dim() == 4 and hm.stride(1) == 0 and hm.shape[1] > 1) else hm
+  height_map = _crop(base.contiguous(), center_dev, crop_height, crop_width, NINF)
+  if base is not hm:
+    height_map = height_map.expand(b, hm.shape[1], crop_height, crop_width)
+  mask = _crop(source.mask.to(torch.bool).contiguous(), center_dev, crop_height, crop_width, False)
+  topdown_map = height_map
+  if not source.is_height_map:
+    topdown_map = _crop(source.topdown_map.contiguous(), center_dev, crop_height, crop_width,
+                        get(fill_value, proj.fill_value))
+  # new offsets (maps.py:2020-2024), float32 host arithmetic
+  cx, cy = center_host[:, 0].clone(), center_host[:, 1].clone()
+  if proj.flip_h:
+    cy = (proj.map_height - 1) - cy
+  width_offset = prm.host_f32(proj.width_offset) + crop_width / 2 - cx
+  height_offset = prm.host_f32(proj.height_offset) + crop_height / 2 - cy
+  new_proj = proj.clone(width_offset=width_offset, height_offset=height_offset, map_width=crop_width,
+                        map_height=crop_height)
+  return TopdownMap(topdown_map=topdown_map, mask=mask, height_map=height_map,
+                    is_height_map=source.is_height_map, map_projector=new_proj)
+
+
+def _fuse_source(m: TopdownMap, target: MapProjector, b: int, C: int, n_total: int, dev: torch.device,
+                 keep: list) -> nat.DmFuseSource:
+  hm = m.height_map.to(device=dev, dtype=torch.float32)
+  if hm.dim() != 4:
+    hm = utils.to_4D_image(hm)
+  h, w = hm.shape[-2:]
+  if hm.stride(-1) != 1 or hm.stride(-2) != w:
+    hm = hm.contiguous()
+  hm = hm.expand(b, C, h, w)
+  mask = m.mask.to(device=dev, dtype=torch.bool).expand(b, C, h, w).contiguous()
+  values = None
+  if not m.is_height_map:
+    values = m.topdown_map.to(device=dev, dtype=torch.float32).expand(b, C, h, w).contiguous()
+  pose = prm.per_sample(get(m.proj.cam_pose, [0., 0., 0.]), b, (3,), "cam_pose")
+  tpose = prm.per_sample(get(target.cam_pose, [0., 0., 0.]), b, (3,), "cam_pose")
+  # maps.py:2059-2060: a local map goes to global space with its own pose;
+  # maps.py:2116-2117: everything goes to the target's local space if the target is local
+  s0 = prm.identity(b) if m.proj.to_global else prm.local_to_global(pose, C * h * w)
+  s1 = prm.identity(b) if target.to_global else prm.global_to_local(tpose, n_total)
+  steps = prm.upload(torch.cat((s0, s1), dim=1), dev)
+  woff = prm.upload(prm.per_sample(get(m.proj.width_offset, 0.), b).contiguous(), dev)
+  hoff = prm.upload(prm.per_sample(get(m.proj.height_offset, 0.), b).contiguous(), dev)
+  keep.extend((hm, mask, values, steps, woff, hoff))
+  src = nat.DmFuseSource()
+  src.height, src.values, src.mask = hm.data_ptr(), nat.ptr(values), mask.data_ptr()
+  src.height_bstride, src.height_cstride = hm.stride(0), hm.stride(1)
+  src.h, src.w = h, w
+  src.flip_h = bool(m.proj.flip_h)
+  src.map_res = m.proj.map_res
+  src.width_offset, src.height_offset, src.steps = woff.data_ptr(), hoff.data_ptr(), steps.data_ptr()
+  return src
+
+
+def fuse_topdown_maps(*maps: List[TopdownMap], map_projector: Optional[MapProjector] = None,
+                      fill_value: Optional[float] = None, reduction: Optional[Reduction] = None) -> TopdownMap:
+  """Re-project several top-down maps into one freshly sized map in `map_projector`'s frame
+  (maps.py:2181-2287): every valid cell becomes a point again, one bounding box over all of them
+  sizes the canvas (host sync), and the points are scatter-maxed into it.  Two fused passes over
+  the source cells (csrc/dm_fuse.cu), no point cloud is materialised."""
+  if len(maps) == 0:
+    return TopdownMap(map_projector=map_projector)
+  proj = map_projector if map_projector is not None else maps[0].proj
+  live = [m for m in maps if not m.is_empty]
+  if not live:
+    return TopdownMap(map_projector=proj)
+  kinds = {bool(m.is_height_map) for m in live}
+  assert len(kinds) == 1, "All maps must be the same type of maps (all height maps or all value maps)."
+  is_height_map = kinds.pop()
+  red = utils._reduction_code(reduction)
+  dev = _pick_device(proj.device, *[m.mask for m in live], *[m.height_map for m in live])
+  shapes = [utils.to_4D_image(m.mask).shape for m in live]
+  b = max(s[0] for s in shapes)
+  C = max(s[1] for s in shapes)
+  n_total = sum(C * s[2] * s[3] for s in shapes)
+  keep: list = []
+  sources = (nat.DmFuseSource * len(live))(*[_fuse_source(m, proj, b, C, n_total, dev, keep) for m in live])
+  lib = nat.lib()
+  bbox = torch.empty((5,), dtype=torch.int64, device=dev)
+  with torch.cuda.device(dev):
+    rc = lib.dm_fuse_bbox_i64(sources, len(live), b, C, proj.map_res, bbox.data_ptr(), nat.stream_ptr(dev))
+  nat.check(rc, "dm_fuse_bbox_i64")
+  min_x, max_x, min_z, max_z, n_valid = (int(v) for v in bbox.cpu())  # the reference's .item() sync
+  if n_valid == 0:  # maps.py:2217-2225
+    last = maps[-1]
+    return TopdownMap(topdown_map=last.topdown_map, mask=last.mask, height_map=last.height_map, map_projector=proj)
+  # maps.py:2171-2178 (float32 host arithmetic; exact for any realistic map size)
+  map_width = (max_x - min_x) + 2
+  map_height = (max_z - min_z) + 2
+  width_offset = torch.tensor(map_width / 2., dtype=torch.float32) - torch.tensor(max_x + min_x) / 2.
+  height_offset = torch.tensor(map_height / 2., dtype=torch.float32) - torch.tensor(max_z + min_z) / 2.
+  tgt = nat.DmFuseTarget()
+  tgt.Mh, tgt.Mw = map_height, map_width
+  tgt.flip_h = bool(proj.flip_h)
+  tgt.map_res = proj.map_res
+  tgt.width_offset, tgt.height_offset = float(width_offset), float(height_offset)
+  tgt.fill_value = get(fill_value, proj.fill_value, NINF)
+  tgt.reduction = red
+  topdown = torch.empty((b, C, map_height, map_width), dtype=torch.float32, device=dev)
+  mask = torch.empty((b, C, map_height, map_width), dtype=torch.bool, device=dev)
+  height = None if is_height_map else torch.empty_like(topdown)
+  with torch.cuda.device(dev):
+    rc = lib.dm_fuse_scatter_f32(sources, len(live), b, C, tgt, topdown.data_ptr(), mask.data_ptr(),
+                                 nat.ptr(height), nat.stream_ptr(dev))
+  nat.check(rc, "dm_fuse_scatter_f32")
+  new_proj = proj.clone(width_offset=width_offset, height_offset=height_offset, map_width=map_width,
+                        map_height=map_height)
+  return TopdownMap(topdown_map=topdown, mask=mask, height_map=topdown if is_height_map else height,
+                    map_projector=new_proj, is_height_map=is_height_map)
+
+
+# ======== MapBuilder (maps.py:2289-2550) ==========================================================
+
+class MapBuilder():
+  """Plots a local top-down map per frame and merges it into a growing world map."""
+
+  def __init__(self, map_projector: MapProjector, world_map: Optional[TopdownMap] = None):
+    self._proj = map_projector
+    self._world_map = world_map if world_map is not None else TopdownMap(map_projector=self.proj.clone())
+
+  @property
+  def proj(self) -> MapProjector:
+    return self._proj
+
+  @property
+  def world_map(self) -> TopdownMap:
+    return self._world_map
+
+  def reset(self, depth_map: Optional[np.ndarray] = None, value_map: Optional[np.ndarray] = None,
+            valid_map: Optional[np.ndarray] = None, cam_pose: Optional[np.ndarray] = None,
+            center_mode: CenterMode = CenterMode.none, **kwargs):
+    """Forget the world map; if a frame is given, plot and merge it (maps.py:2312-2355)."""
+    self._world_map = TopdownMap(map_projector=self.proj.clone())
+    if depth_map is None:
+      return None
+    return self.step(depth_map=depth_map, value_map=value_map, valid_map=valid_map, cam_pose=cam_pose,
+                     center_mode=center_mode, **kwargs)
+
+  def step(self, depth_map: np.ndarray, value_map: Optional[np.ndarray] = None,
+           valid_map: Optional[np.ndarray] = None, cam_pose: Optional[np.ndarray] = None,
+           center_mode: CenterMode = CenterMode.none, merge: bool = True, keep_pose: bool = False,
+           **kwargs: Dict[str, Any]) -> TopdownMap:
+    """Plot the frame's local map and (by default) merge it into the world map
+    (maps.py:2357-2406).  Returns the local map."""
+    topdown_map = self.plot(depth_map=depth_map, value_map=value_map, valid_map=valid_map, cam_pose=cam_pose,
+                            center_mode=center_mode, **kwargs)
+    if merge:
+      self.merge(topdown_map, keep_pose=keep_pose)
+    return topdown_map
+
+  def plot(self, depth_map: np.ndarray, value_map: Optional[np.ndarray] = None,
+           valid_map: Optional[np.ndarray] = None, cam_pose: Optional[np.ndarray] = None,
+           center_mode: CenterMode = CenterMode.none, **kwargs: Dict[str, Any]) -> TopdownMap:
+    """orth_project with get_height_map=True, wrapped as a TopdownMap that remembers the pose and
+    offsets it was plotted with (maps.py:2408-2469)."""
+    cam_pose = get(cam_pose, self.proj.cam_pose, np.array([0., 0., 0.], dtype=np.float32))
+    width_offset, height_offset = self._compute_offsets(cam_pose=cam_pose, center_mode=center_mode, **kwargs)
+    kwargs['width_offset'] = width_offset
+    kwargs['height_offset'] = height_offset
+    kwargs.pop('get_height_map', None)
+    topdown_map, mask, height_map = self.proj.orth_project(
+      depth_map=depth_map, value_map=value_map, valid_map=valid_map, cam_pose=cam_pose,
+      get_height_map=True, **kwargs)
+    clone_kwargs = {k: v for k, v in kwargs.items() if k in _CTOR_ARGS}
+    return TopdownMap(topdown_map=topdown_map, mask=mask, height_map=height_map,
+                      map_projector=self.proj.clone(cam_pose=cam_pose, **clone_kwargs),
+                      is_height_map=(value_map is None))
+
+  def merge(self, topdown_map: TopdownMap, keep_pose: bool = False, fill_value: Optional[float] = None,
+            reduction: Optional[Reduction] = None) -> TopdownMap:
+    """Fuse `topdown_map` into the world map, in the new map's camera frame unless `keep_pose`
+    (maps.py:2471-2508)."""
+    if self._world_map is None:
+      self._world_map = TopdownMap(map_projector=self.proj.clone())
+    cam_pose = self._world_map.proj.cam_pose if keep_pose else topdown_map.proj.cam_pose
+    self._world_map = fuse_topdown_maps(self._world_map, topdown_map,
+                                        map_projector=self.proj.clone(cam_pose=cam_pose),
+                                        fill_value=fill_value, reduction=reduction)
+    return self._world_map
+
+  def _compute_offsets(self, cam_pose: np.ndarray, width_offset: Optional[np.ndarray] = None,
+                       height_offset: Optional[np.ndarray] = None, map_res: Optional[float] = None,
+                       map_width: Optional[int] = None, map_height: Optional[int] = None,
+                       to_global: Optional[bool] = None, center_mode: Optional[CenterMode] = None,
+                       **kw_) -> Tuple[torch.Tensor, torch.Tensor]:
+    return self.proj.compute_center_offsets(cam_pose=cam_pose, width_offset=width_offset,
+                                            height_offset=height_offset, map_res=map_res, map_width=map_width,
+                                            map_height=map_height, to_global=to_global, center_mode=center_mode)

@@ -38,6 +38,8 @@ extern "C" {
  *                                                  local_to_global_space  maps.py:850-895
  *   kind 2 (ADD_THEN_ROT): p' = rot(R, p + t)      local_to_camera_space  maps.py:802-848
  *                                                  global_to_local_space  maps.py:897-942
+ *   kind 3 (ADD): p' = p + t                        utils.translate        utils.py:229-259
+ *   kind 4 (ROT): p' = rot(R, p)                    utils.rotate           utils.py:261-330
  *   kind 0: identity (step skipped)
  * rot(R, p)_i, utils.py:329 (einsum 'bji,b...j->b...i' → at::bmm), depends on how many
  * points n the reference rotates in one call, because ATen switches kernels:
@@ -48,6 +50,8 @@ extern "C" {
 #define DM_STEP_NONE 0
 #define DM_STEP_ROT_THEN_ADD 1
 #define DM_STEP_ADD_THEN_ROT 2
+#define DM_STEP_ADD 3
+#define DM_STEP_ROT 4
 
 typedef struct DmStep {
   float R[9]; /* row-major R[j][i] = R[3*j+i] */
@@ -142,7 +146,9 @@ int dm_affine_grid_f32(const float* depth, const DmFlowSample* samples, const Dm
 
 /* ---- MapBuilder merge: fuse_topdown_maps (maps.py:2181-2287) ---------------- */
 
-/* One source map of a fusion, all samples sharing its geometry. */
+/* One source map of a fusion, all samples sharing its geometry.  The DmFuseSource array
+ * handed to the two calls below lives in HOST memory (at most 8 sources per call); the
+ * pointers inside it are device pointers. */
 typedef struct DmFuseSource {
   const float* height;   /* (b, C, h, w) f32; channel stride may be 0 (stride-0 expand, maps.py:349) */
   const float* values;   /* (b, C, h, w) f32 or NULL for a height map */
@@ -213,11 +219,12 @@ int dm_map_dequantize_f32(const float* x_bin, const float* z_bin, const float* w
 
 /* scatter_tensor utils.py:389-492 / project maps.py:1089-1173 for 2-D canvases:
  * values (B, N) f32, coords (B, N, 2) int64 [row, col], valid (B, N) u8 or NULL,
- * canvas (B, Mh, Mw) f32 in/out (pre-filled by the call when has_fill),
- * mask (B, Mh, Mw) u8 out.  reduction 0 max, 1 min. */
+ * canvas_in (B, Mh, Mw) f32 (ignored / may be NULL when has_fill), canvas_out (B, Mh, Mw) f32,
+ * mask (B, Mh, Mw) u8 out ("changed" vs the starting canvas).  reduction 0 max, 1 min. */
 int dm_scatter_f32(const float* values, const int64_t* coords, const uint8_t* valid, int64_t B,
                    int64_t N, int32_t Mh, int32_t Mw, int32_t has_fill, float fill_value,
-                   int32_t reduction, float* canvas, uint8_t* mask, void* stream);
+                   int32_t reduction, const float* canvas_in, float* canvas_out, uint8_t* mask,
+                   void* stream);
 
 /* crop_topdown_map maps.py:1959-2037 = generate_crop_grid utils.py:571-611 +
  * image_sample utils.py:613-652 (pad 1, grid_sample nearest, align_corners).

@@ -6,7 +6,7 @@
  * and bench.py's cpu_baseline / --impl reference legs may load this.
  *
  * Parity is PINNED: tests/test_oracle_golden.py checks every function here
- * bit-for-bit against tests/golden/*.npz, which oracle/make_golden.py produced
+ * bit-for-bit against tests/golden/ (npz files), which oracle/make_golden.py produced
  * by running the unmodified reference (imported from /root/reference through
  * the torch_scatter stand-in in oracle/ref_shim.py) on CPU.
  *
@@ -62,6 +62,8 @@ static inline vec3 add3(vec3 p, const float* t) {
 static inline vec3 apply_step(const DmStep* s, vec3 p) {
   if (s->kind == DM_STEP_ROT_THEN_ADD) return add3(rot(s->R, p, s->fused), s->t);
   if (s->kind == DM_STEP_ADD_THEN_ROT) return rot(s->R, add3(p, s->t), s->fused);
+  if (s->kind == DM_STEP_ADD) return add3(p, s->t);
+  if (s->kind == DM_STEP_ROT) return rot(s->R, p, s->fused);
   return p;
 }
 
