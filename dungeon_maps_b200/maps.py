@@ -822,8 +822,9 @@ def fuse_topdown_maps(*maps: List[TopdownMap], map_projector: Optional[MapProjec
   # maps.py:2171-2178 (float32 host arithmetic; exact for any realistic map size)
   map_width = (max_x - min_x) + 2
   map_height = (max_z - min_z) + 2
-  width_offset = torch.tensor(map_width / 2., dtype=torch.float32) - torch.tensor(max_x + min_x) / 2.
-  height_offset = torch.tensor(map_height / 2., dtype=torch.float32) - torch.tensor(max_z + min_z) / 2.
+  # shape (1,) like the reference's (the bbox is reduced over a (1, n) view, maps.py:2159-2169)
+  width_offset = torch.tensor(map_width / 2., dtype=torch.float32) - torch.tensor([max_x + min_x]) / 2.
+  height_offset = torch.tensor(map_height / 2., dtype=torch.float32) - torch.tensor([max_z + min_z]) / 2.
   tgt = nat.DmFuseTarget()
   tgt.Mh, tgt.Mw = map_height, map_width
   tgt.flip_h = bool(proj.flip_h)

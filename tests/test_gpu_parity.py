@@ -282,8 +282,8 @@ def test_map_builder_matches_reference(name):
     assert_same(np.asarray(local.proj.width_offset, np.float32).reshape(-1), g[f"local_woff_{t}"].reshape(-1), "local woff")
     wm = builder.world_map
     assert [wm.proj.map_height, wm.proj.map_width] == m["world_shapes"][t], f"step {t} world shape"
-    assert_same(np.float32(wm.proj.width_offset), g[f"world_woff_{t}"], f"step {t} world woff")
-    assert_same(np.float32(wm.proj.height_offset), g[f"world_hoff_{t}"], f"step {t} world hoff")
+    assert_same(np.asarray(wm.proj.width_offset, np.float32).reshape(-1), g[f"world_woff_{t}"].reshape(-1), f"step {t} world woff")
+    assert_same(np.asarray(wm.proj.height_offset, np.float32).reshape(-1), g[f"world_hoff_{t}"].reshape(-1), f"step {t} world hoff")
     assert_same(npy(wm.topdown_map), g[f"world_topdown_{t}"], f"step {t} world topdown")
     assert_same(npy(wm.mask), g[f"world_mask_{t}"], f"step {t} world mask")
     assert_same(npy(wm.height_map), g[f"world_height_{t}"], f"step {t} world height")
