@@ -31,7 +31,7 @@ class DmProjCfg(ctypes.Structure):
     ("trunc_depth_min", c_float), ("trunc_depth_max", c_float), ("trunc_height_max", c_float),
     ("has_trunc_depth_min", c_int32), ("has_trunc_depth_max", c_int32), ("has_trunc_height_max", c_int32),
     ("clip_border", c_int32), ("flip_h", c_int32), ("fill_value", c_float), ("want_height", c_int32),
-    ("reduction", c_int32), ("_pad", c_int32 * 4),
+    ("reduction", c_int32), ("fast_steps", c_int32), ("_pad", c_int32 * 3),
   ]
 
 

@@ -110,6 +110,23 @@ def identity(b: int) -> torch.Tensor:
   return pack_steps(STEP_NONE, None, None, b, 0)
 
 
+def fast_steps(samples: torch.Tensor) -> int:
+  """DmProjCfg.fast_steps for a (b, 48) block of DmProjSample words: 1 / 2 when every sample's
+  steps have the structure the straight-line kernel path assumes (see the public header), else 0."""
+  ints = samples.view(torch.int32)
+  loc, glo = samples[:, 0:16], samples[:, 16:32]
+  local_ok = bool((ints[:, 12] == STEP_ROT_THEN_ADD).all() and (ints[:, 13] == 1).all()
+                  and (loc[:, 0] == 1).all() and (loc[:, [1, 2, 3, 6]] == 0).all()
+                  and (loc[:, [9, 11]] == 0).all())
+  if not local_ok:
+    return 0
+  if bool((ints[:, 28] == STEP_NONE).all()):
+    return 1
+  global_ok = bool((ints[:, 28] == STEP_ROT_THEN_ADD).all() and (ints[:, 29] == 1).all()
+                   and (glo[:, 4] == 1).all() and (glo[:, [1, 3, 5, 7]] == 0).all() and (glo[:, 10] == 0).all())
+  return 2 if global_ok else 0
+
+
 class _DeviceCache:
   """Small LRU of uploaded parameter blocks keyed by their bytes (MapProjector defaults
   repeat call after call)."""

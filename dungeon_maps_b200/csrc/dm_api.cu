@@ -68,12 +68,8 @@ extern "C" int dm_orth_project_host_f32(const float* depth, const float* values,
   const size_t N = (size_t)cfg->H * cfg->W, M = (size_t)cfg->Mh * cfg->Mw;
   const int Cv = cfg->C > 0 ? cfg->C : 1;
   const bool want_h = cfg->C > 0 && cfg->want_height && height;
-  // chunk = as many frames as one accumulation ring holds
-  const size_t ws_one = dm_orth_project_workspace_bytes(cfg, b);
-  DmProjCfg c1 = *cfg;
-  const size_t slot = dm_orth_project_workspace_bytes(&c1, 1);
-  int chunk = (int)(ws_one / (slot ? slot : 1));
-  if (chunk < 1) chunk = 1;
+  // chunk: a few frames per stream so that copies of one chunk overlap kernels of the other
+  int chunk = 8;
   if (chunk > b) chunk = b;
   // staging layout of one chunk (every section 256-byte aligned)
   const size_t o_depth = 0;

@@ -10,14 +10,19 @@
 //    acc[cell][CP] of 32-bit order-preserving keys.  A pixel's CU = C(+1 height) updates then
 //    hit one or two 128-byte lines instead of CU lines in CU different planes: one RED
 //    instruction per pixel-run instead of CU scattered ones.
-//  * Channel planes are staged tile by tile in shared memory ([channel][pixel], 128-bit
-//    coalesced streaming loads), then re-read transposed: lane = channel, a warp walks its
-//    pixels in order and keeps the running max of the current same-cell run in a register;
-//    the atomic is issued once per run (neighbouring pixels mostly land in the same cell).
-//    Values that cannot change the canvas (v <= fill) are never issued.
-//  * acc is a small ring of frame slots that stays resident in the 126 MB L2; the resolve
-//    pass decodes keys into the planar (b, C, Mh, Mw) outputs + "changed" masks and zeroes
-//    the slot again, so HBM sees only the inputs once and the outputs once.
+//  * Channel planes are staged tile by tile in shared memory ([channel][pixel]) by TMA bulk
+//    copies (cp.async.bulk + mbarrier, double buffered, L2 evict-first), then re-read
+//    transposed: lane = channel, a warp walks its pixels in order and keeps the running max of
+//    the current same-cell run in a register; the atomic is issued once per run (neighbouring
+//    pixels mostly land in the same cell).  Values that cannot change the canvas (v <= fill)
+//    are never issued.
+//  * ONE persistent launch per call: CTAs pull (frame, tile) work items from a ticket counter.
+//    Projection tiles of frame f+2 are interleaved with resolve tiles of frame f, which decode
+//    the keys into the planar (b, C, Mh, Mw) outputs + "changed" masks and zero the slot again.
+//    acc is a ring of 4 frame slots (≈44 MB at config 2) that stays resident in the 126 MB L2,
+//    so HBM sees the inputs once and the outputs once.
+//  * Shapes whose planes are not 16-byte aligned take the plain-load kernels (proj_kernel /
+//    resolve_kernel, chunked over the ring) — same device functions, same results.
 #include "dm_common.cuh"
 
 namespace dm {
@@ -25,18 +30,25 @@ namespace dm {
 constexpr int kProjThreads = 256;
 constexpr int kResolveCells = 256;
 constexpr size_t kRingBudgetBytes = 48u << 20;  // accumulation ring kept well inside L2
+constexpr int kLag = 2;                          // resolve(f) is scheduled with proj(f + kLag)
+constexpr int kCtrlWords = 64;                   // control block at the head of the workspace
+constexpr unsigned long long kSpinLimitNs = 4000000000ull;  // dependency wait guard (bug → no hang)
 
 struct ProjPlan {
   int Cv;     // value channels produced (C, or 1 when the heights are the values)
   int hasH;   // separate height channel accumulated after the values
   int CU;     // Cv + hasH: keys per cell
   int CP;     // cell stride in words (odd → conflict-free transposed smem reads)
+  int rows;   // staged rows per tile: C value planes + the depth/height row
   int tile;   // pixels per CTA tile
   int ring;   // frame slots
-  int vec;    // 128-bit path usable
   size_t slot_words;
-  size_t smem_proj;
+  size_t ctrl_bytes;
+  size_t stage_bytes;
+  size_t smem_tile;      // one stage + sample block (plain-load kernel)
   size_t smem_resolve;
+  size_t ws_stage_bytes; // warp-specialised kernel: one 512-pixel stage
+  size_t smem_ws;        // two stages + barriers/items/samples + column/row tables
 };
 
 static ProjPlan make_plan(const DmProjCfg& cfg, int b) {
@@ -45,26 +57,36 @@ static ProjPlan make_plan(const DmProjCfg& cfg, int b) {
   p.hasH = (cfg.C > 0 && cfg.want_height) ? 1 : 0;
   p.CU = p.Cv + p.hasH;
   p.CP = (p.CU & 1) ? p.CU : p.CU + 1;
+  p.rows = cfg.C + 1;
   const size_t M = (size_t)cfg.Mh * cfg.Mw;
   p.slot_words = (M * p.CP + 3) & ~(size_t)3;
   size_t ring = kRingBudgetBytes / (p.slot_words * 4);
-  if (ring < 1) ring = 1;
-  if (ring > (size_t)b) ring = (size_t)(b > 0 ? b : 1);
+  if (ring < 4) ring = 4;  // the persistent schedule needs kLag + 2 slots
   p.ring = (int)ring;
-  // staging rows: values + height row; +4 floats keeps rows 16-byte aligned and the
-  // transposed LDS.128 conflict-free (row stride ≡ 4 mod 8 words)
+  p.ctrl_bytes = ((size_t)(kCtrlWords + 2 * (b > 0 ? b : 1)) * 4 + 255) & ~(size_t)255;
+  // staging rows: +4 floats keeps rows 16-byte aligned and the transposed LDS.128
+  // conflict-free (row stride ≡ 4 mod 8 words)
   int tile = 1024;
-  const int rows = p.CU;
-  while (tile > 128 && (size_t)rows * (tile + 4) * 4 + (size_t)tile * 4 > (size_t)100 * 1024) tile >>= 1;
+  auto stage = [&](int t) { return (size_t)p.rows * (t + 4) * 4 + (size_t)t * 4; };
+  while (tile > 128 && stage(tile) > (size_t)40 * 1024) tile >>= 1;
   p.tile = tile;
-  p.smem_proj = (size_t)rows * (tile + 4) * 4 + (size_t)tile * 4 + sizeof(DmProjSample);
+  p.stage_bytes = (stage(tile) + 127) & ~(size_t)127;
   p.smem_resolve = (size_t)kResolveCells * p.CP * 4;
+  size_t st = p.stage_bytes > p.smem_resolve ? p.stage_bytes : ((p.smem_resolve + 127) & ~(size_t)127);
+  p.stage_bytes = st;
+  p.smem_tile = st + 256;
+  size_t ws = ((size_t)p.rows * (512 + 4) * 4 + 512 * 4 + 127) & ~(size_t)127;
+  const size_t ws_res = ((size_t)1024 * p.CP + 127) & ~(size_t)127;  // 4 warps x 64 cells x CP words
+  if (ws < ws_res) ws = ws_res;
+  p.ws_stage_bytes = ws;
+  p.smem_ws = 2 * ws + 512 + ((size_t)((cfg.W + 3) & ~3) + cfg.H) * 4;
   return p;
 }
 
 struct ProjDims {
-  int Cv, hasH, CU, CP, tile;
+  int Cv, hasH, CU, CP, rows, tile, ring;
   unsigned long long slot_words;
+  unsigned long long stage_bytes;
 };
 
 // One pixel: validity, cell index (or -1) and the height that goes into the height map.
@@ -87,130 +109,91 @@ __device__ __forceinline__ int pixel_cell(const DmProjCfg& cfg, const DmProjSamp
   return ok ? ((int)zf * cfg.Mw + (int)xf) : -1;  // utils.py:332-370
 }
 
-// ---- projection of one tile of one frame ---------------------------------------------------
-template <bool VEC>
-__device__ __forceinline__ void proj_tile(const float* __restrict__ depth, const float* __restrict__ values,
-                                          const uint8_t* __restrict__ valid,
-                                          const DmProjSample* __restrict__ samples, const DmProjCfg& cfg,
-                                          const ProjDims& d, int frame, int tile_idx,
-                                          uint32_t* __restrict__ acc_slot, unsigned char* smem) {
-  const int tid = threadIdx.x;
+// ---- phase A: cells + heights of one staged tile ------------------------------------------
+// The depth row of the stage is overwritten in place by the heights (it becomes the height
+// channel of phase B).  thread = 4 consecutive pixels.
+__device__ __forceinline__ void phase_a(const uint8_t* __restrict__ vplane, const DmProjSample& sp,
+                                        const DmProjCfg& cfg, int tile, int tile0, float* zrow, int* cells) {
   const int N = cfg.H * cfg.W;
-  const int tile = d.tile;
-  const int row_stride = tile + 4;
-  float* vals = reinterpret_cast<float*>(smem);                      // [CU][tile+4]
-  int* cells = reinterpret_cast<int*>(vals + (size_t)d.CU * row_stride);  // [tile]
-  DmProjSample* sp_s = reinterpret_cast<DmProjSample*>(cells + tile);
-
-  // per-sample parameters → smem (192 B)
-  if (tid < (int)(sizeof(DmProjSample) / 4))
-    reinterpret_cast<uint32_t*>(sp_s)[tid] = reinterpret_cast<const uint32_t*>(samples + frame)[tid];
-  __syncthreads();
-  const DmProjSample& sp = *sp_s;
-
-  const int tile0 = tile_idx * tile;
-  const float* dplane = depth + (size_t)frame * N;
-  const uint8_t* vplane = valid ? valid + (size_t)frame * N : nullptr;
-  const float* vbase = values ? values + (size_t)frame * cfg.C * N : nullptr;
-  float* hrow = vals + (size_t)(d.CU - 1) * row_stride;  // C == 0: the only row; hasH: last row
-
-  // ---- phase A: stage value planes, compute cells + heights (thread = 4 consecutive pixels)
-  for (int q = tid * 4; q < tile; q += kProjThreads * 4) {
+  for (int q = threadIdx.x * 4; q < tile; q += kProjThreads * 4) {
     const int n0 = tile0 + q;
-    float z[4];
-    bool ok[4];
-    if (VEC) {
-      if (n0 < N) {
-        const float4 z4 = ld_stream_f4(dplane + n0);
-        z[0] = z4.x; z[1] = z4.y; z[2] = z4.z; z[3] = z4.w;
-        uint32_t vm = 0x01010101u;
-        if (vplane) vm = *reinterpret_cast<const uint32_t*>(vplane + n0);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) ok[k] = ((vm >> (8 * k)) & 0xffu) != 0;
-        if (vbase) {
-#pragma unroll 8
-          for (int ch = 0; ch < cfg.C; ++ch) {
-            const float4 v = ld_stream_f4(vbase + (size_t)ch * N + n0);
-            *reinterpret_cast<float4*>(vals + (size_t)ch * row_stride + q) = v;
-          }
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { z[k] = 0.0f; ok[k] = false; }
-      }
-    } else {
+    int cl[4] = {-1, -1, -1, -1};
+    float y[4] = {0.f, 0.f, 0.f, 0.f};
+    if (n0 < N) {
+      const float4 z4 = *reinterpret_cast<const float4*>(zrow + q);
+      const float z[4] = {z4.x, z4.y, z4.z, z4.w};
+      int r = n0 / cfg.W;
+      int c = n0 - r * cfg.W;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int n = n0 + k;
-        const bool in = n < N;
-        z[k] = in ? ld_stream_f1(dplane + n) : 0.0f;
-        ok[k] = in && (vplane ? vplane[n] != 0 : true);
+        const bool ok = (n0 + k < N) && (vplane ? vplane[n0 + k] != 0 : true);
+        cl[k] = pixel_cell(cfg, sp, r, c, z[k], ok, &y[k]);
+        if (++c == cfg.W) { c = 0; ++r; }
       }
-      if (vbase) {
-        for (int ch = 0; ch < cfg.C; ++ch) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int n = n0 + k;
-            vals[(size_t)ch * row_stride + q + k] = n < N ? ld_stream_f1(vbase + (size_t)ch * N + n) : 0.0f;
-          }
-        }
-      }
-    }
-    int r = n0 / cfg.W;
-    int c = n0 - r * cfg.W;
-    int cl[4];
-    float y[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      cl[k] = pixel_cell(cfg, sp, r, c, z[k], ok[k], &y[k]);
-      if (++c == cfg.W) { c = 0; ++r; }
     }
     *reinterpret_cast<int4*>(cells + q) = make_int4(cl[0], cl[1], cl[2], cl[3]);
-    if (d.hasH || cfg.C == 0)
-      *reinterpret_cast<float4*>(hrow + q) = make_float4(y[0], y[1], y[2], y[3]);
+    *reinterpret_cast<float4*>(zrow + q) = make_float4(y[0], y[1], y[2], y[3]);
   }
-  __syncthreads();
+}
 
-  // ---- phase B: lane = channel; walk pixels in order, one RED per same-cell run
-  const int lane = tid & 31, warp = tid >> 5;
+// ---- phase B: lane = channel; walk pixels in order, one RED per same-cell run ---------------
+template <bool IS_MIN>
+__device__ __forceinline__ void emit_runs(const int* __restrict__ cells, const float* __restrict__ row,
+                                          int beg, int end, float fill, uint32_t* __restrict__ acc_c, int CP) {
+  int run_cell = -1;
+  float run_v = fill;
+  auto flush = [&]() {
+    if (run_cell >= 0 && (IS_MIN ? (run_v < fill) : (run_v > fill)))
+      atomicMax(acc_c + (size_t)run_cell * CP, IS_MIN ? ~enc(run_v) : enc(run_v));
+  };
+  auto visit = [&](int cl, float v) {
+    if (cl >= 0) {
+      if (cl != run_cell) {
+        flush();
+        run_cell = cl;
+        run_v = fill;
+      }
+      // fmaxf/fminf drop a NaN operand: torch_scatter's `src > out` never lets NaN win either
+      run_v = IS_MIN ? fminf(run_v, v) : fmaxf(run_v, v);
+    }
+  };
+  for (int i = beg; i < end; i += 4) {
+    const int4 cl4 = *reinterpret_cast<const int4*>(cells + i);
+    const float4 v4 = *reinterpret_cast<const float4*>(row + i);
+    visit(cl4.x, v4.x);
+    visit(cl4.y, v4.y);
+    visit(cl4.z, v4.z);
+    visit(cl4.w, v4.w);
+  }
+  flush();
+}
+
+__device__ __forceinline__ void phase_b(const DmProjCfg& cfg, const ProjDims& d, const float* vals,
+                                        const int* cells, uint32_t* __restrict__ acc_slot) {
+  const int tile = d.tile;
+  const int row_stride = tile + 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int pxw = tile / (kProjThreads / 32);  // pixels per warp, multiple of 4
   const int cu_eff = d.CU < 32 ? d.CU : 32;
   const int streams = d.CU <= 32 ? 32 / d.CU : 1;
   const int passes = d.CU <= 32 ? 1 : (d.CU + 31) / 32;
   const int s = lane / cu_eff;
   const int per = ((pxw / 4 + streams - 1) / streams) * 4;
-  int beg = warp * pxw + s * per;
+  const int beg = warp * pxw + s * per;
   int end = beg + per;
   if (end > (warp + 1) * pxw) end = (warp + 1) * pxw;
   for (int pass = 0; pass < passes; ++pass) {
     const int c = pass * 32 + (lane - s * cu_eff);
     if (s >= streams || c >= d.CU) continue;
-    const bool is_h = d.hasH && (c == d.CU - 1);
-    const int is_min = is_h ? 0 : cfg.reduction;
-    const float fill = is_h ? -INFINITY : cfg.fill_value;
-    const float* row = vals + (size_t)c * row_stride;
-    uint32_t* acc_c = acc_slot + c;
-    int run_cell = -1;
-    float run_v = fill;
-    for (int i = beg; i < end; i += 4) {
-      const int4 cl4 = *reinterpret_cast<const int4*>(cells + i);
-      const float4 v4 = *reinterpret_cast<const float4*>(row + i);
-      const int cl[4] = {cl4.x, cl4.y, cl4.z, cl4.w};
-      const float v[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (cl[k] < 0) continue;
-        if (cl[k] != run_cell) {
-          if (run_cell >= 0 && better(run_v, fill, is_min))
-            atomicMax(acc_c + (size_t)run_cell * d.CP, enc_red(run_v, is_min));
-          run_cell = cl[k];
-          run_v = fill;
-        }
-        if (better(v[k], run_v, is_min)) run_v = v[k];
-      }
-    }
-    if (run_cell >= 0 && better(run_v, fill, is_min))
-      atomicMax(acc_c + (size_t)run_cell * d.CP, enc_red(run_v, is_min));
+    // channel c of the cell: value planes first, the height channel last.  Its staged row:
+    // value plane c, or the depth/height row (index rows-1) for the height channel and for C == 0.
+    const bool is_h = (c == d.Cv);  // only when hasH
+    const bool from_hrow = is_h || cfg.C == 0;
+    const float* row = vals + (size_t)(from_hrow ? d.rows - 1 : c) * row_stride;
+    if (!is_h && cfg.reduction)
+      emit_runs<true>(cells, row, beg, end, cfg.fill_value, acc_slot + c, d.CP);
+    else
+      emit_runs<false>(cells, row, beg, end, is_h ? -INFINITY : cfg.fill_value, acc_slot + c, d.CP);
   }
 }
 
@@ -259,27 +242,528 @@ __device__ __forceinline__ void resolve_tile(uint32_t* __restrict__ acc_slot, co
   }
 }
 
-template <bool VEC>
+// ================= plain-load kernels (any shape / alignment) ================================
+
 __global__ void __launch_bounds__(kProjThreads)
 proj_kernel(const float* __restrict__ depth, const float* __restrict__ values,
             const uint8_t* __restrict__ valid, const DmProjSample* __restrict__ samples,
             const DmProjCfg cfg, const ProjDims d, int frame0, uint32_t* __restrict__ acc) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  const int slot = blockIdx.y;
-  proj_tile<VEC>(depth, values, valid, samples, cfg, d, frame0 + slot, blockIdx.x,
-                 acc + (size_t)slot * d.slot_words, smem);
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x;
+  const int slot = blockIdx.y, frame = frame0 + slot;
+  const int N = cfg.H * cfg.W;
+  const int tile = d.tile, row_stride = tile + 4;
+  float* vals = reinterpret_cast<float*>(smem);
+  int* cells = reinterpret_cast<int*>(vals + (size_t)d.rows * row_stride);
+  DmProjSample* sp_s = reinterpret_cast<DmProjSample*>(smem + d.stage_bytes);
+  if (tid < (int)(sizeof(DmProjSample) / 4))
+    reinterpret_cast<uint32_t*>(sp_s)[tid] = reinterpret_cast<const uint32_t*>(samples + frame)[tid];
+  const int tile0 = blockIdx.x * tile;
+  const float* dplane = depth + (size_t)frame * N;
+  const float* vbase = values ? values + (size_t)frame * cfg.C * N : nullptr;
+  // stage rows with scalar loads (no alignment assumptions)
+  for (int q = tid; q < tile; q += kProjThreads) {
+    const int n = tile0 + q;
+    const bool in = n < N;
+    for (int ch = 0; ch < cfg.C; ++ch)
+      vals[(size_t)ch * row_stride + q] = in ? ld_stream_f1(vbase + (size_t)ch * N + n) : 0.0f;
+    vals[(size_t)cfg.C * row_stride + q] = in ? ld_stream_f1(dplane + n) : 0.0f;
+  }
+  __syncthreads();
+  phase_a(valid ? valid + (size_t)frame * N : nullptr, *sp_s, cfg, tile, tile0, vals + (size_t)cfg.C * row_stride, cells);
+  __syncthreads();
+  phase_b(cfg, d, vals, cells, acc + (size_t)slot * d.slot_words);
 }
 
 __global__ void __launch_bounds__(kProjThreads)
 resolve_kernel(uint32_t* __restrict__ acc, const DmProjCfg cfg, const ProjDims d, int frame0,
                float* __restrict__ topdown, uint8_t* __restrict__ mask, float* __restrict__ height) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  extern __shared__ __align__(128) unsigned char smem[];
   const int slot = blockIdx.y;
   resolve_tile(acc + (size_t)slot * d.slot_words, cfg, d, frame0 + slot, blockIdx.x, topdown, mask,
                height, smem);
 }
 
+// ================= persistent TMA kernel =======================================================
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "DM_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DM_DONE;\n\t"
+      "bra DM_WAIT;\n\t"
+      "DM_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA bulk copy global → shared, completion on an mbarrier, L2 evict-first (inputs are read once).
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// thread 0 only.  Returns false on timeout (a scheduling bug, never expected) after raising ctrl[2].
+__device__ __forceinline__ bool wait_count(const uint32_t* counter, uint32_t target, uint32_t* ctrl) {
+  if (ld_acquire(counter) >= target) return true;
+  const unsigned long long t0 = globaltimer();
+  while (ld_acquire(counter) < target) {
+    __nanosleep(64);
+    if (globaltimer() - t0 > kSpinLimitNs) {
+      atomicExch(ctrl + 2, 1u);
+      return false;
+    }
+  }
+  return true;
+}
+
+// ---- warp-specialised persistent kernel -----------------------------------------------------
+// CTA = 1 producer warp + kWsWarps consumer warps, two smem stages.
+//   producer : claims tickets, waits for the item's dependency (ring slot free / frame fully
+//              projected), fills the stage by TMA bulk copies (one row per lane) and publishes the
+//              per-frame completion counters once the consumers have released a stage.
+//   consumer : owns 128 pixels (32 lanes x 4) of the 512-pixel tile, or 64 cells of a resolve
+//              tile, and does everything warp-locally (no CTA-wide barrier anywhere):
+//       A  cells + heights of its 4 pixels, in-thread merge of equal neighbouring cells into
+//          "runlets", warp prefix sum → compacted position of every runlet;
+//       B1 lane = pixel quad, loop over channels at full lane utilisation: LDS.128, 3 predicated
+//          max, store the runlet maxima compacted in place (row c of the stage);
+//       B2 lane = channel, loop over runlets only: one RED per runlet covers all channels of the
+//          cell (1-2 cache lines); the height channel goes lane = runlet.
+constexpr int kWsWarps = 4;
+constexpr int kWsThreads = 32 * (kWsWarps + 1);
+constexpr int kWsTile = 128 * kWsWarps;
+constexpr int kWsResolveCells = 64 * kWsWarps;
+enum { kItemProj = 0, kItemResolve = 1, kItemNone = 2, kItemExit = 3 };
+
+struct WsItem {
+  int kind, frame, idx, tile0, r0, c0, ok, _pad;
+};
+
+// ticket → work item.  Step s holds the P projection tiles of frame s and the R resolve tiles
+// of frame s - kLag, interleaved one to one so HBM reads and writes mix evenly.
+__device__ __forceinline__ void decode_ticket(unsigned t, int b, int P, int R, int* kind, int* frame, int* idx) {
+  const unsigned per = (unsigned)(P + R);
+  const int s = (int)(t / per);
+  const int j = (int)(t - (unsigned)s * per);
+  const int m = P < R ? P : R;
+  if (j < 2 * m) {
+    *kind = j & 1;
+    *idx = j >> 1;
+  } else {
+    *kind = P > R ? kItemProj : kItemResolve;
+    *idx = m + (j - 2 * m);
+  }
+  *frame = *kind == kItemProj ? s : s - kLag;
+  if (*frame < 0 || *frame >= b) *kind = kItemNone;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void red_max_u32(uint32_t* p, uint32_t v) { atomicMax(p, v); }
+
+// One pixel on the straight-line path (cfg.fast_steps): xn = rn(rn(c - cx) / fx), yn likewise.
+template <bool GLOBAL>
+__device__ __forceinline__ int pixel_cell_fast(const DmProjCfg& cfg, const DmProjSample& sp, float xn, float yn,
+                                               float z, bool ok, float* y_out) {
+  if (cfg.has_trunc_depth_max) ok = ok && (z <= cfg.trunc_depth_max);
+  if (cfg.has_trunc_depth_min) ok = ok && (z >= cfg.trunc_depth_min);
+  const float X = __fmul_rn(xn, z), Y = __fmul_rn(yn, z);
+  // pitch about x: R[0] = 1, R[1] = R[2] = R[3] = R[6] = 0 (x passes through), then + (0, h, 0)
+  const float* Rl = sp.to_local.R;
+  float ly = __fmaf_rn(Rl[7], z, __fmul_rn(Rl[4], Y));
+  float lz = __fmaf_rn(Rl[8], z, __fmul_rn(Rl[5], Y));
+  ly = __fadd_rn(ly, sp.to_local.t[1]);
+  if (cfg.has_trunc_height_max) ok = ok && (ly <= cfg.trunc_height_max);
+  float gx = X, gz = lz;
+  if (GLOBAL) {  // yaw about y: R[4] = 1, R[1] = R[3] = R[5] = R[7] = 0 (y passes through), + (x, 0, z)
+    const float* Rg = sp.to_global.R;
+    gx = __fadd_rn(__fmaf_rn(Rg[6], lz, __fmul_rn(Rg[0], X)), sp.to_global.t[0]);
+    gz = __fadd_rn(__fmaf_rn(Rg[8], lz, __fmul_rn(Rg[2], X)), sp.to_global.t[2]);
+  }
+  float xf, zf;
+  quantize_f(gx, gz, sp.width_offset, sp.height_offset, cfg.map_res, cfg.Mh, cfg.flip_h, &xf, &zf);
+  ok = ok && (xf >= 0.0f) && (xf < (float)cfg.Mw) && (zf >= 0.0f) && (zf < (float)cfg.Mh);
+  *y_out = ly;
+  return ok ? ((int)zf * cfg.Mw + (int)xf) : -1;
+}
+
+template <bool IS_MIN>
+__device__ __forceinline__ float red2(float a, float b) { return IS_MIN ? fminf(a, b) : fmaxf(a, b); }
+template <bool IS_MIN>
+__device__ __forceinline__ bool beats(float v, float fill) { return IS_MIN ? (v < fill) : (v > fill); }
+template <bool IS_MIN>
+__device__ __forceinline__ uint32_t key_of(float v) { return IS_MIN ? ~enc(v) : enc(v); }
+
+// FAST: 0 generic steps, 1 local only, 2 local + global.  IS_MIN: reduction of the value channels.
+template <int FAST, bool IS_MIN>
+__device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDims& d, const WsItem& it,
+                                              const DmProjSample& sp, const float* xtab, const float* ytab,
+                                              const uint8_t* __restrict__ vplane, float* vals, int* lcell,
+                                              uint32_t* __restrict__ acc_slot, int cw, int lane) {
+  constexpr int RS = kWsTile + 4;
+  const int N = cfg.H * cfg.W;
+  const int sb = cw * 128;
+  const int q = sb + 4 * lane;
+  const int n0 = it.tile0 + q;
+  float* zrow = vals + (size_t)cfg.C * RS;
+  int cl[4] = {-1, -1, -1, -1};
+  float y[4] = {0.f, 0.f, 0.f, 0.f};
+  // ---- A: cells and heights of my 4 pixels
+  if (n0 < N) {
+    const float4 z4 = *reinterpret_cast<const float4*>(zrow + q);
+    const float z[4] = {z4.x, z4.y, z4.z, z4.w};
+    int c = it.c0 + q, r = it.r0;
+    while (c >= cfg.W) { c -= cfg.W; ++r; }
+    uint32_t vm = 0x01010101u;
+    if (vplane) vm = *reinterpret_cast<const uint32_t*>(vplane + n0);
+    if (FAST) {
+      const float4 xn4 = *reinterpret_cast<const float4*>(xtab + c);
+      const float xn[4] = {xn4.x, xn4.y, xn4.z, xn4.w};
+      const float yn = ytab[r];
+      bool rowok = true;
+      const int kb = cfg.clip_border;
+      if (kb > 0) rowok = (r >= kb) && (r < cfg.H - kb);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        bool ok = rowok && (((vm >> (8 * k)) & 0xffu) != 0);
+        if (kb > 0) ok = ok && (c + k >= kb) && (c + k < cfg.W - kb);
+        cl[k] = pixel_cell_fast<FAST == 2>(cfg, sp, xn[k], yn, z[k], ok, &y[k]);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        cl[k] = pixel_cell(cfg, sp, r, c + k, z[k], ((vm >> (8 * k)) & 0xffu) != 0, &y[k]);
+    }
+  }
+  // in-thread runs: pixel k continues into k+1 when both are valid and share the cell
+  const bool p01 = (cl[0] >= 0) && (cl[0] == cl[1]);
+  const bool p12 = (cl[1] >= 0) && (cl[1] == cl[2]);
+  const bool p23 = (cl[2] >= 0) && (cl[2] == cl[3]);
+  const bool t0 = (cl[0] >= 0) && !p01, t1 = (cl[1] >= 0) && !p12, t2 = (cl[2] >= 0) && !p23, t3 = cl[3] >= 0;
+  const int cnt = (int)t0 + (int)t1 + (int)t2 + (int)t3;
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += n;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  const int o0 = sb + incl - cnt, o1 = o0 + (int)t0, o2 = o1 + (int)t1, o3 = o2 + (int)t2;
+  if (t0) lcell[o0] = cl[0];
+  if (t1) lcell[o1] = cl[1];
+  if (t2) lcell[o2] = cl[2];
+  if (t3) lcell[o3] = cl[3];
+  {  // the depth row becomes the (compacted) height row; C == 0: it is the value channel itself
+    const bool hmin = IS_MIN && cfg.C == 0;
+    if (p01) y[1] = hmin ? fminf(y[0], y[1]) : fmaxf(y[0], y[1]);
+    if (p12) y[2] = hmin ? fminf(y[1], y[2]) : fmaxf(y[1], y[2]);
+    if (p23) y[3] = hmin ? fminf(y[2], y[3]) : fmaxf(y[2], y[3]);
+    __syncwarp();  // every lane has read its depths
+    if (t0) zrow[o0] = y[0];
+    if (t1) zrow[o1] = y[1];
+    if (t2) zrow[o2] = y[2];
+    if (t3) zrow[o3] = y[3];
+  }
+  // ---- B1: channel loop at full lane utilisation, compaction in place
+  for (int c = 0; c < cfg.C; c += 2) {
+    float* rowa = vals + (size_t)c * RS;
+    const bool two = (c + 1) < cfg.C;
+    float* rowb = two ? rowa + RS : rowa;
+    float4 a = *reinterpret_cast<const float4*>(rowa + q);
+    float4 b4 = *reinterpret_cast<const float4*>(rowb + q);
+    if (p01) { a.y = red2<IS_MIN>(a.x, a.y); b4.y = red2<IS_MIN>(b4.x, b4.y); }
+    if (p12) { a.z = red2<IS_MIN>(a.y, a.z); b4.z = red2<IS_MIN>(b4.y, b4.z); }
+    if (p23) { a.w = red2<IS_MIN>(a.z, a.w); b4.w = red2<IS_MIN>(b4.z, b4.w); }
+    __syncwarp();  // loads of these rows are done before any lane compacts into them
+    if (t0) rowa[o0] = a.x;
+    if (t1) rowa[o1] = a.y;
+    if (t2) rowa[o2] = a.z;
+    if (t3) rowa[o3] = a.w;
+    if (two) {
+      if (t0) rowb[o0] = b4.x;
+      if (t1) rowb[o1] = b4.y;
+      if (t2) rowb[o2] = b4.z;
+      if (t3) rowb[o3] = b4.w;
+    }
+  }
+  __syncwarp();
+  // ---- B2: one RED per (runlet, channel); lane = channel keeps a runlet's keys in 1-2 lines
+  if (cfg.C > 0) {
+    const int Cv = d.Cv;
+    const int cu_eff = Cv < 32 ? Cv : 32;
+    const int streams = Cv <= 32 ? 32 / Cv : 1;
+    const int passes = Cv <= 32 ? 1 : (Cv + 31) / 32;
+    const int s = lane / cu_eff;
+    const int per = ((total + streams - 1) / streams + 3) & ~3;
+    const int beg = s * per;
+    const int end = min(beg + per, total);
+    for (int pass = 0; pass < passes; ++pass) {
+      const int c = pass * 32 + (lane - s * cu_eff);
+      if (s >= streams || c >= Cv) continue;
+      const float* row = vals + (size_t)c * RS + sb;
+      uint32_t* acc_c = acc_slot + c;
+      for (int i = beg; i < end; i += 4) {
+        const int4 c4 = *reinterpret_cast<const int4*>(lcell + sb + i);
+        const float4 v4 = *reinterpret_cast<const float4*>(row + i);
+        if (beats<IS_MIN>(v4.x, cfg.fill_value)) red_max_u32(acc_c + c4.x * d.CP, key_of<IS_MIN>(v4.x));
+        if (i + 1 < end && beats<IS_MIN>(v4.y, cfg.fill_value)) red_max_u32(acc_c + c4.y * d.CP, key_of<IS_MIN>(v4.y));
+        if (i + 2 < end && beats<IS_MIN>(v4.z, cfg.fill_value)) red_max_u32(acc_c + c4.z * d.CP, key_of<IS_MIN>(v4.z));
+        if (i + 3 < end && beats<IS_MIN>(v4.w, cfg.fill_value)) red_max_u32(acc_c + c4.w * d.CP, key_of<IS_MIN>(v4.w));
+      }
+    }
+  }
+  if (d.hasH) {  // height channel: always max against -inf (maps.py:340-348)
+    for (int i = lane; i < total; i += 32) {
+      const float v = zrow[sb + i];
+      if (v > -INFINITY) red_max_u32(acc_slot + lcell[sb + i] * d.CP + d.Cv, enc(v));
+    }
+  } else if (cfg.C == 0) {  // the heights are the values
+    for (int i = lane; i < total; i += 32) {
+      const float v = zrow[sb + i];
+      if (beats<IS_MIN>(v, cfg.fill_value)) red_max_u32(acc_slot + lcell[sb + i] * d.CP, key_of<IS_MIN>(v));
+    }
+  }
+}
+
+// 64 cells of a resolve tile, warp-local.
+__device__ __forceinline__ void ws_resolve_slice(uint32_t* __restrict__ acc_slot, const DmProjCfg& cfg,
+                                                 const ProjDims& d, int frame, int cell_tile, int cw, int lane,
+                                                 uint32_t* wres, float* __restrict__ topdown,
+                                                 uint8_t* __restrict__ mask, float* __restrict__ height) {
+  const int M = cfg.Mh * cfg.Mw;
+  const int cell0 = cell_tile * kWsResolveCells + cw * 64;
+  const int ncell = min(64, M - cell0);
+  if (ncell <= 0) return;
+  const int nw = ncell * d.CP;
+  uint32_t* src = acc_slot + (size_t)cell0 * d.CP;  // 16-byte aligned: cell0 % 64 == 0 → words % 4 == 0
+  for (int i = lane * 4; i < nw; i += 128) {
+    if (i + 3 < nw) {
+      const uint4 v = __ldcg(reinterpret_cast<const uint4*>(src + i));
+      if (v.x | v.y | v.z | v.w) __stcg(reinterpret_cast<uint4*>(src + i), make_uint4(0, 0, 0, 0));
+      *reinterpret_cast<uint4*>(wres + i) = v;
+    } else {
+      for (int k = i; k < nw; ++k) {
+        const uint32_t v = __ldcg(src + k);
+        if (v) __stcg(src + k, 0u);
+        wres[k] = v;
+      }
+    }
+  }
+  __syncwarp();
+  for (int j = lane; j < ncell; j += 32) {
+    const uint32_t* mine = wres + j * d.CP;
+    const size_t obase = (size_t)frame * d.Cv * M + cell0 + j;
+    for (int c = 0; c < d.Cv; ++c) {
+      const uint32_t k = mine[c];
+      const float out = k ? dec_red(k, cfg.reduction) : cfg.fill_value;  // utils.py:472-491
+      st_stream_f1(topdown + obase + (size_t)c * M, out);
+      st_stream_u8(mask + obase + (size_t)c * M, k ? 1 : 0);
+    }
+    if (d.hasH) {
+      const uint32_t k = mine[d.Cv];
+      st_stream_f1(height + (size_t)frame * M + cell0 + j, k ? dec(k) : -INFINITY);  // maps.py:345
+    }
+  }
+  __syncwarp();
+}
+
+template <int FAST, bool IS_MIN>
+__global__ void __launch_bounds__(kWsThreads)
+proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values,
+               const uint8_t* __restrict__ valid, const DmProjSample* __restrict__ samples,
+               const DmProjCfg cfg, const ProjDims d, int b, uint32_t* __restrict__ ctrl,
+               uint32_t* __restrict__ acc, float* __restrict__ topdown, uint8_t* __restrict__ mask,
+               float* __restrict__ height) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int RS = kWsTile + 4;
+  auto stage_ptr = [&](int st_) { return smem + (size_t)st_ * d.stage_bytes; };
+  unsigned char* tail = smem + 2 * d.stage_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(tail);          // [2]
+  uint64_t* empty = full + 2;                                   // [2]
+  WsItem* items = reinterpret_cast<WsItem*>(tail + 32);        // [2]
+  DmProjSample* sps = reinterpret_cast<DmProjSample*>(tail + 128);  // [2]
+  float* xtab = reinterpret_cast<float*>(tail + 512);
+  float* ytab = xtab + ((cfg.W + 3) & ~3);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = cfg.H * cfg.W, M = cfg.Mh * cfg.Mw;
+  const int P = (N + kWsTile - 1) / kWsTile;
+  const int R = (M + kWsResolveCells - 1) / kWsResolveCells;
+  const unsigned total = (unsigned)(b + kLag) * (unsigned)(P + R);
+  uint32_t* proj_done = ctrl + kCtrlWords;
+  uint32_t* resolve_done = proj_done + b;
+
+  if (tid == 0) {
+    mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+    mbar_init(&empty[0], kWsWarps); mbar_init(&empty[1], kWsWarps);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (FAST) {  // maps.py:677-678 column / row factors, once per CTA
+    for (int c = tid; c < cfg.W; c += kWsThreads) xtab[c] = __fdiv_rn(__fsub_rn((float)c, cfg.cx), cfg.fx);
+    for (int r = tid; r < cfg.H; r += kWsThreads) {
+      const float yy = cfg.flip_h ? __fsub_rn((float)(cfg.H - 1), (float)r) : (float)r;
+      ytab[r] = __fdiv_rn(__fsub_rn(yy, cfg.cy), cfg.fy);
+    }
+  }
+  __syncthreads();
+
+  if (warp == kWsWarps) {
+    // ===================== producer =====================
+    uint64_t policy = policy_evict_first();
+    // per-stage state kept in scalars (no runtime-indexed arrays → no local memory)
+    int pk0 = kItemNone, pk1 = kItemNone, pf0 = 0, pf1 = 0;
+    uint32_t parity = 0;  // bit s = number of times stage s was filled, mod 2
+    int st = 0;
+    auto publish = [&](int s) {  // consumers released stage s: its item is complete
+      const int pk = s ? pk1 : pk0, pf = s ? pf1 : pf0;
+      if (lane == 0 && pk != kItemNone) {
+        __threadfence();
+        atomicAdd((pk == kItemProj ? proj_done : resolve_done) + pf, 1u);
+      }
+      if (s) pk1 = kItemNone; else pk0 = kItemNone;
+    };
+    while (true) {
+      unsigned t = 0;
+      if (lane == 0) t = atomicAdd(ctrl, 1u);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      mbar_wait(&empty[st], ((parity >> st) & 1u) ^ 1u);
+      publish(st);
+      WsItem it{};
+      it.ok = 1;
+      if (t >= total) {
+        it.kind = kItemExit;
+      } else {
+        decode_ticket(t, b, P, R, &it.kind, &it.frame, &it.idx);
+      }
+      // dependency of the item: ring slot resolved by its previous tenant / frame fully projected
+      const uint32_t* dep = nullptr;
+      uint32_t dep_target = 0;
+      if (it.kind == kItemProj) {
+        it.tile0 = it.idx * kWsTile;
+        it.r0 = it.tile0 / cfg.W;
+        it.c0 = it.tile0 - it.r0 * cfg.W;
+        if (it.frame >= d.ring) { dep = resolve_done + (it.frame - d.ring); dep_target = (uint32_t)R; }
+        for (int w = lane; w < (int)(sizeof(DmProjSample) / 4); w += 32)
+          reinterpret_cast<uint32_t*>(&sps[st])[w] = reinterpret_cast<const uint32_t*>(samples + it.frame)[w];
+      } else if (it.kind == kItemResolve) {
+        dep = proj_done + it.frame;
+        dep_target = (uint32_t)P;
+      }
+      if (dep) {
+        int pending = 0;
+        if (lane == 0) pending = ld_acquire(dep) < dep_target;
+        pending = __shfl_sync(0xffffffffu, pending, 0);
+        if (pending) {
+          // about to block: first publish the item still in flight in the other stage, or a
+          // frame could wait on a tile whose completion only this producer can announce
+          const int o = st ^ 1;
+          mbar_wait(&empty[o], ((parity >> o) & 1u) ^ 1u);
+          publish(o);
+          if (lane == 0) it.ok = wait_count(dep, dep_target, ctrl);
+        }
+      }
+      it.ok = __shfl_sync(0xffffffffu, it.ok, 0);
+      if (lane == 0) items[st] = it;
+      __syncwarp();
+      if (it.kind == kItemProj) {
+        const int npx = min(kWsTile, N - it.tile0);
+        const uint32_t row_bytes = (uint32_t)npx * 4u;
+        if (lane == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_expect_tx(&full[st], row_bytes * (uint32_t)d.rows);
+        }
+        __syncwarp();
+        float* vals = reinterpret_cast<float*>(stage_ptr(st));
+        for (int row = lane; row < d.rows; row += 32) {
+          const float* src = row < cfg.C ? values + ((size_t)it.frame * cfg.C + row) * N + it.tile0
+                                         : depth + (size_t)it.frame * N + it.tile0;
+          bulk_g2s(vals + (size_t)row * RS, src, row_bytes, &full[st], policy);
+        }
+      } else {
+        if (lane == 0) mbar_arrive(&full[st]);
+      }
+      {
+        const int pk = (it.kind == kItemProj || it.kind == kItemResolve) ? it.kind : kItemNone;
+        if (st) { pk1 = pk; pf1 = it.frame; } else { pk0 = pk; pf0 = it.frame; }
+      }
+      parity ^= 1u << st;
+      if (it.kind == kItemExit) {  // drain: the other stage's item may still be in flight
+        const int o = st ^ 1;
+        mbar_wait(&empty[o], ((parity >> o) & 1u) ^ 1u);
+        publish(o);
+        break;
+      }
+      st ^= 1;
+    }
+    // the last CTA out re-arms the control block for the next call
+    if (lane == 0) {
+      __threadfence();
+      const uint32_t prev = atomicAdd(ctrl + 3, 1u);
+      if (prev == gridDim.x - 1) {
+        for (int i = 0; i < 2 * b; ++i) proj_done[i] = 0;
+        ctrl[0] = 0; ctrl[1] = 0; ctrl[3] = 0;
+        __threadfence();
+      }
+    }
+  } else {
+    // ===================== consumers =====================
+    uint32_t parity = 0;
+    int st = 0;
+    while (true) {
+      mbar_wait(&full[st], (parity >> st) & 1u);
+      parity ^= 1u << st;
+      const WsItem it = items[st];
+      if (it.kind == kItemExit) break;
+      if (it.ok) {
+        if (it.kind == kItemProj) {
+          float* vals = reinterpret_cast<float*>(stage_ptr(st));
+          int* lcell = reinterpret_cast<int*>(vals + (size_t)d.rows * RS);
+          ws_proj_slice<FAST, IS_MIN>(cfg, d, it, sps[st], xtab, ytab,
+                                      valid ? valid + (size_t)it.frame * N : nullptr, vals, lcell,
+                                      acc + (size_t)(it.frame % d.ring) * d.slot_words, warp, lane);
+        } else if (it.kind == kItemResolve) {
+          uint32_t* wres = reinterpret_cast<uint32_t*>(stage_ptr(st)) + (size_t)warp * 64 * d.CP;
+          ws_resolve_slice(acc + (size_t)(it.frame % d.ring) * d.slot_words, cfg, d, it.frame, it.idx, warp, lane,
+                           wres, topdown, mask, height);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[st]);
+      st ^= 1;
+    }
+  }
+}
+
 static bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+struct DeviceInfo {
+  bool ready = false;
+  int sms = 0;
+};
+static DeviceInfo g_dev[64];
 
 }  // namespace dm
 
@@ -288,7 +772,7 @@ using namespace dm;
 extern "C" size_t dm_orth_project_workspace_bytes(const DmProjCfg* cfg, int32_t b) {
   if (!cfg || b <= 0 || cfg->Mh <= 0 || cfg->Mw <= 0) return 0;
   const ProjPlan p = make_plan(*cfg, b);
-  return p.slot_words * 4 * (size_t)p.ring;
+  return p.ctrl_bytes + p.slot_words * 4 * (size_t)p.ring;
 }
 
 extern "C" int dm_orth_project_f32(const float* depth, const float* values, const uint8_t* valid,
@@ -303,31 +787,65 @@ extern "C" int dm_orth_project_f32(const float* depth, const float* values, cons
   if (cfg->C > 0 && !values) return DM_EINVAL;
   if (cfg->C > 0 && cfg->want_height && !height) return DM_EINVAL;
   if (cfg->reduction != 0 && cfg->reduction != 1) return DM_EINVAL;
+  if (!aligned(workspace, 256)) return DM_EINVAL;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const ProjPlan p = make_plan(*cfg, b);
-  if (workspace_bytes < p.slot_words * 4 * (size_t)p.ring) return DM_EWORKSPACE;
-  const int N = cfg->H * cfg->W, M = cfg->Mh * cfg->Mw;
-  const bool vec = (N % 4 == 0) && aligned(depth, 16) && (!values || aligned(values, 16)) &&
-                   (!valid || aligned(valid, 4));
-  ProjDims d{p.Cv, p.hasH, p.CU, p.CP, p.tile, (unsigned long long)p.slot_words};
-  static bool attr_set = false;
-  if (!attr_set) {
-    DM_CUDA_OK(cudaFuncSetAttribute(proj_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    DM_CUDA_OK(cudaFuncSetAttribute(proj_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    DM_CUDA_OK(cudaFuncSetAttribute(resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+  if (workspace_bytes < p.ctrl_bytes + p.slot_words * 4 * (size_t)p.ring) return DM_EWORKSPACE;
+  int dev = 0;
+  DM_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return DM_EINVAL;
+  if (!g_dev[dev].ready) {
+    DM_CUDA_OK(cudaFuncSetAttribute(proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    DM_CUDA_OK(cudaFuncSetAttribute(resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+#define DM_WS_ATTR(F, MN) \
+    DM_CUDA_OK(cudaFuncSetAttribute(proj_ws_kernel<F, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    DM_WS_ATTR(0, false) DM_WS_ATTR(1, false) DM_WS_ATTR(2, false)
+    DM_WS_ATTR(0, true) DM_WS_ATTR(1, true) DM_WS_ATTR(2, true)
+#undef DM_WS_ATTR
+    DM_CUDA_OK(cudaDeviceGetAttribute(&g_dev[dev].sms, cudaDevAttrMultiProcessorCount, dev));
+    g_dev[dev].ready = true;
   }
-  if (p.smem_proj > 200 * 1024 || p.smem_resolve > 200 * 1024) return DM_EINVAL;  // C too large for one pass
-  uint32_t* acc = static_cast<uint32_t*>(workspace);
+  const int N = cfg->H * cfg->W, M = cfg->Mh * cfg->Mw;
+  uint32_t* ctrl = static_cast<uint32_t*>(workspace);
+  uint32_t* acc = reinterpret_cast<uint32_t*>(static_cast<char*>(workspace) + p.ctrl_bytes);
+  ProjDims d{p.Cv, p.hasH, p.CU, p.CP, p.rows, p.tile, p.ring, (unsigned long long)p.slot_words,
+             (unsigned long long)p.stage_bytes};
   const int tiles = (N + p.tile - 1) / p.tile;
   const int rtiles = (M + kResolveCells - 1) / kResolveCells;
+  // the warp-specialised TMA kernel needs 16-byte aligned plane starts / row sizes, pixel quads
+  // that do not straddle image rows, and two stages that fit in shared memory
+  const long long ws_tiles = (N + kWsTile - 1) / kWsTile;
+  const long long ws_total = (long long)(b + kLag) * (ws_tiles + rtiles);
+  const bool ws_ok = (N % 4 == 0) && (cfg->W % 4 == 0) && aligned(depth, 16) && (!values || aligned(values, 16)) &&
+                     (!valid || aligned(valid, 4)) && p.smem_ws <= 220 * 1024 && ws_total < (1ll << 31) &&
+                     cfg->fast_steps >= 0 && cfg->fast_steps <= 2;
+  if (ws_ok) {
+    ProjDims dw = d;
+    dw.tile = kWsTile;
+    dw.stage_bytes = p.ws_stage_bytes;
+    void (*kern)(const float*, const float*, const uint8_t*, const DmProjSample*, DmProjCfg, ProjDims, int,
+                 uint32_t*, uint32_t*, float*, uint8_t*, float*) = nullptr;
+    const bool mn = cfg->reduction != 0;
+    switch (cfg->fast_steps) {
+      case 1: kern = mn ? proj_ws_kernel<1, true> : proj_ws_kernel<1, false>; break;
+      case 2: kern = mn ? proj_ws_kernel<2, true> : proj_ws_kernel<2, false>; break;
+      default: kern = mn ? proj_ws_kernel<0, true> : proj_ws_kernel<0, false>; break;
+    }
+    int per_sm = 0;
+    DM_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWsThreads, p.smem_ws));
+    if (per_sm < 1) return DM_EINVAL;
+    long long grid = (long long)g_dev[dev].sms * per_sm;
+    if (grid > ws_total) grid = ws_total;
+    kern<<<(unsigned)grid, kWsThreads, p.smem_ws, stream>>>(depth, values, valid, samples, *cfg, dw, b, ctrl, acc,
+                                                            topdown, mask, height);
+    DM_LAUNCHED();
+    return DM_OK;
+  }
+  if (p.smem_tile > 220 * 1024) return DM_EINVAL;  // too many channels for one pass
   for (int f0 = 0; f0 < b; f0 += p.ring) {
     const int nf = (b - f0) < p.ring ? (b - f0) : p.ring;
     dim3 gp(tiles, nf), gr(rtiles, nf);
-    if (vec)
-      proj_kernel<true><<<gp, kProjThreads, p.smem_proj, stream>>>(depth, values, valid, samples, *cfg, d, f0, acc);
-    else
-      proj_kernel<false><<<gp, kProjThreads, p.smem_proj, stream>>>(depth, values, valid, samples, *cfg, d, f0, acc);
+    proj_kernel<<<gp, kProjThreads, p.smem_tile, stream>>>(depth, values, valid, samples, *cfg, d, f0, acc);
     DM_LAUNCHED();
     resolve_kernel<<<gr, kProjThreads, p.smem_resolve, stream>>>(acc, *cfg, d, f0, topdown, mask, height);
     DM_LAUNCHED();

@@ -58,6 +58,7 @@ def orth_project_host(depth_map, value_map, valid_map, cam_pose, width_offset, h
   want_h = bool(get_height_map) and C > 0
   cfg.want_height = want_h
   cfg.reduction = utils._reduction_code(reduction)
+  cfg.fast_steps = prm.fast_steps(torch.from_numpy(samples))
   Cv = max(C, 1)
   if out is None:
     top = np.empty((b, Cv, cfg.Mh, cfg.Mw), np.float32)

@@ -204,6 +204,7 @@ def orth_project(
   want_height = bool(get_height_map) and C > 0
   cfg.want_height = want_height
   cfg.reduction = red
+  cfg.fast_steps = prm.fast_steps(samples)
   Cv = max(C, 1)
   topdown = torch.empty((frames, Cv, cfg.Mh, cfg.Mw), dtype=torch.float32, device=dev)
   masks = torch.empty((frames, Cv, cfg.Mh, cfg.Mw), dtype=torch.bool, device=dev)

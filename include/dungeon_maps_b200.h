@@ -84,7 +84,15 @@ typedef struct DmProjCfg {
   float fill_value;  /* effective initial canvas value: fill_value, or 0 when None (utils.py:472-473) */
   int32_t want_height; /* C>0 only: also produce the 1-channel height map (maps.py:335-349) */
   int32_t reduction;   /* 0 = max (Reduction.max / None), 1 = min */
-  int32_t _pad[4];
+  int32_t fast_steps;  /* caller's promise about EVERY sample, enabling straight-line transform code:
+                          0: nothing promised (steps are interpreted per sample);
+                          1: to_local is {ROT_THEN_ADD, fused, R a rotation about x: R[0]=1,
+                             R[1]=R[2]=R[3]=R[6]=0, t=(0,h,0)} and to_global is NONE;
+                          2: as 1, and to_global is {ROT_THEN_ADD, fused, R a rotation about y:
+                             R[4]=1, R[1]=R[3]=R[5]=R[7]=0, t=(x,0,z)}.
+                          Multiplications by those exact 0/1 entries are skipped; results are
+                          identical for every pixel that lands on the map (DESIGN.md "Numerics"). */
+  int32_t _pad[3];
 } DmProjCfg;
 
 /* Fused orthographic projection.  Replaces the body of orth_project

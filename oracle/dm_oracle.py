@@ -42,7 +42,7 @@ class ProjCfg(ctypes.Structure):
     ("has_trunc_height_max", ctypes.c_int32),
     ("clip_border", ctypes.c_int32), ("flip_h", ctypes.c_int32),
     ("fill_value", ctypes.c_float), ("want_height", ctypes.c_int32),
-    ("reduction", ctypes.c_int32), ("_pad", ctypes.c_int32 * 4),
+    ("reduction", ctypes.c_int32), ("fast_steps", ctypes.c_int32), ("_pad", ctypes.c_int32 * 3),
   ]
 
 

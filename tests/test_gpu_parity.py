@@ -116,7 +116,7 @@ def test_orth_project_edge_shapes():
             center_y=intr["cy"], trunc_depth_min=None, trunc_depth_max=None, trunc_height_max=None,
             clip_border=None, to_global=False, fill_value=-np.inf, get_height_map=True)
   # single pixel frame, 9*N < 400 → the non-fused rotation path of the reference
-  for H, W in ((1, 1), (2, 3), (4, 11)):
+  for H, W in ((1, 1), (2, 3), (4, 11), (2, 4), (5, 8), (3, 12)):
     depth = synth.iid_depth(2, H, W, seed=5).numpy()
     k = dict(kw, **{a: v for a, v in zip(("focal_x", "focal_y", "center_x", "center_y"),
                                          (lambda i: (i["fx"], i["fy"], i["cx"], i["cy"]))(orc.intrinsics(W, H, HFOV)))})
@@ -176,6 +176,11 @@ def test_orth_project_full_config2_properties():
   assert_same(npy(top[sel]), want[0], "topdown slice")
   assert_same(npy(mask[sel]), want[1], "mask slice")
   assert_same(npy(hgt[sel][:, :1]), want[2], "height slice")
+  # the persistent kernel's dependency waits never timed out (sticky flag, word 2 of the control block)
+  from dungeon_maps_b200 import maps as _maps
+  for ws in _maps._workspaces.values():
+    assert int(ws[:16].view(torch.int32)[2]) == 0
+    assert int(ws[:16].view(torch.int32)[0]) == 0 and int(ws[:16].view(torch.int32)[3]) == 0   # re-armed
 
 
 def test_orth_project_host_buffer_entry():
