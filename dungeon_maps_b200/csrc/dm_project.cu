@@ -79,7 +79,7 @@ static ProjPlan make_plan(const DmProjCfg& cfg, int b) {
   const size_t ws_res = ((size_t)1024 * p.CP + 127) & ~(size_t)127;  // 4 warps x 64 cells x CP words
   if (ws < ws_res) ws = ws_res;
   p.ws_stage_bytes = ws;
-  p.smem_ws = 2 * ws + 512 + ((size_t)((cfg.W + 3) & ~3) + cfg.H) * 4;
+  p.smem_ws = ws + 256 + ((size_t)((cfg.W + 3) & ~3) + cfg.H) * 4;
   return p;
 }
 
@@ -428,7 +428,7 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
   const int sb = cw * 128;
   const int q = sb + 4 * lane;
   const int n0 = it.tile0 + q;
-  float* zrow = vals + (size_t)cfg.C * RS;
+  float* zrow = vals + cfg.C * RS;
   int cl[4] = {-1, -1, -1, -1};
   float y[4] = {0.f, 0.f, 0.f, 0.f};
   // ---- A: cells and heights of my 4 pixels
@@ -471,16 +471,20 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
     if (lane >= o) incl += n;
   }
   const int total = __shfl_sync(0xffffffffu, incl, 31);
+  const int padn = (4 - (total & 3)) & 3;  // the runlet list is padded to a multiple of 4 with no-ops
+  // compacted positions of my runlets (word offsets inside a row); dead pixels park on a scratch
+  // word past the slice so that stores need no predicate juggling
   const int o0 = sb + incl - cnt, o1 = o0 + (int)t0, o2 = o1 + (int)t1, o3 = o2 + (int)t2;
   if (t0) lcell[o0] = cl[0];
   if (t1) lcell[o1] = cl[1];
   if (t2) lcell[o2] = cl[2];
   if (t3) lcell[o3] = cl[3];
+  if (lane < padn) lcell[sb + total + lane] = 0;
   {  // the depth row becomes the (compacted) height row; C == 0: it is the value channel itself
     const bool hmin = IS_MIN && cfg.C == 0;
-    if (p01) y[1] = hmin ? fminf(y[0], y[1]) : fmaxf(y[0], y[1]);
-    if (p12) y[2] = hmin ? fminf(y[1], y[2]) : fmaxf(y[1], y[2]);
-    if (p23) y[3] = hmin ? fminf(y[2], y[3]) : fmaxf(y[2], y[3]);
+    y[1] = p01 ? (hmin ? fminf(y[0], y[1]) : fmaxf(y[0], y[1])) : y[1];
+    y[2] = p12 ? (hmin ? fminf(y[1], y[2]) : fmaxf(y[1], y[2])) : y[2];
+    y[3] = p23 ? (hmin ? fminf(y[2], y[3]) : fmaxf(y[2], y[3])) : y[3];
     __syncwarp();  // every lane has read its depths
     if (t0) zrow[o0] = y[0];
     if (t1) zrow[o1] = y[1];
@@ -488,50 +492,75 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
     if (t3) zrow[o3] = y[3];
   }
   // ---- B1: channel loop at full lane utilisation, compaction in place
-  for (int c = 0; c < cfg.C; c += 2) {
-    float* rowa = vals + (size_t)c * RS;
-    const bool two = (c + 1) < cfg.C;
-    float* rowb = two ? rowa + RS : rowa;
-    float4 a = *reinterpret_cast<const float4*>(rowa + q);
-    float4 b4 = *reinterpret_cast<const float4*>(rowb + q);
-    if (p01) { a.y = red2<IS_MIN>(a.x, a.y); b4.y = red2<IS_MIN>(b4.x, b4.y); }
-    if (p12) { a.z = red2<IS_MIN>(a.y, a.z); b4.z = red2<IS_MIN>(b4.y, b4.z); }
-    if (p23) { a.w = red2<IS_MIN>(a.z, a.w); b4.w = red2<IS_MIN>(b4.z, b4.w); }
-    __syncwarp();  // loads of these rows are done before any lane compacts into them
-    if (t0) rowa[o0] = a.x;
-    if (t1) rowa[o1] = a.y;
-    if (t2) rowa[o2] = a.z;
-    if (t3) rowa[o3] = a.w;
-    if (two) {
-      if (t0) rowb[o0] = b4.x;
-      if (t1) rowb[o1] = b4.y;
-      if (t2) rowb[o2] = b4.z;
-      if (t3) rowb[o3] = b4.w;
-    }
+  const float neutral = cfg.fill_value;  // padding value: never beats fill → never emitted
+#define DM_B1_ROW(ROW)                                                     \
+  {                                                                        \
+    float* row_ = (ROW);                                                   \
+    float4 a = *reinterpret_cast<const float4*>(row_ + q);                 \
+    a.y = p01 ? red2<IS_MIN>(a.x, a.y) : a.y;                              \
+    a.z = p12 ? red2<IS_MIN>(a.y, a.z) : a.z;                              \
+    a.w = p23 ? red2<IS_MIN>(a.z, a.w) : a.w;                              \
+    __syncwarp();                                                          \
+    if (t0) row_[o0] = a.x;                                                \
+    if (t1) row_[o1] = a.y;                                                \
+    if (t2) row_[o2] = a.z;                                                \
+    if (t3) row_[o3] = a.w;                                                \
+    if (lane < padn) row_[sb + total + lane] = neutral;                    \
   }
+  {
+    int c = 0;
+    for (; c + 4 <= cfg.C; c += 4) {
+      float* r0 = vals + c * RS;
+      float4 a0 = *reinterpret_cast<const float4*>(r0 + q);
+      float4 a1 = *reinterpret_cast<const float4*>(r0 + RS + q);
+      float4 a2 = *reinterpret_cast<const float4*>(r0 + 2 * RS + q);
+      float4 a3 = *reinterpret_cast<const float4*>(r0 + 3 * RS + q);
+      a0.y = p01 ? red2<IS_MIN>(a0.x, a0.y) : a0.y; a1.y = p01 ? red2<IS_MIN>(a1.x, a1.y) : a1.y;
+      a2.y = p01 ? red2<IS_MIN>(a2.x, a2.y) : a2.y; a3.y = p01 ? red2<IS_MIN>(a3.x, a3.y) : a3.y;
+      a0.z = p12 ? red2<IS_MIN>(a0.y, a0.z) : a0.z; a1.z = p12 ? red2<IS_MIN>(a1.y, a1.z) : a1.z;
+      a2.z = p12 ? red2<IS_MIN>(a2.y, a2.z) : a2.z; a3.z = p12 ? red2<IS_MIN>(a3.y, a3.z) : a3.z;
+      a0.w = p23 ? red2<IS_MIN>(a0.z, a0.w) : a0.w; a1.w = p23 ? red2<IS_MIN>(a1.z, a1.w) : a1.w;
+      a2.w = p23 ? red2<IS_MIN>(a2.z, a2.w) : a2.w; a3.w = p23 ? red2<IS_MIN>(a3.z, a3.w) : a3.w;
+      __syncwarp();  // loads of these rows are done before any lane compacts into them
+      if (t0) { r0[o0] = a0.x; r0[RS + o0] = a1.x; r0[2 * RS + o0] = a2.x; r0[3 * RS + o0] = a3.x; }
+      if (t1) { r0[o1] = a0.y; r0[RS + o1] = a1.y; r0[2 * RS + o1] = a2.y; r0[3 * RS + o1] = a3.y; }
+      if (t2) { r0[o2] = a0.z; r0[RS + o2] = a1.z; r0[2 * RS + o2] = a2.z; r0[3 * RS + o2] = a3.z; }
+      if (t3) { r0[o3] = a0.w; r0[RS + o3] = a1.w; r0[2 * RS + o3] = a2.w; r0[3 * RS + o3] = a3.w; }
+      if (lane < padn) {
+        const int pp = sb + total + lane;
+        r0[pp] = neutral; r0[RS + pp] = neutral; r0[2 * RS + pp] = neutral; r0[3 * RS + pp] = neutral;
+      }
+    }
+    for (; c < cfg.C; ++c) DM_B1_ROW(vals + c * RS)
+  }
+#undef DM_B1_ROW
   __syncwarp();
   // ---- B2: one RED per (runlet, channel); lane = channel keeps a runlet's keys in 1-2 lines
+  const int total4 = total + padn;
   if (cfg.C > 0) {
     const int Cv = d.Cv;
     const int cu_eff = Cv < 32 ? Cv : 32;
     const int streams = Cv <= 32 ? 32 / Cv : 1;
     const int passes = Cv <= 32 ? 1 : (Cv + 31) / 32;
     const int s = lane / cu_eff;
-    const int per = ((total + streams - 1) / streams + 3) & ~3;
+    const int per = ((total4 / 4 + streams - 1) / streams) * 4;
     const int beg = s * per;
-    const int end = min(beg + per, total);
+    const int end = min(beg + per, total4);
     for (int pass = 0; pass < passes; ++pass) {
       const int c = pass * 32 + (lane - s * cu_eff);
       if (s >= streams || c >= Cv) continue;
-      const float* row = vals + (size_t)c * RS + sb;
+      const float* row = vals + c * RS + sb;
+      const int* lc = lcell + sb;
       uint32_t* acc_c = acc_slot + c;
+      const float fill = cfg.fill_value;
+      const int CP = d.CP;
       for (int i = beg; i < end; i += 4) {
-        const int4 c4 = *reinterpret_cast<const int4*>(lcell + sb + i);
+        const int4 c4 = *reinterpret_cast<const int4*>(lc + i);
         const float4 v4 = *reinterpret_cast<const float4*>(row + i);
-        if (beats<IS_MIN>(v4.x, cfg.fill_value)) red_max_u32(acc_c + c4.x * d.CP, key_of<IS_MIN>(v4.x));
-        if (i + 1 < end && beats<IS_MIN>(v4.y, cfg.fill_value)) red_max_u32(acc_c + c4.y * d.CP, key_of<IS_MIN>(v4.y));
-        if (i + 2 < end && beats<IS_MIN>(v4.z, cfg.fill_value)) red_max_u32(acc_c + c4.z * d.CP, key_of<IS_MIN>(v4.z));
-        if (i + 3 < end && beats<IS_MIN>(v4.w, cfg.fill_value)) red_max_u32(acc_c + c4.w * d.CP, key_of<IS_MIN>(v4.w));
+        if (beats<IS_MIN>(v4.x, fill)) red_max_u32(acc_c + c4.x * CP, key_of<IS_MIN>(v4.x));
+        if (beats<IS_MIN>(v4.y, fill)) red_max_u32(acc_c + c4.y * CP, key_of<IS_MIN>(v4.y));
+        if (beats<IS_MIN>(v4.z, fill)) red_max_u32(acc_c + c4.z * CP, key_of<IS_MIN>(v4.z));
+        if (beats<IS_MIN>(v4.w, fill)) red_max_u32(acc_c + c4.w * CP, key_of<IS_MIN>(v4.w));
       }
     }
   }
@@ -548,7 +577,9 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
   }
 }
 
-// 64 cells of a resolve tile, warp-local.
+// 64 cells of a resolve tile, warp-local: load the 64 x CP keys (coalesced 128-bit, all loads in
+// flight before the first use), zero what was set, and write the planar outputs.  Most of a map
+// is empty: a slice without a single key takes a constant-store path.
 __device__ __forceinline__ void ws_resolve_slice(uint32_t* __restrict__ acc_slot, const DmProjCfg& cfg,
                                                  const ProjDims& d, int frame, int cell_tile, int cw, int lane,
                                                  uint32_t* wres, float* __restrict__ topdown,
@@ -558,29 +589,62 @@ __device__ __forceinline__ void ws_resolve_slice(uint32_t* __restrict__ acc_slot
   const int ncell = min(64, M - cell0);
   if (ncell <= 0) return;
   const int nw = ncell * d.CP;
+  const int nw4 = nw & ~3;
   uint32_t* src = acc_slot + (size_t)cell0 * d.CP;  // 16-byte aligned: cell0 % 64 == 0 → words % 4 == 0
-  for (int i = lane * 4; i < nw; i += 128) {
-    if (i + 3 < nw) {
-      const uint4 v = __ldcg(reinterpret_cast<const uint4*>(src + i));
-      if (v.x | v.y | v.z | v.w) __stcg(reinterpret_cast<uint4*>(src + i), make_uint4(0, 0, 0, 0));
-      *reinterpret_cast<uint4*>(wres + i) = v;
-    } else {
-      for (int k = i; k < nw; ++k) {
-        const uint32_t v = __ldcg(src + k);
-        if (v) __stcg(src + k, 0u);
-        wres[k] = v;
+  uint32_t any = 0;
+  for (int base = 0; base < nw4; base += 512) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + (u * 32 + lane) * 4;
+      v[u] = i < nw4 ? __ldcg(reinterpret_cast<const uint4*>(src + i)) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + (u * 32 + lane) * 4;
+      const uint32_t nz = v[u].x | v[u].y | v[u].z | v[u].w;
+      any |= nz;
+      if (i < nw4) {
+        if (nz) __stcg(reinterpret_cast<uint4*>(src + i), make_uint4(0, 0, 0, 0));
+        *reinterpret_cast<uint4*>(wres + i) = v[u];
       }
     }
+  }
+  for (int k = nw4 + lane; k < nw; k += 32) {
+    const uint32_t v = __ldcg(src + k);
+    if (v) __stcg(src + k, 0u);
+    wres[k] = v;
+    any |= v;
+  }
+  const bool occupied = __any_sync(0xffffffffu, any != 0);
+  const size_t plane0 = (size_t)frame * d.Cv * M + cell0;
+  if (!occupied && ncell == 64 && (M & 3) == 0) {
+    // empty slice: 64 x fill per channel as 16 float4 stores, 64 x False as 16 u32 stores
+    const float f = cfg.fill_value;
+    float* tp = topdown + plane0 + (lane & 15) * 4;
+    uint8_t* mp = mask + plane0 + (lane & 15) * 4;
+    for (int c = 0; c < d.Cv; ++c) {
+      if (lane < 16) st_stream_f4(tp, make_float4(f, f, f, f));
+      else asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(mp), "r"(0u) : "memory");
+      tp += M;
+      mp += M;
+    }
+    if (d.hasH && lane < 16)
+      st_stream_f4(height + (size_t)frame * M + cell0 + lane * 4, make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY));
+    return;
   }
   __syncwarp();
   for (int j = lane; j < ncell; j += 32) {
     const uint32_t* mine = wres + j * d.CP;
-    const size_t obase = (size_t)frame * d.Cv * M + cell0 + j;
+    float* tp = topdown + plane0 + j;
+    uint8_t* mp = mask + plane0 + j;
     for (int c = 0; c < d.Cv; ++c) {
       const uint32_t k = mine[c];
       const float out = k ? dec_red(k, cfg.reduction) : cfg.fill_value;  // utils.py:472-491
-      st_stream_f1(topdown + obase + (size_t)c * M, out);
-      st_stream_u8(mask + obase + (size_t)c * M, k ? 1 : 0);
+      st_stream_f1(tp, out);
+      st_stream_u8(mp, k ? 1 : 0);
+      tp += M;
+      mp += M;
     }
     if (d.hasH) {
       const uint32_t k = mine[d.Cv];
@@ -599,13 +663,14 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
                float* __restrict__ height) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int RS = kWsTile + 4;
-  auto stage_ptr = [&](int st_) { return smem + (size_t)st_ * d.stage_bytes; };
-  unsigned char* tail = smem + 2 * d.stage_bytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(tail);          // [2]
-  uint64_t* empty = full + 2;                                   // [2]
-  WsItem* items = reinterpret_cast<WsItem*>(tail + 32);        // [2]
-  DmProjSample* sps = reinterpret_cast<DmProjSample*>(tail + 128);  // [2]
-  float* xtab = reinterpret_cast<float*>(tail + 512);
+  // one stage per CTA: latency is hidden by the 5-6 CTAs resident per SM, not by an in-CTA ring
+  unsigned char* stage = smem;
+  unsigned char* tail = smem + d.stage_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty = full + 1;
+  WsItem* item = reinterpret_cast<WsItem*>(tail + 32);
+  DmProjSample* sps = reinterpret_cast<DmProjSample*>(tail + 64);
+  float* xtab = reinterpret_cast<float*>(tail + 256);
   float* ytab = xtab + ((cfg.W + 3) & ~3);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -617,8 +682,8 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
   uint32_t* resolve_done = proj_done + b;
 
   if (tid == 0) {
-    mbar_init(&full[0], 1); mbar_init(&full[1], 1);
-    mbar_init(&empty[0], kWsWarps); mbar_init(&empty[1], kWsWarps);
+    mbar_init(full, 1);
+    mbar_init(empty, kWsWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (FAST) {  // maps.py:677-678 column / row factors, once per CTA
@@ -632,25 +697,19 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
 
   if (warp == kWsWarps) {
     // ===================== producer =====================
-    uint64_t policy = policy_evict_first();
-    // per-stage state kept in scalars (no runtime-indexed arrays → no local memory)
-    int pk0 = kItemNone, pk1 = kItemNone, pf0 = 0, pf1 = 0;
-    uint32_t parity = 0;  // bit s = number of times stage s was filled, mod 2
-    int st = 0;
-    auto publish = [&](int s) {  // consumers released stage s: its item is complete
-      const int pk = s ? pk1 : pk0, pf = s ? pf1 : pf0;
-      if (lane == 0 && pk != kItemNone) {
-        __threadfence();
-        atomicAdd((pk == kItemProj ? proj_done : resolve_done) + pf, 1u);
-      }
-      if (s) pk1 = kItemNone; else pk0 = kItemNone;
-    };
+    const uint64_t policy = policy_evict_first();
+    int pend_kind = kItemNone, pend_frame = 0;
+    uint32_t fills = 0;
     while (true) {
       unsigned t = 0;
       if (lane == 0) t = atomicAdd(ctrl, 1u);
       t = __shfl_sync(0xffffffffu, t, 0);
-      mbar_wait(&empty[st], ((parity >> st) & 1u) ^ 1u);
-      publish(st);
+      // the stage is free once the consumers released the previous item; that also completes it
+      mbar_wait(empty, (fills & 1u) ^ 1u);
+      if (lane == 0 && pend_kind != kItemNone) {
+        __threadfence();
+        atomicAdd((pend_kind == kItemProj ? proj_done : resolve_done) + pend_frame, 1u);
+      }
       WsItem it{};
       it.ok = 1;
       if (t >= total) {
@@ -667,56 +726,36 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
         it.c0 = it.tile0 - it.r0 * cfg.W;
         if (it.frame >= d.ring) { dep = resolve_done + (it.frame - d.ring); dep_target = (uint32_t)R; }
         for (int w = lane; w < (int)(sizeof(DmProjSample) / 4); w += 32)
-          reinterpret_cast<uint32_t*>(&sps[st])[w] = reinterpret_cast<const uint32_t*>(samples + it.frame)[w];
+          reinterpret_cast<uint32_t*>(sps)[w] = reinterpret_cast<const uint32_t*>(samples + it.frame)[w];
       } else if (it.kind == kItemResolve) {
         dep = proj_done + it.frame;
         dep_target = (uint32_t)P;
       }
-      if (dep) {
-        int pending = 0;
-        if (lane == 0) pending = ld_acquire(dep) < dep_target;
-        pending = __shfl_sync(0xffffffffu, pending, 0);
-        if (pending) {
-          // about to block: first publish the item still in flight in the other stage, or a
-          // frame could wait on a tile whose completion only this producer can announce
-          const int o = st ^ 1;
-          mbar_wait(&empty[o], ((parity >> o) & 1u) ^ 1u);
-          publish(o);
-          if (lane == 0) it.ok = wait_count(dep, dep_target, ctrl);
-        }
-      }
+      if (dep && lane == 0) it.ok = wait_count(dep, dep_target, ctrl);
       it.ok = __shfl_sync(0xffffffffu, it.ok, 0);
-      if (lane == 0) items[st] = it;
+      if (lane == 0) *item = it;
       __syncwarp();
       if (it.kind == kItemProj) {
         const int npx = min(kWsTile, N - it.tile0);
         const uint32_t row_bytes = (uint32_t)npx * 4u;
         if (lane == 0) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_expect_tx(&full[st], row_bytes * (uint32_t)d.rows);
+          mbar_expect_tx(full, row_bytes * (uint32_t)d.rows);
         }
         __syncwarp();
-        float* vals = reinterpret_cast<float*>(stage_ptr(st));
+        float* vals = reinterpret_cast<float*>(stage);
         for (int row = lane; row < d.rows; row += 32) {
           const float* src = row < cfg.C ? values + ((size_t)it.frame * cfg.C + row) * N + it.tile0
                                          : depth + (size_t)it.frame * N + it.tile0;
-          bulk_g2s(vals + (size_t)row * RS, src, row_bytes, &full[st], policy);
+          bulk_g2s(vals + row * RS, src, row_bytes, full, policy);
         }
       } else {
-        if (lane == 0) mbar_arrive(&full[st]);
+        if (lane == 0) mbar_arrive(full);
       }
-      {
-        const int pk = (it.kind == kItemProj || it.kind == kItemResolve) ? it.kind : kItemNone;
-        if (st) { pk1 = pk; pf1 = it.frame; } else { pk0 = pk; pf0 = it.frame; }
-      }
-      parity ^= 1u << st;
-      if (it.kind == kItemExit) {  // drain: the other stage's item may still be in flight
-        const int o = st ^ 1;
-        mbar_wait(&empty[o], ((parity >> o) & 1u) ^ 1u);
-        publish(o);
-        break;
-      }
-      st ^= 1;
+      pend_kind = (it.kind == kItemProj || it.kind == kItemResolve) ? it.kind : kItemNone;
+      pend_frame = it.frame;
+      ++fills;
+      if (it.kind == kItemExit) break;
     }
     // the last CTA out re-arms the control block for the next call
     if (lane == 0) {
@@ -730,29 +769,27 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
     }
   } else {
     // ===================== consumers =====================
-    uint32_t parity = 0;
-    int st = 0;
+    uint32_t uses = 0;
     while (true) {
-      mbar_wait(&full[st], (parity >> st) & 1u);
-      parity ^= 1u << st;
-      const WsItem it = items[st];
+      mbar_wait(full, uses & 1u);
+      ++uses;
+      const WsItem it = *item;
       if (it.kind == kItemExit) break;
       if (it.ok) {
         if (it.kind == kItemProj) {
-          float* vals = reinterpret_cast<float*>(stage_ptr(st));
-          int* lcell = reinterpret_cast<int*>(vals + (size_t)d.rows * RS);
-          ws_proj_slice<FAST, IS_MIN>(cfg, d, it, sps[st], xtab, ytab,
+          float* vals = reinterpret_cast<float*>(stage);
+          int* lcell = reinterpret_cast<int*>(vals + d.rows * RS);
+          ws_proj_slice<FAST, IS_MIN>(cfg, d, it, *sps, xtab, ytab,
                                       valid ? valid + (size_t)it.frame * N : nullptr, vals, lcell,
                                       acc + (size_t)(it.frame % d.ring) * d.slot_words, warp, lane);
         } else if (it.kind == kItemResolve) {
-          uint32_t* wres = reinterpret_cast<uint32_t*>(stage_ptr(st)) + (size_t)warp * 64 * d.CP;
+          uint32_t* wres = reinterpret_cast<uint32_t*>(stage) + warp * 64 * d.CP;
           ws_resolve_slice(acc + (size_t)(it.frame % d.ring) * d.slot_words, cfg, d, it.frame, it.idx, warp, lane,
                            wres, topdown, mask, height);
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[st]);
-      st ^= 1;
+      if (lane == 0) mbar_arrive(empty);
     }
   }
 }
