@@ -308,6 +308,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
       ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
 }
+// L2 prefetch of a row that a later TMA copy will read (hides HBM latency without shared memory)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ uint64_t policy_evict_first() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
@@ -701,15 +705,11 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
     int pend_kind = kItemNone, pend_frame = 0;
     uint32_t fills = 0;
     while (true) {
+      // ---- while the consumers work on the previous item: claim, decode, check the dependency,
+      //      fetch the per-sample parameters (all off the critical path)
       unsigned t = 0;
       if (lane == 0) t = atomicAdd(ctrl, 1u);
       t = __shfl_sync(0xffffffffu, t, 0);
-      // the stage is free once the consumers released the previous item; that also completes it
-      mbar_wait(empty, (fills & 1u) ^ 1u);
-      if (lane == 0 && pend_kind != kItemNone) {
-        __threadfence();
-        atomicAdd((pend_kind == kItemProj ? proj_done : resolve_done) + pend_frame, 1u);
-      }
       WsItem it{};
       it.ok = 1;
       if (t >= total) {
@@ -717,22 +717,44 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
       } else {
         decode_ticket(t, b, P, R, &it.kind, &it.frame, &it.idx);
       }
-      // dependency of the item: ring slot resolved by its previous tenant / frame fully projected
+      // dependency: ring slot resolved by its previous tenant / frame fully projected
       const uint32_t* dep = nullptr;
       uint32_t dep_target = 0;
+      uint32_t spw0 = 0, spw1 = 0;  // my two words of the sample block
       if (it.kind == kItemProj) {
         it.tile0 = it.idx * kWsTile;
         it.r0 = it.tile0 / cfg.W;
         it.c0 = it.tile0 - it.r0 * cfg.W;
         if (it.frame >= d.ring) { dep = resolve_done + (it.frame - d.ring); dep_target = (uint32_t)R; }
-        for (int w = lane; w < (int)(sizeof(DmProjSample) / 4); w += 32)
-          reinterpret_cast<uint32_t*>(sps)[w] = reinterpret_cast<const uint32_t*>(samples + it.frame)[w];
+        const uint32_t* sw = reinterpret_cast<const uint32_t*>(samples + it.frame);
+        spw0 = sw[lane];
+        if (lane < 16) spw1 = sw[32 + lane];
       } else if (it.kind == kItemResolve) {
         dep = proj_done + it.frame;
         dep_target = (uint32_t)P;
       }
-      if (dep && lane == 0) it.ok = wait_count(dep, dep_target, ctrl);
-      it.ok = __shfl_sync(0xffffffffu, it.ok, 0);
+      int pending = 0;
+      if (dep && lane == 0) pending = ld_acquire(dep) < dep_target;
+      pending = __shfl_sync(0xffffffffu, pending, 0);
+      // ---- the stage is free once the consumers released the previous item
+      mbar_wait(empty, (fills & 1u) ^ 1u);
+      const int prev_kind = pend_kind, prev_frame = pend_frame;
+      auto publish_prev = [&]() {  // the release of the stage also completes the previous item
+        if (lane == 0 && prev_kind != kItemNone) {
+          __threadfence();
+          atomicAdd((prev_kind == kItemProj ? proj_done : resolve_done) + prev_frame, 1u);
+        }
+      };
+      if (pending) {
+        // rare: must block.  Publish first — the frame we wait for may need this very tile.
+        publish_prev();
+        if (lane == 0) it.ok = wait_count(dep, dep_target, ctrl);
+        it.ok = __shfl_sync(0xffffffffu, it.ok, 0);
+      }
+      if (it.kind == kItemProj) {
+        reinterpret_cast<uint32_t*>(sps)[lane] = spw0;
+        if (lane < 16) reinterpret_cast<uint32_t*>(sps)[32 + lane] = spw1;
+      }
       if (lane == 0) *item = it;
       __syncwarp();
       if (it.kind == kItemProj) {
@@ -752,6 +774,7 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
       } else {
         if (lane == 0) mbar_arrive(full);
       }
+      if (!pending) publish_prev();  // off the critical path: the next item is already on its way
       pend_kind = (it.kind == kItemProj || it.kind == kItemResolve) ? it.kind : kItemNone;
       pend_frame = it.frame;
       ++fills;

@@ -26,6 +26,19 @@ def npy(t):
   return t.detach().cpu().numpy()
 
 
+@pytest.fixture(autouse=True)
+def _no_device_side_timeouts():
+  """After every test: the persistent kernel's dependency waits never timed out (sticky flag,
+  word 2 of the workspace control block) and the control block was re-armed."""
+  yield
+  from dungeon_maps_b200 import maps as _maps
+  torch.cuda.synchronize()
+  for ws in _maps._workspaces.values():
+    ctrl = ws[:16].view(torch.int32).cpu()
+    assert int(ctrl[2]) == 0, "a device-side dependency wait timed out"
+    assert int(ctrl[0]) == 0 and int(ctrl[3]) == 0, "control block not re-armed"
+
+
 def run_gpu_orth(g, depth, values, valid):
   kw = g.kwargs
   return dmap.orth_project(
