@@ -101,7 +101,8 @@ __device__ __forceinline__ long long f2i64(float v) {
 // stores ~enc() so that one atomicMax serves both.
 __device__ __forceinline__ uint32_t enc(float v) {
   const uint32_t b = __float_as_uint(v);
-  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  // negative: flip all bits; non-negative: set the sign bit  ==  b ^ (sign-extension | 0x80000000)
+  return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
 }
 __device__ __forceinline__ float dec(uint32_t k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);

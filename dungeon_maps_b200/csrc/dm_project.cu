@@ -386,7 +386,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ void red_max_u32(uint32_t* p, uint32_t v) { atomicMax(p, v); }
+// fire-and-forget reduction (RED, never the returning ATOM form)
+__device__ __forceinline__ void red_max_u32(uint32_t* p, uint32_t v) {
+  asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Predicated reduction: no branch, no reconvergence bookkeeping around the RED.
+__device__ __forceinline__ void red_max_u32_if(bool pred, uint32_t* p, uint32_t v) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %0, 0;\n\t"
+      "@p red.global.max.u32 [%1], %2;\n\t}" ::"r"((int)pred), "l"(p), "r"(v) : "memory");
+}
 
 // One pixel on the straight-line path (cfg.fast_steps): xn = rn(rn(c - cx) / fx), yn likewise.
 template <bool GLOBAL>
@@ -426,7 +436,8 @@ template <int FAST, bool IS_MIN>
 __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDims& d, const WsItem& it,
                                               const DmProjSample& sp, const float* xtab, const float* ytab,
                                               const uint8_t* __restrict__ vplane, float* vals, int* lcell,
-                                              uint32_t* __restrict__ acc_slot, int cw, int lane) {
+                                              uint32_t* __restrict__ acc, uint32_t slot_off, int cw, int lane) {
+  // acc is the kernel parameter (uniform); every RED address is acc + a 32-bit word offset
   constexpr int RS = kWsTile + 4;
   const int N = cfg.H * cfg.W;
   const int sb = cw * 128;
@@ -479,10 +490,11 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
   // compacted positions of my runlets (word offsets inside a row); dead pixels park on a scratch
   // word past the slice so that stores need no predicate juggling
   const int o0 = sb + incl - cnt, o1 = o0 + (int)t0, o2 = o1 + (int)t1, o3 = o2 + (int)t2;
-  if (t0) lcell[o0] = cl[0];
-  if (t1) lcell[o1] = cl[1];
-  if (t2) lcell[o2] = cl[2];
-  if (t3) lcell[o3] = cl[3];
+  // the list holds word offsets of the cells in the accumulation slot (cell * CP)
+  if (t0) lcell[o0] = cl[0] * d.CP;
+  if (t1) lcell[o1] = cl[1] * d.CP;
+  if (t2) lcell[o2] = cl[2] * d.CP;
+  if (t3) lcell[o3] = cl[3] * d.CP;
   if (lane < padn) lcell[sb + total + lane] = 0;
   {  // the depth row becomes the (compacted) height row; C == 0: it is the value channel itself
     const bool hmin = IS_MIN && cfg.C == 0;
@@ -555,28 +567,27 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
       if (s >= streams || c >= Cv) continue;
       const float* row = vals + c * RS + sb;
       const int* lc = lcell + sb;
-      uint32_t* acc_c = acc_slot + c;
+      const uint32_t off_c = slot_off + (uint32_t)c;
       const float fill = cfg.fill_value;
-      const int CP = d.CP;
       for (int i = beg; i < end; i += 4) {
-        const int4 c4 = *reinterpret_cast<const int4*>(lc + i);
+        const uint4 c4 = *reinterpret_cast<const uint4*>(lc + i);
         const float4 v4 = *reinterpret_cast<const float4*>(row + i);
-        if (beats<IS_MIN>(v4.x, fill)) red_max_u32(acc_c + c4.x * CP, key_of<IS_MIN>(v4.x));
-        if (beats<IS_MIN>(v4.y, fill)) red_max_u32(acc_c + c4.y * CP, key_of<IS_MIN>(v4.y));
-        if (beats<IS_MIN>(v4.z, fill)) red_max_u32(acc_c + c4.z * CP, key_of<IS_MIN>(v4.z));
-        if (beats<IS_MIN>(v4.w, fill)) red_max_u32(acc_c + c4.w * CP, key_of<IS_MIN>(v4.w));
+        if (beats<IS_MIN>(v4.x, fill)) red_max_u32(acc + (off_c + c4.x), key_of<IS_MIN>(v4.x));
+        if (beats<IS_MIN>(v4.y, fill)) red_max_u32(acc + (off_c + c4.y), key_of<IS_MIN>(v4.y));
+        if (beats<IS_MIN>(v4.z, fill)) red_max_u32(acc + (off_c + c4.z), key_of<IS_MIN>(v4.z));
+        if (beats<IS_MIN>(v4.w, fill)) red_max_u32(acc + (off_c + c4.w), key_of<IS_MIN>(v4.w));
       }
     }
   }
   if (d.hasH) {  // height channel: always max against -inf (maps.py:340-348)
     for (int i = lane; i < total; i += 32) {
       const float v = zrow[sb + i];
-      if (v > -INFINITY) red_max_u32(acc_slot + lcell[sb + i] * d.CP + d.Cv, enc(v));
+      if (v > -INFINITY) red_max_u32(acc + (slot_off + (uint32_t)d.Cv + (uint32_t)lcell[sb + i]), enc(v));
     }
   } else if (cfg.C == 0) {  // the heights are the values
     for (int i = lane; i < total; i += 32) {
       const float v = zrow[sb + i];
-      if (beats<IS_MIN>(v, cfg.fill_value)) red_max_u32(acc_slot + lcell[sb + i] * d.CP, key_of<IS_MIN>(v));
+      if (beats<IS_MIN>(v, cfg.fill_value)) red_max_u32(acc + (slot_off + (uint32_t)lcell[sb + i]), key_of<IS_MIN>(v));
     }
   }
 }
@@ -803,8 +814,8 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
           float* vals = reinterpret_cast<float*>(stage);
           int* lcell = reinterpret_cast<int*>(vals + d.rows * RS);
           ws_proj_slice<FAST, IS_MIN>(cfg, d, it, *sps, xtab, ytab,
-                                      valid ? valid + (size_t)it.frame * N : nullptr, vals, lcell,
-                                      acc + (size_t)(it.frame % d.ring) * d.slot_words, warp, lane);
+                                      valid ? valid + (size_t)it.frame * N : nullptr, vals, lcell, acc,
+                                      (uint32_t)(it.frame % d.ring) * (uint32_t)d.slot_words, warp, lane);
         } else if (it.kind == kItemResolve) {
           uint32_t* wres = reinterpret_cast<uint32_t*>(stage) + warp * 64 * d.CP;
           ws_resolve_slice(acc + (size_t)(it.frame % d.ring) * d.slot_words, cfg, d, it.frame, it.idx, warp, lane,
@@ -878,7 +889,8 @@ extern "C" int dm_orth_project_f32(const float* depth, const float* values, cons
   const long long ws_total = (long long)(b + kLag) * (ws_tiles + rtiles);
   const bool ws_ok = (N % 4 == 0) && (cfg->W % 4 == 0) && aligned(depth, 16) && (!values || aligned(values, 16)) &&
                      (!valid || aligned(valid, 4)) && p.smem_ws <= 220 * 1024 && ws_total < (1ll << 31) &&
-                     cfg->fast_steps >= 0 && cfg->fast_steps <= 2;
+                     cfg->fast_steps >= 0 && cfg->fast_steps <= 2 &&
+                     (unsigned long long)p.ring * p.slot_words < (1ull << 31);
   if (ws_ok) {
     ProjDims dw = d;
     dw.tile = kWsTile;
