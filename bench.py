@@ -175,24 +175,10 @@ def run_ours(args):
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group("nccl", device_id=dev)
 
-  def barrier():
-    if world > 1:
-      dist.barrier()
-    torch.cuda.synchronize(dev)
-
-  def max_over_ranks(x: float) -> float:
-    if world == 1:
-      return x
-    t = torch.tensor([x], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
-
-  def sum_over_ranks(x: float) -> float:
-    if world == 1:
-      return x
-    t = torch.tensor([x], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    return float(t.item())
+  from dungeon_maps_b200 import shard
+  barrier = lambda: shard.barrier(dev)
+  max_over_ranks = lambda x: shard.max_over_ranks(x, dev)
+  sum_over_ranks = lambda x: shard.sum_over_ranks(x, dev)
 
   kw = proj_kwargs()
   # every rank owns 64 environments (weak scaling, no data-path collective)
@@ -276,7 +262,7 @@ def run_ours(args):
     "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                  "traffic": ncu_traffic(), "peak_source": peak_src,
                  "algorithmic_bytes_per_step": algo_bytes,
-                 "kernel": "dm::proj_kernel + dm::resolve_kernel (one step = the launches of dm_orth_project_f32)"},
+                 "kernel": "dm::proj_ws_kernel (one step = ONE persistent launch of dm_orth_project_f32: projection + resolve)"},
     "cpu_baseline": cpu,
   }))
 

@@ -1,0 +1,119 @@
+"""The drop-in boundary without a GPU: include/dungeon_maps_b200.h, the ctypes binding and the
+built .so agree — every declared entry point is exported, every struct has the size/offsets the
+header documents — and the host-side parameter packing equals the oracle's.  No compute calls.
+"""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from dungeon_maps_b200 import _native as nat, _params
+from oracle import dm_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "dungeon_maps_b200.h")
+
+
+def _declared_functions():
+  src = open(HEADER).read()
+  src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)     # comments
+  src = re.sub(r"typedef struct \w+ \{.*?\} \w+;", "", src, flags=re.S)
+  src = re.sub(r"^\s*#.*$", "", src, flags=re.M)
+  return sorted(set(re.findall(r"\b(dm_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_what_the_binding_binds():
+  assert _declared_functions() == sorted(nat.EXPORTS)
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+  handle = ctypes.CDLL(nat.library_path()) if os.path.exists(nat.library_path()) else nat.lib()
+  for name in _declared_functions():
+    assert hasattr(handle, name), f"libdungeon_maps_b200.so does not export {name}"
+  lib = nat.lib()
+  assert lib.dm_abi_version() == nat.ABI_VERSION == 1
+  assert b"sm_100a" in lib.dm_build_info()
+  assert lib.dm_launch_count() >= 0
+
+
+def test_library_is_standalone():
+  """No torch / libcudart.so dependency: plain C ABI, cudart linked statically."""
+  import subprocess
+  out = subprocess.run(["ldd", nat.library_path()], capture_output=True, text=True).stdout
+  assert "libtorch" not in out and "libc10" not in out and "libcudart" not in out, out
+
+
+def test_struct_layouts_match_the_header():
+  assert ctypes.sizeof(nat.DmStep) == 64
+  assert nat.DmStep.t.offset == 36 and nat.DmStep.kind.offset == 48 and nat.DmStep.fused.offset == 52
+  assert nat.PROJ_SAMPLE_WORDS * 4 == 192 == orc.PROJ_SAMPLE_DT.itemsize
+  assert nat.FLOW_SAMPLE_WORDS * 4 == 192 == orc.FLOW_SAMPLE_DT.itemsize
+  assert ctypes.sizeof(nat.DmProjCfg) == ctypes.sizeof(orc.ProjCfg) == 25 * 4
+  assert ctypes.sizeof(nat.DmFlowCfg) == ctypes.sizeof(orc.FlowCfg) == 15 * 4
+  for (n1, t1), (n2, t2) in zip(nat.DmProjCfg._fields_, orc.ProjCfg._fields_):
+    assert n1 == n2 and ctypes.sizeof(t1) == ctypes.sizeof(t2)
+  assert ctypes.sizeof(nat.DmFuseSource) == 3 * 8 + 2 * 8 + 4 * 4 + 3 * 8
+  assert ctypes.sizeof(nat.DmFuseTarget) == 8 * 4
+
+
+def test_workspace_query_needs_no_device():
+  lib = nat.lib()
+  cfg = nat.DmProjCfg(H=480, W=640, C=16, Mh=400, Mw=400, want_height=1)
+  need = lib.dm_orth_project_workspace_bytes(ctypes.byref(cfg), 64)
+  # ring of >= 4 frame slots of 400*400 cells x 17 keys, kept inside the 126 MB L2
+  assert 4 * 160000 * 17 * 4 <= need <= 64 << 20
+  assert lib.dm_orth_project_workspace_bytes(None, 64) == 0
+  assert lib.dm_orth_project_workspace_bytes(ctypes.byref(cfg), 0) == 0
+
+
+def test_usage_errors_are_codes_not_crashes():
+  lib = nat.lib()
+  cfg = nat.DmProjCfg(H=4, W=4, C=0, Mh=4, Mw=4)
+  assert lib.dm_orth_project_f32(0, 0, 0, 0, None, 1, 0, 0, 0, 0, 0, 0) == -1
+  assert lib.dm_orth_project_f32(0, 0, 0, 0, ctypes.byref(cfg), 0, 0, 0, 0, 0, 0, 0) == 0   # empty batch
+  assert lib.dm_orth_project_f32(0, 0, 0, 0, ctypes.byref(cfg), 1, 0, 0, 0, 0, 0, 0) == -1  # null pointers
+  with pytest.raises(nat.NativeError):
+    nat.check(-2, "x")
+
+
+def test_no_cpu_fallback():
+  if torch.cuda.is_available():
+    pytest.skip("CPU-only check")
+  import dungeon_maps_b200 as dmap
+  with pytest.raises(nat.NativeError):
+    dmap.orth_project(torch.ones(1, 1, 4, 4), None, None, [0., 0., 0.], 2., 0., 0., 0.88, 0.5, 4, 4, 2., 2., 2., 2.,
+                      None, None, None, None, False)
+  with pytest.raises(nat.NativeError):
+    dmap.camera_affine_grid(torch.ones(1, 1, 4, 4), [0., 0., 0.], 0., 0.88, 2., 2., 2., 2.)
+  with pytest.raises(nat.NativeError):
+    nat.require_cuda("cpu")
+
+
+def _steps_np(t: torch.Tensor):
+  return np.frombuffer(t.contiguous().numpy().tobytes(), dtype=orc.STEP_DT)
+
+
+@pytest.mark.parametrize("n_points", [1, 33, 44, 45, 307200])
+def test_host_parameter_blocks_equal_the_oracles(n_points):
+  """_params (product host code) and oracle/dm_oracle.py build the DmStep blocks independently
+  (both with the reference's torch-CPU op sequence utils.py:303-327): same bytes."""
+  rng = np.random.default_rng(n_points)
+  b = 7
+  pitch = torch.from_numpy(rng.normal(size=b).astype(np.float32) * 0.3)
+  pitch[0] = 0.0005   # |angle| <= ANGLE_EPS → identity (utils.py:323-324)
+  camh = torch.from_numpy(rng.uniform(0.5, 1.5, size=b).astype(np.float32))
+  pose = torch.from_numpy(rng.normal(size=(b, 3)).astype(np.float32))
+  pairs = [
+    (_params.camera_to_local(pitch, camh, n_points), orc.to_local_steps(pitch.numpy(), camh.numpy(), n_points)),
+    (_params.local_to_camera(pitch, camh, n_points), orc.to_camera_steps(pitch.numpy(), camh.numpy(), n_points)),
+    (_params.local_to_global(pose, n_points), orc.to_global_steps(pose.numpy(), n_points)),
+    (_params.global_to_local(pose, n_points), orc.from_global_steps(pose.numpy(), n_points)),
+  ]
+  for ours, theirs in pairs:
+    ours = _steps_np(ours)
+    for f in ("R", "t", "kind", "fused"):
+      assert np.array_equal(ours[f], np.asarray(theirs)[f]), f
+  assert _params.fused_for(45) and not _params.fused_for(44)   # 9*n >= 400 → MKL sgemm FMA chain
