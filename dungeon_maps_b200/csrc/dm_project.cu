@@ -354,6 +354,14 @@ __device__ __forceinline__ bool wait_count(const uint32_t* counter, uint32_t tar
 //          max, store the runlet maxima compacted in place (row c of the stage);
 //       B2 lane = channel, loop over runlets only: one RED per runlet covers all channels of the
 //          cell (1-2 cache lines); the height channel goes lane = runlet.
+#ifdef DM_PROFILE
+// build-time instrumentation (scripts/exp.py): cycle counters summed over CTAs in ctrl[16..63]
+#define DM_CLK() clock64()
+#define DM_ACC(ctrl_, i_, v_) atomicAdd(reinterpret_cast<unsigned long long*>((ctrl_) + 16) + (i_), (unsigned long long)(v_))
+#else
+#define DM_CLK() 0ll
+#define DM_ACC(ctrl_, i_, v_) ((void)0)
+#endif
 constexpr int kWsWarps = 4;
 constexpr int kWsThreads = 32 * (kWsWarps + 1);
 constexpr int kWsTile = 128 * kWsWarps;
@@ -436,8 +444,10 @@ template <int FAST, bool IS_MIN>
 __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDims& d, const WsItem& it,
                                               const DmProjSample& sp, const float* xtab, const float* ytab,
                                               const uint8_t* __restrict__ vplane, float* vals, int* lcell,
-                                              uint32_t* __restrict__ acc, uint32_t slot_off, int cw, int lane) {
+                                              uint32_t* __restrict__ acc, uint32_t slot_off, int cw, int lane,
+                                              long long* tprof) {
   // acc is the kernel parameter (uniform); every RED address is acc + a 32-bit word offset
+  [[maybe_unused]] const long long tp0 = DM_CLK();
   constexpr int RS = kWsTile + 4;
   const int N = cfg.H * cfg.W;
   const int sb = cw * 128;
@@ -507,6 +517,7 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
     if (t2) zrow[o2] = y[2];
     if (t3) zrow[o3] = y[3];
   }
+  [[maybe_unused]] const long long tp1 = DM_CLK();
   // ---- B1: channel loop at full lane utilisation, compaction in place
   const float neutral = cfg.fill_value;  // padding value: never beats fill → never emitted
 #define DM_B1_ROW(ROW)                                                     \
@@ -551,6 +562,7 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
   }
 #undef DM_B1_ROW
   __syncwarp();
+  [[maybe_unused]] const long long tp2 = DM_CLK();
   // ---- B2: one RED per (runlet, channel); lane = channel keeps a runlet's keys in 1-2 lines
   const int total4 = total + padn;
   if (cfg.C > 0) {
@@ -590,6 +602,10 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
       if (beats<IS_MIN>(v, cfg.fill_value)) red_max_u32(acc + (slot_off + (uint32_t)lcell[sb + i]), key_of<IS_MIN>(v));
     }
   }
+#ifdef DM_PROFILE
+  [[maybe_unused]] const long long tp3 = DM_CLK();
+  tprof[0] += tp1 - tp0; tprof[1] += tp2 - tp1; tprof[2] += tp3 - tp2; tprof[3] += total;
+#endif
 }
 
 // 64 cells of a resolve tile, warp-local: load the 64 x CP keys (coalesced 128-bit, all loads in
@@ -715,7 +731,9 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
     const uint64_t policy = policy_evict_first();
     int pend_kind = kItemNone, pend_frame = 0;
     uint32_t fills = 0;
+    [[maybe_unused]] long long pp[4] = {0, 0, 0, 0};
     while (true) {
+      [[maybe_unused]] const long long tq0 = DM_CLK();
       // ---- while the consumers work on the previous item: claim, decode, check the dependency,
       //      fetch the per-sample parameters (all off the critical path)
       unsigned t = 0;
@@ -748,7 +766,9 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
       if (dep && lane == 0) pending = ld_acquire(dep) < dep_target;
       pending = __shfl_sync(0xffffffffu, pending, 0);
       // ---- the stage is free once the consumers released the previous item
+      [[maybe_unused]] const long long tq1 = DM_CLK();
       mbar_wait(empty, (fills & 1u) ^ 1u);
+      [[maybe_unused]] const long long tq2 = DM_CLK();
       const int prev_kind = pend_kind, prev_frame = pend_frame;
       auto publish_prev = [&]() {  // the release of the stage also completes the previous item
         if (lane == 0 && prev_kind != kItemNone) {
@@ -762,6 +782,7 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
         if (lane == 0) it.ok = wait_count(dep, dep_target, ctrl);
         it.ok = __shfl_sync(0xffffffffu, it.ok, 0);
       }
+      [[maybe_unused]] const long long tq3 = DM_CLK();
       if (it.kind == kItemProj) {
         reinterpret_cast<uint32_t*>(sps)[lane] = spw0;
         if (lane < 16) reinterpret_cast<uint32_t*>(sps)[32 + lane] = spw1;
@@ -789,8 +810,14 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
       pend_kind = (it.kind == kItemProj || it.kind == kItemResolve) ? it.kind : kItemNone;
       pend_frame = it.frame;
       ++fills;
+#ifdef DM_PROFILE
+      pp[0] += tq1 - tq0; pp[1] += tq2 - tq1; pp[2] += tq3 - tq2; pp[3] += DM_CLK() - tq3;
+#endif
       if (it.kind == kItemExit) break;
     }
+#ifdef DM_PROFILE
+    if (lane == 0) { DM_ACC(ctrl, 8, pp[0]); DM_ACC(ctrl, 9, pp[1]); DM_ACC(ctrl, 10, pp[2]); DM_ACC(ctrl, 11, pp[3]); }
+#endif
     // the last CTA out re-arms the control block for the next call
     if (lane == 0) {
       __threadfence();
@@ -804,10 +831,13 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
   } else {
     // ===================== consumers =====================
     uint32_t uses = 0;
+    [[maybe_unused]] long long cp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     while (true) {
+      [[maybe_unused]] const long long tc0 = DM_CLK();
       mbar_wait(full, uses & 1u);
       ++uses;
       const WsItem it = *item;
+      [[maybe_unused]] const long long tc1 = DM_CLK();
       if (it.kind == kItemExit) break;
       if (it.ok) {
         if (it.kind == kItemProj) {
@@ -815,16 +845,26 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
           int* lcell = reinterpret_cast<int*>(vals + d.rows * RS);
           ws_proj_slice<FAST, IS_MIN>(cfg, d, it, *sps, xtab, ytab,
                                       valid ? valid + (size_t)it.frame * N : nullptr, vals, lcell, acc,
-                                      (uint32_t)(it.frame % d.ring) * (uint32_t)d.slot_words, warp, lane);
+                                      (uint32_t)(it.frame % d.ring) * (uint32_t)d.slot_words, warp, lane, cp);
+#ifdef DM_PROFILE
+          cp[4] += tc1 - tc0; cp[7] += 1;
+#endif
         } else if (it.kind == kItemResolve) {
           uint32_t* wres = reinterpret_cast<uint32_t*>(stage) + warp * 64 * d.CP;
           ws_resolve_slice(acc + (size_t)(it.frame % d.ring) * d.slot_words, cfg, d, it.frame, it.idx, warp, lane,
                            wres, topdown, mask, height);
+#ifdef DM_PROFILE
+          cp[5] += tc1 - tc0; cp[6] += DM_CLK() - tc1;
+#endif
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(empty);
     }
+#ifdef DM_PROFILE
+    if (warp == 0 && lane == 0)
+      for (int i = 0; i < 8; ++i) DM_ACC(ctrl, i, cp[i]);
+#endif
   }
 }
 
