@@ -33,7 +33,7 @@ ws = [w for w in dmaps._workspaces.values()]
 prof = os.environ.get("DM_PROFILE") == "1"
 if prof:
   for w in ws:
-    w.view(torch.int32)[16:64].zero_()
+    w.view(torch.int32)[320:384].zero_()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(a.steps):
@@ -44,14 +44,22 @@ ms = e0.elapsed_time(e1) / a.steps
 out = {"lib": os.environ.get("DM_B200_LIB", "default"), "scene": a.scene, "fill": a.fill, "ms_per_step": round(ms, 4),
        "maps_per_s": round(a.b / ms * 1e3)}
 if prof:
-  c = ws[0].view(torch.int64)[8:32].cpu().tolist()
+  c = ws[0].view(torch.int64)[160:184].cpu().tolist()
   n = a.steps
-  names = ["A", "B1", "B2", "runlets", "waitfull_proj", "waitfull_res", "resolve", "n_proj",
-           "prod_claim", "prod_wait_empty", "prod_block", "prod_issue"]
-  d = dict(zip(names, c))
-  npj = max(d["n_proj"], 1)
-  out["per_proj_tile_cycles(warp0)"] = {k: round(d[k] / npj) for k in ("A", "B1", "B2", "waitfull_proj")}
-  out["runlets_per_warp_tile"] = round(d["runlets"] / npj, 1)
-  out["n_proj_per_step"] = d["n_proj"] / n
-  out["raw_per_step"] = {k: round(v / n) for k, v in d.items()}
+  if os.environ.get("DM_PROJ_KERNEL", "rl")[0] == "w":
+    names = ["A", "B1", "B2", "runlets", "waitfull_proj", "waitfull_res", "resolve", "n_proj",
+             "prod_claim", "prod_wait_empty", "prod_block", "prod_issue"]
+    d = dict(zip(names, c))
+    npj = max(d["n_proj"], 1)
+    out["per_proj_tile_cycles(warp0)"] = {k: round(d[k] / npj) for k in ("A", "B1", "B2", "waitfull_proj")}
+    out["runlets_per_warp_tile"] = round(d["runlets"] / npj, 1)
+    out["raw_per_step"] = {k: round(v / n) for k, v in d.items()}
+  else:
+    names = ["A", "B1", "publish", "next", "depwait", "B2", "n", "_7", "depwait", "load", "publish", "next", "store", "n", "occupied"]
+    npj, nrs = max(c[6], 1), max(c[13], 1)
+    out["proj_ticket_cycles(warp0)"] = {names[i]: round(c[i] / npj) for i in range(6)}
+    out["proj_ticket_total"] = round(sum(c[:6]) / npj)
+    out["resolve_ticket_cycles(warp0)"] = {names[i]: round(c[i] / nrs) for i in range(8, 13)}
+    out["resolve_ticket_total"] = round(sum(c[8:13]) / nrs)
+    out["tickets_per_warp0_per_step"] = {"proj": c[6] / n / 592, "resolve": c[13] / n / 592, "occupied_frac": c[14] / nrs}
 print(json.dumps(out))
