@@ -11,48 +11,35 @@
 //    hit one or two 128-byte lines instead of CU lines in CU different planes: one RED
 //    instruction per pixel-run instead of CU scattered ones.
 //  * Channel planes are staged tile by tile in shared memory ([channel][pixel]) by TMA bulk
-//    copies (cp.async.bulk + mbarrier, double buffered, L2 evict-first), then re-read
-//    transposed: lane = channel, a warp walks its pixels in order and keeps the running max of
-//    the current same-cell run in a register; the atomic is issued once per run (neighbouring
-//    pixels mostly land in the same cell).  Values that cannot change the canvas (v <= fill)
-//    are never issued.
+//    copies (cp.async.bulk + mbarrier, L2 evict-first), then re-read transposed: lane = channel,
+//    one RED per run of pixels that share a cell (neighbouring pixels mostly do).  Values that
+//    cannot change the canvas (v <= fill) are never issued.
 //  * ONE persistent launch per call: CTAs pull (frame, tile) work items from a ticket counter.
-//    Projection tiles of frame f+2 are interleaved with resolve tiles of frame f, which decode
+//    Projection tiles of frame f + lag are interleaved with resolve tiles of frame f, which decode
 //    the keys into the planar (b, C, Mh, Mw) outputs + "changed" masks and zero the slot again.
-//    acc is a ring of 4 frame slots (≈44 MB at config 2) that stays resident in the 126 MB L2,
-//    so HBM sees the inputs once and the outputs once.
+//  * acc is a ring of up to 10 frame slots used SPARSELY: a flag per 64-cell slice says whether any
+//    key of the slice was touched; the resolve pass only reads (and re-zeroes) flagged slices, so
+//    the lines of a slot that no pixel hit are never brought on chip.  What is resident in the
+//    126 MB L2 is the touched part of the ring (a few MB per slot), HBM sees the inputs once and
+//    the outputs once, and the lag between projecting and resolving a frame can be several frames
+//    — which is what keeps the dependency waits of a deep, many-tiles-in-flight schedule rare.
 //  * Shapes whose planes are not 16-byte aligned take the plain-load kernels (proj_kernel /
 //    resolve_kernel, chunked over the ring) — same device functions, same results.
 #include "dm_common.cuh"
-
-#include <cstdlib>
 
 namespace dm {
 
 constexpr int kProjThreads = 256;
 constexpr int kResolveCells = 256;
-#ifndef DM_RING_MB
-#define DM_RING_MB 48
+constexpr int kSliceCells = 64;                  // cells per sparse-ring flag (one resolve slice of a warp)
+#ifndef DM_FLAG_STRIDE
+#define DM_FLAG_STRIDE 8
 #endif
-#ifndef DM_LAG
-#define DM_LAG 2
-#endif
-#ifndef DM_RL_AHEAD
-#define DM_RL_AHEAD 2
-#endif
-#ifndef DM_WS_AHEAD
-#define DM_WS_AHEAD 1
-#endif
-constexpr size_t kRingBudgetBytes = (size_t)DM_RING_MB << 20;  // accumulation ring kept well inside L2
-constexpr int kLag = DM_LAG;                     // resolve(f) is scheduled with proj(f + kLag)
+constexpr int kFlagStride = DM_FLAG_STRIDE;      // words between two flags: every tile of a frame stores into the
+                                                 // same few hundred flags, so each gets its own 32-byte sector
+constexpr int kMaxRing = 10;                     // frame slots of the accumulation ring
+constexpr size_t kRingBudgetBytes = (size_t)1 << 30;  // ... unless that exceeds 1 GiB of workspace
 constexpr int kCtrlWords = 512;                  // control block at the head of the workspace
-// Register-landed kernel: ctrl[2] timeout flag, ctrl[3] exit count, ticket counter k at ctrl[32 + 32 k] (one
-// 128-byte line each), per-frame completion counters one 32-byte sector each behind the control block.
-#ifndef DM_RL_COUNTERS
-#define DM_RL_COUNTERS 8
-#endif
-constexpr int kRlCounters = DM_RL_COUNTERS;      // independent ticket counters (same-address atomics serialise)
-constexpr int kDoneStride = 8;                   // words between two completion counters
 constexpr unsigned long long kSpinLimitNs = 4000000000ull;  // dependency wait guard (bug → no hang)
 
 struct ProjPlan {
@@ -63,13 +50,17 @@ struct ProjPlan {
   int rows;   // staged rows per tile: C value planes + the depth/height row
   int tile;   // pixels per CTA tile
   int ring;   // frame slots
+  int lag;    // resolve(f) is scheduled with proj(f + lag); ring > lag
+  int nsl;    // slices (flags) per slot
   size_t slot_words;
   size_t ctrl_bytes;
+  size_t flag_bytes;
   size_t stage_bytes;
   size_t smem_tile;      // one stage + sample block (plain-load kernel)
   size_t smem_resolve;
   size_t ws_stage_bytes; // warp-specialised kernel: one 512-pixel stage
-  size_t smem_ws;        // two stages + barriers/items/samples + column/row tables
+  size_t smem_ws;        // stage + barriers/items/samples + column/row tables
+  size_t workspace_bytes() const { return ctrl_bytes + flag_bytes + slot_words * 4 * (size_t)ring; }
 };
 
 static ProjPlan make_plan(const DmProjCfg& cfg, int b) {
@@ -82,9 +73,14 @@ static ProjPlan make_plan(const DmProjCfg& cfg, int b) {
   const size_t M = (size_t)cfg.Mh * cfg.Mw;
   p.slot_words = (M * p.CP + 3) & ~(size_t)3;
   size_t ring = kRingBudgetBytes / (p.slot_words * 4);
-  if (ring < (size_t)kLag + 2) ring = kLag + 2;  // the persistent schedule needs kLag + 2 slots
+  if (ring > (size_t)kMaxRing) ring = kMaxRing;
+  if (ring > (size_t)(b > 0 ? b : 1)) ring = (size_t)(b > 0 ? b : 1);
+  if (ring < 2) ring = 2;
   p.ring = (int)ring;
-  p.ctrl_bytes = ((size_t)(kCtrlWords + 2 * kDoneStride * (b > 0 ? b : 1)) * 4 + 255) & ~(size_t)255;
+  p.lag = p.ring / 2;
+  p.nsl = (int)((M + kSliceCells - 1) / kSliceCells);
+  p.ctrl_bytes = ((size_t)(kCtrlWords + 2 * (b > 0 ? b : 1)) * 4 + 255) & ~(size_t)255;
+  p.flag_bytes = ((size_t)p.ring * p.nsl * kFlagStride * 4 + 255) & ~(size_t)255;
   // staging rows: +4 floats keeps rows 16-byte aligned and the transposed LDS.128
   // conflict-free (row stride ≡ 4 mod 8 words)
   int tile = 1024;
@@ -105,22 +101,10 @@ static ProjPlan make_plan(const DmProjCfg& cfg, int b) {
 }
 
 struct ProjDims {
-  int Cv, hasH, CU, CP, rows, tile, ring;
+  int Cv, hasH, CU, CP, rows, tile, ring, lag, nsl;
   unsigned long long slot_words;
   unsigned long long stage_bytes;
-  unsigned per_magic, w_magic;  // register-landed kernel: division by (P + R) and by W, see udiv_magic
 };
-
-// floor(t / x) and t mod x for t < 2^32, 2 <= x < 2^31 with magic = floor(2^32 / x) + 1 (host): the high product
-// overshoots the quotient by at most one.
-__host__ __device__ __forceinline__ unsigned magic_of(unsigned x) { return (unsigned)((1ull << 32) / x) + 1u; }
-__device__ __forceinline__ unsigned udiv_magic(unsigned t, unsigned x, unsigned magic, unsigned* rem) {
-  unsigned q = __umulhi(t, magic);
-  int r = (int)(t - q * x);
-  if (r < 0) { --q; r += (int)x; }
-  *rem = (unsigned)r;
-  return q;
-}
 
 // One pixel: validity, cell index (or -1) and the height that goes into the height map.
 __device__ __forceinline__ int pixel_cell(const DmProjCfg& cfg, const DmProjSample& sp, int r, int c,
@@ -411,8 +395,9 @@ struct WsItem {
 };
 
 // ticket → work item.  Step s holds the P projection tiles of frame s and the R resolve tiles
-// of frame s - kLag, interleaved one to one so HBM reads and writes mix evenly.
-__device__ __forceinline__ void decode_ticket(unsigned t, int b, int P, int R, int* kind, int* frame, int* idx) {
+// of frame s - lag, interleaved one to one so HBM reads and writes mix evenly.
+__device__ __forceinline__ void decode_ticket(unsigned t, int b, int P, int R, int lag, int* kind, int* frame,
+                                              int* idx) {
   const unsigned per = (unsigned)(P + R);
   const int s = (int)(t / per);
   const int j = (int)(t - (unsigned)s * per);
@@ -424,7 +409,7 @@ __device__ __forceinline__ void decode_ticket(unsigned t, int b, int P, int R, i
     *kind = P > R ? kItemProj : kItemResolve;
     *idx = m + (j - 2 * m);
   }
-  *frame = *kind == kItemProj ? s : s - kLag;
+  *frame = *kind == kItemProj ? s : s - lag;
   if (*frame < 0 || *frame >= b) *kind = kItemNone;
 }
 
@@ -432,11 +417,15 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// sparse-ring slice flag: plain idempotent store, published with the tile's REDs
+__device__ __forceinline__ void st_flag(uint32_t* p) {
+#ifdef DM_NO_FLAGST
+  if (p == nullptr)
+#endif
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(1u) : "memory");
+}
 // fire-and-forget reduction (RED, never the returning ATOM form)
 __device__ __forceinline__ void red_max_u32(uint32_t* p, uint32_t v) {
-#ifdef DM_ABLATE_RED
-  if (v == 0x12345u)  // never true for the keys of the bench scenes: timing experiment only
-#endif
   asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 // Predicated reduction: no branch, no reconvergence bookkeeping around the RED.
@@ -505,7 +494,8 @@ template <int FAST, bool IS_MIN>
 __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDims& d, const WsItem& it,
                                               const DmProjSample& sp, const float* xtab, const float* ytab,
                                               const uint8_t* __restrict__ vplane, float* vals, int* lcell,
-                                              uint32_t* __restrict__ acc, uint32_t slot_off, int cw, int lane,
+                                              uint32_t* __restrict__ acc, uint32_t slot_off,
+                                              uint32_t* __restrict__ slot_flags, float rres, int cw, int lane,
                                               long long* tprof) {
   // acc is the kernel parameter (uniform); every RED address is acc + a 32-bit word offset
   [[maybe_unused]] const long long tp0 = DM_CLK();
@@ -536,7 +526,7 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
       for (int k = 0; k < 4; ++k) {
         bool ok = rowok && (((vm >> (8 * k)) & 0xffu) != 0);
         if (kb > 0) ok = ok && (c + k >= kb) && (c + k < cfg.W - kb);
-        cl[k] = pixel_cell_fast<FAST == 2>(cfg, sp, xn[k], yn, z[k], ok, &y[k]);
+        cl[k] = pixel_cell_fast<FAST == 2, true>(cfg, sp, xn[k], yn, z[k], ok, &y[k], rres);
       }
     } else {
 #pragma unroll
@@ -567,6 +557,19 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
   if (t2) lcell[o2] = cl[2] * d.CP;
   if (t3) lcell[o3] = cl[3] * d.CP;
   if (lane < padn) lcell[sb + total + lane] = 0;
+  {  // sparse ring: flag the 64-cell slices my runlets touch (one store per change of slice, not per runlet)
+    const int s0 = cl[0] >> 6, s1 = cl[1] >> 6, s2 = cl[2] >> 6, s3 = cl[3] >> 6;
+    const int lastv = t3 ? s3 : t2 ? s2 : t1 ? s1 : t0 ? s0 : -1;
+    int prev = __shfl_up_sync(0xffffffffu, lastv, 1);
+    if (lane == 0) prev = -1;
+    if (t0 && s0 != prev) st_flag(slot_flags + s0 * kFlagStride);
+    prev = t0 ? s0 : prev;
+    if (t1 && s1 != prev) st_flag(slot_flags + s1 * kFlagStride);
+    prev = t1 ? s1 : prev;
+    if (t2 && s2 != prev) st_flag(slot_flags + s2 * kFlagStride);
+    prev = t2 ? s2 : prev;
+    if (t3 && s3 != prev) st_flag(slot_flags + s3 * kFlagStride);
+  }
   {  // the depth row becomes the (compacted) height row; C == 0: it is the value channel itself
     const bool hmin = IS_MIN && cfg.C == 0;
     y[1] = p01 ? (hmin ? fminf(y[0], y[1]) : fmaxf(y[0], y[1])) : y[1];
@@ -644,23 +647,44 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
       const float fill = cfg.fill_value;
       for (int i = beg; i < end; i += 4) {
         const uint4 c4 = *reinterpret_cast<const uint4*>(lc + i);
-        const float4 v4 = *reinterpret_cast<const float4*>(row + i);
-        if (beats<IS_MIN>(v4.x, fill)) red_max_u32(acc + (off_c + c4.x), key_of<IS_MIN>(v4.x));
-        if (beats<IS_MIN>(v4.y, fill)) red_max_u32(acc + (off_c + c4.y), key_of<IS_MIN>(v4.y));
-        if (beats<IS_MIN>(v4.z, fill)) red_max_u32(acc + (off_c + c4.z), key_of<IS_MIN>(v4.z));
+        float4 v4 = *reinterpret_cast<const float4*>(row + i);
+        // runs longer than a pixel quad arrive as neighbouring runlets of one cell: fold them, RED the last
+#ifdef DM_NO_MERGE
+        const bool m01 = false, m12 = false, m23 = false;
+#else
+        const bool m01 = c4.x == c4.y, m12 = c4.y == c4.z, m23 = c4.z == c4.w;
+#endif
+        v4.y = m01 ? red2<IS_MIN>(v4.x, v4.y) : v4.y;
+        v4.z = m12 ? red2<IS_MIN>(v4.y, v4.z) : v4.z;
+        v4.w = m23 ? red2<IS_MIN>(v4.z, v4.w) : v4.w;
+        if (!m01 && beats<IS_MIN>(v4.x, fill)) red_max_u32(acc + (off_c + c4.x), key_of<IS_MIN>(v4.x));
+        if (!m12 && beats<IS_MIN>(v4.y, fill)) red_max_u32(acc + (off_c + c4.y), key_of<IS_MIN>(v4.y));
+        if (!m23 && beats<IS_MIN>(v4.z, fill)) red_max_u32(acc + (off_c + c4.z), key_of<IS_MIN>(v4.z));
         if (beats<IS_MIN>(v4.w, fill)) red_max_u32(acc + (off_c + c4.w), key_of<IS_MIN>(v4.w));
       }
     }
   }
-  if (d.hasH) {  // height channel: always max against -inf (maps.py:340-348)
-    for (int i = lane; i < total; i += 32) {
-      const float v = zrow[sb + i];
-      if (v > -INFINITY) red_max_u32(acc + (slot_off + (uint32_t)d.Cv + (uint32_t)lcell[sb + i]), enc(v));
-    }
-  } else if (cfg.C == 0) {  // the heights are the values
-    for (int i = lane; i < total; i += 32) {
-      const float v = zrow[sb + i];
-      if (beats<IS_MIN>(v, cfg.fill_value)) red_max_u32(acc + (slot_off + (uint32_t)lcell[sb + i]), key_of<IS_MIN>(v));
+  // lane = runlet for the heights.  Neighbouring runlets of one cell are folded by a segmented scan over the
+  // lanes and only the last one of a run issues its RED.
+  if (d.hasH || cfg.C == 0) {
+    const bool hmin = IS_MIN && cfg.C == 0;  // C == 0: the heights are the values (fill / reduction apply)
+    const float hfill = cfg.C == 0 ? cfg.fill_value : -INFINITY;  // height channel: max against -inf (maps.py:340-348)
+    const uint32_t hoff = slot_off + (cfg.C == 0 ? 0u : (uint32_t)d.Cv);
+    for (int base = 0; base < total; base += 32) {
+      const int i = base + lane;
+      const bool active = i < total;
+      const uint32_t cellv = active ? (uint32_t)lcell[sb + i] : 0xffffffffu;
+      float v = active ? zrow[sb + i] : hfill;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float pv = __shfl_up_sync(0xffffffffu, v, o);
+        const uint32_t pc = __shfl_up_sync(0xffffffffu, cellv, o);
+        if (lane >= o && pc == cellv) v = hmin ? fminf(v, pv) : fmaxf(v, pv);
+      }
+      const uint32_t nc = __shfl_down_sync(0xffffffffu, cellv, 1);
+      const bool last = lane == 31 || nc != cellv;
+      const bool win = hmin ? (v < hfill) : (v > hfill);
+      if (active && last && win) red_max_u32(acc + (hoff + cellv), hmin ? ~enc(v) : enc(v));
     }
   }
 #ifdef DM_PROFILE
@@ -672,18 +696,31 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
 // 64 cells of a resolve tile, warp-local: load the 64 x CP keys (coalesced 128-bit, all loads in
 // flight before the first use), zero what was set, and write the planar outputs.  Most of a map
 // is empty: a slice without a single key takes a constant-store path.
-__device__ __forceinline__ void ws_resolve_slice(uint32_t* __restrict__ acc_slot, const DmProjCfg& cfg,
-                                                 const ProjDims& d, int frame, int cell_tile, int cw, int lane,
-                                                 uint32_t* wres, float* __restrict__ topdown,
+__device__ __forceinline__ bool ws_resolve_slice(uint32_t* __restrict__ acc_slot, const DmProjCfg& cfg,
+                                                 const ProjDims& d, uint32_t* __restrict__ slot_flags, int frame,
+                                                 int cell_tile, int cw, int lane, uint32_t* wres,
+                                                 float* __restrict__ topdown,
                                                  uint8_t* __restrict__ mask, float* __restrict__ height) {
   const int M = cfg.Mh * cfg.Mw;
   const int cell0 = cell_tile * kWsResolveCells + cw * 64;
   const int ncell = min(64, M - cell0);
-  if (ncell <= 0) return;
+  if (ncell <= 0) return false;
+  uint32_t* slice_flag = slot_flags + (size_t)(cell0 >> 6) * kFlagStride;
   const int nw = ncell * d.CP;
   const int nw4 = nw & ~3;
   uint32_t* src = acc_slot + (size_t)cell0 * d.CP;  // 16-byte aligned: cell0 % 64 == 0 → words % 4 == 0
   uint32_t any = 0;
+  // sparse ring: a slice nobody flagged holds no key and is not even read
+  uint32_t flagged = 0;
+  if (lane == 0) {
+    flagged = __ldcg(slice_flag);
+    if (flagged) __stcg(slice_flag, 0u);
+  }
+  flagged = __shfl_sync(0xffffffffu, flagged, 0);
+  if (!flagged) {
+    if (!(ncell == 64 && (M & 3) == 0))
+      for (int k = lane; k < nw; k += 32) wres[k] = 0;
+  } else {
   for (int base = 0; base < nw4; base += 512) {
     uint4 v[4];
 #pragma unroll
@@ -708,6 +745,7 @@ __device__ __forceinline__ void ws_resolve_slice(uint32_t* __restrict__ acc_slot
     wres[k] = v;
     any |= v;
   }
+  }
   const bool occupied = __any_sync(0xffffffffu, any != 0);
   const size_t plane0 = (size_t)frame * d.Cv * M + cell0;
   if (!occupied && ncell == 64 && (M & 3) == 0) {
@@ -723,7 +761,7 @@ __device__ __forceinline__ void ws_resolve_slice(uint32_t* __restrict__ acc_slot
     }
     if (d.hasH && lane < 16)
       st_stream_f4(height + (size_t)frame * M + cell0 + lane * 4, make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY));
-    return;
+    return flagged != 0;
   }
   __syncwarp();
   for (int j = lane; j < ncell; j += 32) {
@@ -744,6 +782,7 @@ __device__ __forceinline__ void ws_resolve_slice(uint32_t* __restrict__ acc_slot
     }
   }
   __syncwarp();
+  return flagged != 0;
 }
 
 template <int FAST, bool IS_MIN>
@@ -751,10 +790,11 @@ __global__ void __launch_bounds__(kWsThreads)
 proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values,
                const uint8_t* __restrict__ valid, const DmProjSample* __restrict__ samples,
                const DmProjCfg cfg, const ProjDims d, int b, uint32_t* __restrict__ ctrl,
-               uint32_t* __restrict__ acc, float* __restrict__ topdown, uint8_t* __restrict__ mask,
-               float* __restrict__ height) {
+               uint32_t* __restrict__ flags, uint32_t* __restrict__ acc, float* __restrict__ topdown,
+               uint8_t* __restrict__ mask, float* __restrict__ height) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int RS = kWsTile + 4;
+  const float rres = __frcp_rn(cfg.map_res);
   // one stage per CTA: latency is hidden by the 5-6 CTAs resident per SM, not by an in-CTA ring
   unsigned char* stage = smem;
   unsigned char* tail = smem + d.stage_bytes;
@@ -769,11 +809,33 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
   const int N = cfg.H * cfg.W, M = cfg.Mh * cfg.Mw;
   const int P = (N + kWsTile - 1) / kWsTile;
   const int R = (M + kWsResolveCells - 1) / kWsResolveCells;
-  const unsigned total = (unsigned)(b + kLag) * (unsigned)(P + R);
   uint32_t* proj_done = ctrl + kCtrlWords;
   uint32_t* resolve_done = proj_done + b;
+  uint32_t* occ_count = reinterpret_cast<uint32_t*>(tail + 16);  // flagged slices seen by this CTA
+
+  // How far the resolve pass trails the projection (in frames) is chosen from how densely the previous call
+  // on this workspace filled its maps (ctrl[4], written by that call's last CTA; 0: unknown, assume sparse):
+  // the touched part of lag + 2 slots should fit in ~48 MB of L2.  A long lag makes dependency waits rare and
+  // lets the producers claim two tickets ahead; densely hit maps fall back to the short schedule.
+  int lag = d.lag;
+  {
+    const uint32_t hint = __ldcg(ctrl + 4);
+    if (hint) {
+      const float touched = (float)(hint - 1u) * (1.0f / 65536.0f) * (float)d.slot_words * 4.0f;
+      const int fit = (int)fminf((float)(48u << 20) / fmaxf(touched, 1.0f), 64.0f) - 2;
+      lag = max(min(2, d.lag), min(fit, d.lag));
+    }
+  }
+#ifdef DM_FORCE_LAG
+  lag = min(DM_FORCE_LAG, d.lag);
+#endif
+  const int ahead = lag >= 3 ? 2 : 1;
+  // slots in use: a slot that is re-used soon keeps its lines in L2 (a densely hit ring must stay small)
+  const int ring = min(d.ring, 2 * lag);
+  const unsigned total = (unsigned)(b + lag) * (unsigned)(P + R);
 
   if (tid == 0) {
+    *occ_count = 0;
     mbar_init(full, 1);
     mbar_init(empty, kWsWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -797,7 +859,7 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
     unsigned raw0 = 0, raw1 = 0;
     if (lane == 0) {
       raw0 = atomicAdd(ctrl, 1u);
-      if (DM_WS_AHEAD == 2) raw1 = atomicAdd(ctrl, 1u);
+      if (ahead == 2) raw1 = atomicAdd(ctrl, 1u);
     }
     while (true) {
       [[maybe_unused]] const long long tq0 = DM_CLK();
@@ -805,7 +867,7 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
       //      fetch the per-sample parameters (all off the critical path)
       const unsigned t = __shfl_sync(0xffffffffu, raw0, 0);
       if (lane == 0) {
-        if (DM_WS_AHEAD == 2) {
+        if (ahead == 2) {
           raw0 = raw1;
           if (t < total) raw1 = atomicAdd(ctrl, 1u);
         } else if (t < total) {
@@ -817,7 +879,7 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
       if (t >= total) {
         it.kind = kItemExit;
       } else {
-        decode_ticket(t, b, P, R, &it.kind, &it.frame, &it.idx);
+        decode_ticket(t, b, P, R, lag, &it.kind, &it.frame, &it.idx);
       }
       // dependency: ring slot resolved by its previous tenant / frame fully projected
       const uint32_t* dep = nullptr;
@@ -827,7 +889,7 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
         it.tile0 = it.idx * kWsTile;
         it.r0 = it.tile0 / cfg.W;
         it.c0 = it.tile0 - it.r0 * cfg.W;
-        if (it.frame >= d.ring) { dep = resolve_done + (it.frame - d.ring); dep_target = (uint32_t)R; }
+        if (it.frame >= ring) { dep = resolve_done + (it.frame - ring); dep_target = (uint32_t)R; }
 #ifdef DM_WS_PREFETCH
         {  // pull the tile into L2 while the consumers are still busy with the previous one
           const int npx = min(kWsTile, N - it.tile0);
@@ -845,7 +907,7 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
         dep = proj_done + it.frame;
         dep_target = (uint32_t)P;
       }
-      // relaxed load, evaluated after the wait below (see the note on ordering at proj_rl_kernel)
+      // relaxed load, evaluated after the wait below (ordering: everything that depends on it is issued after a branch on the loaded value and bypasses L1 — RED, ld.cg, st.cg, TMA through L2)
       uint32_t dep_seen = 0;
       if (dep && lane == 0) dep_seen = ld_relaxed(dep);
       // ---- the stage is free once the consumers released the previous item
@@ -905,11 +967,19 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
 #ifdef DM_PROFILE
     if (lane == 0) { DM_ACC(ctrl, 8, pp[0]); DM_ACC(ctrl, 9, pp[1]); DM_ACC(ctrl, 10, pp[2]); DM_ACC(ctrl, 11, pp[3]); }
 #endif
-    // the last CTA out re-arms the control block for the next call
+    // the consumers have added their flagged-slice counts; the last CTA out re-arms the control block for
+    // the next call and leaves it the density of this call's maps
+    mbar_wait(empty, (fills & 1u) ^ 1u);
     if (lane == 0) {
+      atomicAdd(ctrl + 5, *reinterpret_cast<volatile uint32_t*>(occ_count));
       __threadfence();
       const uint32_t prev = atomicAdd(ctrl + 3, 1u);
       if (prev == gridDim.x - 1) {
+        const unsigned long long flagged = atomicAdd(ctrl + 5, 0u);
+        const unsigned long long slices = (unsigned long long)b * (unsigned long long)d.nsl;
+        const unsigned long long f16 = slices ? (flagged << 16) / slices : 0ull;
+        ctrl[4] = 1u + (uint32_t)(f16 < 65535ull ? f16 : 65535ull);
+        ctrl[5] = 0;
         for (int i = 0; i < 2 * b; ++i) proj_done[i] = 0;
         ctrl[0] = 0; ctrl[1] = 0; ctrl[3] = 0;
         __threadfence();
@@ -917,7 +987,7 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
     }
   } else {
     // ===================== consumers =====================
-    uint32_t uses = 0;
+    uint32_t uses = 0, my_flagged = 0;
     [[maybe_unused]] long long cp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     while (true) {
       [[maybe_unused]] const long long tc0 = DM_CLK();
@@ -925,21 +995,30 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
       ++uses;
       const WsItem it = *item;
       [[maybe_unused]] const long long tc1 = DM_CLK();
-      if (it.kind == kItemExit) break;
+      if (it.kind == kItemExit) {
+        if (lane == 0) {
+          atomicAdd(occ_count, my_flagged);
+          mbar_arrive(empty);
+        }
+        break;
+      }
       if (it.ok) {
         if (it.kind == kItemProj) {
           float* vals = reinterpret_cast<float*>(stage);
           int* lcell = reinterpret_cast<int*>(vals + d.rows * RS);
+          const int slot = it.frame % ring;
           ws_proj_slice<FAST, IS_MIN>(cfg, d, it, *sps, xtab, ytab,
                                       valid ? valid + (size_t)it.frame * N : nullptr, vals, lcell, acc,
-                                      (uint32_t)(it.frame % d.ring) * (uint32_t)d.slot_words, warp, lane, cp);
+                                      (uint32_t)slot * (uint32_t)d.slot_words, flags + (size_t)slot * d.nsl * kFlagStride, rres,
+                                      warp, lane, cp);
 #ifdef DM_PROFILE
           cp[4] += tc1 - tc0; cp[7] += 1;
 #endif
         } else if (it.kind == kItemResolve) {
           uint32_t* wres = reinterpret_cast<uint32_t*>(stage) + warp * 64 * d.CP;
-          ws_resolve_slice(acc + (size_t)(it.frame % d.ring) * d.slot_words, cfg, d, it.frame, it.idx, warp, lane,
-                           wres, topdown, mask, height);
+          const int slot = it.frame % ring;
+          my_flagged += ws_resolve_slice(acc + (size_t)slot * d.slot_words, cfg, d, flags + (size_t)slot * d.nsl * kFlagStride,
+                                         it.frame, it.idx, warp, lane, wres, topdown, mask, height) ? 1u : 0u;
 #ifdef DM_PROFILE
           cp[5] += tc1 - tc0; cp[6] += DM_CLK() - tc1;
 #endif
@@ -956,531 +1035,6 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
 }
 
 
-// ================= register-landed persistent kernel =============================================
-// No shared-memory stage for the inputs and no producer warp: every warp is an independent worker.
-//   * A warp claims tickets from the global counter two tickets ahead, so the claim's round trip is hidden.
-//     A ticket is one PASS of 128 pixels of a frame (4 per lane) or one SLICE of 64 cells to resolve.  Small
-//     tickets keep the span of tickets in flight (one per resident warp) well below one frame, which is what
-//     the 2-frame lag between projecting and resolving a frame assumes.
-//   * Projection pass: the depth quad and up to 16 value planes land in REGISTERS straight from HBM
-//     (17 x LD.128 per lane in flight, 512 contiguous bytes per warp and plane, L2 evict-first); the loads of
-//     the warp's next ticket are issued as soon as B1 has consumed the registers, so they fly while the warp
-//     issues its reductions.
-//       A  cells + heights of the 4 pixels, in-thread merge of equal neighbouring cells into runlets, warp
-//          prefix sum -> record index of every runlet;
-//       B1 per-thread running max over each runlet, 4 channels at a time, written TRANSPOSED into the warp's
-//          record buffer in shared memory: record = 16 channel values + the cell's word offset (80 bytes;
-//          STS.128, conflict-free);
-//       B2 lane = channel: one RED.MAX per (runlet, channel); a warp instruction covers the 16 keys of two
-//          cells (1-2 cache lines each).  Heights go straight from registers, lane = runlet.
-//     More than 16 channels: the value planes are streamed in chunks of 16 through the same registers.
-//   * Completion is published per ticket (fence + one RED on the frame's counter), deferred to the point of
-//     the NEXT ticket where the warp has no loads in flight, so the fence never waits for HBM.
-//   * The dependency of a ticket (ring slot resolved / frame fully projected) is read with a relaxed load when
-//     the ticket starts and only waited for right before the first reduction / key load.  No acquire fence:
-//     everything ordered after it is issued after a branch on the loaded value (in-order issue, no speculative
-//     memory operations) and bypasses L1 (RED, ld.cg, st.cg), so L2 is the single point of coherence.
-constexpr int kRlWarps = 4;
-constexpr int kRlThreads = 32 * kRlWarps;
-constexpr int kRlCtasPerSm = 4;
-constexpr int kRlPass = 128;  // pixels per projection ticket
-constexpr int kRlRec = 20;    // words per record: 16 values, cell offset, 3 unused (16-byte aligned rows)
-constexpr int kRlWarpWords = kRlPass * kRlRec;  // per-warp buffer: 128 records, or the keys of one resolve slice
-
-struct Landing {
-  float4 v[16];
-  float4 z;
-  uint32_t vm;
-};
-
-__device__ __forceinline__ float4 ld_first_f4(const float* p, uint64_t policy) {
-  float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "l"(p), "l"(policy));
-  return v;
-}
-__device__ __forceinline__ void sts_v4(uint32_t* p, float a, float b, float c, float d) {
-  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(smem_u32(p)), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-// lane 0 only.  Returns false on timeout (a scheduling bug, never expected) after raising ctrl[2].
-__device__ __forceinline__ bool wait_count_relaxed(const uint32_t* counter, uint32_t target, uint32_t* ctrl) {
-  if (ld_relaxed(counter) >= target) return true;
-  const unsigned long long t0 = globaltimer();
-  while (ld_relaxed(counter) < target) {
-    __nanosleep(32);
-    if (ld_relaxed(ctrl + 2)) return false;  // sticky: somebody timed out already, do not wait again
-    if (globaltimer() - t0 > kSpinLimitNs) {
-      atomicExch(ctrl + 2, 1u);
-      return false;
-    }
-  }
-  return true;
-}
-
-struct RlItem {
-  int kind, frame, idx;
-};
-
-// depth quad (+ valid bytes) of a projection ticket
-__device__ __forceinline__ void rl_issue_depth(Landing& L, const float* __restrict__ depth,
-                                               const uint8_t* __restrict__ valid, const RlItem& it, int lane, int N,
-                                               uint64_t policy) {
-  const int n0 = it.idx * kRlPass + 4 * lane;
-  L.z = make_float4(0.f, 0.f, 0.f, 0.f);
-  L.vm = 0x01010101u;
-  if (n0 < N) {
-    L.z = ld_first_f4(depth + (size_t)it.frame * N + n0, policy);
-    if (valid) L.vm = __ldg(reinterpret_cast<const uint32_t*>(valid + (size_t)it.frame * N + n0));
-  }
-}
-// value planes [16 j, 16 j + 16) of a projection ticket
-__device__ __forceinline__ void rl_issue_values(Landing& L, const float* __restrict__ values, const RlItem& it, int j,
-                                                int lane, int N, int C, uint64_t policy) {
-  const int n0 = it.idx * kRlPass + 4 * lane;
-  const int c0 = 16 * j;
-  const int nch = n0 < N ? C - c0 : 0;  // planes this lane loads (lanes past the frame load nothing)
-  const float* p = values + ((size_t)it.frame * C + c0) * N + n0;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    L.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i < nch) L.v[i] = ld_first_f4(p, policy);
-    p += N;
-  }
-}
-
-// Resolve slice, part 1: load the ncell x CP keys (coalesced 128-bit, all loads in flight before the first
-// use), zero what was set, park the keys in the warp's buffer.  Returns whether any key was set.  cell0 % 4 == 0.
-__device__ __forceinline__ bool rl_resolve_load(uint32_t* __restrict__ acc_slot, const ProjDims& d, int cell0,
-                                                int ncell, int lane, uint32_t* wres) {
-  const int nw = ncell * d.CP;
-  const int nw4 = nw & ~3;
-  uint32_t* src = acc_slot + (size_t)cell0 * d.CP;  // 16-byte aligned: cell0 % 4 == 0
-  uint32_t any = 0;
-  for (int base = 0; base < nw4; base += 512) {
-    uint4 v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = base + (u * 32 + lane) * 4;
-      v[u] = i < nw4 ? __ldcg(reinterpret_cast<const uint4*>(src + i)) : make_uint4(0, 0, 0, 0);
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = base + (u * 32 + lane) * 4;
-      const uint32_t nz = v[u].x | v[u].y | v[u].z | v[u].w;
-      any |= nz;
-      if (i < nw4) {
-        if (nz) __stcg(reinterpret_cast<uint4*>(src + i), make_uint4(0, 0, 0, 0));
-        *reinterpret_cast<uint4*>(wres + i) = v[u];
-      }
-    }
-  }
-  for (int k = nw4 + lane; k < nw; k += 32) {
-    const uint32_t v = __ldcg(src + k);
-    if (v) __stcg(src + k, 0u);
-    wres[k] = v;
-    any |= v;
-  }
-  return __any_sync(0xffffffffu, any != 0);
-}
-
-// Resolve slice, part 2: the planar outputs.  Most of a map is empty: a slice without a single key takes a
-// constant-store path.
-__device__ __forceinline__ void rl_resolve_store(bool occupied, const DmProjCfg& cfg, const ProjDims& d, int frame,
-                                                 int cell0, int ncell, int lane, const uint32_t* wres,
-                                                 float* __restrict__ topdown, uint8_t* __restrict__ mask,
-                                                 float* __restrict__ height) {
-  const int M = cfg.Mh * cfg.Mw;
-  const size_t plane0 = (size_t)frame * d.Cv * M + cell0;
-  if (!occupied && (ncell & 3) == 0 && (M & 3) == 0) {
-    // ncell x fill per channel as float4 stores (lanes 0-15), ncell x False as u32 stores (lanes 16-31)
-    const int nq = ncell >> 2;
-    const float f = cfg.fill_value;
-    const int ql = lane & 15;
-    float* tp = topdown + plane0 + ql * 4;
-    uint8_t* mp = mask + plane0 + ql * 4;
-    if (ql < nq) {
-      for (int c = 0; c < d.Cv; ++c) {
-        if (lane < 16) st_stream_f4(tp, make_float4(f, f, f, f));
-        else asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(mp), "r"(0u) : "memory");
-        tp += M;
-        mp += M;
-      }
-      if (d.hasH && lane < 16)
-        st_stream_f4(height + (size_t)frame * M + cell0 + lane * 4, make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY));
-    }
-    return;
-  }
-  __syncwarp();
-  for (int j = lane; j < ncell; j += 32) {
-    const uint32_t* mine = wres + j * d.CP;
-    float* tp = topdown + plane0 + j;
-    uint8_t* mp = mask + plane0 + j;
-    for (int c = 0; c < d.Cv; ++c) {
-      const uint32_t k = mine[c];
-      const float out = k ? dec_red(k, cfg.reduction) : cfg.fill_value;  // utils.py:472-491
-      st_stream_f1(tp, out);
-      st_stream_u8(mp, k ? 1 : 0);
-      tp += M;
-      mp += M;
-    }
-    if (d.hasH) {
-      const uint32_t k = mine[d.Cv];
-      st_stream_f1(height + (size_t)frame * M + cell0 + j, k ? dec(k) : -INFINITY);  // maps.py:345
-    }
-  }
-}
-
-__host__ __device__ __forceinline__ int rl_resolve_cells(int CP) { return (64 * CP <= kRlWarpWords) ? 64 : 32; }
-
-template <int FAST, bool IS_MIN>
-__global__ void __launch_bounds__(kRlThreads, kRlCtasPerSm)
-proj_rl_kernel(const float* __restrict__ depth, const float* __restrict__ values,
-               const uint8_t* __restrict__ valid, const DmProjSample* __restrict__ samples,
-               const DmProjCfg cfg, const ProjDims d, int b, uint32_t* __restrict__ ctrl,
-               uint32_t* __restrict__ acc, float* __restrict__ topdown, uint8_t* __restrict__ mask,
-               float* __restrict__ height) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint32_t* rec = reinterpret_cast<uint32_t*>(smem) + warp * kRlWarpWords;
-  DmProjSample* sps = reinterpret_cast<DmProjSample*>(smem + (size_t)kRlWarps * kRlWarpWords * 4) + warp;
-  float* xtab = reinterpret_cast<float*>(smem + (size_t)kRlWarps * (kRlWarpWords * 4 + sizeof(DmProjSample)));
-  float* ytab = xtab + ((cfg.W + 3) & ~3);
-
-  const int N = cfg.H * cfg.W, M = cfg.Mh * cfg.Mw;
-  const int rcells = rl_resolve_cells(d.CP);  // cells per resolve ticket
-  const int P = (N + kRlPass - 1) / kRlPass;
-  const int R = (M + rcells - 1) / rcells;
-  const unsigned total = (unsigned)(b + kLag) * (unsigned)(P + R);
-  uint32_t* proj_done = ctrl + kCtrlWords;                 // counter of frame f at [kDoneStride * f]
-  uint32_t* resolve_done = proj_done + kDoneStride * b;
-  // ticket counter of this warp: counter k hands out the tickets n * kRlCounters + k in order
-  const unsigned ck = (blockIdx.x * kRlWarps + warp) % kRlCounters;
-  uint32_t* counter = ctrl + 32 + 32 * ck;
-  auto claim = [&]() { return atomicAdd(counter, 1u) * kRlCounters + ck; };
-  const int nchunks = cfg.C > 16 ? (cfg.C + 15) >> 4 : 1;
-
-  if (FAST) {  // maps.py:677-678 column / row factors, once per CTA
-    for (int c = tid; c < cfg.W; c += kRlThreads) xtab[c] = __fdiv_rn(__fsub_rn((float)c, cfg.cx), cfg.fx);
-    for (int r = tid; r < cfg.H; r += kRlThreads) {
-      const float yy = cfg.flip_h ? __fsub_rn((float)(cfg.H - 1), (float)r) : (float)r;
-      ytab[r] = __fdiv_rn(__fsub_rn(yy, cfg.cy), cfg.fy);
-    }
-  }
-  __syncthreads();
-
-  // ticket -> work item.  Step s holds the P passes of frame s and the R slices of frame s - kLag, interleaved
-  // one to one so HBM reads and writes mix evenly.
-  const int mPR = P < R ? P : R;
-  auto decode = [&](unsigned t) {
-    RlItem it{kItemExit, 0, 0};
-    if (t >= total) return it;
-    unsigned j;
-    const int s = (int)udiv_magic(t, (unsigned)(P + R), d.per_magic, &j);
-    if ((int)j < 2 * mPR) {
-      it.kind = (int)(j & 1u);
-      it.idx = (int)(j >> 1);
-    } else {
-      it.kind = P > R ? kItemProj : kItemResolve;
-      it.idx = (int)j - mPR;
-    }
-    it.frame = it.kind == kItemProj ? s : s - kLag;
-    if (it.frame < 0 || it.frame >= b) it.kind = kItemNone;
-    return it;
-  };
-  // claims run two tickets ahead; lane 0 holds the raw results until they are needed
-  unsigned raw0 = 0, raw1 = 0;
-  if (lane == 0) {
-    raw0 = claim();
-    if (DM_RL_AHEAD == 2) raw1 = claim();
-  }
-  RlItem cur = decode(__shfl_sync(0xffffffffu, raw0, 0));
-  if (lane == 0) {
-    if (DM_RL_AHEAD == 2) {
-      raw0 = raw1;
-      raw1 = claim();
-    } else {
-      raw0 = claim();
-    }
-  }
-
-  const uint64_t policy = policy_evict_first();  // inputs are read once; the ring must stay in L2
-  const float rres = __frcp_rn(cfg.map_res);
-  Landing L;
-  uint32_t spw0 = 0, spw1 = 0;  // my two words of the next projection ticket's sample block
-  auto prefetch_ticket = [&](const RlItem& it) {
-    if (it.kind != kItemProj) return;
-    rl_issue_depth(L, depth, valid, it, lane, N, policy);
-    if (cfg.C > 0) rl_issue_values(L, values, it, 0, lane, N, cfg.C, policy);
-    const uint32_t* sw = reinterpret_cast<const uint32_t*>(samples + it.frame);
-    spw0 = __ldg(sw + lane);
-    if (lane < 16) spw1 = __ldg(sw + 32 + lane);
-  };
-  auto next_ticket = [&]() {
-    const unsigned t = __shfl_sync(0xffffffffu, raw0, 0);
-    const RlItem nxt = decode(t);
-    if (lane == 0) {
-      if (DM_RL_AHEAD == 2) {
-        raw0 = raw1;
-        if (t < total) raw1 = claim();
-      } else if (t < total) {
-        raw0 = claim();
-      }
-    }
-    prefetch_ticket(nxt);
-    return nxt;
-  };
-  // deferred completion of the previous ticket: called where this warp has no loads in flight
-  uint32_t* pending = nullptr;
-  auto publish_pending = [&](uint32_t* mine) {
-    if (pending) {
-      // release: fence.acq_rel, not __threadfence() (= fence.sc: MEMBAR.SC + ERRBAR + L1 invalidate)
-      asm volatile("fence.acq_rel.gpu;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(pending) : "memory");
-    }
-    pending = mine;
-  };
-  auto dep_wait = [&](const uint32_t* dep, uint32_t target, uint32_t seen) -> bool {
-    int ok = 1;
-    if (lane == 0 && dep && seen < target) ok = wait_count_relaxed(dep, target, ctrl);
-    ok = __shfl_sync(0xffffffffu, ok, 0);
-    return ok != 0;
-  };
-
-  prefetch_ticket(cur);
-  [[maybe_unused]] long long pr[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-#ifdef DM_PROFILE
-#define DM_LAP(i_) { const long long now_ = clock64(); pr[i_] += now_ - lap_; lap_ = now_; }
-#else
-#define DM_LAP(i_)
-#endif
-  while (cur.kind != kItemExit) {
-    RlItem nxt{kItemExit, 0, 0};
-    [[maybe_unused]] long long lap_ = DM_CLK();
-    if (cur.kind == kItemProj) {
-      const uint32_t* dep = cur.frame >= d.ring ? resolve_done + kDoneStride * (cur.frame - d.ring) : nullptr;
-      uint32_t seen = 0;
-      if (lane == 0 && dep) seen = ld_relaxed(dep);
-      reinterpret_cast<uint32_t*>(sps)[lane] = spw0;
-      if (lane < 16) reinterpret_cast<uint32_t*>(sps)[32 + lane] = spw1;
-      __syncwarp();
-      const DmProjSample& sp = *sps;
-      const uint32_t slot_off = (uint32_t)(cur.frame % d.ring) * (uint32_t)d.slot_words;
-      const int n0 = cur.idx * kRlPass + 4 * lane;
-      // ---- A: cells and heights of my 4 pixels
-      int cl[4] = {-1, -1, -1, -1};
-      float y[4] = {0.f, 0.f, 0.f, 0.f};
-#ifdef DM_ABLATE_COMPUTE
-      {  // timing experiment: consume the landed registers with one add each, no projection work
-        float acc_ = L.z.x + L.z.w;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) acc_ += L.v[i].x + L.v[i].w;
-        if (acc_ == 123.456f) cl[0] = 1;
-      }
-      if (false) {
-#else
-      if (n0 < N) {
-#endif
-        const float z[4] = {L.z.x, L.z.y, L.z.z, L.z.w};
-        unsigned cu;
-        const int r = (int)udiv_magic((unsigned)n0, (unsigned)cfg.W, d.w_magic, &cu);
-        const int c = (int)cu;
-        const uint32_t vm = L.vm;
-        if (FAST) {
-          const float4 xn4 = *reinterpret_cast<const float4*>(xtab + c);
-          const float xn[4] = {xn4.x, xn4.y, xn4.z, xn4.w};
-          const float yn = ytab[r];
-          bool rowok = true;
-          const int kb = cfg.clip_border;
-          if (kb > 0) rowok = (r >= kb) && (r < cfg.H - kb);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            bool ok = rowok && (((vm >> (8 * q)) & 0xffu) != 0);
-            if (kb > 0) ok = ok && (c + q >= kb) && (c + q < cfg.W - kb);
-            cl[q] = pixel_cell_fast<FAST == 2, true>(cfg, sp, xn[q], yn, z[q], ok, &y[q], rres);
-          }
-        } else {
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            cl[q] = pixel_cell(cfg, sp, r, c + q, z[q], ((vm >> (8 * q)) & 0xffu) != 0, &y[q]);
-        }
-      }
-      // in-thread runs: pixel q continues into q+1 when both are valid and share the cell
-      const bool p01 = (cl[0] >= 0) && (cl[0] == cl[1]);
-      const bool p12 = (cl[1] >= 0) && (cl[1] == cl[2]);
-      const bool p23 = (cl[2] >= 0) && (cl[2] == cl[3]);
-      const bool t0 = (cl[0] >= 0) && !p01, t1 = (cl[1] >= 0) && !p12, t2 = (cl[2] >= 0) && !p23, t3 = cl[3] >= 0;
-      const int cnt = (int)t0 + (int)t1 + (int)t2 + (int)t3;
-      int incl = cnt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int n = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += n;
-      }
-      const int total_r = __shfl_sync(0xffffffffu, incl, 31);
-      DM_LAP(0)  // A (includes the wait for the depth quad)
-      // my runlets' records and their cells' word offsets in the accumulation slot
-      uint32_t* r0 = rec + (incl - cnt) * kRlRec;
-      uint32_t* r1 = r0 + (int)t0 * kRlRec;
-      uint32_t* r2 = r1 + (int)t1 * kRlRec;
-      uint32_t* r3 = r2 + (int)t2 * kRlRec;
-      const uint32_t off0 = (uint32_t)cl[0] * (uint32_t)d.CP, off1 = (uint32_t)cl[1] * (uint32_t)d.CP;
-      const uint32_t off2 = (uint32_t)cl[2] * (uint32_t)d.CP, off3 = (uint32_t)cl[3] * (uint32_t)d.CP;
-      {  // heights of the runlets; C == 0: they are the values themselves
-        const bool hmin = IS_MIN && cfg.C == 0;
-        y[1] = p01 ? (hmin ? fminf(y[0], y[1]) : fmaxf(y[0], y[1])) : y[1];
-        y[2] = p12 ? (hmin ? fminf(y[1], y[2]) : fmaxf(y[1], y[2])) : y[2];
-        y[3] = p23 ? (hmin ? fminf(y[2], y[3]) : fmaxf(y[2], y[3])) : y[3];
-      }
-      bool ok_item = true;
-#pragma unroll 1
-      for (int j = 0; j < nchunks; ++j) {
-        const int c0 = 16 * j;
-        // ---- B1: running max over each runlet, transposed into the records
-        if (cfg.C > 0) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (c0 + 4 * g < cfg.C) {
-              float4 a0 = L.v[4 * g], a1 = L.v[4 * g + 1], a2 = L.v[4 * g + 2], a3 = L.v[4 * g + 3];
-              a0.y = p01 ? red2<IS_MIN>(a0.x, a0.y) : a0.y; a1.y = p01 ? red2<IS_MIN>(a1.x, a1.y) : a1.y;
-              a2.y = p01 ? red2<IS_MIN>(a2.x, a2.y) : a2.y; a3.y = p01 ? red2<IS_MIN>(a3.x, a3.y) : a3.y;
-              a0.z = p12 ? red2<IS_MIN>(a0.y, a0.z) : a0.z; a1.z = p12 ? red2<IS_MIN>(a1.y, a1.z) : a1.z;
-              a2.z = p12 ? red2<IS_MIN>(a2.y, a2.z) : a2.z; a3.z = p12 ? red2<IS_MIN>(a3.y, a3.z) : a3.z;
-              a0.w = p23 ? red2<IS_MIN>(a0.z, a0.w) : a0.w; a1.w = p23 ? red2<IS_MIN>(a1.z, a1.w) : a1.w;
-              a2.w = p23 ? red2<IS_MIN>(a2.z, a2.w) : a2.w; a3.w = p23 ? red2<IS_MIN>(a3.z, a3.w) : a3.w;
-              if (t0) sts_v4(r0 + 4 * g, a0.x, a1.x, a2.x, a3.x);
-              if (t1) sts_v4(r1 + 4 * g, a0.y, a1.y, a2.y, a3.y);
-              if (t2) sts_v4(r2 + 4 * g, a0.z, a1.z, a2.z, a3.z);
-              if (t3) sts_v4(r3 + 4 * g, a0.w, a1.w, a2.w, a3.w);
-            }
-          }
-          if (j == 0) {
-            if (t0) r0[16] = off0;
-            if (t1) r1[16] = off1;
-            if (t2) r2[16] = off2;
-            if (t3) r3[16] = off3;
-          }
-        }
-        // ---- the registers are free and nothing is in flight: complete the previous ticket, then issue the
-        //      loads of the next chunk / ticket
-        __syncwarp();
-        DM_LAP(1)  // B1 (includes the wait for the value planes)
-        if (j == 0) publish_pending(proj_done + kDoneStride * cur.frame);
-        DM_LAP(2)  // fence + publish
-        if (j + 1 < nchunks) rl_issue_values(L, values, cur, j + 1, lane, N, cfg.C, policy);
-        else nxt = next_ticket();
-        __syncwarp();
-        DM_LAP(3)  // claim hand-over + prefetch issue
-        if (j == 0) ok_item = dep_wait(dep, (uint32_t)R, seen);  // the ring slot is free
-        DM_LAP(4)  // dependency wait
-        if (ok_item) {
-          // ---- B2: one RED per (runlet, channel); lane = channel keeps a runlet's keys in 1-2 lines
-          if (cfg.C > 0) {
-            const int nch = min(16, cfg.C - c0);
-            const int streams = 32 / nch;
-            const int s = lane / nch;
-            const int c = lane - s * nch;
-            if (s < streams) {
-              const float fill = cfg.fill_value;
-              uint32_t* accc = acc + (slot_off + (uint32_t)(c0 + c));
-              // stream s takes runlets 4 s + (0..3) of every block of 4 * streams: with 16 channels the two
-              // streams of a warp instruction then read disjoint banks (20 * 4 = 16 mod 32).  Records past
-              // total_r hold stale data inside the buffer: they are read but never used.
-              const uint32_t* rv = rec + 4 * s * kRlRec + c;   // my channel of the stream's first record
-              const uint32_t* ro = rec + 4 * s * kRlRec + 16;  // its cell offset
-              const int step = 4 * streams;
-              for (int left = total_r - 4 * s; left > 0; left -= step, rv += step * kRlRec, ro += step * kRlRec) {
-                const float v0 = __uint_as_float(rv[0]), v1 = __uint_as_float(rv[kRlRec]);
-                const float v2 = __uint_as_float(rv[2 * kRlRec]), v3 = __uint_as_float(rv[3 * kRlRec]);
-                const uint32_t o0 = ro[0], o1 = ro[kRlRec], o2 = ro[2 * kRlRec], o3 = ro[3 * kRlRec];
-                if (beats<IS_MIN>(v0, fill)) red_max_u32(accc + o0, key_of<IS_MIN>(v0));
-                if (left > 1 && beats<IS_MIN>(v1, fill)) red_max_u32(accc + o1, key_of<IS_MIN>(v1));
-                if (left > 2 && beats<IS_MIN>(v2, fill)) red_max_u32(accc + o2, key_of<IS_MIN>(v2));
-                if (left > 3 && beats<IS_MIN>(v3, fill)) red_max_u32(accc + o3, key_of<IS_MIN>(v3));
-              }
-            }
-            if (d.hasH && j == 0) {  // height channel: always max against -inf (maps.py:340-348)
-              uint32_t* acch = acc + (slot_off + (uint32_t)d.Cv);
-              if (t0 && y[0] > -INFINITY) red_max_u32(acch + off0, enc(y[0]));
-              if (t1 && y[1] > -INFINITY) red_max_u32(acch + off1, enc(y[1]));
-              if (t2 && y[2] > -INFINITY) red_max_u32(acch + off2, enc(y[2]));
-              if (t3 && y[3] > -INFINITY) red_max_u32(acch + off3, enc(y[3]));
-            }
-          } else {  // the heights are the values
-            uint32_t* acc0 = acc + slot_off;
-            const float fill = cfg.fill_value;
-            if (t0 && beats<IS_MIN>(y[0], fill)) red_max_u32(acc0 + off0, key_of<IS_MIN>(y[0]));
-            if (t1 && beats<IS_MIN>(y[1], fill)) red_max_u32(acc0 + off1, key_of<IS_MIN>(y[1]));
-            if (t2 && beats<IS_MIN>(y[2], fill)) red_max_u32(acc0 + off2, key_of<IS_MIN>(y[2]));
-            if (t3 && beats<IS_MIN>(y[3], fill)) red_max_u32(acc0 + off3, key_of<IS_MIN>(y[3]));
-          }
-        }
-        __syncwarp();  // the records are rewritten by the next B1
-        DM_LAP(5)  // B2
-      }
-#ifdef DM_PROFILE
-      pr[6] += 1;
-#endif
-    } else if (cur.kind == kItemResolve) {
-      const uint32_t* dep = proj_done + kDoneStride * cur.frame;
-      uint32_t seen = 0;
-      if (lane == 0) seen = ld_relaxed(dep);
-      const int cell0 = cur.idx * rcells;
-      const int ncell = min(rcells, M - cell0);
-      // never block with an unpublished ticket in hand: the frame may be waiting for exactly that one
-      const bool must_wait = __shfl_sync(0xffffffffu, (int)(seen < (uint32_t)P), 0) != 0;
-      if (must_wait) publish_pending(nullptr);
-      const bool ok_item = dep_wait(dep, (uint32_t)P, seen);  // the frame is fully projected
-      DM_LAP(8)  // dependency wait
-      bool occupied = false;
-#ifdef DM_ABLATE_RLOAD
-      if (ok_item && cur.frame < 0)
-#else
-      if (ok_item)
-#endif
-        occupied = rl_resolve_load(acc + (size_t)(cur.frame % d.ring) * d.slot_words, d, cell0, ncell, lane, rec);
-      DM_LAP(9)  // key load
-      publish_pending(resolve_done + kDoneStride * cur.frame);
-      DM_LAP(10)  // fence + publish
-      nxt = next_ticket();
-      DM_LAP(11)  // claim hand-over + prefetch issue
-#ifdef DM_ABLATE_STORE
-      if (ok_item && cur.frame < 0)
-#else
-      if (ok_item)
-#endif
-        rl_resolve_store(occupied, cfg, d, cur.frame, cell0, ncell, lane, rec, topdown, mask, height);
-      __syncwarp();
-      DM_LAP(12)  // output stores
-#ifdef DM_PROFILE
-      pr[13] += 1; pr[14] += occupied ? 1 : 0;
-#endif
-    } else {
-      nxt = next_ticket();
-    }
-    cur = nxt;
-  }
-  publish_pending(nullptr);
-#ifdef DM_PROFILE
-  if (warp == 0 && lane == 0)
-    for (int i = 0; i < 15; ++i) DM_ACC(ctrl, i, pr[i]);
-#endif
-#undef DM_LAP
-  // the last CTA out re-arms the control block for the next call
-  __syncthreads();
-  if (tid == 0) {
-    __threadfence();
-    const uint32_t prev = atomicAdd(ctrl + 3, 1u);
-    if (prev == gridDim.x - 1) {
-      for (int i = 0; i < 2 * b; ++i) proj_done[kDoneStride * i] = 0;
-      for (int k = 0; k < kRlCounters; ++k) ctrl[32 + 32 * k] = 0;
-      ctrl[3] = 0;
-      __threadfence();
-    }
-  }
-}
-
 static bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 struct DeviceInfo {
@@ -1496,7 +1050,7 @@ using namespace dm;
 extern "C" size_t dm_orth_project_workspace_bytes(const DmProjCfg* cfg, int32_t b) {
   if (!cfg || b <= 0 || cfg->Mh <= 0 || cfg->Mw <= 0) return 0;
   const ProjPlan p = make_plan(*cfg, b);
-  return p.ctrl_bytes + p.slot_words * 4 * (size_t)p.ring;
+  return p.workspace_bytes();
 }
 
 extern "C" int dm_orth_project_f32(const float* depth, const float* values, const uint8_t* valid,
@@ -1514,7 +1068,7 @@ extern "C" int dm_orth_project_f32(const float* depth, const float* values, cons
   if (!aligned(workspace, 256)) return DM_EINVAL;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const ProjPlan p = make_plan(*cfg, b);
-  if (workspace_bytes < p.ctrl_bytes + p.slot_words * 4 * (size_t)p.ring) return DM_EWORKSPACE;
+  if (workspace_bytes < p.workspace_bytes()) return DM_EWORKSPACE;
   int dev = 0;
   DM_CUDA_OK(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) return DM_EINVAL;
@@ -1526,63 +1080,31 @@ extern "C" int dm_orth_project_f32(const float* depth, const float* values, cons
     DM_WS_ATTR(0, false) DM_WS_ATTR(1, false) DM_WS_ATTR(2, false)
     DM_WS_ATTR(0, true) DM_WS_ATTR(1, true) DM_WS_ATTR(2, true)
 #undef DM_WS_ATTR
-#define DM_RL_ATTR(F, MN) \
-    DM_CUDA_OK(cudaFuncSetAttribute(proj_rl_kernel<F, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    DM_RL_ATTR(0, false) DM_RL_ATTR(1, false) DM_RL_ATTR(2, false)
-    DM_RL_ATTR(0, true) DM_RL_ATTR(1, true) DM_RL_ATTR(2, true)
-#undef DM_RL_ATTR
     DM_CUDA_OK(cudaDeviceGetAttribute(&g_dev[dev].sms, cudaDevAttrMultiProcessorCount, dev));
     g_dev[dev].ready = true;
   }
   const int N = cfg->H * cfg->W, M = cfg->Mh * cfg->Mw;
   uint32_t* ctrl = static_cast<uint32_t*>(workspace);
-  uint32_t* acc = reinterpret_cast<uint32_t*>(static_cast<char*>(workspace) + p.ctrl_bytes);
-  ProjDims d{p.Cv, p.hasH, p.CU, p.CP, p.rows, p.tile, p.ring, (unsigned long long)p.slot_words,
-             (unsigned long long)p.stage_bytes, 0u, 0u};
+  uint32_t* flags = reinterpret_cast<uint32_t*>(static_cast<char*>(workspace) + p.ctrl_bytes);
+  uint32_t* acc = reinterpret_cast<uint32_t*>(static_cast<char*>(workspace) + p.ctrl_bytes + p.flag_bytes);
+  ProjDims d{p.Cv, p.hasH, p.CU, p.CP, p.rows, p.tile, p.ring, p.lag, p.nsl, (unsigned long long)p.slot_words,
+             (unsigned long long)p.stage_bytes};
   const int tiles = (N + p.tile - 1) / p.tile;
   const int rtiles = (M + kResolveCells - 1) / kResolveCells;
   // the warp-specialised TMA kernel needs 16-byte aligned plane starts / row sizes, pixel quads
   // that do not straddle image rows, and two stages that fit in shared memory
   const long long ws_tiles = (N + kWsTile - 1) / kWsTile;
-  const long long ws_total = (long long)(b + kLag) * (ws_tiles + rtiles);
+  const long long ws_total = (long long)(b + p.lag) * (ws_tiles + rtiles);
   const bool ws_ok = (N % 4 == 0) && (cfg->W % 4 == 0) && aligned(depth, 16) && (!values || aligned(values, 16)) &&
                      (!valid || aligned(valid, 4)) && p.smem_ws <= 220 * 1024 && ws_total < (1ll << 31) &&
                      cfg->fast_steps >= 0 && cfg->fast_steps <= 2 &&
                      (unsigned long long)p.ring * p.slot_words < (1ull << 31);
-  static const bool force_ws = [] { const char* e = getenv("DM_PROJ_KERNEL"); return e && e[0] == 'w'; }();
-  const size_t smem_rl = (size_t)kRlWarps * (kRlWarpWords * 4 + sizeof(DmProjSample)) +
-                         ((size_t)((cfg->W + 3) & ~3) + cfg->H) * 4;
-  const bool rl_ok = ws_ok && !force_ws && 32 * p.CP <= kRlWarpWords && smem_rl <= 220 * 1024 && (M % 4 == 0) &&
-                     (long long)(b + kLag) * ((N + kRlPass - 1) / kRlPass + (M + 31) / 32) < (1ll << 31);
-  if (rl_ok) {
-    void (*kern)(const float*, const float*, const uint8_t*, const DmProjSample*, DmProjCfg, ProjDims, int,
-                 uint32_t*, uint32_t*, float*, uint8_t*, float*) = nullptr;
-    const bool mn = cfg->reduction != 0;
-    switch (cfg->fast_steps) {
-      case 1: kern = mn ? proj_rl_kernel<1, true> : proj_rl_kernel<1, false>; break;
-      case 2: kern = mn ? proj_rl_kernel<2, true> : proj_rl_kernel<2, false>; break;
-      default: kern = mn ? proj_rl_kernel<0, true> : proj_rl_kernel<0, false>; break;
-    }
-    int per_sm = 0;
-    DM_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRlThreads, smem_rl));
-    if (per_sm < 1) return DM_EINVAL;
-    const int rcells = rl_resolve_cells(p.CP);
-    d.per_magic = magic_of((unsigned)((N + kRlPass - 1) / kRlPass + (M + rcells - 1) / rcells));
-    d.w_magic = magic_of((unsigned)cfg->W);
-    const long long rl_total = (long long)(b + kLag) * ((N + kRlPass - 1) / kRlPass + (M + rcells - 1) / rcells);
-    long long grid = (long long)g_dev[dev].sms * per_sm;
-    if (grid * kRlWarps > rl_total) grid = (rl_total + kRlWarps - 1) / kRlWarps;
-    kern<<<(unsigned)grid, kRlThreads, smem_rl, stream>>>(depth, values, valid, samples, *cfg, d, b, ctrl, acc,
-                                                          topdown, mask, height);
-    DM_LAUNCHED();
-    return DM_OK;
-  }
   if (ws_ok) {
     ProjDims dw = d;
     dw.tile = kWsTile;
     dw.stage_bytes = p.ws_stage_bytes;
     void (*kern)(const float*, const float*, const uint8_t*, const DmProjSample*, DmProjCfg, ProjDims, int,
-                 uint32_t*, uint32_t*, float*, uint8_t*, float*) = nullptr;
+                 uint32_t*, uint32_t*, uint32_t*, float*, uint8_t*, float*) = nullptr;
     const bool mn = cfg->reduction != 0;
     switch (cfg->fast_steps) {
       case 1: kern = mn ? proj_ws_kernel<1, true> : proj_ws_kernel<1, false>; break;
@@ -1594,8 +1116,8 @@ extern "C" int dm_orth_project_f32(const float* depth, const float* values, cons
     if (per_sm < 1) return DM_EINVAL;
     long long grid = (long long)g_dev[dev].sms * per_sm;
     if (grid > ws_total) grid = ws_total;
-    kern<<<(unsigned)grid, kWsThreads, p.smem_ws, stream>>>(depth, values, valid, samples, *cfg, dw, b, ctrl, acc,
-                                                            topdown, mask, height);
+    kern<<<(unsigned)grid, kWsThreads, p.smem_ws, stream>>>(depth, values, valid, samples, *cfg, dw, b, ctrl, flags,
+                                                            acc, topdown, mask, height);
     DM_LAUNCHED();
     return DM_OK;
   }

@@ -63,3 +63,5 @@ if prof:
     out["resolve_ticket_total"] = round(sum(c[8:13]) / nrs)
     out["tickets_per_warp0_per_step"] = {"proj": c[6] / n / 592, "resolve": c[13] / n / 592, "occupied_frac": c[14] / nrs}
 print(json.dumps(out))
+if os.environ.get("DM_SHOW_HINT"):
+  print("density hint ctrl[4] =", int(ws[0].view(torch.int32)[4]), "-> touched fraction", (int(ws[0].view(torch.int32)[4]) - 1) / 65536)
