@@ -59,7 +59,7 @@ struct ProjPlan {
   size_t smem_tile;      // one stage + sample block (plain-load kernel)
   size_t smem_resolve;
   size_t ws_stage_bytes; // warp-specialised kernel: one 512-pixel stage
-  size_t smem_ws;        // stage + barriers/items/samples + column/row tables
+  size_t smem_ws;        // stage + barriers/item/sample block
   size_t workspace_bytes() const { return ctrl_bytes + flag_bytes + slot_words * 4 * (size_t)ring; }
 };
 
@@ -96,7 +96,7 @@ static ProjPlan make_plan(const DmProjCfg& cfg, int b) {
   const size_t ws_res = ((size_t)1024 * p.CP + 127) & ~(size_t)127;  // 4 warps x 64 cells x CP words
   if (ws < ws_res) ws = ws_res;
   p.ws_stage_bytes = ws;
-  p.smem_ws = ws + 256 + ((size_t)((cfg.W + 3) & ~3) + cfg.H) * 4;
+  p.smem_ws = ws + 256;
   return p;
 }
 
@@ -489,13 +489,17 @@ __device__ __forceinline__ bool beats(float v, float fill) { return IS_MIN ? (v 
 template <bool IS_MIN>
 __device__ __forceinline__ uint32_t key_of(float v) { return IS_MIN ? ~enc(v) : enc(v); }
 
+struct Rcps {
+  float res, fx, fy;  // rn(1 / map_res), rn(1 / fx), rn(1 / fy)
+};
+
 // FAST: 0 generic steps, 1 local only, 2 local + global.  IS_MIN: reduction of the value channels.
 template <int FAST, bool IS_MIN>
 __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDims& d, const WsItem& it,
-                                              const DmProjSample& sp, const float* xtab, const float* ytab,
+                                              const DmProjSample& sp, const Rcps& rcp,
                                               const uint8_t* __restrict__ vplane, float* vals, int* lcell,
                                               uint32_t* __restrict__ acc, uint32_t slot_off,
-                                              uint32_t* __restrict__ slot_flags, float rres, int cw, int lane,
+                                              uint32_t* __restrict__ slot_flags, int cw, int lane,
                                               long long* tprof) {
   // acc is the kernel parameter (uniform); every RED address is acc + a 32-bit word offset
   [[maybe_unused]] const long long tp0 = DM_CLK();
@@ -516,9 +520,13 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
     uint32_t vm = 0x01010101u;
     if (vplane) vm = *reinterpret_cast<const uint32_t*>(vplane + n0);
     if (FAST) {
-      const float4 xn4 = *reinterpret_cast<const float4*>(xtab + c);
-      const float xn[4] = {xn4.x, xn4.y, xn4.z, xn4.w};
-      const float yn = ytab[r];
+      // maps.py:677-678 column / row factors rn(rn(c - cx) / fx), rn(rn(yy - cy) / fy): exact division
+      // through the reciprocals (div_by_rcp), no table in shared memory
+      float xn[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) xn[k] = div_by_rcp(__fsub_rn((float)(c + k), cfg.cx), cfg.fx, rcp.fx);
+      const float yy = cfg.flip_h ? __fsub_rn((float)(cfg.H - 1), (float)r) : (float)r;
+      const float yn = div_by_rcp(__fsub_rn(yy, cfg.cy), cfg.fy, rcp.fy);
       bool rowok = true;
       const int kb = cfg.clip_border;
       if (kb > 0) rowok = (r >= kb) && (r < cfg.H - kb);
@@ -526,7 +534,7 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
       for (int k = 0; k < 4; ++k) {
         bool ok = rowok && (((vm >> (8 * k)) & 0xffu) != 0);
         if (kb > 0) ok = ok && (c + k >= kb) && (c + k < cfg.W - kb);
-        cl[k] = pixel_cell_fast<FAST == 2, true>(cfg, sp, xn[k], yn, z[k], ok, &y[k], rres);
+        cl[k] = pixel_cell_fast<FAST == 2, true>(cfg, sp, xn[k], yn, z[k], ok, &y[k], rcp.res);
       }
     } else {
 #pragma unroll
@@ -794,7 +802,7 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
                uint8_t* __restrict__ mask, float* __restrict__ height) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int RS = kWsTile + 4;
-  const float rres = __frcp_rn(cfg.map_res);
+  const Rcps rcp{__frcp_rn(cfg.map_res), __frcp_rn(cfg.fx), __frcp_rn(cfg.fy)};
   // one stage per CTA: latency is hidden by the 5-6 CTAs resident per SM, not by an in-CTA ring
   unsigned char* stage = smem;
   unsigned char* tail = smem + d.stage_bytes;
@@ -802,8 +810,6 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
   uint64_t* empty = full + 1;
   WsItem* item = reinterpret_cast<WsItem*>(tail + 32);
   DmProjSample* sps = reinterpret_cast<DmProjSample*>(tail + 64);
-  float* xtab = reinterpret_cast<float*>(tail + 256);
-  float* ytab = xtab + ((cfg.W + 3) & ~3);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = cfg.H * cfg.W, M = cfg.Mh * cfg.Mw;
@@ -839,13 +845,6 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
     mbar_init(full, 1);
     mbar_init(empty, kWsWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (FAST) {  // maps.py:677-678 column / row factors, once per CTA
-    for (int c = tid; c < cfg.W; c += kWsThreads) xtab[c] = __fdiv_rn(__fsub_rn((float)c, cfg.cx), cfg.fx);
-    for (int r = tid; r < cfg.H; r += kWsThreads) {
-      const float yy = cfg.flip_h ? __fsub_rn((float)(cfg.H - 1), (float)r) : (float)r;
-      ytab[r] = __fdiv_rn(__fsub_rn(yy, cfg.cy), cfg.fy);
-    }
   }
   __syncthreads();
 
@@ -890,16 +889,6 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
         it.r0 = it.tile0 / cfg.W;
         it.c0 = it.tile0 - it.r0 * cfg.W;
         if (it.frame >= ring) { dep = resolve_done + (it.frame - ring); dep_target = (uint32_t)R; }
-#ifdef DM_WS_PREFETCH
-        {  // pull the tile into L2 while the consumers are still busy with the previous one
-          const int npx = min(kWsTile, N - it.tile0);
-          for (int row = lane; row < d.rows; row += 32) {
-            const float* src = row < cfg.C ? values + ((size_t)it.frame * cfg.C + row) * N + it.tile0
-                                           : depth + (size_t)it.frame * N + it.tile0;
-            bulk_prefetch_l2(src, (uint32_t)npx * 4u);
-          }
-        }
-#endif
         const uint32_t* sw = reinterpret_cast<const uint32_t*>(samples + it.frame);
         spw0 = sw[lane];
         if (lane < 16) spw1 = sw[32 + lane];
@@ -1007,10 +996,9 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
           float* vals = reinterpret_cast<float*>(stage);
           int* lcell = reinterpret_cast<int*>(vals + d.rows * RS);
           const int slot = it.frame % ring;
-          ws_proj_slice<FAST, IS_MIN>(cfg, d, it, *sps, xtab, ytab,
-                                      valid ? valid + (size_t)it.frame * N : nullptr, vals, lcell, acc,
-                                      (uint32_t)slot * (uint32_t)d.slot_words, flags + (size_t)slot * d.nsl * kFlagStride, rres,
-                                      warp, lane, cp);
+          ws_proj_slice<FAST, IS_MIN>(cfg, d, it, *sps, rcp, valid ? valid + (size_t)it.frame * N : nullptr, vals,
+                                      lcell, acc, (uint32_t)slot * (uint32_t)d.slot_words,
+                                      flags + (size_t)slot * d.nsl * kFlagStride, warp, lane, cp);
 #ifdef DM_PROFILE
           cp[4] += tc1 - tc0; cp[7] += 1;
 #endif
