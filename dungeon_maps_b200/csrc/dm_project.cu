@@ -39,6 +39,9 @@ constexpr int kFlagStride = DM_FLAG_STRIDE;      // words between two flags: eve
                                                  // same few hundred flags, so each gets its own 32-byte sector
 constexpr int kMaxRing = 10;                     // frame slots of the accumulation ring
 constexpr size_t kRingBudgetBytes = (size_t)1 << 30;  // ... unless that exceeds 1 GiB of workspace
+#ifndef DM_SUSPEND_NS
+#define DM_SUSPEND_NS 20000u
+#endif
 constexpr int kCtrlWords = 512;                  // control block at the head of the workspace
 constexpr unsigned long long kSpinLimitNs = 4000000000ull;  // dependency wait guard (bug → no hang)
 
@@ -310,24 +313,22 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// The suspend-time hint lets the hardware park the warp until the phase completes (or the hint expires)
+// instead of re-issuing the try_wait every few cycles: waiting warps must not eat the issue slots of working ones.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "DM_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra DM_DONE;\n\t"
       "bra DM_WAIT;\n\t"
-      "DM_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+      "DM_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(DM_SUSPEND_NS) : "memory");
 }
 // TMA bulk copy global → shared, completion on an mbarrier, L2 evict-first (inputs are read once).
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
       ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
-}
-// L2 prefetch of a row that a later TMA copy will read (hides HBM latency without shared memory)
-__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ uint64_t policy_evict_first() {
   uint64_t p;
@@ -419,9 +420,6 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 
 // sparse-ring slice flag: plain idempotent store, published with the tile's REDs
 __device__ __forceinline__ void st_flag(uint32_t* p) {
-#ifdef DM_NO_FLAGST
-  if (p == nullptr)
-#endif
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(1u) : "memory");
 }
 // fire-and-forget reduction (RED, never the returning ATOM form)
@@ -657,11 +655,7 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
         const uint4 c4 = *reinterpret_cast<const uint4*>(lc + i);
         float4 v4 = *reinterpret_cast<const float4*>(row + i);
         // runs longer than a pixel quad arrive as neighbouring runlets of one cell: fold them, RED the last
-#ifdef DM_NO_MERGE
-        const bool m01 = false, m12 = false, m23 = false;
-#else
         const bool m01 = c4.x == c4.y, m12 = c4.y == c4.z, m23 = c4.z == c4.w;
-#endif
         v4.y = m01 ? red2<IS_MIN>(v4.x, v4.y) : v4.y;
         v4.z = m12 ? red2<IS_MIN>(v4.y, v4.z) : v4.z;
         v4.w = m23 ? red2<IS_MIN>(v4.z, v4.w) : v4.w;
@@ -832,9 +826,6 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
       lag = max(min(2, d.lag), min(fit, d.lag));
     }
   }
-#ifdef DM_FORCE_LAG
-  lag = min(DM_FORCE_LAG, d.lag);
-#endif
   const int ahead = lag >= 3 ? 2 : 1;
   // slots in use: a slot that is re-used soon keeps its lines in L2 (a densely hit ring must stay small)
   const int ring = min(d.ring, 2 * lag);
