@@ -78,6 +78,9 @@ _SIGNATURES = {
   "dm_fuse_bbox_i64": (ctypes.c_int, [POINTER(DmFuseSource), c_int32, c_int32, c_int32, c_float, c_void_p, c_void_p]),
   "dm_fuse_scatter_f32": (ctypes.c_int, [POINTER(DmFuseSource), c_int32, c_int32, c_int32, POINTER(DmFuseTarget),
                                          c_void_p, c_void_p, c_void_p, c_void_p]),
+  "dm_fuse_inplace_f32": (ctypes.c_int, [POINTER(DmFuseSource), c_int32, c_int32, c_int32, POINTER(DmFuseTarget),
+                                         c_void_p, c_void_p, c_void_p, c_void_p]),
+  "dm_fuse_canvas_init_f32": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_void_p]),
   "dm_transform_points_f32": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int64, c_void_p, c_void_p]),
   "dm_image_camera_f32": (ctypes.c_int, [c_void_p, c_int64, c_float, c_float, c_float, c_float, c_int32, c_int32,
                                          c_int32, c_void_p, c_void_p]),

@@ -12,42 +12,64 @@ namespace dm {
 
 constexpr int kFuseThreads = 256;
 constexpr int kMaxSources = 8;
+constexpr int kGroup = 16;  // mask bytes examined per work item (one 128-bit load)
 
 struct FuseSources {
   DmFuseSource s[kMaxSources];
-  long long first_item[kMaxSources + 1];  // prefix of b*C*h*w per source
+  long long first_group[kMaxSources + 1];  // prefix of ceil(b*C*h*w / 16) per source
+  long long cells[kMaxSources];            // b*C*h*w per source
+  int vec_ok[kMaxSources];                 // mask base 16-byte aligned
   int n;
 };
 
-// Point of source cell `cell` (row-major in h×w), channel ch, sample smp, in the target frame.
-__device__ __forceinline__ V3 source_point(const DmFuseSource& src, int smp, int ch, int cell) {
-  const int r = cell / src.w, c = cell - r * src.w;
+// Point of source cell (row r, col c), channel ch, sample smp, in the target frame.
+__device__ __forceinline__ V3 source_point(const DmFuseSource& src, int smp, int ch, int r, int c) {
   // maps.py:1081-1086 map_dequantize
   float zb = (float)r;
   if (src.flip_h) zb = __fsub_rn((float)(src.h - 1), zb);
   V3 p;
   p.z = __fmul_rn(__fsub_rn(zb, src.height_offset[smp]), src.map_res);
   p.x = __fmul_rn(__fsub_rn((float)c, src.width_offset[smp]), src.map_res);
-  p.y = src.height[(long long)smp * src.height_bstride + (long long)ch * src.height_cstride + cell];
+  p.y = src.height[(long long)smp * src.height_bstride + (long long)ch * src.height_cstride + (long long)r * src.w + c];
   p = apply_step(src.steps[smp * 2 + 0], p);
   p = apply_step(src.steps[smp * 2 + 1], p);
   return p;
 }
 
-__device__ __forceinline__ bool locate(const FuseSources& fs, long long item, int C, int* si, int* smp,
-                                       int* ch, int* cell) {
+// Walks the valid cells of one 16-byte group of a source's flat (b, C, h, w) mask.  Most groups of a
+// world map are empty (every environment explored a corner of the batch-wide canvas): those cost one
+// 128-bit load and nothing else, so the heights / values of empty regions are never read.
+template <typename F>
+__device__ __forceinline__ void for_valid_cells(const FuseSources& fs, int C, long long group, F&& visit) {
   int k = 0;
-  while (k < fs.n && item >= fs.first_item[k + 1]) ++k;
-  if (k >= fs.n) return false;
+  while (k + 1 < fs.n && group >= fs.first_group[k + 1]) ++k;
   const DmFuseSource& src = fs.s[k];
-  const long long local = item - fs.first_item[k];
+  const long long i0 = (group - fs.first_group[k]) * kGroup;
+  const long long left = fs.cells[k] - i0;
+  uint32_t m[4] = {0u, 0u, 0u, 0u};
+  if (left >= kGroup && fs.vec_ok[k]) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src.mask + i0));
+    m[0] = v.x; m[1] = v.y; m[2] = v.z; m[3] = v.w;
+  } else {
+    const int cnt = left < kGroup ? (int)left : kGroup;
+    for (int j = 0; j < cnt; ++j) m[j >> 2] |= (uint32_t)(src.mask[i0 + j] != 0) << ((j & 3) * 8);
+  }
+  if ((m[0] | m[1] | m[2] | m[3]) == 0u) return;
   const int n = src.h * src.w;
-  const long long sc = local / n;
-  *cell = (int)(local - sc * n);
-  *smp = (int)(sc / C);
-  *ch = (int)(sc - (long long)(*smp) * C);
-  *si = k;
-  return true;
+  const long long sc = i0 / n;
+  int cell = (int)(i0 - sc * n);
+  int smp = (int)(sc / C);
+  int ch = (int)(sc - (long long)smp * C);
+  int r = cell / src.w, c = cell - r * src.w;
+#pragma unroll
+  for (int j = 0; j < kGroup; ++j) {
+    if ((m[j >> 2] >> ((j & 3) * 8)) & 0xffu) visit(src, i0 + j, smp, ch, r, c);
+    if (++c == src.w) { c = 0; ++r; }
+    if (++cell == n) {
+      cell = 0; r = 0; c = 0;
+      if (++ch == C) { ch = 0; ++smp; }
+    }
+  }
 }
 
 __global__ void fuse_bbox_init(long long* out) {
@@ -59,24 +81,23 @@ __global__ void fuse_bbox_init(long long* out) {
 }
 
 __global__ void __launch_bounds__(kFuseThreads)
-fuse_bbox_kernel(const FuseSources fs, int C, float res, long long total, long long* __restrict__ out) {
+fuse_bbox_kernel(const __grid_constant__ FuseSources fs, int C, float res, long long total_groups,
+                 long long* __restrict__ out) {
   long long mnx = 0x7fffffffffffffffLL, mxx = (long long)0x8000000000000000ULL;
   long long mnz = mnx, mxz = mxx;
   unsigned long long cnt = 0;
-  for (long long item = (long long)blockIdx.x * kFuseThreads + threadIdx.x; item < total;
-       item += (long long)gridDim.x * kFuseThreads) {
-    int si, smp, ch, cell;
-    if (!locate(fs, item, C, &si, &smp, &ch, &cell)) continue;
-    const DmFuseSource& src = fs.s[si];
-    if (!src.mask[((long long)smp * C + ch) * src.h * src.w + cell]) continue;
-    const V3 p = source_point(src, smp, ch, cell);
-    // maps.py:2159-2165: map_quantize(width_offset=0., height_offset=0., flip_h=False)
-    float xf, zf;
-    quantize_f(p.x, p.z, 0.0f, 0.0f, res, 0, 0, &xf, &zf);
-    const long long xi = f2i64(xf), zi = f2i64(zf);
-    mnx = xi < mnx ? xi : mnx; mxx = xi > mxx ? xi : mxx;
-    mnz = zi < mnz ? zi : mnz; mxz = zi > mxz ? zi : mxz;
-    ++cnt;
+  for (long long g = (long long)blockIdx.x * kFuseThreads + threadIdx.x; g < total_groups;
+       g += (long long)gridDim.x * kFuseThreads) {
+    for_valid_cells(fs, C, g, [&](const DmFuseSource& src, long long, int smp, int ch, int r, int c) {
+      const V3 p = source_point(src, smp, ch, r, c);
+      // maps.py:2159-2165: map_quantize(width_offset=0., height_offset=0., flip_h=False)
+      float xf, zf;
+      quantize_f(p.x, p.z, 0.0f, 0.0f, res, 0, 0, &xf, &zf);
+      const long long xi = f2i64(xf), zi = f2i64(zf);
+      mnx = xi < mnx ? xi : mnx; mxx = xi > mxx ? xi : mxx;
+      mnz = zi < mnz ? zi : mnz; mxz = zi > mxz ? zi : mxz;
+      ++cnt;
+    });
   }
   // warp then block reduction, one atomic per block per quantity
 #pragma unroll
@@ -107,36 +128,54 @@ fuse_bbox_kernel(const FuseSources fs, int C, float res, long long total, long l
   }
 }
 
+// Fresh canvases: topdown = fill (utils.py:472-473), height = -inf (maps.py:2268), mask = false.
+// 16 cells per thread: 128-bit stores only (the tail and unaligned bases take the scalar loop).
 __global__ void __launch_bounds__(kFuseThreads)
-fuse_fill_kernel(float* __restrict__ topdown, float* __restrict__ height, long long n, float fill) {
-  for (long long i = (long long)blockIdx.x * kFuseThreads + threadIdx.x; i < n;
+fuse_fill_kernel(float* __restrict__ topdown, float* __restrict__ height, uint8_t* __restrict__ mask, long long n,
+                 float fill, int vec_ok) {
+  const long long n16 = vec_ok ? n / 16 : 0;
+  const float4 f4 = make_float4(fill, fill, fill, fill);
+  const float4 h4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  for (long long i = (long long)blockIdx.x * kFuseThreads + threadIdx.x; i < n16;
        i += (long long)gridDim.x * kFuseThreads) {
-    topdown[i] = fill;                       // utils.py:472-473
-    if (height) height[i] = -INFINITY;       // maps.py:2268
+#pragma unroll
+    for (int q = 0; q < 4; ++q) st_stream_f4(topdown + i * 16 + q * 4, f4);
+    if (height) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) st_stream_f4(height + i * 16 + q * 4, h4);
+    }
+    *reinterpret_cast<uint4*>(mask + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  for (long long i = n16 * 16 + (long long)blockIdx.x * kFuseThreads + threadIdx.x; i < n;
+       i += (long long)gridDim.x * kFuseThreads) {
+    topdown[i] = fill;
+    if (height) height[i] = -INFINITY;
+    mask[i] = 0;
   }
 }
 
+// mask_inline: the mask (utils.py:489-491: the cell differs from what the canvas was filled with) is
+// stored right where a value beats `fill`; with a NaN fill the generic pass below is used instead.
 __global__ void __launch_bounds__(kFuseThreads)
-fuse_scatter_kernel(const FuseSources fs, int C, const DmFuseTarget tgt, long long total,
-                    float* __restrict__ topdown, float* __restrict__ height) {
+fuse_scatter_kernel(const __grid_constant__ FuseSources fs, int C, const DmFuseTarget tgt, long long total_groups,
+                    float* __restrict__ topdown, float* __restrict__ height, uint8_t* __restrict__ mask,
+                    int mask_inline) {
   const long long M = (long long)tgt.Mh * tgt.Mw;
-  for (long long item = (long long)blockIdx.x * kFuseThreads + threadIdx.x; item < total;
-       item += (long long)gridDim.x * kFuseThreads) {
-    int si, smp, ch, cell;
-    if (!locate(fs, item, C, &si, &smp, &ch, &cell)) continue;
-    const DmFuseSource& src = fs.s[si];
-    const long long in_idx = ((long long)smp * C + ch) * src.h * src.w + cell;
-    if (!src.mask[in_idx]) continue;
-    const V3 p = source_point(src, smp, ch, cell);
-    float xf, zf;  // maps.py:2232-2238
-    quantize_f(p.x, p.z, tgt.width_offset, tgt.height_offset, tgt.map_res, tgt.Mh, tgt.flip_h, &xf, &zf);
-    if (!(xf >= 0.0f && xf < (float)tgt.Mw && zf >= 0.0f && zf < (float)tgt.Mh)) continue;
-    const long long o = ((long long)smp * C + ch) * M + (long long)zf * tgt.Mw + (long long)xf;
-    const float v = src.values ? src.values[in_idx] : p.y;  // maps.py:2214-2216
-    if (v == v) {
-      if (tgt.reduction) atomic_min_f32(topdown + o, v); else atomic_max_f32(topdown + o, v);
-    }
-    if (height && p.y == p.y) atomic_max_f32(height + o, p.y);  // maps.py:2258-2271
+  for (long long g = (long long)blockIdx.x * kFuseThreads + threadIdx.x; g < total_groups;
+       g += (long long)gridDim.x * kFuseThreads) {
+    for_valid_cells(fs, C, g, [&](const DmFuseSource& src, long long in_idx, int smp, int ch, int r, int c) {
+      const V3 p = source_point(src, smp, ch, r, c);
+      float xf, zf;  // maps.py:2232-2238
+      quantize_f(p.x, p.z, tgt.width_offset, tgt.height_offset, tgt.map_res, tgt.Mh, tgt.flip_h, &xf, &zf);
+      if (!(xf >= 0.0f && xf < (float)tgt.Mw && zf >= 0.0f && zf < (float)tgt.Mh)) return;
+      const long long o = ((long long)smp * C + ch) * M + (long long)zf * tgt.Mw + (long long)xf;
+      const float v = src.values ? src.values[in_idx] : p.y;  // maps.py:2214-2216
+      if (v == v) {
+        if (tgt.reduction) atomic_min_f32(topdown + o, v); else atomic_max_f32(topdown + o, v);
+        if (mask_inline && better(v, tgt.fill_value, tgt.reduction)) mask[o] = 1;
+      }
+      if (height && p.y == p.y) atomic_max_f32(height + o, p.y);  // maps.py:2258-2271
+    });
   }
 }
 
@@ -158,18 +197,21 @@ static int pack_sources(const DmFuseSource* sources, int n, int b, int C, FuseSo
     const DmFuseSource& s = sources[i];
     if (!s.height || !s.mask || !s.width_offset || !s.height_offset || !s.steps || s.h <= 0 || s.w <= 0)
       return DM_EINVAL;
+    if ((long long)s.h * s.w >= (1ll << 31)) return DM_EINVAL;
     fs->s[i] = s;
-    fs->first_item[i] = acc;
-    acc += (long long)b * C * s.h * s.w;
+    fs->first_group[i] = acc;
+    fs->cells[i] = (long long)b * C * s.h * s.w;
+    fs->vec_ok[i] = reinterpret_cast<uintptr_t>(s.mask) % 16 == 0;
+    acc += (fs->cells[i] + kGroup - 1) / kGroup;
   }
-  fs->first_item[n] = acc;
+  fs->first_group[n] = acc;
   *total = acc;
   return DM_OK;
 }
 
 static unsigned grid_for(long long items) {
   long long blocks = (items + kFuseThreads - 1) / kFuseThreads;
-  const long long cap = (long long)kNumSMs * 8 * 2;
+  const long long cap = (long long)kNumSMs * 8 * 4;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (unsigned)blocks;
@@ -206,11 +248,51 @@ extern "C" int dm_fuse_scatter_f32(const DmFuseSource* sources, int32_t n_source
   if (rc != DM_OK) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const long long n_out = (long long)b * C * target->Mh * target->Mw;
-  fuse_fill_kernel<<<grid_for(n_out), kFuseThreads, 0, stream>>>(topdown, height, n_out, target->fill_value);
+  const int vec_ok = reinterpret_cast<uintptr_t>(topdown) % 16 == 0 && reinterpret_cast<uintptr_t>(mask) % 16 == 0 &&
+                     (!height || reinterpret_cast<uintptr_t>(height) % 16 == 0);
+  const int mask_inline = target->fill_value == target->fill_value;  // not NaN
+  fuse_fill_kernel<<<grid_for((n_out + 15) / 16), kFuseThreads, 0, stream>>>(topdown, height, mask, n_out,
+                                                                             target->fill_value, vec_ok);
   DM_LAUNCHED();
-  fuse_scatter_kernel<<<grid_for(total), kFuseThreads, 0, stream>>>(fs, C, *target, total, topdown, height);
+  fuse_scatter_kernel<<<grid_for(total), kFuseThreads, 0, stream>>>(fs, C, *target, total, topdown, height, mask,
+                                                                    mask_inline);
   DM_LAUNCHED();
-  changed_mask_kernel<<<grid_for(n_out), kFuseThreads, 0, stream>>>(topdown, n_out, target->fill_value, mask);
+  if (!mask_inline) {
+    changed_mask_kernel<<<grid_for(n_out), kFuseThreads, 0, stream>>>(topdown, n_out, target->fill_value, mask);
+    DM_LAUNCHED();
+  }
+  return DM_OK;
+}
+
+// Opt-in fixed-canvas merge (no reference equivalent of the call; the semantics are those of the
+// reference's project(..., canvas=, canvas_masks=), maps.py:1089-1173 / utils.py:462-491): the valid
+// cells of the sources are max-merged IN PLACE into canvases that already hold a world map.  No
+// bounding box, no host sync, no reallocation: one launch.  Invariant kept: mask == (cell != fill).
+extern "C" int dm_fuse_inplace_f32(const DmFuseSource* sources, int32_t n_sources, int32_t b, int32_t C,
+                                   const DmFuseTarget* target, float* topdown, uint8_t* mask, float* height,
+                                   void* stream_) {
+  if (!target || !topdown || !mask || target->Mh <= 0 || target->Mw <= 0) return DM_EINVAL;
+  if (target->reduction != 0 && target->reduction != 1) return DM_EINVAL;
+  if (!(target->fill_value == target->fill_value)) return DM_EINVAL;  // NaN fill has no in-place mask rule
+  FuseSources fs;
+  long long total = 0;
+  const int rc = pack_sources(sources, n_sources, b, C, &fs, &total);
+  if (rc != DM_OK) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  fuse_scatter_kernel<<<grid_for(total), kFuseThreads, 0, stream>>>(fs, C, *target, total, topdown, height, mask, 1);
+  DM_LAUNCHED();
+  return DM_OK;
+}
+
+/* Fills fresh world canvases for dm_fuse_inplace_f32: topdown = fill_value, height = -inf (may be NULL), mask = 0. */
+extern "C" int dm_fuse_canvas_init_f32(float* topdown, uint8_t* mask, float* height, int64_t n, float fill_value,
+                                       void* stream_) {
+  if (!topdown || !mask || n < 0) return DM_EINVAL;
+  if (n == 0) return DM_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int vec_ok = reinterpret_cast<uintptr_t>(topdown) % 16 == 0 && reinterpret_cast<uintptr_t>(mask) % 16 == 0 &&
+                     (!height || reinterpret_cast<uintptr_t>(height) % 16 == 0);
+  fuse_fill_kernel<<<grid_for((n + 15) / 16), kFuseThreads, 0, stream>>>(topdown, height, mask, n, fill_value, vec_ok);
   DM_LAUNCHED();
   return DM_OK;
 }

@@ -42,7 +42,7 @@ __all__ = [
   'height_map_to_point_cloud', 'image_to_camera_space', 'camera_to_image_space', 'camera_to_local_space',
   'local_to_camera_space', 'local_to_global_space', 'global_to_local_space', 'map_quantize',
   'map_dequantize', 'project', 'compute_center_offsets', 'MapProjector', 'TopdownMap', 'crop_topdown_map',
-  'fuse_topdown_maps', 'MapBuilder', 'Reduction', 'CameraIntrinsics', 'NINF', 'Float3D',
+  'fuse_topdown_maps', 'merge_into_canvas', 'MapBuilder', 'Reduction', 'CameraIntrinsics', 'NINF', 'Float3D',
 ]
 
 
@@ -846,14 +846,71 @@ def fuse_topdown_maps(*maps: List[TopdownMap], map_projector: Optional[MapProjec
                     map_projector=new_proj, is_height_map=is_height_map)
 
 
+def merge_into_canvas(world: TopdownMap, new_map: TopdownMap, canvas_shape: Tuple[int, int],
+                      map_projector: MapProjector, fill_value: Optional[float] = None,
+                      reduction: Optional[Reduction] = None) -> TopdownMap:
+  """Opt-in fixed-canvas merge (not in the reference; its closest relative is project(..., canvas=,
+  canvas_masks=), maps.py:1089-1173): the valid cells of `new_map` become points again exactly as in
+  fuse_topdown_maps (dequantise, local → global with the map's own pose), are quantised with the
+  canvases' FIXED offsets (map_width / 2, map_height / 2: world origin at the centre) and max-merged in
+  place into `world`'s tensors, which are allocated on the first call.  One launch, no host sync.
+  `world`'s tensors are updated in place and shared with the returned map."""
+  Hc, Wc = int(canvas_shape[0]), int(canvas_shape[1])
+  red = utils._reduction_code(reduction)
+  if new_map.is_empty:
+    return world
+  dev = _pick_device(map_projector.device, new_map.mask, new_map.height_map)
+  b, C, _, _ = utils.to_4D_image(new_map.mask).shape
+  is_height_map = bool(new_map.is_height_map)
+  fill = get(fill_value, map_projector.fill_value, NINF)
+  lib = nat.lib()
+  if world is None or world.is_empty:
+    topdown = torch.empty((b, C, Hc, Wc), dtype=torch.float32, device=dev)
+    mask = torch.empty((b, C, Hc, Wc), dtype=torch.bool, device=dev)
+    height = None if is_height_map else torch.empty_like(topdown)
+    with torch.cuda.device(dev):
+      rc = lib.dm_fuse_canvas_init_f32(topdown.data_ptr(), mask.data_ptr(), nat.ptr(height), topdown.numel(),
+                                       fill, nat.stream_ptr(dev))
+    nat.check(rc, "dm_fuse_canvas_init_f32")
+  else:
+    assert bool(world.is_height_map) == is_height_map, "All maps must be the same type of maps"
+    topdown, mask = world.topdown_map, world.mask
+    height = None if is_height_map else world.height_map
+    assert tuple(topdown.shape) == (b, C, Hc, Wc), f"world canvas {tuple(topdown.shape)} != {(b, C, Hc, Wc)}"
+  target = map_projector.clone(to_global=True, width_offset=Wc / 2., height_offset=Hc / 2., map_width=Wc,
+                               map_height=Hc)
+  keep: list = []
+  h, w = new_map.mask.shape[-2:]
+  sources = (nat.DmFuseSource * 1)(_fuse_source(new_map, target, b, C, C * h * w, dev, keep))
+  tgt = nat.DmFuseTarget()
+  tgt.Mh, tgt.Mw = Hc, Wc
+  tgt.flip_h = bool(target.flip_h)
+  tgt.map_res = target.map_res
+  tgt.width_offset, tgt.height_offset = Wc / 2., Hc / 2.
+  tgt.fill_value = fill
+  tgt.reduction = red
+  with torch.cuda.device(dev):
+    rc = lib.dm_fuse_inplace_f32(sources, 1, b, C, tgt, topdown.data_ptr(), mask.data_ptr(), nat.ptr(height),
+                                 nat.stream_ptr(dev))
+  nat.check(rc, "dm_fuse_inplace_f32")
+  return TopdownMap(topdown_map=topdown, mask=mask, height_map=topdown if is_height_map else height,
+                    map_projector=target, is_height_map=is_height_map)
+
+
 # ======== MapBuilder (maps.py:2289-2550) ==========================================================
 
 class MapBuilder():
   """Plots a local top-down map per frame and merges it into a growing world map."""
 
-  def __init__(self, map_projector: MapProjector, world_map: Optional[TopdownMap] = None):
+  def __init__(self, map_projector: MapProjector, world_map: Optional[TopdownMap] = None,
+               fixed_canvas: Optional[Tuple[int, int]] = None):
+    """`fixed_canvas=(map_height, map_width)` opts into the in-place world map (not in the reference,
+    SURVEY.md §8f-2): global canvases of that size are allocated at the first merge, the world origin sits
+    at their centre, and every merge max-merges the new map's cells into them with one kernel launch —
+    no bounding box, no host sync, no reallocation.  Points that fall outside the canvas are dropped."""
     self._proj = map_projector
     self._world_map = world_map if world_map is not None else TopdownMap(map_projector=self.proj.clone())
+    self._fixed = None if fixed_canvas is None else (int(fixed_canvas[0]), int(fixed_canvas[1]))
 
   @property
   def proj(self) -> MapProjector:
@@ -910,6 +967,11 @@ class MapBuilder():
     if self._world_map is None:
       self._world_map = TopdownMap(map_projector=self.proj.clone())
     cam_pose = self._world_map.proj.cam_pose if keep_pose else topdown_map.proj.cam_pose
+    if self._fixed is not None:
+      self._world_map = merge_into_canvas(self._world_map, topdown_map, canvas_shape=self._fixed,
+                                          map_projector=self.proj.clone(cam_pose=cam_pose),
+                                          fill_value=fill_value, reduction=reduction)
+      return self._world_map
     self._world_map = fuse_topdown_maps(self._world_map, topdown_map,
                                         map_projector=self.proj.clone(cam_pose=cam_pose),
                                         fill_value=fill_value, reduction=reduction)

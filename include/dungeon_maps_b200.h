@@ -195,6 +195,19 @@ int dm_fuse_scatter_f32(const DmFuseSource* sources, int32_t n_sources, int32_t 
                         const DmFuseTarget* target, float* topdown, uint8_t* mask, float* height,
                         void* stream);
 
+/* Opt-in fixed-canvas merge (no reference call does this — the closest is
+ * project(..., canvas=, canvas_masks=), maps.py:1089-1173 with utils.py:462-491, whose semantics it keeps):
+ * the valid cells of the sources are re-projected and max/min-merged IN PLACE into canvases that
+ * already hold a world map; mask |= "cell now differs from fill_value".  One launch, no host sync.
+ * target->width_offset/height_offset are the canvases' fixed offsets. */
+int dm_fuse_inplace_f32(const DmFuseSource* sources, int32_t n_sources, int32_t b, int32_t C,
+                        const DmFuseTarget* target, float* topdown, uint8_t* mask, float* height,
+                        void* stream);
+/* Fresh canvases for the call above: topdown = fill_value, height = -inf (NULL for height maps), mask = 0;
+ * n = b*C*Mh*Mw cells. */
+int dm_fuse_canvas_init_f32(float* topdown, uint8_t* mask, float* height, int64_t n, float fill_value,
+                            void* stream);
+
 /* ---- materialising primitives (the reference's public L0/L1 functions) ------ */
 
 /* points (b, n, 3) f32 → out (b, n, 3): applies steps[b][n_steps] in order.

@@ -396,6 +396,45 @@ def fuse(sources, target_to_global, target_pose, target_res, target_flip_h, fill
               width_offset=woff, height_offset=hoff)
 
 
+def fuse_inplace(world, source, canvas_shape, target_res, target_flip_h, fill_value=NINF, reduction=None):
+  """Restatement of the opt-in fixed-canvas merge (dungeon_maps_b200.merge_into_canvas; NOT a reference
+  function): the source map's valid cells become points as in fuse() above (maps.py:2039-2069), are
+  quantised with the fixed offsets (Wc/2, Hc/2) (maps.py:944-1019) and scattered into the existing
+  canvases with the reference's project(canvas=, canvas_masks=) rule (maps.py:1089-1173, utils.py:462-491):
+  new = max(old, hits); mask |= changed.  `world` is None (fresh canvases) or the dict returned before."""
+  Hc, Wc = canvas_shape
+  s = source
+  b, C, h, w = s.mask.shape
+  is_height = s.values is None
+  if world is None:
+    world = dict(topdown=np.full((b, C, Hc, Wc), fill_value, np.float32), mask=np.zeros((b, C, Hc, Wc), bool),
+                 height=None if is_height else np.full((b, C, Hc, Wc), NINF, np.float32))
+  hm_c = np.ascontiguousarray(np.broadcast_to(s.height, (b, C, h, w)))
+  pose = np.asarray(s.cam_pose, np.float32).reshape(-1, 3)
+  if pose.shape[0] == 1 and b > 1:
+    pose = np.repeat(pose, b, 0)
+  n = h * w
+  st = np.zeros((b, 2), dtype=STEP_DT)
+  st[:, 0] = identity_steps(b) if s.to_global else to_global_steps(pose, C * n)
+  st[:, 1] = identity_steps(b)
+  st = np.ascontiguousarray(st)
+  px = np.empty((b, C, n), np.float32); py = np.empty((b, C, n), np.float32); pz = np.empty((b, C, n), np.float32)
+  woff, hoff = _vec(s.width_offset, b), _vec(s.height_offset, b)
+  lib().dmo_fuse_points(_p(hm_c), ctypes.c_int64(C * n), ctypes.c_int64(n), b, C, h, w,
+                        int(bool(s.flip_h)), ctypes.c_float(f32(s.map_res)), _p(woff), _p(hoff),
+                        _p(st), _p(px), _p(py), _p(pz))
+  xb, zb = map_quantize(px.reshape(1, -1), pz.reshape(1, -1), np.float32(Wc / 2.), np.float32(Hc / 2.), target_res,
+                        Hc, target_flip_h)
+  coords = np.stack((zb.reshape(b, C, n), xb.reshape(b, C, n)), -1)
+  Mk = s.mask.reshape(b, C, n)
+  V = py if is_height else s.values.reshape(b, C, n)
+  top, changed = scatter(V, coords, Mk, world["topdown"], None, reduction)
+  out = dict(topdown=top, mask=world["mask"] | changed, height=None)
+  if not is_height:
+    out["height"], _ = scatter(py, coords, Mk, world["height"], None, None)
+  return out
+
+
 def crop_nearest(image, center, crop_w, crop_h, fill_value):
   """image_sample(generate_crop_grid(...)), utils.py:571-652, on (b,c,h,w) float32."""
   image = np.ascontiguousarray(image, dtype=np.float32)

@@ -255,6 +255,63 @@ def builder_cases():
   run("builder_local_values_keep_pose", False, 2, "none", 3, keep_pose=True)
 
 
+# ------------------------------------------------------------------ fixed-canvas merge
+
+def canvas_cases():
+  """The opt-in fixed-canvas merge is not a reference function; its definition is a composition of
+  reference functions, which is what runs here: MapBuilder.plot (local map) → _flattened_topdown_map
+  (cells → global points, maps.py:2039-2069) → MapProjector.map_quantize with the canvas' fixed offsets
+  (maps.py:944-1019) → project(canvas=, canvas_masks=) (maps.py:1089-1173)."""
+  H, W = 60, 80
+  Hc, Wc = 150, 170
+
+  def run(name, C, steps, fill_value=dm.NINF):
+    proj = dm.MapProjector(width=W, height=H, hfov=HFOV, cam_pose=[0., 0., 0.], width_offset=0., height_offset=0.,
+                           cam_pitch=PITCH, cam_height=0.88, map_res=0.1, map_width=60, map_height=60,
+                           trunc_depth_min=0.15, trunc_depth_max=5.05, clip_border=3, to_global=True,
+                           fill_value=fill_value)
+    builder = dm.MapBuilder(map_projector=proj)
+    world_proj = proj.clone(to_global=True, width_offset=Wc / 2., height_offset=Hc / 2., map_width=Wc, map_height=Hc)
+    Cv = max(C, 1)
+    canvas = torch.full((1, Cv, Hc, Wc), float(fill_value))
+    cmask = torch.zeros((1, Cv, Hc, Wc), dtype=torch.bool)
+    hcanvas = torch.full((1, Cv, Hc, Wc), -np.inf)
+    pose = torch.zeros(1, 3)
+    arrays = {}
+    for t in range(steps):
+      pose = pose + synth.poses(1, 2000 + t, xz=0.6, yaw=0.7)
+      depth = synth.room_depth(1, H, W, HFOV, PITCH, 0.88, pose, seed=9)
+      vals = synth.block_onehot(1, C, H, W, seed=300 + t, block=8) if C > 0 else None
+      cam_pose = pose[0].numpy().copy()
+      local = builder.plot(depth_map=depth[0].numpy(), value_map=None if vals is None else vals[0].numpy(),
+                           cam_pose=cam_pose, to_global=False, width_offset=30., height_offset=0.)
+      points, mask, values = dm.maps._flattened_topdown_map(local)
+      x_bin, z_bin = world_proj.map_quantize(points[..., 0], points[..., 2])
+      coords = torch.stack((z_bin, x_bin), dim=-1)  # as orth_project does, maps.py:318
+      if values is None:
+        values = points[..., 1]
+      # the module-level function with _validate_args=False, as orth_project calls it (maps.py:320-331): the
+      # validating path broadcasts the canvas over the point dimension, and MapProjector.project would re-fill
+      canvas, cmask = dm.maps.project(coords=coords.clone(), values=values, masks=mask, canvas=canvas,
+                                      canvas_masks=cmask, fill_value=None, _validate_args=False)
+      if C > 0:
+        hcanvas, _ = dm.maps.project(coords=coords.clone(), values=points[..., 1], masks=mask, canvas=hcanvas,
+                                     fill_value=None, _validate_args=False)
+      arrays[f"depth_{t}"] = depth
+      if vals is not None:
+        arrays[f"values_{t}"] = vals
+      arrays[f"pose_{t}"] = cam_pose
+      arrays[f"world_topdown_{t}"] = canvas.clone()
+      arrays[f"world_mask_{t}"] = cmask.clone()
+      if C > 0:
+        arrays[f"world_height_{t}"] = hcanvas.clone()
+    save(name, dict(kind="fixed_canvas", C=C, steps=steps, fill_value=float(fill_value), H=H, W=W, Hc=Hc, Wc=Wc),
+         **arrays)
+
+  run("canvas_height", 0, 4)
+  run("canvas_values_fill0", 3, 3, fill_value=0.)
+
+
 # ------------------------------------------------------------------ primitives
 
 def primitive_cases():
@@ -362,9 +419,10 @@ def crop_cases():
 
 if __name__ == "__main__":
   os.makedirs(OUT, exist_ok=True)
-  which = sys.argv[1:] or ["orth", "flow", "builder", "prim", "crop"]
+  which = sys.argv[1:] or ["orth", "flow", "builder", "canvas", "prim", "crop"]
   if "orth" in which: orth_cases()
   if "flow" in which: flow_cases()
   if "builder" in which: builder_cases()
+  if "canvas" in which: canvas_cases()
   if "prim" in which: primitive_cases()
   if "crop" in which: crop_cases()

@@ -309,6 +309,59 @@ def test_map_builder_matches_reference(name):
   assert_same(npy(builder.world_map.get_origin()), g["world_origin"], "get_origin")
 
 
+@pytest.mark.parametrize("name", names("canvas_"))
+def test_fixed_canvas_builder_matches_reference_ops(name):
+  """MapBuilder(fixed_canvas=...) (opt-in in-place merge) against the composition of reference functions
+  that defines it (oracle/make_golden.py: canvas_cases)."""
+  g = Golden(name)
+  m = g.meta
+  H, W, C = m["H"], m["W"], m["C"]
+  proj = dmap.MapProjector(width=W, height=H, hfov=HFOV, cam_pose=[0., 0., 0.], width_offset=0., height_offset=0.,
+                           cam_pitch=PITCH, cam_height=0.88, map_res=0.1, map_width=60, map_height=60,
+                           trunc_depth_min=0.15, trunc_depth_max=5.05, clip_border=3, to_global=True,
+                           fill_value=m["fill_value"], device="cuda")
+  builder = dmap.MapBuilder(map_projector=proj, fixed_canvas=(m["Hc"], m["Wc"]))
+  first = None
+  for t in range(m["steps"]):
+    vals = g.get(f"values_{t}")
+    builder.step(depth_map=g[f"depth_{t}"][0], value_map=None if vals is None else vals[0], cam_pose=g[f"pose_{t}"],
+                 to_global=False, width_offset=30., height_offset=0.)
+    wm = builder.world_map
+    if first is None:
+      first = wm.topdown_map.data_ptr()
+    assert wm.topdown_map.data_ptr() == first, "the world canvas must be updated in place"
+    assert_same(npy(wm.topdown_map), g[f"world_topdown_{t}"], f"step {t} world topdown")
+    assert_same(npy(wm.mask), g[f"world_mask_{t}"], f"step {t} world mask")
+    if C > 0:
+      assert_same(npy(wm.height_map), g[f"world_height_{t}"], f"step {t} world height")
+  assert [wm.proj.map_height, wm.proj.map_width] == [m["Hc"], m["Wc"]]
+
+
+def test_fixed_canvas_builder_random_vs_oracle():
+  """Batch of 3 environments, min reduction off, odd canvas, points falling outside the canvas are dropped."""
+  b, H, W = 3, 90, 120
+  proj = dmap.MapProjector(width=W, height=H, hfov=HFOV, cam_pose=[0., 0., 0.], width_offset=0., height_offset=0.,
+                           cam_pitch=PITCH, cam_height=0.88, map_res=0.05, map_width=80, map_height=80,
+                           trunc_depth_min=0.15, trunc_depth_max=5.05, clip_border=2, to_global=True,
+                           fill_value=dmap.NINF, device="cuda")
+  builder = dmap.MapBuilder(map_projector=proj, fixed_canvas=(101, 97))
+  k = orc.intrinsics(W, H, HFOV)
+  fx, fy, cx, cy = k["fx"], k["fy"], k["cx"], k["cy"]
+  world = None
+  pose = torch.zeros(b, 3)
+  for t in range(4):
+    pose = pose + synth.poses(b, 50 + t, xz=0.8, yaw=0.9)
+    depth = synth.room_depth(b, H, W, HFOV, PITCH, 0.88, pose, seed=3)
+    builder.step(depth_map=depth, cam_pose=pose, to_global=False, width_offset=40., height_offset=0.)
+    top, mask, hgt = orc.orth_project(depth.numpy(), None, None, pose.numpy(), 40., 0., PITCH, 0.88, 0.05, 80, 80,
+                                      fx, fy, cx, cy, 0.15, 5.05, None, 2, False, True, -np.inf, None, True)
+    src = orc.FuseSource(hgt, mask, None, 40., 0., 0.05, True, False, pose.numpy())
+    world = orc.fuse_inplace(world, src, (101, 97), 0.05, True, -np.inf, None)
+    assert_same(npy(builder.world_map.topdown_map), world["topdown"], f"step {t} topdown")
+    assert_same(npy(builder.world_map.mask), world["mask"], f"step {t} mask")
+  assert 0 < int(world["mask"].sum()) < world["mask"].size
+
+
 def test_crop_matches_reference():
   g = Golden("crop")
   h, w = g.meta["h"], g.meta["w"]

@@ -163,6 +163,36 @@ def test_fuse_topdown_maps_matches_reference(name):
     assert_same(out["height"], g[f"world_height_{t}"], f"step {t} height")
 
 
+def _canvas_local(g, t, C):
+  """The local map of step t through the oracle (the fixture stores inputs and world canvases only)."""
+  m = g.meta
+  k = orc.intrinsics(m["W"], m["H"], np.radians(70))
+  fx, fy, cx, cy = k["fx"], k["fy"], k["cx"], k["cy"]
+  vals = g.get(f"values_{t}")
+  return orc.orth_project(g[f"depth_{t}"], vals, None, g[f"pose_{t}"], 30., 0., np.radians(-10), 0.88, 0.1, 60, 60,
+                          fx, fy, cx, cy, 0.15, 5.05, None, 3, False, True, m["fill_value"], None, True)
+
+
+@pytest.mark.parametrize("name", names("canvas_"))
+def test_fixed_canvas_merge_matches_reference_ops(name):
+  """fuse_inplace (restatement of the opt-in fixed-canvas merge) against the composition of reference
+  functions that defines it (oracle/make_golden.py: canvas_cases)."""
+  g = Golden(name)
+  m = g.meta
+  C = m["C"]
+  world = None
+  for t in range(m["steps"]):
+    top, mask, hgt = _canvas_local(g, t, C)
+    if C > 0:
+      hgt = np.broadcast_to(hgt, top.shape)
+    src = orc.FuseSource(hgt, mask, top if C > 0 else None, 30., 0., 0.1, True, False, g[f"pose_{t}"])
+    world = orc.fuse_inplace(world, src, (m["Hc"], m["Wc"]), 0.1, True, m["fill_value"], None)
+    assert_same(world["topdown"], g[f"world_topdown_{t}"], f"step {t} topdown")
+    assert_same(world["mask"], g[f"world_mask_{t}"], f"step {t} mask")
+    if C > 0:
+      assert_same(world["height"], g[f"world_height_{t}"], f"step {t} height")
+
+
 def test_crop_matches_reference():
   g = Golden("crop")
   for i, (center, cw, ch) in enumerate(g.meta["cases"]):
