@@ -44,66 +44,104 @@ def fused_for(n_points: int) -> bool:
   return 9 * int(n_points) >= 400
 
 
-def rotation_matrices(axis: Sequence[float], angle: torch.Tensor, angle_eps: float = ANGLE_EPS) -> torch.Tensor:
-  """(b, 9) float32, R = I + sin(a) S + (1 - cos(a)) S², |a| <= eps → identity (utils.py:303-327)."""
+_axis_terms = {}
+
+
+def _skew_terms(axis: Sequence[float]):
+  """(skew (1,9), skew² (1,9), I (1,9)) of the normalised axis, utils.py:303-318; they depend on the axis only and
+  are built once with the reference's torch ops."""
+  key = tuple(float(a) for a in axis)
+  hit = _axis_terms.get(key)
+  if hit is None:
+    ax = host_f32(axis, (3,))
+    ax = ax / torch.linalg.norm(ax, dim=-1, keepdim=True)
+    zero = torch.zeros((1,), dtype=torch.float32)
+    skew = torch.stack((zero, -ax[:, 2], ax[:, 1], ax[:, 2], zero, -ax[:, 0], -ax[:, 1], ax[:, 0], zero), dim=-1)
+    skew3 = skew.view(1, 3, 3)
+    skew_sq = torch.einsum("bij,bjk->bik", skew3, skew3).reshape(1, 9)
+    hit = _axis_terms[key] = (skew.numpy().copy(), skew_sq.numpy().copy(), np.eye(3, dtype=np.float32).reshape(1, 9))
+  return hit
+
+
+def rotation_matrices(axis: Sequence[float], angle: torch.Tensor, angle_eps: float = ANGLE_EPS) -> np.ndarray:
+  """(b, 9) float32, R = I + sin(a) S + (1 - cos(a)) S², |a| <= eps → identity (utils.py:303-327).
+  sin / cos come from torch (the reference's libm path: the last ulp matters); the products and sums around them
+  are single IEEE float32 operations in the reference's order, which numpy rounds identically."""
   angle = angle.reshape(-1, 1).to(torch.float32)
-  b = angle.shape[0]
-  ax = host_f32(axis, (3,))
-  ax = ax / torch.linalg.norm(ax, dim=-1, keepdim=True)
-  if ax.shape[0] != b:
-    ax = ax.expand(b, 3)
-  zero = torch.zeros((b,), dtype=torch.float32)
-  skew = torch.stack((zero, -ax[:, 2], ax[:, 1], ax[:, 2], zero, -ax[:, 0], -ax[:, 1], ax[:, 0], zero), dim=-1)
-  skew3 = skew.view(b, 3, 3)
-  skew_sq = torch.einsum("bij,bjk->bik", skew3, skew3).reshape(b, 9)
-  eye = torch.eye(3, dtype=torch.float32).view(1, 9)
-  angle = torch.where(torch.abs(angle) > angle_eps, angle, torch.tensor(0.0))
-  return eye + torch.sin(angle) * skew + (1 - torch.cos(angle)) * skew_sq
+  skew, skew_sq, eye = _skew_terms(axis)
+  angle = torch.where(torch.abs(angle) > angle_eps, angle, torch.zeros((), dtype=torch.float32))
+  sin, cos = torch.sin(angle).numpy(), torch.cos(angle).numpy()
+  return (eye + sin * skew) + (np.float32(1) - cos) * skew_sq
 
 
-def pack_steps(kind: int, R: Optional[torch.Tensor], t: Optional[torch.Tensor], b: int, n_points: int) -> torch.Tensor:
+def pack_steps(kind: int, R, t, b: int, n_points: int) -> torch.Tensor:
   """(b, 16) float32 words laid out as DmStep."""
-  out = torch.zeros((b, STEP_WORDS), dtype=torch.float32)
-  if kind == STEP_NONE:
-    return out
-  if R is not None:
-    out[:, 0:9] = R
-  if t is not None:
-    out[:, 9:12] = t
-  ints = out.view(torch.int32)
-  ints[:, 12] = kind
-  ints[:, 13] = 1 if fused_for(n_points) else 0
-  return out
+  out = np.zeros((b, STEP_WORDS), dtype=np.float32)
+  if kind != STEP_NONE:
+    if R is not None:
+      out[:, 0:9] = R
+    if t is not None:
+      out[:, 9:12] = t
+    ints = out.view(np.int32)
+    ints[:, 12] = kind
+    ints[:, 13] = 1 if fused_for(n_points) else 0
+  return torch.from_numpy(out)
 
 
-def xyz(b: int, x=None, y=None, z=None) -> torch.Tensor:
-  t = torch.zeros((b, 3), dtype=torch.float32)
-  if x is not None: t[:, 0] = x
-  if y is not None: t[:, 1] = y
-  if z is not None: t[:, 2] = z
+def xyz(b: int, x=None, y=None, z=None) -> np.ndarray:
+  t = np.zeros((b, 3), dtype=np.float32)
+  if x is not None: t[:, 0] = np.asarray(x, dtype=np.float32)
+  if y is not None: t[:, 1] = np.asarray(y, dtype=np.float32)
+  if z is not None: t[:, 2] = np.asarray(z, dtype=np.float32)
   return t
+
+
+class _StepCache:
+  """LRU of packed step blocks keyed by the bytes of their inputs: pitch / camera height repeat call after
+  call, poses repeat whenever a caller projects the same frames again.  Entries are read-only."""
+
+  def __init__(self, capacity: int = 256):
+    self._d = OrderedDict()
+    self._cap = capacity
+
+  def get(self, tag: str, build, n_points: int, *tensors: torch.Tensor) -> torch.Tensor:
+    key = (tag, fused_for(n_points)) + tuple(t.contiguous().numpy().tobytes() for t in tensors)
+    hit = self._d.get(key)
+    if hit is not None:
+      self._d.move_to_end(key)
+      return hit
+    out = build()
+    self._d[key] = out
+    if len(self._d) > self._cap:
+      self._d.popitem(last=False)
+    return out
+
+
+_steps = _StepCache()
 
 
 def camera_to_local(pitch: torch.Tensor, cam_h: torch.Tensor, n_points: int) -> torch.Tensor:
   b = pitch.shape[0]  # maps.py:789-797
-  return pack_steps(STEP_ROT_THEN_ADD, rotation_matrices([1., 0., 0.], pitch), xyz(b, y=cam_h), b, n_points)
+  return _steps.get("c2l", lambda: pack_steps(STEP_ROT_THEN_ADD, rotation_matrices([1., 0., 0.], pitch),
+                                              xyz(b, y=cam_h), b, n_points), n_points, pitch, cam_h)
 
 
 def local_to_camera(pitch: torch.Tensor, cam_h: torch.Tensor, n_points: int) -> torch.Tensor:
   b = pitch.shape[0]  # maps.py:838-845
-  return pack_steps(STEP_ADD_THEN_ROT, rotation_matrices([1., 0., 0.], -pitch), xyz(b, y=-cam_h), b, n_points)
+  return _steps.get("l2c", lambda: pack_steps(STEP_ADD_THEN_ROT, rotation_matrices([1., 0., 0.], -pitch),
+                                              xyz(b, y=-cam_h), b, n_points), n_points, pitch, cam_h)
 
 
 def local_to_global(pose: torch.Tensor, n_points: int) -> torch.Tensor:
   b = pose.shape[0]  # maps.py:883-892
-  return pack_steps(STEP_ROT_THEN_ADD, rotation_matrices([0., 1., 0.], pose[:, 2]),
-                    xyz(b, x=pose[:, 0], z=pose[:, 1]), b, n_points)
+  return _steps.get("l2g", lambda: pack_steps(STEP_ROT_THEN_ADD, rotation_matrices([0., 1., 0.], pose[:, 2]),
+                                              xyz(b, x=pose[:, 0], z=pose[:, 1]), b, n_points), n_points, pose)
 
 
 def global_to_local(pose: torch.Tensor, n_points: int) -> torch.Tensor:
   b = pose.shape[0]  # maps.py:930-939: translate(-pos) then rotate(-yaw)
-  return pack_steps(STEP_ADD_THEN_ROT, rotation_matrices([0., 1., 0.], -pose[:, 2]),
-                    -xyz(b, x=pose[:, 0], z=pose[:, 1]), b, n_points)
+  return _steps.get("g2l", lambda: pack_steps(STEP_ADD_THEN_ROT, rotation_matrices([0., 1., 0.], -pose[:, 2]),
+                                              -xyz(b, x=pose[:, 0], z=pose[:, 1]), b, n_points), n_points, pose)
 
 
 def identity(b: int) -> torch.Tensor:
@@ -113,17 +151,16 @@ def identity(b: int) -> torch.Tensor:
 def fast_steps(samples: torch.Tensor) -> int:
   """DmProjCfg.fast_steps for a (b, 48) block of DmProjSample words: 1 / 2 when every sample's
   steps have the structure the straight-line kernel path assumes (see the public header), else 0."""
-  ints = samples.view(torch.int32)
-  loc, glo = samples[:, 0:16], samples[:, 16:32]
-  local_ok = bool((ints[:, 12] == STEP_ROT_THEN_ADD).all() and (ints[:, 13] == 1).all()
-                  and (loc[:, 0] == 1).all() and (loc[:, [1, 2, 3, 6]] == 0).all()
-                  and (loc[:, [9, 11]] == 0).all())
+  a = samples.numpy()
+  ints = a.view(np.int32)
+  local_ok = ((ints[:, 12:14] == (STEP_ROT_THEN_ADD, 1)).all() and (a[:, 0] == 1).all()
+              and not a[:, (1, 2, 3, 6, 9, 11)].any())
   if not local_ok:
     return 0
-  if bool((ints[:, 28] == STEP_NONE).all()):
+  if not ints[:, 28].any():  # STEP_NONE
     return 1
-  global_ok = bool((ints[:, 28] == STEP_ROT_THEN_ADD).all() and (ints[:, 29] == 1).all()
-                   and (glo[:, 4] == 1).all() and (glo[:, [1, 3, 5, 7]] == 0).all() and (glo[:, 10] == 0).all())
+  global_ok = ((ints[:, 28:30] == (STEP_ROT_THEN_ADD, 1)).all() and (a[:, 16 + 4] == 1).all()
+               and not a[:, (16 + 1, 16 + 3, 16 + 5, 16 + 7, 16 + 10)].any())
   return 2 if global_ok else 0
 
 

@@ -61,7 +61,8 @@ struct ProjPlan {
   size_t stage_bytes;
   size_t smem_tile;      // one stage + sample block (plain-load kernel)
   size_t smem_resolve;
-  size_t ws_stage_bytes; // warp-specialised kernel: one 512-pixel stage
+  int ws_warps;          // warp-specialised kernel: consumer warps per CTA (tile = 128 px each)
+  size_t ws_stage_bytes; // warp-specialised kernel: one stage of 128 * ws_warps pixels
   size_t smem_ws;        // stage + barriers/item/sample block
   size_t workspace_bytes() const { return ctrl_bytes + flag_bytes + slot_words * 4 * (size_t)ring; }
 };
@@ -95,11 +96,15 @@ static ProjPlan make_plan(const DmProjCfg& cfg, int b) {
   size_t st = p.stage_bytes > p.smem_resolve ? p.stage_bytes : ((p.smem_resolve + 127) & ~(size_t)127);
   p.stage_bytes = st;
   p.smem_tile = st + 256;
-  size_t ws = ((size_t)p.rows * (512 + 4) * 4 + 512 * 4 + 127) & ~(size_t)127;
-  const size_t ws_res = ((size_t)1024 * p.CP + 127) & ~(size_t)127;  // 4 warps x 64 cells x CP words
-  if (ws < ws_res) ws = ws_res;
-  p.ws_stage_bytes = ws;
-  p.smem_ws = ws + 256;
+  // warp-specialised kernel: 4 consumer warps (512-pixel tiles) while 4 CTAs still fit an SM, else 2 (256-pixel tiles)
+  auto ws_stage = [&](int ww) {
+    size_t ws = ((size_t)p.rows * (128 * ww + 4) * 4 + (size_t)128 * ww * 4 + 127) & ~(size_t)127;
+    const size_t ws_res = ((size_t)ww * 64 * p.CP * 4 + 127) & ~(size_t)127;  // ww warps x 64 cells x CP words
+    return ws < ws_res ? ws_res : ws;
+  };
+  p.ws_warps = (ws_stage(4) + 256 + 1024) * 4 <= (size_t)228 * 1024 ? 4 : 2;
+  p.ws_stage_bytes = ws_stage(p.ws_warps);
+  p.smem_ws = p.ws_stage_bytes + 256;
   return p;
 }
 
@@ -385,10 +390,10 @@ __device__ __forceinline__ bool wait_count(const uint32_t* counter, uint32_t tar
 #define DM_CLK() 0ll
 #define DM_ACC(ctrl_, i_, v_) ((void)0)
 #endif
-constexpr int kWsWarps = 4;
-constexpr int kWsThreads = 32 * (kWsWarps + 1);
-constexpr int kWsTile = 128 * kWsWarps;
-constexpr int kWsResolveCells = 64 * kWsWarps;
+// WW = consumer warps per CTA (template parameter of the kernel): 4 by default; 2 when the C + 1 staged rows of a
+// 512-pixel tile would leave fewer than 4 CTAs per SM (many value channels) — stages in flight per SM, not pixels per
+// stage, are what keeps HBM busy.  tile = 128 * WW pixels, resolve tile = 64 * WW cells.
+constexpr int kWsMaxWarps = 4;
 enum { kItemProj = 0, kItemResolve = 1, kItemNone = 2, kItemExit = 3 };
 
 struct WsItem {
@@ -492,7 +497,7 @@ struct Rcps {
 };
 
 // FAST: 0 generic steps, 1 local only, 2 local + global.  IS_MIN: reduction of the value channels.
-template <int FAST, bool IS_MIN>
+template <int FAST, bool IS_MIN, int WW>
 __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDims& d, const WsItem& it,
                                               const DmProjSample& sp, const Rcps& rcp,
                                               const uint8_t* __restrict__ vplane, float* vals, int* lcell,
@@ -501,7 +506,7 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
                                               long long* tprof) {
   // acc is the kernel parameter (uniform); every RED address is acc + a 32-bit word offset
   [[maybe_unused]] const long long tp0 = DM_CLK();
-  constexpr int RS = kWsTile + 4;
+  constexpr int RS = 128 * WW + 4;
   const int N = cfg.H * cfg.W;
   const int sb = cw * 128;
   const int q = sb + 4 * lane;
@@ -700,11 +705,11 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
 // is empty: a slice without a single key takes a constant-store path.
 __device__ __forceinline__ bool ws_resolve_slice(uint32_t* __restrict__ acc_slot, const DmProjCfg& cfg,
                                                  const ProjDims& d, uint32_t* __restrict__ slot_flags, int frame,
-                                                 int cell_tile, int cw, int lane, uint32_t* wres,
+                                                 int cell_tile, int tile_cells, int cw, int lane, uint32_t* wres,
                                                  float* __restrict__ topdown,
                                                  uint8_t* __restrict__ mask, float* __restrict__ height) {
   const int M = cfg.Mh * cfg.Mw;
-  const int cell0 = cell_tile * kWsResolveCells + cw * 64;
+  const int cell0 = cell_tile * tile_cells + cw * 64;
   const int ncell = min(64, M - cell0);
   if (ncell <= 0) return false;
   uint32_t* slice_flag = slot_flags + (size_t)(cell0 >> 6) * kFlagStride;
@@ -787,14 +792,15 @@ __device__ __forceinline__ bool ws_resolve_slice(uint32_t* __restrict__ acc_slot
   return flagged != 0;
 }
 
-template <int FAST, bool IS_MIN>
-__global__ void __launch_bounds__(kWsThreads)
+template <int FAST, bool IS_MIN, int WW>
+__global__ void __launch_bounds__(32 * (WW + 1))
 proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values,
                const uint8_t* __restrict__ valid, const DmProjSample* __restrict__ samples,
                const DmProjCfg cfg, const ProjDims d, int b, uint32_t* __restrict__ ctrl,
                uint32_t* __restrict__ flags, uint32_t* __restrict__ acc, float* __restrict__ topdown,
                uint8_t* __restrict__ mask, float* __restrict__ height) {
   extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int kWsWarps = WW, kWsTile = 128 * WW, kWsResolveCells = 64 * WW;
   constexpr int RS = kWsTile + 4;
   const Rcps rcp{__frcp_rn(cfg.map_res), __frcp_rn(cfg.fx), __frcp_rn(cfg.fy)};
   // one stage per CTA: latency is hidden by the 5-6 CTAs resident per SM, not by an in-CTA ring
@@ -987,7 +993,7 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
           float* vals = reinterpret_cast<float*>(stage);
           int* lcell = reinterpret_cast<int*>(vals + d.rows * RS);
           const int slot = it.frame % ring;
-          ws_proj_slice<FAST, IS_MIN>(cfg, d, it, *sps, rcp, valid ? valid + (size_t)it.frame * N : nullptr, vals,
+          ws_proj_slice<FAST, IS_MIN, WW>(cfg, d, it, *sps, rcp, valid ? valid + (size_t)it.frame * N : nullptr, vals,
                                       lcell, acc, (uint32_t)slot * (uint32_t)d.slot_words,
                                       flags + (size_t)slot * d.nsl * kFlagStride, warp, lane, cp);
 #ifdef DM_PROFILE
@@ -997,7 +1003,7 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
           uint32_t* wres = reinterpret_cast<uint32_t*>(stage) + warp * 64 * d.CP;
           const int slot = it.frame % ring;
           my_flagged += ws_resolve_slice(acc + (size_t)slot * d.slot_words, cfg, d, flags + (size_t)slot * d.nsl * kFlagStride,
-                                         it.frame, it.idx, warp, lane, wres, topdown, mask, height) ? 1u : 0u;
+                                         it.frame, it.idx, kWsResolveCells, warp, lane, wres, topdown, mask, height) ? 1u : 0u;
 #ifdef DM_PROFILE
           cp[5] += tc1 - tc0; cp[6] += DM_CLK() - tc1;
 #endif
@@ -1055,7 +1061,8 @@ extern "C" int dm_orth_project_f32(const float* depth, const float* values, cons
     DM_CUDA_OK(cudaFuncSetAttribute(proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     DM_CUDA_OK(cudaFuncSetAttribute(resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
 #define DM_WS_ATTR(F, MN) \
-    DM_CUDA_OK(cudaFuncSetAttribute(proj_ws_kernel<F, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    DM_CUDA_OK(cudaFuncSetAttribute(proj_ws_kernel<F, MN, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); \
+    DM_CUDA_OK(cudaFuncSetAttribute(proj_ws_kernel<F, MN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     DM_WS_ATTR(0, false) DM_WS_ATTR(1, false) DM_WS_ATTR(2, false)
     DM_WS_ATTR(0, true) DM_WS_ATTR(1, true) DM_WS_ATTR(2, true)
 #undef DM_WS_ATTR
@@ -1072,30 +1079,35 @@ extern "C" int dm_orth_project_f32(const float* depth, const float* values, cons
   const int rtiles = (M + kResolveCells - 1) / kResolveCells;
   // the warp-specialised TMA kernel needs 16-byte aligned plane starts / row sizes, pixel quads
   // that do not straddle image rows, and two stages that fit in shared memory
-  const long long ws_tiles = (N + kWsTile - 1) / kWsTile;
-  const long long ws_total = (long long)(b + p.lag) * (ws_tiles + rtiles);
+  const int ws_tile = 128 * p.ws_warps, ws_threads = 32 * (p.ws_warps + 1);
+  const long long ws_tiles = (N + ws_tile - 1) / ws_tile;
+  const int ws_rtiles = (M + 64 * p.ws_warps - 1) / (64 * p.ws_warps);
+  const long long ws_total = (long long)(b + p.lag) * (ws_tiles + ws_rtiles);
   const bool ws_ok = (N % 4 == 0) && (cfg->W % 4 == 0) && aligned(depth, 16) && (!values || aligned(values, 16)) &&
                      (!valid || aligned(valid, 4)) && p.smem_ws <= 220 * 1024 && ws_total < (1ll << 31) &&
                      cfg->fast_steps >= 0 && cfg->fast_steps <= 2 &&
                      (unsigned long long)p.ring * p.slot_words < (1ull << 31);
   if (ws_ok) {
     ProjDims dw = d;
-    dw.tile = kWsTile;
+    dw.tile = ws_tile;
     dw.stage_bytes = p.ws_stage_bytes;
     void (*kern)(const float*, const float*, const uint8_t*, const DmProjSample*, DmProjCfg, ProjDims, int,
                  uint32_t*, uint32_t*, uint32_t*, float*, uint8_t*, float*) = nullptr;
     const bool mn = cfg->reduction != 0;
-    switch (cfg->fast_steps) {
-      case 1: kern = mn ? proj_ws_kernel<1, true> : proj_ws_kernel<1, false>; break;
-      case 2: kern = mn ? proj_ws_kernel<2, true> : proj_ws_kernel<2, false>; break;
-      default: kern = mn ? proj_ws_kernel<0, true> : proj_ws_kernel<0, false>; break;
+#define DM_WS_PICK(WW)                                                                         \
+    switch (cfg->fast_steps) {                                                                 \
+      case 1: kern = mn ? proj_ws_kernel<1, true, WW> : proj_ws_kernel<1, false, WW>; break;   \
+      case 2: kern = mn ? proj_ws_kernel<2, true, WW> : proj_ws_kernel<2, false, WW>; break;   \
+      default: kern = mn ? proj_ws_kernel<0, true, WW> : proj_ws_kernel<0, false, WW>; break;  \
     }
+    if (p.ws_warps == 4) { DM_WS_PICK(4) } else { DM_WS_PICK(2) }
+#undef DM_WS_PICK
     int per_sm = 0;
-    DM_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWsThreads, p.smem_ws));
+    DM_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ws_threads, p.smem_ws));
     if (per_sm < 1) return DM_EINVAL;
     long long grid = (long long)g_dev[dev].sms * per_sm;
     if (grid > ws_total) grid = ws_total;
-    kern<<<(unsigned)grid, kWsThreads, p.smem_ws, stream>>>(depth, values, valid, samples, *cfg, dw, b, ctrl, flags,
+    kern<<<(unsigned)grid, ws_threads, p.smem_ws, stream>>>(depth, values, valid, samples, *cfg, dw, b, ctrl, flags,
                                                             acc, topdown, mask, height);
     DM_LAUNCHED();
     return DM_OK;

@@ -150,6 +150,29 @@ def test_orth_project_edge_shapes():
                       **dict(k, reduction="sum", focal_x=5., focal_y=5., center_x=3.5, center_y=3.))
 
 
+@pytest.mark.parametrize("C,get_height,reduction,to_global", [(40, True, None, False), (33, False, "min", True),
+                                                             (64, True, None, True)])
+def test_orth_project_many_channels(C, get_height, reduction, to_global):
+  """Many value channels (BASELINE config 5 has 40): the kernel switches to 256-pixel tiles with two consumer
+  warps per CTA so that enough stages stay resident per SM."""
+  b, H, W = 5, 72, 128
+  intr = orc.intrinsics(W, H, HFOV)
+  kw = dict(map_res=0.05, map_width=120, map_height=100, focal_x=intr["fx"], focal_y=intr["fy"], center_x=intr["cx"],
+            center_y=intr["cy"], trunc_depth_min=0.15, trunc_depth_max=5.05, trunc_height_max=None,
+            clip_border=2, to_global=to_global, fill_value=0.25 if reduction else -np.inf, reduction=reduction,
+            get_height_map=get_height)
+  depth, values, pose = synth.frames("room", b, H, W, C, seed=31)
+  values = values * synth.uniform(values.shape, 5, -1.0, 2.0)  # not just {0, 1}
+  d, v, p = depth.numpy(), values.numpy(), pose.numpy()
+  want = orc.orth_project(d, v, None, p, 60., 0., PITCH, 0.88, **kw)
+  for rep in range(2):
+    got = dmap.orth_project(depth, values, None, p, 60., 0., PITCH, 0.88, device="cuda", **kw)
+    assert_same(npy(got[0]), want[0], f"topdown rep{rep}")
+    assert_same(npy(got[1]), want[1], f"mask rep{rep}")
+    if get_height:
+      assert_same(npy(got[2][:, :1]), want[2][:, :1], f"height rep{rep}")
+
+
 def test_orth_project_depth_channels_fold_into_batch():
   H, W = 20, 24
   intr = orc.intrinsics(W, H, HFOV)
