@@ -63,11 +63,31 @@ def _skew_terms(axis: Sequence[float]):
   return hit
 
 
+def _rotation_matrices_per_sample_axis(ax: torch.Tensor, angle: torch.Tensor, angle_eps: float) -> np.ndarray:
+  """utils.rotate with one axis per sample (utils.py:303-327), all in torch like the reference."""
+  b = angle.shape[0]
+  ax = ax / torch.linalg.norm(ax, dim=-1, keepdim=True)
+  if ax.shape[0] != b:
+    ax = ax.expand(b, 3)
+  zero = torch.zeros((b,), dtype=torch.float32)
+  skew = torch.stack((zero, -ax[:, 2], ax[:, 1], ax[:, 2], zero, -ax[:, 0], -ax[:, 1], ax[:, 0], zero), dim=-1)
+  skew3 = skew.view(b, 3, 3)
+  skew_sq = torch.einsum("bij,bjk->bik", skew3, skew3).reshape(b, 9)
+  eye = torch.eye(3, dtype=torch.float32).view(1, 9)
+  angle = torch.where(torch.abs(angle) > angle_eps, angle, torch.tensor(0.0))
+  return (eye + torch.sin(angle) * skew + (1 - torch.cos(angle)) * skew_sq).numpy()
+
+
 def rotation_matrices(axis: Sequence[float], angle: torch.Tensor, angle_eps: float = ANGLE_EPS) -> np.ndarray:
   """(b, 9) float32, R = I + sin(a) S + (1 - cos(a)) S², |a| <= eps → identity (utils.py:303-327).
   sin / cos come from torch (the reference's libm path: the last ulp matters); the products and sums around them
   are single IEEE float32 operations in the reference's order, which numpy rounds identically."""
   angle = angle.reshape(-1, 1).to(torch.float32)
+  if torch.is_tensor(axis) or isinstance(axis, np.ndarray):
+    ax = host_f32(axis, (3,))
+    if ax.shape[0] != 1:
+      return _rotation_matrices_per_sample_axis(ax, angle, angle_eps)
+    axis = ax[0].tolist()
   skew, skew_sq, eye = _skew_terms(axis)
   angle = torch.where(torch.abs(angle) > angle_eps, angle, torch.zeros((), dtype=torch.float32))
   sin, cos = torch.sin(angle).numpy(), torch.cos(angle).numpy()

@@ -46,37 +46,46 @@ __device__ __forceinline__ void for_valid_cells(const FuseSources& fs, int C, lo
   const DmFuseSource& src = fs.s[k];
   const long long i0 = (group - fs.first_group[k]) * kGroup;
   const long long left = fs.cells[k] - i0;
-  uint32_t m[4] = {0u, 0u, 0u, 0u};
+  // one bit per valid cell of the group
+  uint32_t bits = 0;
   if (left >= kGroup && fs.vec_ok[k]) {
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(src.mask + i0));
-    m[0] = v.x; m[1] = v.y; m[2] = v.z; m[3] = v.w;
+    if ((v.x | v.y | v.z | v.w) == 0u) return;
+    const uint32_t m[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < kGroup; ++j) bits |= ((m[j >> 2] >> ((j & 3) * 8)) & 0xffu) ? (1u << j) : 0u;
   } else {
     const int cnt = left < kGroup ? (int)left : kGroup;
-    for (int j = 0; j < cnt; ++j) m[j >> 2] |= (uint32_t)(src.mask[i0 + j] != 0) << ((j & 3) * 8);
+    for (int j = 0; j < cnt; ++j) bits |= src.mask[i0 + j] ? (1u << j) : 0u;
+    if (!bits) return;
   }
-  if ((m[0] | m[1] | m[2] | m[3]) == 0u) return;
-  // one bit per valid cell of the group; the loop below has ONE copy of the visitor (an unrolled 16-way
-  // version thrashed the instruction cache: 7 stall_no_instruction cycles per issue in ncu)
-  uint32_t bits = 0;
-#pragma unroll
-  for (int j = 0; j < kGroup; ++j) bits |= ((m[j >> 2] >> ((j & 3) * 8)) & 0xffu) ? (1u << j) : 0u;
+  // the loop below has ONE copy of the visitor (an unrolled 16-way version thrashed the instruction cache:
+  // 7 stall_no_instruction cycles per issue in ncu)
   const int n = src.h * src.w;
-  const long long sc0 = i0 / n;
-  const int cell0 = (int)(i0 - sc0 * n);
+  int smp0, ch0, cell0;
+  if (fs.cells[k] < (1ll << 31)) {  // 32-bit divisions whenever the source allows it
+    const unsigned sc = (unsigned)i0 / (unsigned)n;
+    cell0 = (int)((unsigned)i0 - sc * (unsigned)n);
+    smp0 = (int)(sc / (unsigned)C);
+    ch0 = (int)(sc - (unsigned)smp0 * (unsigned)C);
+  } else {
+    const long long sc = i0 / n;
+    cell0 = (int)(i0 - sc * n);
+    smp0 = (int)(sc / C);
+    ch0 = (int)(sc - (long long)smp0 * C);
+  }
   const int r0 = cell0 / src.w, c0 = cell0 - r0 * src.w;
   while (bits) {
     const int j = __ffs(bits) - 1;
     bits &= bits - 1;
-    long long sc = sc0;
-    int cell = cell0 + j, r = r0, c = c0 + j;
+    int smp = smp0, ch = ch0, cell = cell0 + j, r = r0, c = c0 + j;
     if (cell >= n) {  // the group straddles two planes (n is not a multiple of 16)
-      cell -= n; ++sc;
+      cell -= n;
+      if (++ch == C) { ch = 0; ++smp; }
       r = cell / src.w; c = cell - r * src.w;
     } else {
       while (c >= src.w) { c -= src.w; ++r; }
     }
-    const int smp = (int)(sc / C);
-    const int ch = (int)(sc - (long long)smp * C);
     visit(src, i0 + j, smp, ch, r, c);
   }
 }

@@ -25,6 +25,8 @@
 //    — which is what keeps the dependency waits of a deep, many-tiles-in-flight schedule rare.
 //  * Shapes whose planes are not 16-byte aligned take the plain-load kernels (proj_kernel /
 //    resolve_kernel, chunked over the ring) — same device functions, same results.
+#include <cstdlib>
+
 #include "dm_common.cuh"
 
 namespace dm {
@@ -103,6 +105,10 @@ static ProjPlan make_plan(const DmProjCfg& cfg, int b) {
     return ws < ws_res ? ws_res : ws;
   };
   p.ws_warps = (ws_stage(4) + 256 + 1024) * 4 <= (size_t)228 * 1024 ? 4 : 2;
+  if (const char* e = getenv("DM_WS_WARPS")) {  // kernel experiments only (scripts/time_proj.py)
+    const int ww = atoi(e);
+    if (ww == 2 || ww == 4) p.ws_warps = ww;
+  }
   p.ws_stage_bytes = ws_stage(p.ws_warps);
   p.smem_ws = p.ws_stage_bytes + 256;
   return p;
@@ -393,6 +399,9 @@ __device__ __forceinline__ bool wait_count(const uint32_t* counter, uint32_t tar
 // WW = consumer warps per CTA (template parameter of the kernel): 4 by default; 2 when the C + 1 staged rows of a
 // 512-pixel tile would leave fewer than 4 CTAs per SM (many value channels) — stages in flight per SM, not pixels per
 // stage, are what keeps HBM busy.  tile = 128 * WW pixels, resolve tile = 64 * WW cells.
+// Measured on the B200 (scripts/exp_ww.sh, ms per 64-frame step, room / iid scene | config 5 shapes, 32 frames):
+//   C = 16: WW 8: 0.511 / 0.582   6: 0.511 / 0.579   4: 0.499 / 0.585   3: 0.541 / 0.632   2: 0.551 / 0.682   1: 0.694 / 1.059
+//   C = 40: WW 8: 2.32            6: 3.01            4: 2.26            3: 2.04            2: 1.87            1: 2.07
 constexpr int kWsMaxWarps = 4;
 enum { kItemProj = 0, kItemResolve = 1, kItemNone = 2, kItemExit = 3 };
 

@@ -21,47 +21,82 @@ G = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
 os.makedirs(P, exist_ok=True)
 
-# launch list: keep kernel name (short), grid, block, duration
-src = os.path.join(G, f"launches_{run}.csv")
-if os.path.exists(src):
+def short(name):
+  return name.split("(")[0].replace("void ", "")
+
+
+def save_launches(src, dst, cmd):
+  if not os.path.exists(src):
+    return
   lines = [l for l in open(src) if l.startswith('"')]
   rows = list(csv.DictReader(io.StringIO("".join(lines))))
-  with open(os.path.join(P, f"{tag}_launches.csv"), "w") as f:
-    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none ... python bench.py --steps 3 --warmup 3 "
-            "--no-cpu-baseline --e2e-steps 2   (cold-cache, serialised: compare shares, not absolutes)\n")
+  with open(dst, "w") as f:
+    f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none ... {cmd}   (cold-cache, serialised: compare shares, not absolutes)\n")
     f.write("id,kernel,grid,block,stream,duration_ns\n")
     for r in rows:
-      name = r["Kernel Name"].split("(")[0].replace("void ", "")
-      f.write(f'{r["ID"]},{name},"{r["Grid Size"]}","{r["Block Size"]}",{r["Stream"]},{r["Metric Value"]}\n')
+      f.write(f'{r["ID"]},{short(r["Kernel Name"])},"{r["Grid Size"]}","{r["Block Size"]}",{r["Stream"]},{r["Metric Value"]}\n')
   tot = sum(float(r["Metric Value"]) for r in rows)
   by = {}
   for r in rows:
-    n = r["Kernel Name"].split("(")[0].replace("void ", "")
-    by[n] = by.get(n, 0.0) + float(r["Metric Value"])
-  print("launch shares:", {k: f"{100 * v / tot:.1f}%" for k, v in by.items()}, f"{len(rows)} launches")
+    by[short(r["Kernel Name"])] = by.get(short(r["Kernel Name"]), 0.0) + float(r["Metric Value"])
+  print(os.path.basename(dst), "launch shares:", {k: f"{100 * v / tot:.1f}%" for k, v in by.items()}, f"{len(rows)} launches")
 
-rep = os.path.join(G, f"prof_proj_{run}.ncu-rep")
-if os.path.exists(rep):
-  out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summary.py"), rep, "0", "40"],
-                       capture_output=True, text=True).stdout
-  with open(os.path.join(P, f"{tag}_proj_full.txt"), "w") as f:
-    f.write(f"# ncu --set full --clock-control none --import-source on -k regex:proj_ws -s 4 -c 1  (run {run})\n")
-    f.write(out)
+
+save_launches(os.path.join(G, f"launches_{run}.csv"), os.path.join(P, f"{tag}_launches.csv"),
+              "python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 2")
+save_launches(os.path.join(G, f"launches_flow_{run}.csv"), os.path.join(P, f"{tag}_launches_flow.csv"),
+              "python bench.py --workload flow --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 2")
+save_launches(os.path.join(G, f"launches_builder_{run}.csv"), os.path.join(P, f"{tag}_launches_builder.csv"),
+              "python bench.py --workload builder --steps 40 --warmup 3 --no-cpu-baseline --e2e-steps 2")
+
+
+def raw_rows(rep):
   raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
   rows = list(csv.reader(io.StringIO(raw)))
-  H, units, r = rows[0], rows[1], rows[2]
+  H, units = rows[0], rows[1]
 
-  def val(name):
+  def val(r, name):
     v, u = float(r[H.index(name)]), units[H.index(name)]
-    return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
-  rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
-  json.dump({"kernel": r[H.index("Kernel Name")].split("(")[0], "run": run,
-             "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_step": rd + wr,
-             "duration_us_under_ncu": float(r[H.index("gpu__time_duration.sum")])},
-            open(os.path.join(P, "traffic.json"), "w"), indent=1)
-  print("traffic:", (rd + wr) / 1e9, "GB per launch")
+    return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(u, 1.0)
+  return [dict(kernel=short(r[H.index("Kernel Name")]), rd=val(r, "dram__bytes_read.sum"),
+               wr=val(r, "dram__bytes_write.sum"), us=float(r[H.index("gpu__time_duration.sum")])) for r in rows[2:]]
 
-for scene in ("room", "iid"):
-  b = os.path.join(G, f"bench_{scene}_{run}.json")
+
+traffic_path = os.path.join(P, "traffic.json")
+traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
+for what, pattern, n_kernels in (("proj", "proj_ws", 1), ("flow", "flow_", 1), ("fuse", "fuse_|changed_", 5)):
+  rep = os.path.join(G, f"prof_{what}_{run}.ncu-rep")
+  if not os.path.exists(rep):
+    continue
+  with open(os.path.join(P, f"{tag}_{what}_full.txt"), "w") as f:
+    f.write(f"# ncu --set full --clock-control none --import-source on -k regex:{pattern}  (run {run})\n")
+    for i in range(n_kernels):
+      out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summary.py"), rep, str(i), "30"],
+                           capture_output=True, text=True).stdout
+      f.write(out + "\n")
+  rows = raw_rows(rep)
+  if what == "proj":
+    r = rows[0]
+    traffic.update({"kernel": r["kernel"], "run": run, "dram_bytes_read": r["rd"], "dram_bytes_write": r["wr"],
+                    "dram_bytes_per_step": r["rd"] + r["wr"], "duration_us_under_ncu": r["us"]})
+  elif what == "flow":
+    r = rows[0]
+    traffic["flow"] = {"kernel": r["kernel"], "run": run, "dram_bytes_per_step": r["rd"] + r["wr"],
+                       "duration_us_under_ncu": r["us"]}
+  else:  # one merge = bbox_init + bbox + fill + scatter: sum the consecutive kernels of one step
+    names = [r["kernel"] for r in rows]
+    want = ["fuse_bbox_kernel", "fuse_fill_kernel", "fuse_scatter_kernel"]
+    for i in range(len(names) - 2):
+      if names[i:i + 3] == want:
+        step = rows[i:i + 3]
+        traffic["builder"] = {"kernels": want, "run": run,
+                              "dram_bytes_per_step": sum(r["rd"] + r["wr"] for r in step),
+                              "duration_us_under_ncu": sum(r["us"] for r in step)}
+        break
+  print(what, "traffic ok")
+json.dump(traffic, open(traffic_path, "w"), indent=1)
+
+for name in ("room", "iid", "flow", "builder", "builder_fixed", "proj5"):
+  b = os.path.join(G, f"bench_{name}_{run}.json")
   if os.path.exists(b) and os.path.getsize(b):
-    shutil.copy(b, os.path.join(P, f"{tag}_bench_{scene}.json"))
+    shutil.copy(b, os.path.join(P, f"{tag}_bench_{name}.json"))
