@@ -6,6 +6,9 @@
 // all samples and channels to size a fresh canvas (maps.py:2146-2179, host sync), re-quantises
 // and scatter-maxes (maps.py:2232-2272).  Here that is two fused passes over the source cells,
 // neither of which materialises a point: pass 1 reduces the bounding box, pass 2 scatters.
+// Both passes give a block ONE plane (sample, channel) of ONE source at a time, so the sample's two
+// transform steps and offsets sit in shared memory and all index arithmetic is 32-bit; a kernel is
+// launched per source (at most 8).
 #include "dm_common.cuh"
 
 namespace dm {
@@ -14,80 +17,91 @@ constexpr int kFuseThreads = 256;
 constexpr int kMaxSources = 8;
 constexpr int kGroup = 16;  // mask bytes examined per work item (one 128-bit load)
 
-struct FuseSources {
-  DmFuseSource s[kMaxSources];
-  long long first_group[kMaxSources + 1];  // prefix of ceil(b*C*h*w / 16) per source
-  long long cells[kMaxSources];            // b*C*h*w per source
-  int vec_ok[kMaxSources];                 // mask base 16-byte aligned
-  int n;
+// Block-uniform state of the plane (one (sample, channel) image of one source) a block is scanning.
+struct PlaneCtx {
+  DmStep step0, step1;  // source local→global, global→target local (kind 0: none)
+  float woff, hoff;
 };
 
-// Point of source cell (row r, col c), channel ch, sample smp, in the target frame.
-__device__ __forceinline__ V3 source_point(const DmFuseSource& src, int smp, int ch, int r, int c) {
+// Walks the valid cells of plane `plane` of `src`: 16 mask bytes per thread and iteration through one aligned
+// 128-bit load.  Most groups of a world map are empty (every environment explored a corner of the batch-wide
+// canvas): those cost one load, one OR and a branch, and the heights / values of empty regions are never read.
+// visit(cell index in the plane, row, col) is instantiated ONCE, in a loop over the set bits (an unrolled
+// 16-way version thrashed the instruction cache: 7 stall_no_instruction cycles per issue in ncu).
+template <typename F>
+__device__ __forceinline__ void visit_bits(const DmFuseSource& src, int o, uint32_t bits, F&& visit) {
+  const int first = o + (__ffs(bits) - 1);
+  int r = first / src.w, c = first - r * src.w, cell = first;
+  bits >>= (__ffs(bits) - 1);
+  while (true) {
+    visit(cell, r, c);
+    bits >>= 1;
+    if (!bits) break;
+    const int skip = __ffs(bits);  // distance to the next valid cell
+    bits >>= skip - 1;
+    cell += skip;
+    c += skip;
+    while (c >= src.w) { c -= src.w; ++r; }
+  }
+}
+
+__device__ __forceinline__ uint32_t bits_of(const uint4 v) {
+  const uint32_t m[4] = {v.x, v.y, v.z, v.w};
+  uint32_t bits = 0;
+#pragma unroll
+  for (int j = 0; j < kGroup; ++j) bits |= ((m[j >> 2] >> ((j & 3) * 8)) & 0xffu) ? (1u << j) : 0u;
+  return bits;
+}
+
+template <typename F>
+__device__ __forceinline__ void for_valid_cells_of_plane(const DmFuseSource& src, long long plane, F&& visit) {
+  // (four loads in flight per thread were tried: more instructions, no gain — the passes are bound by the work on
+  // the valid cells, not by the latency of the mask loads)
+  const int n = src.h * src.w;
+  const uint8_t* base = src.mask + plane * n;
+  const int a0 = (int)(reinterpret_cast<uintptr_t>(base) & 15);  // bytes between the aligned-down start and the plane
+  const int groups = (n + a0 + kGroup - 1) / kGroup;
+  for (int g = blockIdx.x * kFuseThreads + threadIdx.x; g < groups; g += gridDim.x * kFuseThreads) {
+    const int o = g * kGroup - a0;  // plane-relative offset of the group's first byte (negative in the head group)
+    uint32_t bits = 0;
+    if (o >= 0 && o + kGroup <= n) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + o));
+      if ((v.x | v.y | v.z | v.w) == 0u) continue;
+      bits = bits_of(v);
+    } else {  // head / tail group of a plane whose start or size is not a multiple of 16: byte loads inside the plane
+      for (int j = 0; j < kGroup; ++j)
+        if (o + j >= 0 && o + j < n && base[o + j]) bits |= 1u << j;
+      if (!bits) continue;
+    }
+    visit_bits(src, o, bits, visit);
+  }
+}
+
+// Loads the plane's sample parameters into shared memory (block-uniform), once per sample change.
+__device__ __forceinline__ void load_plane_ctx(const DmFuseSource& src, int smp, PlaneCtx* ctx) {
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(src.steps + smp * 2);
+    reinterpret_cast<uint32_t*>(&ctx->step0)[threadIdx.x] = s[threadIdx.x];  // 2 x 64 bytes = 32 words
+  }
+  if (threadIdx.x == 32) ctx->woff = src.width_offset[smp];
+  if (threadIdx.x == 33) ctx->hoff = src.height_offset[smp];
+  __syncthreads();
+}
+
+// Point of source cell (row r, col c) of the plane, in the target frame.
+__device__ __forceinline__ V3 source_point(const DmFuseSource& src, const PlaneCtx& ctx, const float* hplane, int cell,
+                                           int r, int c) {
   // maps.py:1081-1086 map_dequantize
   float zb = (float)r;
   if (src.flip_h) zb = __fsub_rn((float)(src.h - 1), zb);
   V3 p;
-  p.z = __fmul_rn(__fsub_rn(zb, src.height_offset[smp]), src.map_res);
-  p.x = __fmul_rn(__fsub_rn((float)c, src.width_offset[smp]), src.map_res);
-  p.y = src.height[(long long)smp * src.height_bstride + (long long)ch * src.height_cstride + (long long)r * src.w + c];
-  p = apply_step(src.steps[smp * 2 + 0], p);
-  p = apply_step(src.steps[smp * 2 + 1], p);
+  p.z = __fmul_rn(__fsub_rn(zb, ctx.hoff), src.map_res);
+  p.x = __fmul_rn(__fsub_rn((float)c, ctx.woff), src.map_res);
+  p.y = hplane[cell];
+  if (ctx.step0.kind != DM_STEP_NONE) p = apply_step(ctx.step0, p);  // block-uniform branches
+  if (ctx.step1.kind != DM_STEP_NONE) p = apply_step(ctx.step1, p);
   return p;
-}
-
-// Walks the valid cells of one 16-byte group of a source's flat (b, C, h, w) mask.  Most groups of a
-// world map are empty (every environment explored a corner of the batch-wide canvas): those cost one
-// 128-bit load and nothing else, so the heights / values of empty regions are never read.
-template <typename F>
-__device__ __forceinline__ void for_valid_cells(const FuseSources& fs, int C, long long group, F&& visit) {
-  int k = 0;
-  while (k + 1 < fs.n && group >= fs.first_group[k + 1]) ++k;
-  const DmFuseSource& src = fs.s[k];
-  const long long i0 = (group - fs.first_group[k]) * kGroup;
-  const long long left = fs.cells[k] - i0;
-  // one bit per valid cell of the group
-  uint32_t bits = 0;
-  if (left >= kGroup && fs.vec_ok[k]) {
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src.mask + i0));
-    if ((v.x | v.y | v.z | v.w) == 0u) return;
-    const uint32_t m[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int j = 0; j < kGroup; ++j) bits |= ((m[j >> 2] >> ((j & 3) * 8)) & 0xffu) ? (1u << j) : 0u;
-  } else {
-    const int cnt = left < kGroup ? (int)left : kGroup;
-    for (int j = 0; j < cnt; ++j) bits |= src.mask[i0 + j] ? (1u << j) : 0u;
-    if (!bits) return;
-  }
-  // the loop below has ONE copy of the visitor (an unrolled 16-way version thrashed the instruction cache:
-  // 7 stall_no_instruction cycles per issue in ncu)
-  const int n = src.h * src.w;
-  int smp0, ch0, cell0;
-  if (fs.cells[k] < (1ll << 31)) {  // 32-bit divisions whenever the source allows it
-    const unsigned sc = (unsigned)i0 / (unsigned)n;
-    cell0 = (int)((unsigned)i0 - sc * (unsigned)n);
-    smp0 = (int)(sc / (unsigned)C);
-    ch0 = (int)(sc - (unsigned)smp0 * (unsigned)C);
-  } else {
-    const long long sc = i0 / n;
-    cell0 = (int)(i0 - sc * n);
-    smp0 = (int)(sc / C);
-    ch0 = (int)(sc - (long long)smp0 * C);
-  }
-  const int r0 = cell0 / src.w, c0 = cell0 - r0 * src.w;
-  while (bits) {
-    const int j = __ffs(bits) - 1;
-    bits &= bits - 1;
-    int smp = smp0, ch = ch0, cell = cell0 + j, r = r0, c = c0 + j;
-    if (cell >= n) {  // the group straddles two planes (n is not a multiple of 16)
-      cell -= n;
-      if (++ch == C) { ch = 0; ++smp; }
-      r = cell / src.w; c = cell - r * src.w;
-    } else {
-      while (c >= src.w) { c -= src.w; ++r; }
-    }
-    visit(src, i0 + j, smp, ch, r, c);
-  }
 }
 
 __global__ void fuse_bbox_init(long long* out) {
@@ -98,16 +112,20 @@ __global__ void fuse_bbox_init(long long* out) {
   out[4] = 0;                              // n_valid
 }
 
-__global__ void __launch_bounds__(kFuseThreads)
-fuse_bbox_kernel(const __grid_constant__ FuseSources fs, int C, float res, long long total_groups,
-                 long long* __restrict__ out) {
+// grid = (blocks per plane, planes folded into y)
+__global__ void __launch_bounds__(kFuseThreads, 4)
+fuse_bbox_kernel(const __grid_constant__ DmFuseSource src, int planes, int C, float res, long long* __restrict__ out) {
+  __shared__ PlaneCtx ctx;
   long long mnx = 0x7fffffffffffffffLL, mxx = (long long)0x8000000000000000ULL;
   long long mnz = mnx, mxz = mxx;
   unsigned long long cnt = 0;
-  for (long long g = (long long)blockIdx.x * kFuseThreads + threadIdx.x; g < total_groups;
-       g += (long long)gridDim.x * kFuseThreads) {
-    for_valid_cells(fs, C, g, [&](const DmFuseSource& src, long long, int smp, int ch, int r, int c) {
-      const V3 p = source_point(src, smp, ch, r, c);
+  int loaded = -1;
+  for (int plane = blockIdx.y; plane < planes; plane += gridDim.y) {
+    const int smp = plane / C, ch = plane - smp * C;
+    if (smp != loaded) { load_plane_ctx(src, smp, &ctx); loaded = smp; }
+    const float* hplane = src.height + (long long)smp * src.height_bstride + (long long)ch * src.height_cstride;
+    for_valid_cells_of_plane(src, plane, [&](int cell, int r, int c) {
+      const V3 p = source_point(src, ctx, hplane, cell, r, c);
       // maps.py:2159-2165: map_quantize(width_offset=0., height_offset=0., flip_h=False)
       float xf, zf;
       quantize_f(p.x, p.z, 0.0f, 0.0f, res, 0, 0, &xf, &zf);
@@ -169,25 +187,34 @@ fuse_fill_kernel(float* __restrict__ topdown, float* __restrict__ height, uint8_
 
 // mask_inline: the mask (utils.py:489-491: the cell differs from what the canvas was filled with) is
 // stored right where a value beats `fill`; with a NaN fill the generic pass below is used instead.
-__global__ void __launch_bounds__(kFuseThreads)
-fuse_scatter_kernel(const __grid_constant__ FuseSources fs, int C, const DmFuseTarget tgt, long long total_groups,
+__global__ void __launch_bounds__(kFuseThreads, 4)
+fuse_scatter_kernel(const __grid_constant__ DmFuseSource src, int planes, int C, const DmFuseTarget tgt,
                     float* __restrict__ topdown, float* __restrict__ height, uint8_t* __restrict__ mask,
                     int mask_inline) {
+  __shared__ PlaneCtx ctx;
   const long long M = (long long)tgt.Mh * tgt.Mw;
-  for (long long g = (long long)blockIdx.x * kFuseThreads + threadIdx.x; g < total_groups;
-       g += (long long)gridDim.x * kFuseThreads) {
-    for_valid_cells(fs, C, g, [&](const DmFuseSource& src, long long in_idx, int smp, int ch, int r, int c) {
-      const V3 p = source_point(src, smp, ch, r, c);
+  const int n = src.h * src.w;
+  int loaded = -1;
+  for (int plane = blockIdx.y; plane < planes; plane += gridDim.y) {
+    const int smp = plane / C, ch = plane - smp * C;
+    if (smp != loaded) { load_plane_ctx(src, smp, &ctx); loaded = smp; }
+    const float* hplane = src.height + (long long)smp * src.height_bstride + (long long)ch * src.height_cstride;
+    const float* vplane = src.values ? src.values + (long long)plane * n : nullptr;
+    float* tplane = topdown + (long long)plane * M;
+    float* oplane = height ? height + (long long)plane * M : nullptr;
+    uint8_t* mplane = mask + (long long)plane * M;
+    for_valid_cells_of_plane(src, plane, [&](int cell, int r, int c) {
+      const V3 p = source_point(src, ctx, hplane, cell, r, c);
       float xf, zf;  // maps.py:2232-2238
       quantize_f(p.x, p.z, tgt.width_offset, tgt.height_offset, tgt.map_res, tgt.Mh, tgt.flip_h, &xf, &zf);
       if (!(xf >= 0.0f && xf < (float)tgt.Mw && zf >= 0.0f && zf < (float)tgt.Mh)) return;
-      const long long o = ((long long)smp * C + ch) * M + (long long)zf * tgt.Mw + (long long)xf;
-      const float v = src.values ? src.values[in_idx] : p.y;  // maps.py:2214-2216
+      const int o = (int)zf * tgt.Mw + (int)xf;
+      const float v = vplane ? vplane[cell] : p.y;  // maps.py:2214-2216
       if (v == v) {
-        if (tgt.reduction) atomic_min_f32(topdown + o, v); else atomic_max_f32(topdown + o, v);
-        if (mask_inline && better(v, tgt.fill_value, tgt.reduction)) mask[o] = 1;
+        if (tgt.reduction) atomic_min_f32(tplane + o, v); else atomic_max_f32(tplane + o, v);
+        if (mask_inline && better(v, tgt.fill_value, tgt.reduction)) mplane[o] = 1;
       }
-      if (height && p.y == p.y) atomic_max_f32(height + o, p.y);  // maps.py:2258-2271
+      if (oplane && p.y == p.y) atomic_max_f32(oplane + o, p.y);  // maps.py:2258-2271
     });
   }
 }
@@ -202,24 +229,27 @@ changed_mask_kernel(const float* __restrict__ canvas, long long n, float fill, u
   }
 }
 
-static int pack_sources(const DmFuseSource* sources, int n, int b, int C, FuseSources* fs, long long* total) {
+static int check_sources(const DmFuseSource* sources, int n, int b, int C) {
   if (!sources || n <= 0 || n > kMaxSources || b <= 0 || C <= 0) return DM_EINVAL;
-  fs->n = n;
-  long long acc = 0;
+  if ((long long)b * C >= (1ll << 31)) return DM_EINVAL;
   for (int i = 0; i < n; ++i) {
     const DmFuseSource& s = sources[i];
     if (!s.height || !s.mask || !s.width_offset || !s.height_offset || !s.steps || s.h <= 0 || s.w <= 0)
       return DM_EINVAL;
-    if ((long long)s.h * s.w >= (1ll << 31)) return DM_EINVAL;
-    fs->s[i] = s;
-    fs->first_group[i] = acc;
-    fs->cells[i] = (long long)b * C * s.h * s.w;
-    fs->vec_ok[i] = reinterpret_cast<uintptr_t>(s.mask) % 16 == 0;
-    acc += (fs->cells[i] + kGroup - 1) / kGroup;
+    if ((long long)s.h * s.w >= (1ll << 30)) return DM_EINVAL;
   }
-  fs->first_group[n] = acc;
-  *total = acc;
   return DM_OK;
+}
+
+// (blocks per plane, planes): about two waves of 8 resident CTAs per SM in total
+static dim3 plane_grid(const DmFuseSource& s, int planes) {
+  const long long groups = ((long long)s.h * s.w + 2 * kGroup - 1) / kGroup;
+  const int gy = planes < 65535 ? planes : 65535;
+  long long gx = ((long long)kNumSMs * 8 * 2 + gy - 1) / gy;
+  const long long gx_max = (groups + kFuseThreads - 1) / kFuseThreads;
+  if (gx > gx_max) gx = gx_max;
+  if (gx < 1) gx = 1;
+  return dim3((unsigned)gx, (unsigned)gy);
 }
 
 static unsigned grid_for(long long items) {
@@ -230,6 +260,16 @@ static unsigned grid_for(long long items) {
   return (unsigned)blocks;
 }
 
+static int launch_scatter(const DmFuseSource* sources, int n_sources, int b, int C, const DmFuseTarget& tgt,
+                          float* topdown, uint8_t* mask, float* height, int mask_inline, cudaStream_t stream) {
+  for (int i = 0; i < n_sources; ++i) {
+    fuse_scatter_kernel<<<plane_grid(sources[i], b * C), kFuseThreads, 0, stream>>>(sources[i], b * C, C, tgt, topdown,
+                                                                                  height, mask, mask_inline);
+    DM_LAUNCHED();
+  }
+  return DM_OK;
+}
+
 }  // namespace dm
 
 using namespace dm;
@@ -237,16 +277,16 @@ using namespace dm;
 extern "C" int dm_fuse_bbox_i64(const DmFuseSource* sources, int32_t n_sources, int32_t b, int32_t C,
                                 float target_res, int64_t* out, void* stream_) {
   if (!out) return DM_EINVAL;
-  FuseSources fs;
-  long long total = 0;
-  const int rc = pack_sources(sources, n_sources, b, C, &fs, &total);
+  const int rc = check_sources(sources, n_sources, b, C);
   if (rc != DM_OK) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   fuse_bbox_init<<<1, 1, 0, stream>>>(reinterpret_cast<long long*>(out));
   DM_LAUNCHED();
-  fuse_bbox_kernel<<<grid_for(total), kFuseThreads, 0, stream>>>(fs, C, target_res, total,
-                                                                  reinterpret_cast<long long*>(out));
-  DM_LAUNCHED();
+  for (int i = 0; i < n_sources; ++i) {
+    fuse_bbox_kernel<<<plane_grid(sources[i], b * C), kFuseThreads, 0, stream>>>(sources[i], b * C, C, target_res,
+                                                                               reinterpret_cast<long long*>(out));
+    DM_LAUNCHED();
+  }
   return DM_OK;
 }
 
@@ -255,21 +295,19 @@ extern "C" int dm_fuse_scatter_f32(const DmFuseSource* sources, int32_t n_source
                                    void* stream_) {
   if (!target || !topdown || !mask || target->Mh <= 0 || target->Mw <= 0) return DM_EINVAL;
   if (target->reduction != 0 && target->reduction != 1) return DM_EINVAL;
-  FuseSources fs;
-  long long total = 0;
-  const int rc = pack_sources(sources, n_sources, b, C, &fs, &total);
+  const int rc = check_sources(sources, n_sources, b, C);
   if (rc != DM_OK) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const long long n_out = (long long)b * C * target->Mh * target->Mw;
+  if ((long long)target->Mh * target->Mw >= (1ll << 31)) return DM_EINVAL;
   const int vec_ok = reinterpret_cast<uintptr_t>(topdown) % 16 == 0 && reinterpret_cast<uintptr_t>(mask) % 16 == 0 &&
                      (!height || reinterpret_cast<uintptr_t>(height) % 16 == 0);
   const int mask_inline = target->fill_value == target->fill_value;  // not NaN
   fuse_fill_kernel<<<grid_for((n_out + 3) / 4), kFuseThreads, 0, stream>>>(topdown, height, mask, n_out,
-                                                                             target->fill_value, vec_ok);
+                                                                           target->fill_value, vec_ok);
   DM_LAUNCHED();
-  fuse_scatter_kernel<<<grid_for(total), kFuseThreads, 0, stream>>>(fs, C, *target, total, topdown, height, mask,
-                                                                    mask_inline);
-  DM_LAUNCHED();
+  const int rs = launch_scatter(sources, n_sources, b, C, *target, topdown, mask, height, mask_inline, stream);
+  if (rs != DM_OK) return rs;
   if (!mask_inline) {
     changed_mask_kernel<<<grid_for(n_out), kFuseThreads, 0, stream>>>(topdown, n_out, target->fill_value, mask);
     DM_LAUNCHED();
@@ -287,14 +325,10 @@ extern "C" int dm_fuse_inplace_f32(const DmFuseSource* sources, int32_t n_source
   if (!target || !topdown || !mask || target->Mh <= 0 || target->Mw <= 0) return DM_EINVAL;
   if (target->reduction != 0 && target->reduction != 1) return DM_EINVAL;
   if (!(target->fill_value == target->fill_value)) return DM_EINVAL;  // NaN fill has no in-place mask rule
-  FuseSources fs;
-  long long total = 0;
-  const int rc = pack_sources(sources, n_sources, b, C, &fs, &total);
+  const int rc = check_sources(sources, n_sources, b, C);
   if (rc != DM_OK) return rc;
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  fuse_scatter_kernel<<<grid_for(total), kFuseThreads, 0, stream>>>(fs, C, *target, total, topdown, height, mask, 1);
-  DM_LAUNCHED();
-  return DM_OK;
+  if ((long long)target->Mh * target->Mw >= (1ll << 31)) return DM_EINVAL;
+  return launch_scatter(sources, n_sources, b, C, *target, topdown, mask, height, 1, static_cast<cudaStream_t>(stream_));
 }
 
 /* Fills fresh world canvases for dm_fuse_inplace_f32: topdown = fill_value, height = -inf (may be NULL), mask = 0. */
