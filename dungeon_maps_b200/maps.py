@@ -147,6 +147,11 @@ def orth_project(
   `topdown_map` when `value_map` is None, otherwise a stride-0 expand of the (b,1,mh,mw)
   max-height map with -inf in empty cells.
   """
+  if utils._reduction_code(reduction, fused=False) > 1:
+    return _orth_project_composed(
+      depth_map, value_map, valid_map, cam_pose, width_offset, height_offset, cam_pitch, cam_height, map_res,
+      map_width, map_height, focal_x, focal_y, center_x, center_y, trunc_depth_min, trunc_depth_max,
+      trunc_height_max, clip_border, to_global, flip_h, fill_value, reduction, get_height_map, device)
   red = utils._reduction_code(reduction)
   dev = _pick_device(device, depth_map, value_map)
   depth = _image(depth_map, dev, torch.float32)
@@ -226,6 +231,46 @@ def orth_project(
   if value_map is None:
     return topdown, masks, topdown          # maps.py:333-334: the very same tensor
   return topdown, masks, torch.broadcast_to(height, topdown.shape)  # maps.py:349
+
+
+def _orth_project_composed(depth_map, value_map, valid_map, cam_pose, width_offset, height_offset, cam_pitch,
+                            cam_height, map_res, map_width, map_height, focal_x, focal_y, center_x, center_y,
+                            trunc_depth_min, trunc_depth_max, trunc_height_max, clip_border, to_global, flip_h,
+                            fill_value, reduction, get_height_map, device):
+  """orth_project for the reductions the fused kernel does not cover (sum, mean, prod): the reference's own
+  sequence of public steps (maps.py:259-351), each of them one kernel of this package — points are materialised
+  here, the price of the rarely used reductions."""
+  dev = _pick_device(device, depth_map, value_map)
+  depth = _image(depth_map, dev, torch.float32)
+  b, dc, H, W = depth.shape
+  points, valid = depth_map_to_point_cloud(depth, valid_map, focal_x, focal_y, center_x, center_y, trunc_depth_min,
+                                           trunc_depth_max, flip_h, device=dev)          # (b, c, h, w, 3)
+  if clip_border is not None and clip_border > 0:                                        # maps.py:48-70
+    k = int(clip_border)
+    border = torch.zeros((H, W), dtype=torch.bool, device=dev)
+    border[k:H - k, k:W - k] = True
+    valid = valid & border
+  points = camera_to_local_space(points, cam_pitch, cam_height, device=dev)
+  if trunc_height_max is not None:                                                       # maps.py:286-288
+    valid = valid & (points[..., 1] <= trunc_height_max)
+  if to_global:
+    points = local_to_global_space(points, cam_pose, device=dev)
+  flat = points.reshape(b, dc, H * W, 3)
+  flat_mask = valid.reshape(b, dc, H * W)
+  x_bin, z_bin = map_quantize(flat[..., 0].reshape(b, -1), flat[..., 2].reshape(b, -1), width_offset, height_offset,
+                              map_res, map_height, flip_h, device=dev)
+  coords = torch.stack((z_bin, x_bin), dim=-1).reshape(b, dc, H * W, 2)
+  heights = flat[..., 1]
+  values = heights if value_map is None else _image(value_map, dev, torch.float32).reshape(b, -1, H * W)
+  canvas = torch.zeros(values.shape[:-1] + (int(map_height), int(map_width)), dtype=torch.float32, device=dev)
+  topdown, masks = project(coords, values, flat_mask, canvas, fill_value=fill_value, reduction=reduction, device=dev)
+  if not get_height_map:
+    return topdown, masks
+  if value_map is None:
+    return topdown, masks, topdown                                                       # maps.py:333-334
+  hcanvas = torch.zeros((b, dc, int(map_height), int(map_width)), dtype=torch.float32, device=dev)
+  height, _ = project(coords, heights, flat_mask, hcanvas, fill_value=NINF, reduction=Reduction.max, device=dev)
+  return topdown, masks, torch.broadcast_to(height, topdown.shape)                       # maps.py:349
 
 
 def camera_affine_grid(

@@ -46,14 +46,19 @@ class Reduction(str, enum.Enum):
       return cls.max
 
 
-def _reduction_code(reduction) -> int:
+_RED_CODES = {Reduction.max: 0, Reduction.min: 1, Reduction.sum: 2, Reduction.mean: 3, Reduction.prod: 4}
+
+
+def _reduction_code(reduction, fused: bool = True) -> int:
+  """Kernel code of a Reduction.  The fused kernels (projection, map fusion) implement max and min;
+  scatter_tensor / project implement all five (fused=False)."""
   red = Reduction(reduction)
-  if red is Reduction.max:
-    return 0
-  if red is Reduction.min:
-    return 1
-  raise NotImplementedError(
-    f"Reduction.{red.value} is not implemented by the B200 kernels yet (max and min are)")
+  code = _RED_CODES[red]
+  if fused and code > 1:
+    raise NotImplementedError(
+      f"Reduction.{red.value} is not implemented by this fused kernel (max and min are); "
+      "scatter_tensor / project / orth_project handle it through the scatter kernel")
+  return code
 
 
 @dataclass
@@ -188,7 +193,7 @@ def scatter_tensor(canvas: torch.Tensor, indices: torch.Tensor, values: torch.Te
                    _validate_args: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
   """Scatter-reduce `values` (b..., N) into an n-D `canvas` (b..., d1..dn) at `indices`
   (b..., N, n); returns the new canvas and the "cell changed" mask (utils.py:389-492)."""
-  red = _reduction_code(reduction)
+  red = _reduction_code(reduction, fused=False)
   dev = _device_of(canvas, indices, values)
   canvas = to_tensor(canvas).to(device=dev, dtype=torch.float32)
   indices = to_tensor(indices).to(device=dev, dtype=torch.int64)

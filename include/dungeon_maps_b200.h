@@ -241,7 +241,10 @@ int dm_map_dequantize_f32(const float* x_bin, const float* z_bin, const float* w
 /* scatter_tensor utils.py:389-492 / project maps.py:1089-1173 for 2-D canvases:
  * values (B, N) f32, coords (B, N, 2) int64 [row, col], valid (B, N) u8 or NULL,
  * canvas_in (B, Mh, Mw) f32 (ignored / may be NULL when has_fill), canvas_out (B, Mh, Mw) f32,
- * mask (B, Mh, Mw) u8 out ("changed" vs the starting canvas).  reduction 0 max, 1 min. */
+ * mask (B, Mh, Mw) u8 out ("changed" vs the starting canvas).
+ * reduction (utils.py:44-76): 0 max, 1 min, 2 sum, 3 mean, 4 prod.  max / min are exact; sum / mean / prod use float
+ * atomics (hit order differs from the reference's index order: equal to rounding).  mean follows torch_scatter:
+ * (starting canvas + sum of hits) / max(number of hits, 1). */
 int dm_scatter_f32(const float* values, const int64_t* coords, const uint8_t* valid, int64_t B,
                    int64_t N, int32_t Mh, int32_t Mw, int32_t has_fill, float fill_value,
                    int32_t reduction, const float* canvas_in, float* canvas_out, uint8_t* mask,

@@ -295,21 +295,30 @@ int dmo_map_dequantize(const float* xb, const float* zb, const float* woff, cons
 int dmo_scatter(const float* values, const int64_t* coords, const uint8_t* valid, int64_t B,
                 int64_t N, int32_t Mh, int32_t Mw, int32_t has_fill, float fill, int32_t reduction,
                 float* canvas, uint8_t* mask) {
+  /* reduction (utils.py:44-76): 0 max, 1 min, 2 sum, 3 mean, 4 prod; hits are applied in index order like
+   * torch_scatter's CPU loops.  mean (torch_scatter.scatter_mean with out=): the starting canvas takes part in
+   * the sum, not in the count; count is clamped to >= 1. */
   const int64_t M = (int64_t)Mh * Mw;
   float* before = (float*)malloc(sizeof(float) * (size_t)M);
-  if (!before) return -1;
+  int32_t* count = (int32_t*)malloc(sizeof(int32_t) * (size_t)M);
+  if (!before || !count) { free(before); free(count); return -1; }
   for (int64_t s = 0; s < B; ++s) {
     float* cv = canvas + s * M;
     if (has_fill) for (int64_t i = 0; i < M; ++i) cv[i] = fill;
     memcpy(before, cv, sizeof(float) * (size_t)M);
+    memset(count, 0, sizeof(int32_t) * (size_t)M);
     for (int64_t i = 0; i < N; ++i) {
       if (valid && !valid[s * N + i]) continue;
       const int64_t r = coords[(s * N + i) * 2], c = coords[(s * N + i) * 2 + 1];
       if (r < 0 || r >= Mh || c < 0 || c >= Mw) continue;
       float* t = &cv[r * Mw + c];
       const float v = values[s * N + i];
-      if (better(v, *t, reduction)) *t = v;
+      if (reduction == 2 || reduction == 3) { *t = *t + v; count[r * Mw + c] += 1; }
+      else if (reduction == 4) *t = *t * v;
+      else if (better(v, *t, reduction)) *t = v;
     }
+    if (reduction == 3)
+      for (int64_t i = 0; i < M; ++i) cv[i] = cv[i] / (float)(count[i] < 1 ? 1 : count[i]);
     for (int64_t i = 0; i < M; ++i) {
       float d = fabsf(cv[i] - before[i]);
       if (isnan(d)) d = 0.0f;
@@ -317,6 +326,7 @@ int dmo_scatter(const float* values, const int64_t* coords, const uint8_t* valid
     }
   }
   free(before);
+  free(count);
   return 0;
 }
 

@@ -315,7 +315,7 @@ def scatter(values, coords, valid, canvas, fill_value, reduction=None):
   rc = lib().dmo_scatter(_p(values), _p(coords), _p(valid), ctypes.c_int64(B), ctypes.c_int64(N),
                          Mh, Mw, int(fill_value is not None),
                          ctypes.c_float(f32(0. if fill_value is None else fill_value)),
-                         {"max": 0, "min": 1}[red], _p(cv), _p(mask))
+                         {"max": 0, "min": 1, "sum": 2, "mean": 3, "prod": 4}[red], _p(cv), _p(mask))
   assert rc == 0
   return cv, mask.astype(bool)
 

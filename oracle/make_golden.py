@@ -312,6 +312,41 @@ def canvas_cases():
   run("canvas_values_fill0", 3, 3, fill_value=0.)
 
 
+# ------------------------------------------------------------------ sum / mean / prod reductions
+
+def reduce_cases():
+  """Reduction.sum / mean / prod (utils.py:70-76) through project() and orth_project().  sum and prod run on the
+  shim's scatter_reduce_ (exact semantics of torch_scatter with out=); mean on the restated scatter_mean."""
+  arrays = {}
+  N, Mh, Mw = 500, 9, 11
+  vals = synth.uniform((2, 3, N), 405, -3., 3.)
+  rows = (synth.hash_u24(2 * N, 406) % (Mh + 4)).reshape(2, 1, N) - 2
+  cols = (synth.hash_u24(2 * N, 407) % (Mw + 4)).reshape(2, 1, N) - 2
+  coords = torch.stack((rows, cols), -1)
+  mk = synth.uniform((2, 1, N), 408) > 0.25
+  canvas0 = synth.uniform((2, 3, Mh, Mw), 409, -1., 1.)
+  arrays.update(sc_vals=vals, sc_coords=coords, sc_valid=mk, sc_canvas=canvas0)
+  tags = (("zero_sum", 0., "sum"), ("none_sum", None, "sum"), ("one_prod", 1., "prod"), ("none_prod", None, "prod"),
+          ("zero_mean", 0., "mean"), ("none_mean", None, "mean"))
+  for tag, fill, red in tags:
+    cv, m = dm.project(coords=coords.clone(), values=vals, masks=mk, canvas=canvas0.clone(), fill_value=fill,
+                       reduction=red, _validate_args=False)
+    arrays[f"sc_out_{tag}"], arrays[f"sc_mask_{tag}"] = cv, m
+  H, W = 48, 64
+  depth = synth.room_depth(1, H, W, HFOV, PITCH, 0.88, synth.poses(1, 61), seed=61)
+  values = synth.uniform((1, 2, H, W), 62, 0.5, 1.5)
+  pose = synth.poses(1, 61)
+  kw = dict(map_res=0.1, map_width=50, map_height=50, trunc_depth_min=0.15, trunc_depth_max=5.05,
+            trunc_height_max=None, clip_border=2, to_global=False, flip_h=True, get_height_map=True, **intr(W, H))
+  arrays.update(depth=depth, values=values, pose=pose)
+  for red, fill in (("sum", 0.), ("mean", 0.), ("prod", 1.)):
+    out = dm.orth_project(depth_map=depth, value_map=values, valid_map=None, cam_pose=pose, width_offset=torch.tensor([25.]),
+                          height_offset=torch.tensor([0.]), cam_pitch=torch.tensor([PITCH]), cam_height=torch.tensor([0.88]),
+                          fill_value=fill, reduction=red, **kw)
+    arrays[f"orth_top_{red}"], arrays[f"orth_mask_{red}"], arrays[f"orth_height_{red}"] = out[0], out[1], out[2][:, :1].contiguous()
+  save("reduce", dict(kind="reductions", scatter_tags=[list(t) for t in tags], kwargs=kw, H=H, W=W), **arrays)
+
+
 # ------------------------------------------------------------------ primitives
 
 def primitive_cases():
@@ -419,10 +454,11 @@ def crop_cases():
 
 if __name__ == "__main__":
   os.makedirs(OUT, exist_ok=True)
-  which = sys.argv[1:] or ["orth", "flow", "builder", "canvas", "prim", "crop"]
+  which = sys.argv[1:] or ["orth", "flow", "builder", "canvas", "reduce", "prim", "crop"]
   if "orth" in which: orth_cases()
   if "flow" in which: flow_cases()
   if "builder" in which: builder_cases()
   if "canvas" in which: canvas_cases()
+  if "reduce" in which: reduce_cases()
   if "prim" in which: primitive_cases()
   if "crop" in which: crop_cases()

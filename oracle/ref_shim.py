@@ -7,7 +7,7 @@ installed.  A stand-in is registered first: scatter_{max,min,add,mul} with an
 `out=` tensor are `out.scatter_reduce_(dim, index.expand_as(src), src, reduce,
 include_self=True)`, which for max/min is semantically identical to
 torch_scatter (the existing `out` participates, the result is order-independent).
-scatter_mean is not equivalent and raises.
+scatter_mean is restated from torch_scatter's published source (unpinned, see _mean).
 """
 import sys
 import types
@@ -25,8 +25,17 @@ def _make(reduce: str):
   return scatter
 
 
-def _mean(*args, **kwargs):
-  raise NotImplementedError("scatter_mean has no faithful stand-in (SURVEY.md §8c)")
+def _mean(src, index, dim=-1, out=None, dim_size=None):
+  """torch_scatter.scatter_mean restated from its published source (torch_scatter/scatter.py, 2.x: scatter_sum
+  into out, scatter_sum of ones into a fresh count, count.clamp_(1), out.true_divide_(count)).  The package is not
+  installed here, so this stand-in is NOT pinned against the real one: parity of Reduction.mean is unpinned."""
+  assert out is not None, "the reference always passes out="
+  idx = index.expand_as(src)
+  out.scatter_add_(dim, idx, src)
+  count = torch.zeros_like(out).scatter_add_(dim, idx, torch.ones_like(src))
+  count.clamp_(min=1)
+  out.true_divide_(count)
+  return out
 
 
 def load_reference():

@@ -42,6 +42,6 @@ if [ "$2" = full ]; then
   timeout 600 $FULL -k regex:"flow_" -s 4 -c 1 -o gpurun_out/prof_flow_${TAG} python bench.py --workload flow --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 2 > gpurun_out/ncu_full_flow_${TAG}.log 2>&1
   tail -2 gpurun_out/ncu_full_flow_${TAG}.log
   # the merge kernels of builder step 30 (world map fully grown by then)
-  timeout 600 $FULL -k regex:"fuse_|changed_" -s 150 -c 5 -o gpurun_out/prof_fuse_${TAG} python bench.py --workload builder --steps 40 --warmup 3 --no-cpu-baseline --e2e-steps 2 > gpurun_out/ncu_full_fuse_${TAG}.log 2>&1
+  timeout 600 $FULL -k regex:"fuse_|changed_" -s 150 -c 13 -o gpurun_out/prof_fuse_${TAG} python bench.py --workload builder --steps 40 --warmup 3 --no-cpu-baseline --e2e-steps 2 > gpurun_out/ncu_full_fuse_${TAG}.log 2>&1
   tail -2 gpurun_out/ncu_full_fuse_${TAG}.log
 fi

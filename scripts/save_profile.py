@@ -64,7 +64,7 @@ def raw_rows(rep):
 
 traffic_path = os.path.join(P, "traffic.json")
 traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
-for what, pattern, n_kernels in (("proj", "proj_ws", 1), ("flow", "flow_", 1), ("fuse", "fuse_|changed_", 5)):
+for what, pattern, n_kernels in (("proj", "proj_ws", 1), ("flow", "flow_", 1), ("fuse", "fuse_|changed_", 7)):
   rep = os.path.join(G, f"prof_{what}_{run}.ncu-rep")
   if not os.path.exists(rep):
     continue
@@ -85,14 +85,12 @@ for what, pattern, n_kernels in (("proj", "proj_ws", 1), ("flow", "flow_", 1), (
                        "duration_us_under_ncu": r["us"]}
   else:  # one merge = bbox_init + bbox + fill + scatter: sum the consecutive kernels of one step
     names = [r["kernel"] for r in rows]
-    want = ["fuse_bbox_kernel", "fuse_fill_kernel", "fuse_scatter_kernel"]
-    for i in range(len(names) - 2):
-      if names[i:i + 3] == want:
-        step = rows[i:i + 3]
-        traffic["builder"] = {"kernels": want, "run": run,
-                              "dram_bytes_per_step": sum(r["rd"] + r["wr"] for r in step),
-                              "duration_us_under_ncu": sum(r["us"] for r in step)}
-        break
+    inits = [i for i, k in enumerate(names) if k == "fuse_bbox_init"]
+    if len(inits) >= 2:  # one complete merge: everything between two bbox_init launches
+      step = rows[inits[0]:inits[1]]
+      traffic["builder"] = {"kernels": [r["kernel"] for r in step], "run": run,
+                            "dram_bytes_per_step": sum(r["rd"] + r["wr"] for r in step),
+                            "duration_us_under_ncu": sum(r["us"] for r in step)}
   print(what, "traffic ok")
 json.dump(traffic, open(traffic_path, "w"), indent=1)
 

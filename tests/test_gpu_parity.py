@@ -144,10 +144,10 @@ def test_orth_project_edge_shapes():
   top, mask, _ = dmap.orth_project(torch.from_numpy(depth), None, None, [0., 0., 0.], 4., 0., PITCH, 0.88,
                                    device="cuda", **dict(k, focal_x=5., focal_y=5., center_x=3.5, center_y=3.))
   assert (npy(top) == 0.25).all() and not npy(mask).any()
-  # unsupported reductions say so
-  with pytest.raises(NotImplementedError):
+  # an unknown reduction is a ValueError like the reference's Reduction(...) (utils.py:52-67)
+  with pytest.raises(ValueError):
     dmap.orth_project(torch.from_numpy(depth), None, None, [0., 0., 0.], 4., 0., PITCH, 0.88, device="cuda",
-                      **dict(k, reduction="sum", focal_x=5., focal_y=5., center_x=3.5, center_y=3.))
+                      **dict(k, reduction="median", focal_x=5., focal_y=5., center_x=3.5, center_y=3.))
 
 
 @pytest.mark.parametrize("C,get_height,reduction,to_global", [(40, True, None, False), (33, False, "min", True),
@@ -302,6 +302,35 @@ def test_primitives_match_reference():
                        canvas_masks=cu(g["sc_canvas_masks"]), fill_value=-np.inf)
   assert_same(npy(m), g["sc_mask_or"], "project canvas_masks")
   assert_same(npy(dmap.utils.ravel_index(torch.tensor([[3, 2, 3], [0, 2, 1]]), (6, 5, 4))), g["ravel"], "ravel")
+
+
+def _close(got, want, what, rtol=1e-5, atol=1e-6):
+  """sum / mean / prod accumulate with float atomics: hit order differs from the reference's index order."""
+  got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+  assert got.shape == want.shape, f"{what}: shape {got.shape} != {want.shape}"
+  both_inf = np.isinf(got) & np.isinf(want) & (np.sign(got) == np.sign(want))
+  ok = both_inf | (np.isnan(got) & np.isnan(want)) | (np.abs(got - want) <= atol + rtol * np.abs(want))
+  assert ok.all(), f"{what}: {np.count_nonzero(~ok)} / {ok.size} elements differ beyond rtol {rtol}"
+
+
+def test_sum_mean_prod_reductions_match_reference():
+  """Reduction.sum / mean / prod through project() and orth_project(): equal to the reference
+  within 1e-5 relative (float atomics reorder the additions); masks, which are exact either way, bit-for-bit."""
+  g = Golden("reduce")
+  cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+  for tag, fill, red in g.meta["scatter_tags"]:
+    cv, m = dmap.project(cu(g["sc_coords"]), cu(g["sc_vals"]), cu(g["sc_valid"]), cu(g["sc_canvas"]),
+                         fill_value=fill, reduction=red)
+    _close(npy(cv), g[f"sc_out_{tag}"], f"project {tag}")
+    assert (npy(m) != g[f"sc_mask_{tag}"]).mean() < 0.01, f"project mask {tag}"
+  kw = g.kwargs
+  for red, fill in (("sum", 0.), ("mean", 0.), ("prod", 1.)):
+    top, mask, hgt = dmap.orth_project(cu(g["depth"]), cu(g["values"]), None, g["pose"], 25., 0., PITCH, 0.88,
+                                       fill_value=fill, reduction=red, device="cuda", **kw)
+    _close(npy(top), g[f"orth_top_{red}"], f"orth_project {red} topdown")
+    assert (npy(mask) != g[f"orth_mask_{red}"]).mean() < 0.01, f"orth_project {red} mask"
+    assert_same(npy(hgt[:, :1]), g[f"orth_height_{red}"], f"orth_project {red} height (max, exact)")
+    assert hgt.shape == top.shape and hgt.stride(1) == 0, "height_map is a stride-0 expand (maps.py:349)"
 
 
 @pytest.mark.parametrize("name", names("builder_"))

@@ -129,6 +129,16 @@ def test_primitives_match_reference():
     assert_same(m, g[f"sc_mask_{tag}"], f"scatter mask {tag}")
 
 
+def test_sum_mean_prod_scatter_matches_reference():
+  """Reduction.sum / mean / prod of scatter_tensor (utils.py:70-76, 389-492): the oracle applies the hits in index
+  order like the reference's CPU scatter, so even the float sums are bit-identical here."""
+  g = Golden("reduce")
+  for tag, fill, red in g.meta["scatter_tags"]:
+    cv, m = orc.scatter(g["sc_vals"], g["sc_coords"], g["sc_valid"], g["sc_canvas"], fill, red)
+    assert_same(cv, g[f"sc_out_{tag}"], f"scatter {tag}")
+    assert_same(m, g[f"sc_mask_{tag}"], f"scatter mask {tag}")
+
+
 def _builder_sources(g, t, C, to_global):
   """(world map after step t-1, local map of step t) as oracle FuseSource objects."""
   srcs = []
