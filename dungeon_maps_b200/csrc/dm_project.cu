@@ -438,7 +438,11 @@ __device__ __forceinline__ void st_flag(uint32_t* p) {
 }
 // fire-and-forget reduction (RED, never the returning ATOM form)
 __device__ __forceinline__ void red_max_u32(uint32_t* p, uint32_t v) {
+#ifdef DM_ABL_NORED  // ablation build (wrong results): what the kernel costs without its REDs
+  asm volatile("" ::"l"(p), "r"(v) : "memory");
+#else
   asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#endif
 }
 // Predicated reduction: no branch, no reconvergence bookkeeping around the RED.
 __device__ __forceinline__ void red_max_u32_if(bool pred, uint32_t* p, uint32_t v) {
@@ -512,7 +516,7 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
                                               const uint8_t* __restrict__ vplane, float* vals, int* lcell,
                                               uint32_t* __restrict__ acc, uint32_t slot_off,
                                               uint32_t* __restrict__ slot_flags, int cw, int lane,
-                                              long long* tprof) {
+                                              uint64_t* full_vals, uint32_t phase, long long* tprof) {
   // acc is the kernel parameter (uniform); every RED address is acc + a 32-bit word offset
   [[maybe_unused]] const long long tp0 = DM_CLK();
   constexpr int RS = 128 * WW + 4;
@@ -601,6 +605,11 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
     if (t2) zrow[o2] = y[2];
     if (t3) zrow[o3] = y[3];
   }
+  // phase A needed the depth row only; the value rows (their own barrier) had this long to arrive
+  mbar_wait(full_vals, phase);
+#ifdef DM_ABL_NOB  // ablation build (wrong results): load pipeline + phase A + resolve only
+  return;
+#endif
   [[maybe_unused]] const long long tp1 = DM_CLK();
   // ---- B1: channel loop at full lane utilisation, compaction in place
   const float neutral = cfg.fill_value;  // padding value: never beats fill → never emitted
@@ -815,8 +824,9 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
   // one stage per CTA: latency is hidden by the 5-6 CTAs resident per SM, not by an in-CTA ring
   unsigned char* stage = smem;
   unsigned char* tail = smem + d.stage_bytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* full = reinterpret_cast<uint64_t*>(tail);        // item + depth row of a projection tile
   uint64_t* empty = full + 1;
+  uint64_t* full_vals = reinterpret_cast<uint64_t*>(tail + 24);  // value rows of a projection tile
   WsItem* item = reinterpret_cast<WsItem*>(tail + 32);
   DmProjSample* sps = reinterpret_cast<DmProjSample*>(tail + 64);
 
@@ -849,6 +859,7 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
   if (tid == 0) {
     *occ_count = 0;
     mbar_init(full, 1);
+    mbar_init(full_vals, 1);
     mbar_init(empty, kWsWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -938,17 +949,18 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
         const uint32_t row_bytes = (uint32_t)npx * 4u;
         if (lane == 0) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_expect_tx(full, row_bytes * (uint32_t)d.rows);
+          mbar_expect_tx(full, row_bytes);
+          if (cfg.C > 0) mbar_expect_tx(full_vals, row_bytes * (uint32_t)cfg.C); else mbar_arrive(full_vals);
         }
         __syncwarp();
         float* vals = reinterpret_cast<float*>(stage);
-        for (int row = lane; row < d.rows; row += 32) {
-          const float* src = row < cfg.C ? values + ((size_t)it.frame * cfg.C + row) * N + it.tile0
-                                         : depth + (size_t)it.frame * N + it.tile0;
-          bulk_g2s(vals + row * RS, src, row_bytes, full, policy);
-        }
+        // the depth row goes first and completes `full` on its own: the consumers run phase A (cells, heights,
+        // runlets) while the value rows are still in flight
+        if (lane == 0) bulk_g2s(vals + cfg.C * RS, depth + (size_t)it.frame * N + it.tile0, row_bytes, full, policy);
+        for (int row = lane; row < cfg.C; row += 32)
+          bulk_g2s(vals + row * RS, values + ((size_t)it.frame * cfg.C + row) * N + it.tile0, row_bytes, full_vals, policy);
       } else {
-        if (lane == 0) mbar_arrive(full);
+        if (lane == 0) { mbar_arrive(full); mbar_arrive(full_vals); }
       }
       if (!pending) publish_prev();  // off the critical path: the next item is already on its way
       pend_kind = (it.kind == kItemProj || it.kind == kItemResolve) ? it.kind : kItemNone;
@@ -1004,7 +1016,8 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
           const int slot = it.frame % ring;
           ws_proj_slice<FAST, IS_MIN, WW>(cfg, d, it, *sps, rcp, valid ? valid + (size_t)it.frame * N : nullptr, vals,
                                       lcell, acc, (uint32_t)slot * (uint32_t)d.slot_words,
-                                      flags + (size_t)slot * d.nsl * kFlagStride, warp, lane, cp);
+                                      flags + (size_t)slot * d.nsl * kFlagStride, warp, lane, full_vals,
+                                      (uses - 1u) & 1u, cp);
 #ifdef DM_PROFILE
           cp[4] += tc1 - tc0; cp[7] += 1;
 #endif
