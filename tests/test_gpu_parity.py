@@ -173,6 +173,23 @@ def test_orth_project_many_channels(C, get_height, reduction, to_global):
       assert_same(npy(got[2][:, :1]), want[2][:, :1], f"height rep{rep}")
 
 
+def test_orth_project_config5_shapes():
+  """BASELINE config 5's frame shape (1280x720 depth + 40 semantic channels → 400x400), a few frames bit-exact."""
+  b, H, W, C = 3, 720, 1280, 40
+  depth, values, pose = synth.frames("room", b, H, W, C, seed=5, device="cuda")
+  proj = dmap.MapProjector(width=W, height=H, hfov=HFOV, cam_pose=[0., 0., 0.], width_offset=200., height_offset=0.,
+                           cam_pitch=PITCH, cam_height=0.88, map_res=0.03, map_width=400, map_height=400,
+                           trunc_depth_min=0.15, trunc_depth_max=5.05, clip_border=10, to_global=False,
+                           fill_value=dmap.NINF)
+  top, mask, hgt = proj.orth_project(depth, values, cam_pose=pose, get_height_map=True)
+  k = proj.cam_params
+  want = orc.orth_project(npy(depth), npy(values), None, npy(pose), 200., 0., PITCH, 0.88, 0.03, 400, 400,
+                          k.fx, k.fy, k.cx, k.cy, 0.15, 5.05, None, 10, False, True, -np.inf, None, True, threads=3)
+  assert_same(npy(top), want[0], "topdown")
+  assert_same(npy(mask), want[1], "mask")
+  assert_same(npy(hgt[:, :1]), want[2], "height")
+
+
 def test_orth_project_depth_channels_fold_into_batch():
   H, W = 20, 24
   intr = orc.intrinsics(W, H, HFOV)
@@ -246,6 +263,35 @@ def test_camera_affine_grid_480x640_and_flow():
   proj = dmap.MapProjector(width=64, height=48, hfov=HFOV, cam_pitch=PITCH, cam_height=0.88)
   flow = dmap.compute_ego_flow(proj, torch.from_numpy(g2["depth"]), g2["pose"])
   assert_same(npy(flow), g2["out_flow"], "ego flow")
+
+
+def test_camera_affine_grid_full_config3():
+  """BASELINE config 3 at full size (256 x 480x640, random pose deltas): frames bit-exact against the oracle —
+  among them frames salted with NaN / inf / zero / negative / huge depths, which leave the packed straight-line
+  path for the generic one inside the same kernel — plus size-independent properties on the whole batch."""
+  b, H, W = 256, 480, 640
+  depth, _, pose = synth.frames("room", b, H, W, 0, seed=11, device="cuda")
+  flat = depth[5].view(-1)
+  flat[::17] = float("nan"); flat[5::29] = float("inf"); flat[3::31] = 0.0; flat[7::37] = -1.5
+  flat[11::41] = float("-inf"); flat[13::43] = 1e30; flat[1::47] = 1e-30
+  delta = (pose * torch.tensor([0.25, 0.25, 0.1], device="cuda")).cpu()
+  delta[9] = 0.0                                 # no motion
+  delta[10, 2] = 0.0005                          # yaw inside the |a| <= 0.001 clamp (utils.py:323-324)
+  proj = dmap.MapProjector(width=W, height=H, hfov=HFOV, cam_pitch=PITCH, cam_height=0.88)
+  grid = proj.camera_affine_grid(depth, delta)
+  assert grid.shape == (b, 1, H, W, 2)
+  assert torch.equal(grid.nan_to_num(), proj.camera_affine_grid(depth, delta).nan_to_num())   # deterministic
+  sel = [0, 5, 9, 10, 255]
+  k = proj.cam_params
+  want = orc.camera_affine_grid(npy(depth[sel]), delta[sel].numpy(), PITCH, 0.88, k.fx, k.fy, k.cx, k.cy, threads=5)
+  assert_same(npy(grid[sel]), want, "grid slice")
+  # no motion: every pixel lands on itself (up to the rounding of the round trip)
+  cols = torch.arange(W, dtype=torch.float32, device="cuda").view(1, W)
+  rows = torch.arange(H, dtype=torch.float32, device="cuda").view(H, 1)
+  assert (grid[9, 0, ..., 0] - cols).abs().max() < 2e-3 and (grid[9, 0, ..., 1] - rows).abs().max() < 2e-3
+  # the demo's ego flow is (x - gx, -(y - gy)) of the same grid (demos/ego_flow/run.py:86-89)
+  flow = dmap.compute_ego_flow(proj, depth[:1], delta[:1])
+  assert torch.equal(flow[..., 0], cols - grid[0, 0, ..., 0]) and torch.equal(flow[..., 1], -(rows - grid[0, 0, ..., 1]))
 
 
 def test_camera_affine_grid_odd_shapes_vs_oracle():
@@ -412,6 +458,40 @@ def test_fixed_canvas_builder_random_vs_oracle():
     assert_same(npy(builder.world_map.topdown_map), world["topdown"], f"step {t} topdown")
     assert_same(npy(builder.world_map.mask), world["mask"], f"step {t} mask")
   assert 0 < int(world["mask"].sum()) < world["mask"].size
+
+
+def test_map_builder_config4_shapes_vs_oracle():
+  """BASELINE config 4's shapes (480x640 depth → 400x400 local height maps at 3 cm, merged into a growing
+  global map), 4 environments in one batch (one bounding box over all of them, maps.py:2166-2173), 4 steps: every
+  world map bit-exact against the oracle's restatement of fuse_topdown_maps."""
+  import sys
+  sys.path.insert(0, str(__import__("pathlib").Path(__file__).resolve().parents[1]))
+  from bench import BuilderWorkload
+  b, H, W, T = 4, 480, 640, 4
+  poses = BuilderWorkload.walk(b, T, seed=2, half=4.0)
+  proj = dmap.MapProjector(width=W, height=H, hfov=HFOV, cam_pose=[0., 0., 0.], width_offset=0., height_offset=0.,
+                           cam_pitch=PITCH, cam_height=0.88, map_res=0.03, map_width=400, map_height=400,
+                           trunc_depth_min=0.15, trunc_depth_max=5.05, clip_border=10, fill_value=dmap.NINF,
+                           to_global=True, device="cuda")
+  builder = dmap.MapBuilder(map_projector=proj)
+  world = None
+  for t in range(T):
+    depth = synth.room_depth(b, H, W, HFOV, PITCH, 0.88, poses[t].cuda(), seed=2, half=6.0, device="cuda")
+    local = builder.step(depth, cam_pose=poses[t], to_global=False, width_offset=200., height_offset=0.,
+                         map_width=400, map_height=400)
+    p = poses[t].numpy()
+    src = [orc.FuseSource(npy(local.height_map), npy(local.mask), None, 200., 0., 0.03, True, False, p)]
+    if world is not None:
+      src.insert(0, orc.FuseSource(world["height"], world["mask"], None, world["width_offset"], world["height_offset"],
+                                   0.03, True, True, p))
+    world = orc.fuse(src, True, p, 0.03, True)
+    wm = builder.world_map
+    assert [wm.proj.map_height, wm.proj.map_width] == [world["map_height"], world["map_width"]], f"step {t} shape"
+    assert_same(np.asarray(wm.proj.width_offset, np.float32).reshape(()), np.float32(world["width_offset"]), "woff")
+    assert_same(np.asarray(wm.proj.height_offset, np.float32).reshape(()), np.float32(world["height_offset"]), "hoff")
+    assert_same(npy(wm.topdown_map), world["topdown"], f"step {t} world")
+    assert_same(npy(wm.mask), world["mask"], f"step {t} world mask")
+  assert wm.mask.any(dim=(1, 2, 3)).all()
 
 
 def test_crop_matches_reference():
