@@ -23,10 +23,15 @@ STEP_WORDS = 16
 def host_f32(x, shape_tail=()) -> torch.Tensor:
   """Any scalar / list / ndarray / tensor (any device) → float32 CPU tensor (-1, *shape_tail)."""
   if torch.is_tensor(x):
-    t = x.detach().to(device="cpu", dtype=torch.float32)
+    t = x.detach()
+    if t.dtype is not torch.float32 or t.device.type != "cpu":
+      t = t.to(device="cpu", dtype=torch.float32)
   else:
     t = torch.as_tensor(np.asarray(x, dtype=np.float32))
-  return t.reshape((-1,) + tuple(shape_tail))
+  want = (-1,) + tuple(shape_tail)
+  if t.dim() == len(want) and tuple(t.shape[1:]) == want[1:]:
+    return t
+  return t.reshape(want)
 
 
 def per_sample(x, b: int, shape_tail=(), what: str = "argument") -> torch.Tensor:
@@ -184,6 +189,43 @@ def fast_steps(samples: torch.Tensor) -> int:
   return 2 if global_ok else 0
 
 
+class _PinnedRing:
+  """Pinned staging slots for the small per-call parameter blocks.  `tensor.to(device)` from pageable memory
+  synchronises the stream (torch waits for the copy, i.e. for everything queued before it), which would
+  serialise the host with the GPU once per call whenever a pose changes; a copy from a pinned slot is queued
+  like a kernel.  A slot is re-used `slots` uploads later, after waiting on the event recorded behind its copy."""
+
+  def __init__(self, slots: int = 64, slot_bytes: int = 1 << 16):
+    self.slots, self.slot_bytes = slots, slot_bytes
+    self._bufs, self._events, self._next = {}, {}, {}
+
+  def to_device(self, host: torch.Tensor, device: torch.device) -> torch.Tensor:
+    nbytes = host.numel() * host.element_size()
+    if nbytes == 0 or nbytes > self.slot_bytes:
+      return host.to(device)
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in self._bufs:
+      self._bufs[key] = [None] * self.slots
+      self._events[key] = [None] * self.slots
+      self._next[key] = 0
+    i = self._next[key]
+    self._next[key] = (i + 1) % self.slots
+    if self._bufs[key][i] is None:
+      self._bufs[key][i] = torch.empty(self.slot_bytes, dtype=torch.uint8).pin_memory()
+      self._events[key][i] = torch.cuda.Event()
+    else:
+      self._events[key][i].synchronize()  # the copy that last read this slot has run (it was queued long ago)
+    staged = self._bufs[key][i][:nbytes].view(host.dtype).view(host.shape)
+    staged.copy_(host)
+    dev = torch.empty(host.shape, dtype=host.dtype, device=device)
+    dev.copy_(staged, non_blocking=True)
+    self._events[key][i].record(torch.cuda.current_stream(device))
+    return dev
+
+
+_ring = _PinnedRing()
+
+
 class _DeviceCache:
   """Small LRU of uploaded parameter blocks keyed by their bytes (MapProjector defaults
   repeat call after call)."""
@@ -200,7 +242,7 @@ class _DeviceCache:
     if hit is not None:
       self._d.move_to_end(key)
       return hit
-    dev = host.to(device)
+    dev = _ring.to_device(host, device)
     self._d[key] = dev
     if len(self._d) > self._cap:
       self._d.popitem(last=False)

@@ -11,6 +11,7 @@ There is no CPU path: inputs that are not on a CUDA device are moved to one
 is supported and defined as "the reference applied to every sample"
 (the reference itself raises for batch > 1, utils.py:311-316).
 """
+import copy
 import enum
 import inspect
 from typing import Any, Dict, List, Optional, Tuple, Union
@@ -560,6 +561,7 @@ _CTOR_ARGS = (
   "map_res", "map_width", "map_height", "trunc_depth_min", "trunc_depth_max", "trunc_height_max",
   "clip_border", "to_global", "flip_h", "fill_value", "reduction", "device",
 )
+_CTOR_ARG_SET = frozenset(_CTOR_ARGS)
 
 
 def _with_projector_defaults(fn):
@@ -640,10 +642,18 @@ class MapProjector():
   def clone(self, **overrides) -> "MapProjector":
     """Shallow copy with some constructor arguments replaced (None keeps the stored value),
     maps.py:1349-1404."""
-    unknown = set(overrides) - set(_CTOR_ARGS)
-    if unknown:
-      raise TypeError(f"clone() got unexpected keyword arguments {sorted(unknown)}")
-    return MapProjector(**{name: get(overrides.get(name), getattr(self, name)) for name in _CTOR_ARGS})
+    other = copy.copy(self)  # no constructor run: clones happen several times per MapBuilder step
+    intrinsics_changed = False
+    for name, value in overrides.items():
+      if name not in _CTOR_ARG_SET:
+        raise TypeError(f"clone() got unexpected keyword arguments {sorted(set(overrides) - _CTOR_ARG_SET)}")
+      if value is not None:
+        setattr(other, name, value)
+        intrinsics_changed = intrinsics_changed or name in ("width", "height", "hfov", "vfov")
+    if intrinsics_changed:
+      other.cam_params = utils.get_camera_intrinsics(width=other.width, height=other.height, hfov=other.hfov,
+                                                     vfov=other.vfov)
+    return other
 
   orth_project = _with_projector_defaults(orth_project)
   camera_affine_grid = _with_projector_defaults(camera_affine_grid)
