@@ -64,6 +64,8 @@ struct ProjPlan {
   size_t smem_tile;      // one stage + sample block (plain-load kernel)
   size_t smem_resolve;
   int ws_warps;          // warp-specialised kernel: consumer warps per CTA (tile = 128 px each)
+  int ws_groups;         // ... channel groups a frame's value planes are staged in (each group re-reads the depth row)
+  int ws_cg;             // ... value channels per group
   size_t ws_stage_bytes; // warp-specialised kernel: one stage of 128 * ws_warps pixels
   size_t smem_ws;        // stage + barriers/item/sample block
   size_t workspace_bytes() const { return ctrl_bytes + flag_bytes + slot_words * 4 * (size_t)ring; }
@@ -99,17 +101,34 @@ static ProjPlan make_plan(const DmProjCfg& cfg, int b) {
   p.stage_bytes = st;
   p.smem_tile = st + 256;
   // warp-specialised kernel: 4 consumer warps (512-pixel tiles) while 4 CTAs still fit an SM, else 2 (256-pixel tiles)
-  auto ws_stage = [&](int ww) {
-    size_t ws = ((size_t)p.rows * (128 * ww + 4) * 4 + (size_t)128 * ww * 4 + 127) & ~(size_t)127;
+  auto ws_stage = [&](int ww, int rows) {
+    size_t ws = ((size_t)rows * (128 * ww + 4) * 4 + (size_t)128 * ww * 4 + 127) & ~(size_t)127;
     const size_t ws_res = ((size_t)ww * 64 * p.CP * 4 + 127) & ~(size_t)127;  // ww warps x 64 cells x CP words
     return ws < ws_res ? ws_res : ws;
   };
-  p.ws_warps = (ws_stage(4) + 256 + 1024) * 4 <= (size_t)228 * 1024 ? 4 : 2;
+  auto fits4 = [&](int ww, int rows) { return (ws_stage(ww, rows) + 256 + 1024) * 4 <= (size_t)228 * 1024; };
+  // many value channels: stage them in groups of at most 24 planes (each group a tile of its own that re-reads the
+  // depth row from L2 and repeats phase A), 2 consumer warps per CTA.  Measured at C = 40, 1280x720, ms per 32 frames
+  // (groups x consumer warps): 1x4 2.26, 1x2 1.71, 2x4 1.46, **2x2 1.38**, 3x4 1.54, 3x2 1.59, 4x2 1.89; at C = 16
+  // grouping only costs (2x4: 0.62 ms instead of 0.50).
+  p.ws_warps = 4;
+  p.ws_groups = 1;
+  if (!fits4(4, cfg.C + 1)) {
+    p.ws_groups = (cfg.C + 23) / 24;
+    p.ws_warps = 2;
+  }
   if (const char* e = getenv("DM_WS_WARPS")) {  // kernel experiments only (scripts/time_proj.py)
     const int ww = atoi(e);
     if (ww == 2 || ww == 4) p.ws_warps = ww;
   }
-  p.ws_stage_bytes = ws_stage(p.ws_warps);
+  if (const char* e = getenv("DM_WS_GROUPS")) {
+    const int g = atoi(e);
+    if (g >= 1 && g <= 8) p.ws_groups = g;
+  }
+  if (cfg.C <= 0) p.ws_groups = 1;
+  p.ws_cg = cfg.C > 0 ? (cfg.C + p.ws_groups - 1) / p.ws_groups : 0;
+  p.ws_groups = cfg.C > 0 ? (cfg.C + p.ws_cg - 1) / p.ws_cg : 1;
+  p.ws_stage_bytes = ws_stage(p.ws_warps, p.ws_cg + 1);
   p.smem_ws = p.ws_stage_bytes + 256;
   return p;
 }
@@ -118,6 +137,7 @@ struct ProjDims {
   int Cv, hasH, CU, CP, rows, tile, ring, lag, nsl;
   unsigned long long slot_words;
   unsigned long long stage_bytes;
+  int groups = 1, cg = 0;  // warp-specialised kernel: channel groups per frame, channels per group
 };
 
 // One pixel: validity, cell index (or -1) and the height that goes into the height map.
@@ -396,9 +416,9 @@ __device__ __forceinline__ bool wait_count(const uint32_t* counter, uint32_t tar
 #define DM_CLK() 0ll
 #define DM_ACC(ctrl_, i_, v_) ((void)0)
 #endif
-// WW = consumer warps per CTA (template parameter of the kernel): 4 by default; 2 when the C + 1 staged rows of a
-// 512-pixel tile would leave fewer than 4 CTAs per SM (many value channels) — stages in flight per SM, not pixels per
-// stage, are what keeps HBM busy.  tile = 128 * WW pixels, resolve tile = 64 * WW cells.
+// WW = consumer warps per CTA (template parameter of the kernel): 4 by default; 2, together with channel groups
+// (make_plan), when the C + 1 staged rows of a 512-pixel tile would leave fewer than 4 CTAs per SM (many value
+// channels) — consumer warps per SM are what sets the throughput.  tile = 128 * WW pixels, resolve tile = 64 * WW cells.
 // Measured on the B200 (scripts/exp_ww.sh, ms per 64-frame step, room / iid scene | config 5 shapes, 32 frames):
 //   C = 16: WW 8: 0.511 / 0.582   6: 0.511 / 0.579   4: 0.499 / 0.585   3: 0.541 / 0.632   2: 0.551 / 0.682   1: 0.694 / 1.059
 //   C = 40: WW 8: 2.32            6: 3.01            4: 2.26            3: 2.04            2: 1.87            1: 2.07
@@ -516,7 +536,8 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
                                               const uint8_t* __restrict__ vplane, float* vals, int* lcell,
                                               uint32_t* __restrict__ acc, uint32_t slot_off,
                                               uint32_t* __restrict__ slot_flags, int cw, int lane,
-                                              uint64_t* full_vals, uint32_t phase, long long* tprof) {
+                                              uint64_t* full_vals, uint32_t phase, int ch0, int nch,
+                                              long long* tprof) {
   // acc is the kernel parameter (uniform); every RED address is acc + a 32-bit word offset
   [[maybe_unused]] const long long tp0 = DM_CLK();
   constexpr int RS = 128 * WW + 4;
@@ -524,7 +545,7 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
   const int sb = cw * 128;
   const int q = sb + 4 * lane;
   const int n0 = it.tile0 + q;
-  float* zrow = vals + cfg.C * RS;
+  float* zrow = vals + nch * RS;  // the depth row follows the group's value rows
   int cl[4] = {-1, -1, -1, -1};
   float y[4] = {0.f, 0.f, 0.f, 0.f};
   // ---- A: cells and heights of my 4 pixels
@@ -629,7 +650,7 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
   }
   {
     int c = 0;
-    for (; c + 4 <= cfg.C; c += 4) {
+    for (; c + 4 <= nch; c += 4) {
       float* r0 = vals + c * RS;
       float4 a0 = *reinterpret_cast<const float4*>(r0 + q);
       float4 a1 = *reinterpret_cast<const float4*>(r0 + RS + q);
@@ -651,7 +672,7 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
         r0[pp] = neutral; r0[RS + pp] = neutral; r0[2 * RS + pp] = neutral; r0[3 * RS + pp] = neutral;
       }
     }
-    for (; c < cfg.C; ++c) DM_B1_ROW(vals + c * RS)
+    for (; c < nch; ++c) DM_B1_ROW(vals + c * RS)
   }
 #undef DM_B1_ROW
   __syncwarp();
@@ -659,7 +680,7 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
   // ---- B2: one RED per (runlet, channel); lane = channel keeps a runlet's keys in 1-2 lines
   const int total4 = total + padn;
   if (cfg.C > 0) {
-    const int Cv = d.Cv;
+    const int Cv = nch;  // this group's channels; their keys start at ch0
     const int cu_eff = Cv < 32 ? Cv : 32;
     const int streams = Cv <= 32 ? 32 / Cv : 1;
     const int passes = Cv <= 32 ? 1 : (Cv + 31) / 32;
@@ -672,7 +693,7 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
       if (s >= streams || c >= Cv) continue;
       const float* row = vals + c * RS + sb;
       const int* lc = lcell + sb;
-      const uint32_t off_c = slot_off + (uint32_t)c;
+      const uint32_t off_c = slot_off + (uint32_t)(ch0 + c);
       const float fill = cfg.fill_value;
       for (int i = beg; i < end; i += 4) {
         const uint4 c4 = *reinterpret_cast<const uint4*>(lc + i);
@@ -691,7 +712,7 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
   }
   // lane = runlet for the heights.  Neighbouring runlets of one cell are folded by a segmented scan over the
   // lanes and only the last one of a run issues its RED.
-  if (d.hasH || cfg.C == 0) {
+  if ((d.hasH || cfg.C == 0) && ch0 == 0) {  // once per tile: the first channel group
     const bool hmin = IS_MIN && cfg.C == 0;  // C == 0: the heights are the values (fill / reduction apply)
     const float hfill = cfg.C == 0 ? cfg.fill_value : -INFINITY;  // height channel: max against -inf (maps.py:340-348)
     const uint32_t hoff = slot_off + (cfg.C == 0 ? 0u : (uint32_t)d.Cv);
@@ -832,7 +853,7 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = cfg.H * cfg.W, M = cfg.Mh * cfg.Mw;
-  const int P = (N + kWsTile - 1) / kWsTile;
+  const int P = ((N + kWsTile - 1) / kWsTile) * d.groups;  // projection tickets per frame: tiles x channel groups
   const int R = (M + kWsResolveCells - 1) / kWsResolveCells;
   uint32_t* proj_done = ctrl + kCtrlWords;
   uint32_t* resolve_done = proj_done + b;
@@ -902,7 +923,10 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
       uint32_t dep_target = 0;
       uint32_t spw0 = 0, spw1 = 0;  // my two words of the sample block
       if (it.kind == kItemProj) {
-        it.tile0 = it.idx * kWsTile;
+        const int grp = it.idx % d.groups;  // neighbouring tickets share the tile: its depth row is re-read from L2
+        const int ch0 = grp * d.cg;
+        it._pad = ch0 | (min(d.cg, cfg.C - ch0) << 16);
+        it.tile0 = (it.idx / d.groups) * kWsTile;
         it.r0 = it.tile0 / cfg.W;
         it.c0 = it.tile0 - it.r0 * cfg.W;
         if (it.frame >= ring) { dep = resolve_done + (it.frame - ring); dep_target = (uint32_t)R; }
@@ -947,18 +971,20 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
       if (it.kind == kItemProj) {
         const int npx = min(kWsTile, N - it.tile0);
         const uint32_t row_bytes = (uint32_t)npx * 4u;
+        const int ch0 = it._pad & 0xffff, nch = it._pad >> 16;
         if (lane == 0) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           mbar_expect_tx(full, row_bytes);
-          if (cfg.C > 0) mbar_expect_tx(full_vals, row_bytes * (uint32_t)cfg.C); else mbar_arrive(full_vals);
+          if (nch > 0) mbar_expect_tx(full_vals, row_bytes * (uint32_t)nch); else mbar_arrive(full_vals);
         }
         __syncwarp();
         float* vals = reinterpret_cast<float*>(stage);
         // the depth row goes first and completes `full` on its own: the consumers run phase A (cells, heights,
         // runlets) while the value rows are still in flight
-        if (lane == 0) bulk_g2s(vals + cfg.C * RS, depth + (size_t)it.frame * N + it.tile0, row_bytes, full, policy);
-        for (int row = lane; row < cfg.C; row += 32)
-          bulk_g2s(vals + row * RS, values + ((size_t)it.frame * cfg.C + row) * N + it.tile0, row_bytes, full_vals, policy);
+        if (lane == 0) bulk_g2s(vals + nch * RS, depth + (size_t)it.frame * N + it.tile0, row_bytes, full, policy);
+        for (int row = lane; row < nch; row += 32)
+          bulk_g2s(vals + row * RS, values + ((size_t)it.frame * cfg.C + ch0 + row) * N + it.tile0, row_bytes, full_vals,
+                   policy);
       } else {
         if (lane == 0) { mbar_arrive(full); mbar_arrive(full_vals); }
       }
@@ -1017,7 +1043,7 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
           ws_proj_slice<FAST, IS_MIN, WW>(cfg, d, it, *sps, rcp, valid ? valid + (size_t)it.frame * N : nullptr, vals,
                                       lcell, acc, (uint32_t)slot * (uint32_t)d.slot_words,
                                       flags + (size_t)slot * d.nsl * kFlagStride, warp, lane, full_vals,
-                                      (uses - 1u) & 1u, cp);
+                                      (uses - 1u) & 1u, it._pad & 0xffff, it._pad >> 16, cp);
 #ifdef DM_PROFILE
           cp[4] += tc1 - tc0; cp[7] += 1;
 #endif
@@ -1102,7 +1128,7 @@ extern "C" int dm_orth_project_f32(const float* depth, const float* values, cons
   // the warp-specialised TMA kernel needs 16-byte aligned plane starts / row sizes, pixel quads
   // that do not straddle image rows, and two stages that fit in shared memory
   const int ws_tile = 128 * p.ws_warps, ws_threads = 32 * (p.ws_warps + 1);
-  const long long ws_tiles = (N + ws_tile - 1) / ws_tile;
+  const long long ws_tiles = (long long)((N + ws_tile - 1) / ws_tile) * p.ws_groups;
   const int ws_rtiles = (M + 64 * p.ws_warps - 1) / (64 * p.ws_warps);
   const long long ws_total = (long long)(b + p.lag) * (ws_tiles + ws_rtiles);
   const bool ws_ok = (N % 4 == 0) && (cfg->W % 4 == 0) && aligned(depth, 16) && (!values || aligned(values, 16)) &&
@@ -1112,6 +1138,9 @@ extern "C" int dm_orth_project_f32(const float* depth, const float* values, cons
   if (ws_ok) {
     ProjDims dw = d;
     dw.tile = ws_tile;
+    dw.rows = p.ws_cg + 1;
+    dw.groups = p.ws_groups;
+    dw.cg = p.ws_cg;
     dw.stage_bytes = p.ws_stage_bytes;
     void (*kern)(const float*, const float*, const uint8_t*, const DmProjSample*, DmProjCfg, ProjDims, int,
                  uint32_t*, uint32_t*, uint32_t*, float*, uint8_t*, float*) = nullptr;
