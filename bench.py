@@ -57,6 +57,12 @@ class ClockSampler:
     for line in self.proc.stdout:
       self.rows.append((time.perf_counter(), line.strip()))
 
+  def wait_ready(self, timeout: float = 3.0) -> None:
+    """nvidia-smi needs a moment before its first sample; short timed regions would otherwise see none."""
+    t_end = time.perf_counter() + timeout
+    while self.proc is not None and not self.rows and time.perf_counter() < t_end:
+      time.sleep(0.01)
+
   def stop(self, t0: float, t1: float) -> dict:
     if self.proc is None:
       return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
@@ -474,6 +480,7 @@ def run_ours(args):
   if world > 1:
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group("nccl", device_id=dev)
+    shard.bind_to_gpu_numa_node(local)  # the e2e leg streams GBs through pinned host memory per rank
   barrier = lambda: shard.barrier(dev)
   max_over_ranks = lambda x: shard.max_over_ranks(x, dev)
   sum_over_ranks = lambda x: shard.sum_over_ranks(x, dev)
@@ -489,6 +496,9 @@ def run_ours(args):
     wl.reset_counters()
   barrier()
   sampler = ClockSampler(local) if rank == 0 else None
+  if sampler:
+    sampler.wait_ready()
+  barrier()
   launches0 = nat.launch_count()
   ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   t_wall0 = time.perf_counter()

@@ -90,3 +90,29 @@ def gather_frames(local: torch.Tensor, n_frames: int, dst: int = 0) -> Optional[
   if rank != dst:
     return None
   return torch.cat([b[:h - l] for b, (l, h) in zip(bufs, ranges)], dim=0)
+
+
+def bind_to_gpu_numa_node(local_rank: int) -> Optional[int]:
+  """Host-buffer entries are PCIe-bound: pin this process (and therefore the pinned staging memory it touches
+  first) to the CPUs of the NUMA node the rank's GPU hangs off, so that N ranks do not all stream through one
+  socket's memory.  Returns the node, or None when the topology cannot be read (then nothing is changed)."""
+  try:
+    props = torch.cuda.get_device_properties(local_rank)
+    bdf = f"{int(props.pci_domain_id):04x}:{int(props.pci_bus_id):02x}:{int(props.pci_device_id):02x}.0"
+    with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+      node = int(f.read().strip())
+    if node < 0:
+      return None
+    with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+      cpus = set()
+      for part in f.read().strip().split(","):
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    allowed = cpus & os.sched_getaffinity(0)
+    if not allowed:
+      return None
+    os.sched_setaffinity(0, allowed)
+    return node
+  except Exception:
+    return None
+
