@@ -423,6 +423,10 @@ __device__ __forceinline__ bool wait_count(const uint32_t* counter, uint32_t tar
 //   C = 16: WW 8: 0.511 / 0.582   6: 0.511 / 0.579   4: 0.499 / 0.585   3: 0.541 / 0.632   2: 0.551 / 0.682   1: 0.694 / 1.059
 //   C = 40: WW 8: 2.32            6: 3.01            4: 2.26            3: 2.04            2: 1.87            1: 2.07
 constexpr int kWsMaxWarps = 4;
+#ifndef DM_RES_K
+#define DM_RES_K 2  // 64-cell slices a consumer warp resolves per resolve ticket (measured: 1: 0.494, 2: 0.470, 3: 0.473, 4: 0.485 ms)
+#endif
+constexpr int kResK = DM_RES_K;
 enum { kItemProj = 0, kItemResolve = 1, kItemNone = 2, kItemExit = 3 };
 
 struct WsItem {
@@ -430,19 +434,22 @@ struct WsItem {
 };
 
 // ticket → work item.  Step s holds the P projection tiles of frame s and the R resolve tiles
-// of frame s - lag, interleaved one to one so HBM reads and writes mix evenly.
+// of frame s - lag, interleaved evenly so HBM reads and writes mix.
 __device__ __forceinline__ void decode_ticket(unsigned t, int b, int P, int R, int lag, int* kind, int* frame,
                                               int* idx) {
   const unsigned per = (unsigned)(P + R);
   const int s = (int)(t / per);
   const int j = (int)(t - (unsigned)s * per);
-  const int m = P < R ? P : R;
-  if (j < 2 * m) {
-    *kind = j & 1;
-    *idx = j >> 1;
+  // the R resolve tickets are spread evenly among the P projection tickets of the step (HBM reads and writes
+  // stay mixed whatever the ratio): ticket j is a resolve ticket when floor((j + 1) R / per) steps up
+  const unsigned rb0 = (unsigned)(((unsigned long long)j * (unsigned)R) / per);
+  const unsigned rb1 = (unsigned)(((unsigned long long)(j + 1) * (unsigned)R) / per);
+  if (rb1 > rb0) {
+    *kind = kItemResolve;
+    *idx = (int)rb0;
   } else {
-    *kind = P > R ? kItemProj : kItemResolve;
-    *idx = m + (j - 2 * m);
+    *kind = kItemProj;
+    *idx = j - (int)rb0;
   }
   *frame = *kind == kItemProj ? s : s - lag;
   if (*frame < 0 || *frame >= b) *kind = kItemNone;
@@ -839,7 +846,7 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
                uint32_t* __restrict__ flags, uint32_t* __restrict__ acc, float* __restrict__ topdown,
                uint8_t* __restrict__ mask, float* __restrict__ height) {
   extern __shared__ __align__(128) unsigned char smem[];
-  constexpr int kWsWarps = WW, kWsTile = 128 * WW, kWsResolveCells = 64 * WW;
+  constexpr int kWsWarps = WW, kWsTile = 128 * WW, kWsResolveCells = 64 * WW * kResK;
   constexpr int RS = kWsTile + 4;
   const Rcps rcp{__frcp_rn(cfg.map_res), __frcp_rn(cfg.fx), __frcp_rn(cfg.fy)};
   // one stage per CTA: latency is hidden by the 5-6 CTAs resident per SM, not by an in-CTA ring
@@ -1050,8 +1057,11 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
         } else if (it.kind == kItemResolve) {
           uint32_t* wres = reinterpret_cast<uint32_t*>(stage) + warp * 64 * d.CP;
           const int slot = it.frame % ring;
-          my_flagged += ws_resolve_slice(acc + (size_t)slot * d.slot_words, cfg, d, flags + (size_t)slot * d.nsl * kFlagStride,
-                                         it.frame, it.idx, kWsResolveCells, warp, lane, wres, topdown, mask, height) ? 1u : 0u;
+#pragma unroll 1
+          for (int k = 0; k < kResK; ++k)
+            my_flagged += ws_resolve_slice(acc + (size_t)slot * d.slot_words, cfg, d,
+                                           flags + (size_t)slot * d.nsl * kFlagStride, it.frame, it.idx * kResK + k,
+                                           64 * WW, warp, lane, wres, topdown, mask, height) ? 1u : 0u;
 #ifdef DM_PROFILE
           cp[5] += tc1 - tc0; cp[6] += DM_CLK() - tc1;
 #endif
@@ -1129,7 +1139,7 @@ extern "C" int dm_orth_project_f32(const float* depth, const float* values, cons
   // that do not straddle image rows, and two stages that fit in shared memory
   const int ws_tile = 128 * p.ws_warps, ws_threads = 32 * (p.ws_warps + 1);
   const long long ws_tiles = (long long)((N + ws_tile - 1) / ws_tile) * p.ws_groups;
-  const int ws_rtiles = (M + 64 * p.ws_warps - 1) / (64 * p.ws_warps);
+  const int ws_rtiles = (M + 64 * p.ws_warps * kResK - 1) / (64 * p.ws_warps * kResK);
   const long long ws_total = (long long)(b + p.lag) * (ws_tiles + ws_rtiles);
   const bool ws_ok = (N % 4 == 0) && (cfg->W % 4 == 0) && aligned(depth, 16) && (!values || aligned(values, 16)) &&
                      (!valid || aligned(valid, 4)) && p.smem_ws <= 220 * 1024 && ws_total < (1ll << 31) &&
