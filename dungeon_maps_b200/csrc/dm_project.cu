@@ -39,7 +39,10 @@ constexpr int kSliceCells = 64;                  // cells per sparse-ring flag (
 #endif
 constexpr int kFlagStride = DM_FLAG_STRIDE;      // words between two flags: every tile of a frame stores into the
                                                  // same few hundred flags, so each gets its own 32-byte sector
-constexpr int kMaxRing = 10;                     // frame slots of the accumulation ring
+#ifndef DM_MAX_RING
+#define DM_MAX_RING 10  // measured at config 2 (room / iid ms): 6: 0.573 / 0.656, 8: 0.496 / 0.586, 10: 0.469 / 0.563, 14: 0.476 / 0.579, 20: 0.480 / 0.614
+#endif
+constexpr int kMaxRing = DM_MAX_RING;                     // frame slots of the accumulation ring
 constexpr size_t kRingBudgetBytes = (size_t)1 << 30;  // ... unless that exceeds 1 GiB of workspace
 #ifndef DM_SUSPEND_NS
 #define DM_SUSPEND_NS 20000u
