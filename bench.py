@@ -479,6 +479,7 @@ def run_ours(args):
   dev = torch.device("cuda", local)
   if world > 1:
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line and nothing else
     dist.init_process_group("nccl", device_id=dev)
     shard.bind_to_gpu_numa_node(local)  # the e2e leg streams GBs through pinned host memory per rank
   barrier = lambda: shard.barrier(dev)
