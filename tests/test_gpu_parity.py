@@ -246,6 +246,28 @@ def test_orth_project_host_buffer_entry():
   assert_same(got[1], want[1], "mask")
 
 
+@pytest.mark.parametrize("chunk", ["1", "2", "3"])
+def test_orth_project_host_buffer_pipeline_reuses_slots(chunk, monkeypatch):
+  """More chunks than staging slots (4): every slot of the three-stream pipeline is re-used, with ragged last
+  chunks; results (heights included) must equal the oracle's, call after call."""
+  from dungeon_maps_b200 import hostapi
+  monkeypatch.setenv("DM_HOST_CHUNK", chunk)
+  b, H, W, C = 11, 48, 64, 3
+  depth = synth.iid_depth(b, H, W, seed=77).numpy()
+  values = synth.uniform((b, C, H, W), 78, -2., 2.).numpy()
+  pose = synth.poses(b, 79).numpy()
+  intr = orc.intrinsics(W, H, HFOV)
+  kw = dict(map_res=0.1, map_width=40, map_height=36, focal_x=intr["fx"], focal_y=intr["fy"], center_x=intr["cx"],
+            center_y=intr["cy"], trunc_depth_min=0.15, trunc_depth_max=5.05, trunc_height_max=None, clip_border=2,
+            to_global=False, fill_value=-np.inf, get_height_map=True)
+  want = orc.orth_project(depth, values, None, pose, 20., 0., PITCH, 0.88, **kw)
+  for rep in range(2):
+    got = hostapi.orth_project_host(depth, values, None, pose, 20., 0., PITCH, 0.88, **kw)
+    assert_same(got[0], want[0], f"topdown rep{rep}")
+    assert_same(got[1], want[1], f"mask rep{rep}")
+    assert_same(got[2][:, :1], want[2][:, :1], f"height rep{rep}")
+
+
 @pytest.mark.parametrize("name", ["flow_small", "flow_small_noflip_vfov"])
 def test_camera_affine_grid_matches_reference(name):
   g = Golden(name)
