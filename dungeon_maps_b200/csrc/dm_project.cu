@@ -705,19 +705,27 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
       const int* lc = lcell + sb;
       const uint32_t off_c = slot_off + (uint32_t)(ch0 + c);
       const float fill = cfg.fill_value;
+      // runs longer than a pixel quad arrive as neighbouring runlets of one cell: they are folded and the RED goes
+      // out when the cell changes; (pc, pv) is the runlet that has not been issued yet, carried across the quads of
+      // the list (folding inside a quad only: 70 k REDs per room frame, carried: 56 k; 0.470 -> 0.457 ms)
+      uint32_t pc = 0xffffffffu;
+      float pv = fill;
       for (int i = beg; i < end; i += 4) {
         const uint4 c4 = *reinterpret_cast<const uint4*>(lc + i);
         float4 v4 = *reinterpret_cast<const float4*>(row + i);
-        // runs longer than a pixel quad arrive as neighbouring runlets of one cell: fold them, RED the last
-        const bool m01 = c4.x == c4.y, m12 = c4.y == c4.z, m23 = c4.z == c4.w;
+        const bool mp = pc == c4.x, m01 = c4.x == c4.y, m12 = c4.y == c4.z, m23 = c4.z == c4.w;
+        if (!mp && beats<IS_MIN>(pv, fill)) red_max_u32(acc + (off_c + pc), key_of<IS_MIN>(pv));
+        v4.x = mp ? red2<IS_MIN>(pv, v4.x) : v4.x;
         v4.y = m01 ? red2<IS_MIN>(v4.x, v4.y) : v4.y;
         v4.z = m12 ? red2<IS_MIN>(v4.y, v4.z) : v4.z;
         v4.w = m23 ? red2<IS_MIN>(v4.z, v4.w) : v4.w;
         if (!m01 && beats<IS_MIN>(v4.x, fill)) red_max_u32(acc + (off_c + c4.x), key_of<IS_MIN>(v4.x));
         if (!m12 && beats<IS_MIN>(v4.y, fill)) red_max_u32(acc + (off_c + c4.y), key_of<IS_MIN>(v4.y));
         if (!m23 && beats<IS_MIN>(v4.z, fill)) red_max_u32(acc + (off_c + c4.z), key_of<IS_MIN>(v4.z));
-        if (beats<IS_MIN>(v4.w, fill)) red_max_u32(acc + (off_c + c4.w), key_of<IS_MIN>(v4.w));
+        pc = c4.w;
+        pv = v4.w;
       }
+      if (beats<IS_MIN>(pv, fill)) red_max_u32(acc + (off_c + pc), key_of<IS_MIN>(pv));
     }
   }
   // lane = runlet for the heights.  Neighbouring runlets of one cell are folded by a segmented scan over the
