@@ -1,6 +1,6 @@
 """HOST-buffer entry of the projection: numpy / pinned CPU tensors in, numpy out, through
-`dm_orth_project_host_f32` (host→device copy, kernels, device→host copy pipelined over two
-streams inside the library).  This is what a non-torch host (or the reference's numpy-facing
+`dm_orth_project_host_f32` (host→device copy, kernels, device→host copy as a three-stream
+pipeline inside the library).  This is what a non-torch host (or the reference's numpy-facing
 MapBuilder.step) would call, and what bench.py times as `e2e`.
 """
 from typing import Optional
