@@ -14,6 +14,9 @@
 namespace dm {
 
 constexpr int kFuseThreads = 256;
+// block size of the two scanning passes (bbox, scatter): a block lives as long as its slowest warp, and the valid cells
+// of a plane sit in one corner (config 4, µs per merge of all fuse kernels: 256 threads 343, 128: 323, 64: 334, 32: 349)
+constexpr int kScanThreads = 128;
 constexpr int kMaxSources = 8;
 constexpr int kGroup = 16;  // mask bytes examined per work item (one 128-bit load)
 
@@ -23,28 +26,13 @@ struct PlaneCtx {
   float woff, hoff;
 };
 
-// Walks the valid cells of plane `plane` of `src`: 16 mask bytes per thread and iteration through one aligned
-// 128-bit load.  Most groups of a world map are empty (every environment explored a corner of the batch-wide
-// canvas): those cost one load, one OR and a branch, and the heights / values of empty regions are never read.
-// visit(cell index in the plane, row, col) is instantiated ONCE, in a loop over the set bits (an unrolled
-// 16-way version thrashed the instruction cache: 7 stall_no_instruction cycles per issue in ncu).
-template <typename F>
-__device__ __forceinline__ void visit_bits(const DmFuseSource& src, int o, uint32_t bits, F&& visit) {
-  const int first = o + (__ffs(bits) - 1);
-  int r = first / src.w, c = first - r * src.w, cell = first;
-  bits >>= (__ffs(bits) - 1);
-  while (true) {
-    visit(cell, r, c);
-    bits >>= 1;
-    if (!bits) break;
-    const int skip = __ffs(bits);  // distance to the next valid cell
-    bits >>= skip - 1;
-    cell += skip;
-    c += skip;
-    while (c >= src.w) { c -= src.w; ++r; }
-  }
-}
-
+// Walks the valid cells of plane `plane` of `src`.  A lane examines kAhead groups of 16 mask bytes per round (aligned
+// 128-bit loads, all in flight before the first is looked at), the warp then shares the valid cells it found evenly:
+// cell number i of the round goes to lane i % 32, whichever lane's group it came from.  World maps are sparse — a
+// grown config-4 canvas has ~5 valid cells per 512 examined, and even inside the explored corner they are outlines,
+// not areas — so visiting a lane's own cells one after the other ran the ~150-instruction visitor with 4 of 32 lanes
+// active on average (ncu r01k: 10.7 active threads per instruction, 75 M warp instructions for 1.5 M cells).
+// visit(cell index in the plane, row, col) is instantiated once and reached by the whole warp together.
 __device__ __forceinline__ uint32_t bits_of(const uint4 v) {
   const uint32_t m[4] = {v.x, v.y, v.z, v.w};
   uint32_t bits = 0;
@@ -55,25 +43,73 @@ __device__ __forceinline__ uint32_t bits_of(const uint4 v) {
 
 template <typename F>
 __device__ __forceinline__ void for_valid_cells_of_plane(const DmFuseSource& src, long long plane, F&& visit) {
-  // (four loads in flight per thread were tried: more instructions, no gain — the passes are bound by the work on
-  // the valid cells, not by the latency of the mask loads)
+  constexpr int kAhead = 4;  // groups per lane and round: 64 cells, one bit each in a 64-bit word
   const int n = src.h * src.w;
   const uint8_t* base = src.mask + plane * n;
   const int a0 = (int)(reinterpret_cast<uintptr_t>(base) & 15);  // bytes between the aligned-down start and the plane
   const int groups = (n + a0 + kGroup - 1) / kGroup;
-  for (int g = blockIdx.x * kFuseThreads + threadIdx.x; g < groups; g += gridDim.x * kFuseThreads) {
-    const int o = g * kGroup - a0;  // plane-relative offset of the group's first byte (negative in the head group)
-    uint32_t bits = 0;
-    if (o >= 0 && o + kGroup <= n) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + o));
-      if ((v.x | v.y | v.z | v.w) == 0u) continue;
-      bits = bits_of(v);
-    } else {  // head / tail group of a plane whose start or size is not a multiple of 16: byte loads inside the plane
-      for (int j = 0; j < kGroup; ++j)
-        if (o + j >= 0 && o + j < n && base[o + j]) bits |= 1u << j;
-      if (!bits) continue;
+  const int stride = gridDim.x * kScanThreads;
+  const int lane = threadIdx.x & 31;
+  // warp-uniform loop: gw is the group of lane 0
+  for (int gw = blockIdx.x * kScanThreads + (threadIdx.x & ~31); gw < groups; gw += kAhead * stride) {
+    const int g0 = gw + lane;
+    uint4 v[kAhead];
+#pragma unroll
+    for (int k = 0; k < kAhead; ++k) {
+      const int g = g0 + k * stride;
+      const int o = g * kGroup - a0;  // plane-relative offset of the group's first byte (negative in the head group)
+      v[k] = make_uint4(0u, 0u, 0u, 0u);
+      if (g < groups && o >= 0 && o + kGroup <= n) v[k] = __ldg(reinterpret_cast<const uint4*>(base + o));
     }
-    visit_bits(src, o, bits, visit);
+    unsigned long long bits = 0;
+#pragma unroll
+    for (int k = 0; k < kAhead; ++k) {
+      const int g = g0 + k * stride;
+      const int o = g * kGroup - a0;
+      uint32_t bk = 0;
+      if (g < groups) {
+        if (o >= 0 && o + kGroup <= n) {
+          if (v[k].x | v[k].y | v[k].z | v[k].w) bk = bits_of(v[k]);
+        } else {  // head / tail group of a plane whose start or size is not a multiple of 16: byte loads inside the plane
+          for (int j = 0; j < kGroup; ++j)
+            if (o + j >= 0 && o + j < n && base[o + j]) bk |= 1u << j;
+        }
+      }
+      bits |= (unsigned long long)bk << (16 * k);
+    }
+    if (!__any_sync(0xffffffffu, bits != 0ull)) continue;
+    // inclusive prefix sum of the lanes' cell counts
+    const int cnt = __popcll(bits);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const uint32_t blo = (uint32_t)bits, bhi = (uint32_t)(bits >> 32);
+    const int o0 = g0 * kGroup - a0;
+    for (int first = 0; first < total; first += 32) {
+      const int idx = first + lane;  // the cell of this round that is mine
+      // owner = first lane whose inclusive count exceeds idx (binary search over the lanes)
+      int L = 0;
+#pragma unroll
+      for (int step = 16; step >= 1; step >>= 1) {
+        const int t = __shfl_sync(0xffffffffu, incl, L + step - 1);
+        if (t <= idx) L += step;
+      }
+      L &= 31;  // idx >= total: any lane, result unused
+      const int o_own = __shfl_sync(0xffffffffu, o0, L);
+      const uint32_t lo_own = __shfl_sync(0xffffffffu, blo, L), hi_own = __shfl_sync(0xffffffffu, bhi, L);
+      const int excl_own = __shfl_sync(0xffffffffu, incl - cnt, L);
+      if (idx < total) {
+        const int rank = idx - excl_own, nlo = __popc(lo_own);
+        const int bit = rank < nlo ? (int)__fns(lo_own, 0, rank + 1) : 32 + (int)__fns(hi_own, 0, rank - nlo + 1);
+        const int cell = o_own + (bit >> 4) * (stride * kGroup) + (bit & 15);
+        const int r = cell / src.w;
+        visit(cell, r, cell - r * src.w);
+      }
+    }
   }
 }
 
@@ -84,8 +120,10 @@ __device__ __forceinline__ void load_plane_ctx(const DmFuseSource& src, int smp,
     const uint32_t* s = reinterpret_cast<const uint32_t*>(src.steps + smp * 2);
     reinterpret_cast<uint32_t*>(&ctx->step0)[threadIdx.x] = s[threadIdx.x];  // 2 x 64 bytes = 32 words
   }
-  if (threadIdx.x == 32) ctx->woff = src.width_offset[smp];
-  if (threadIdx.x == 33) ctx->hoff = src.height_offset[smp];
+  if (threadIdx.x == 0) {
+    ctx->woff = src.width_offset[smp];
+    ctx->hoff = src.height_offset[smp];
+  }
   __syncthreads();
 }
 
@@ -113,7 +151,7 @@ __global__ void fuse_bbox_init(long long* out) {
 }
 
 // grid = (blocks per plane, planes folded into y)
-__global__ void __launch_bounds__(kFuseThreads, 4)
+__global__ void __launch_bounds__(kScanThreads, 1024 / kScanThreads)
 fuse_bbox_kernel(const __grid_constant__ DmFuseSource src, int planes, int C, float res, long long* __restrict__ out) {
   __shared__ PlaneCtx ctx;
   long long mnx = 0x7fffffffffffffffLL, mxx = (long long)0x8000000000000000ULL;
@@ -145,13 +183,13 @@ fuse_bbox_kernel(const __grid_constant__ DmFuseSource src, int planes, int C, fl
     mnz = c2 < mnz ? c2 : mnz; mxz = d2 > mxz ? d2 : mxz;
     cnt += e2;
   }
-  __shared__ long long sm[kFuseThreads / 32][4];
-  __shared__ unsigned long long sc[kFuseThreads / 32];
+  __shared__ long long sm[kScanThreads / 32][4];
+  __shared__ unsigned long long sc[kScanThreads / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0) { sm[warp][0] = mnx; sm[warp][1] = mxx; sm[warp][2] = mnz; sm[warp][3] = mxz; sc[warp] = cnt; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int w = 1; w < kFuseThreads / 32; ++w) {
+    for (int w = 1; w < kScanThreads / 32; ++w) {
       mnx = sm[w][0] < mnx ? sm[w][0] : mnx; mxx = sm[w][1] > mxx ? sm[w][1] : mxx;
       mnz = sm[w][2] < mnz ? sm[w][2] : mnz; mxz = sm[w][3] > mxz ? sm[w][3] : mxz;
       cnt += sc[w];
@@ -187,7 +225,7 @@ fuse_fill_kernel(float* __restrict__ topdown, float* __restrict__ height, uint8_
 
 // mask_inline: the mask (utils.py:489-491: the cell differs from what the canvas was filled with) is
 // stored right where a value beats `fill`; with a NaN fill the generic pass below is used instead.
-__global__ void __launch_bounds__(kFuseThreads, 4)
+__global__ void __launch_bounds__(kScanThreads, 1024 / kScanThreads)
 fuse_scatter_kernel(const __grid_constant__ DmFuseSource src, int planes, int C, const DmFuseTarget tgt,
                     float* __restrict__ topdown, float* __restrict__ height, uint8_t* __restrict__ mask,
                     int mask_inline) {
@@ -241,12 +279,13 @@ static int check_sources(const DmFuseSource* sources, int n, int b, int C) {
   return DM_OK;
 }
 
-// (blocks per plane, planes): about two waves of 8 resident CTAs per SM in total
+// (blocks per plane, planes folded into y): about `waves` waves of 8 resident 256-thread CTAs per SM in total
 static dim3 plane_grid(const DmFuseSource& s, int planes) {
+  constexpr int waves = 2, max_gy = 65535;
   const long long groups = ((long long)s.h * s.w + 2 * kGroup - 1) / kGroup;
-  const int gy = planes < 65535 ? planes : 65535;
-  long long gx = ((long long)kNumSMs * 8 * 2 + gy - 1) / gy;
-  const long long gx_max = (groups + kFuseThreads - 1) / kFuseThreads;
+  const int gy = planes < max_gy ? planes : max_gy;
+  long long gx = (((long long)kNumSMs * 8 * waves + gy - 1) / gy) * (256 / kScanThreads);
+  const long long gx_max = (groups + kScanThreads - 1) / kScanThreads;
   if (gx > gx_max) gx = gx_max;
   if (gx < 1) gx = 1;
   return dim3((unsigned)gx, (unsigned)gy);
@@ -263,7 +302,7 @@ static unsigned grid_for(long long items) {
 static int launch_scatter(const DmFuseSource* sources, int n_sources, int b, int C, const DmFuseTarget& tgt,
                           float* topdown, uint8_t* mask, float* height, int mask_inline, cudaStream_t stream) {
   for (int i = 0; i < n_sources; ++i) {
-    fuse_scatter_kernel<<<plane_grid(sources[i], b * C), kFuseThreads, 0, stream>>>(sources[i], b * C, C, tgt, topdown,
+    fuse_scatter_kernel<<<plane_grid(sources[i], b * C), kScanThreads, 0, stream>>>(sources[i], b * C, C, tgt, topdown,
                                                                                   height, mask, mask_inline);
     DM_LAUNCHED();
   }
@@ -283,7 +322,9 @@ extern "C" int dm_fuse_bbox_i64(const DmFuseSource* sources, int32_t n_sources, 
   fuse_bbox_init<<<1, 1, 0, stream>>>(reinterpret_cast<long long*>(out));
   DM_LAUNCHED();
   for (int i = 0; i < n_sources; ++i) {
-    fuse_bbox_kernel<<<plane_grid(sources[i], b * C), kFuseThreads, 0, stream>>>(sources[i], b * C, C, target_res,
+    // (fewer, longer blocks that walk several planes each were tried for the five same-address atomics at the end of
+    // every block: slower, 103-113 us instead of 76 us for the config-4 world map — the planes are unevenly filled)
+    fuse_bbox_kernel<<<plane_grid(sources[i], b * C), kScanThreads, 0, stream>>>(sources[i], b * C, C, target_res,
                                                                                reinterpret_cast<long long*>(out));
     DM_LAUNCHED();
   }
