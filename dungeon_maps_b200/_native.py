@@ -78,6 +78,10 @@ _SIGNATURES = {
   "dm_fuse_bbox_i64": (ctypes.c_int, [POINTER(DmFuseSource), c_int32, c_int32, c_int32, c_float, c_void_p, c_void_p]),
   "dm_fuse_scatter_f32": (ctypes.c_int, [POINTER(DmFuseSource), c_int32, c_int32, c_int32, POINTER(DmFuseTarget),
                                          c_void_p, c_void_p, c_void_p, c_void_p]),
+  "dm_fuse_bbox_seeded_i64": (ctypes.c_int, [POINTER(DmFuseSource), c_int32, c_int32, c_int32, c_float, c_void_p,
+                                             c_void_p, c_void_p]),
+  "dm_fuse_scatter_track_f32": (ctypes.c_int, [POINTER(DmFuseSource), c_int32, c_int32, c_int32, POINTER(DmFuseTarget),
+                                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
   "dm_fuse_inplace_f32": (ctypes.c_int, [POINTER(DmFuseSource), c_int32, c_int32, c_int32, POINTER(DmFuseTarget),
                                          c_void_p, c_void_p, c_void_p, c_void_p]),
   "dm_fuse_canvas_init_f32": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_void_p]),

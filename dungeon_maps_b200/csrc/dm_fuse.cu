@@ -142,7 +142,11 @@ __device__ __forceinline__ V3 source_point(const DmFuseSource& src, const PlaneC
   return p;
 }
 
-__global__ void fuse_bbox_init(long long* out) {
+__global__ void fuse_bbox_init(long long* out, const long long* seed = nullptr) {
+  if (seed) {  // start from a bounding box that an earlier scatter pass left for its output map
+    for (int i = 0; i < 5; ++i) out[i] = seed[i];
+    return;
+  }
   out[0] = 0x7fffffffffffffffLL;          // min_x
   out[1] = (long long)0x8000000000000000ULL;  // max_x
   out[2] = 0x7fffffffffffffffLL;          // min_z
@@ -228,8 +232,13 @@ fuse_fill_kernel(float* __restrict__ topdown, float* __restrict__ height, uint8_
 __global__ void __launch_bounds__(kScanThreads, 1024 / kScanThreads)
 fuse_scatter_kernel(const __grid_constant__ DmFuseSource src, int planes, int C, const DmFuseTarget tgt,
                     float* __restrict__ topdown, float* __restrict__ height, uint8_t* __restrict__ mask,
-                    int mask_inline) {
+                    int mask_inline, long long* __restrict__ next_bbox) {
   __shared__ PlaneCtx ctx;
+  // next_bbox: what pass 1 of a FOLLOWING merge would find for the map written here, taken as a global-frame
+  // source of the same resolution: min / max over its valid cells of quantize0(dequantize(cell)) (maps.py:1081-1086,
+  // 2159-2165) — a function of the cell and this target's offsets only.  Bins are whole numbers held in floats.
+  float nmnx = INFINITY, nmxx = -INFINITY, nmnz = INFINITY, nmxz = -INFINITY;
+  unsigned nset = 0;
   const long long M = (long long)tgt.Mh * tgt.Mw;
   const int n = src.h * src.w;
   int loaded = -1;
@@ -250,10 +259,36 @@ fuse_scatter_kernel(const __grid_constant__ DmFuseSource src, int planes, int C,
       const float v = vplane ? vplane[cell] : p.y;  // maps.py:2214-2216
       if (v == v) {
         if (tgt.reduction) atomic_min_f32(tplane + o, v); else atomic_max_f32(tplane + o, v);
-        if (mask_inline && better(v, tgt.fill_value, tgt.reduction)) mplane[o] = 1;
+        if (mask_inline && better(v, tgt.fill_value, tgt.reduction)) {
+          mplane[o] = 1;
+          if (next_bbox) {
+            float zb = zf;
+            if (tgt.flip_h) zb = __fsub_rn((float)(tgt.Mh - 1), zb);
+            const float pz = __fmul_rn(__fsub_rn(zb, tgt.height_offset), tgt.map_res);
+            const float px = __fmul_rn(__fsub_rn(xf, tgt.width_offset), tgt.map_res);
+            float qx, qz;
+            quantize_f(px, pz, 0.0f, 0.0f, tgt.map_res, 0, 0, &qx, &qz);
+            nmnx = fminf(nmnx, qx); nmxx = fmaxf(nmxx, qx);
+            nmnz = fminf(nmnz, qz); nmxz = fmaxf(nmxz, qz);
+            ++nset;
+          }
+        }
       }
       if (oplane && p.y == p.y) atomic_max_f32(oplane + o, p.y);  // maps.py:2258-2271
     });
+  }
+  if (next_bbox) {  // warp reduction, one set of atomics per warp that set a cell
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      nmnx = fminf(nmnx, __shfl_xor_sync(0xffffffffu, nmnx, o)); nmxx = fmaxf(nmxx, __shfl_xor_sync(0xffffffffu, nmxx, o));
+      nmnz = fminf(nmnz, __shfl_xor_sync(0xffffffffu, nmnz, o)); nmxz = fmaxf(nmxz, __shfl_xor_sync(0xffffffffu, nmxz, o));
+      nset += __shfl_xor_sync(0xffffffffu, nset, o);
+    }
+    if ((threadIdx.x & 31) == 0 && nset) {
+      atomicMin(next_bbox + 0, f2i64(nmnx)); atomicMax(next_bbox + 1, f2i64(nmxx));
+      atomicMin(next_bbox + 2, f2i64(nmnz)); atomicMax(next_bbox + 3, f2i64(nmxz));
+      atomicAdd(reinterpret_cast<unsigned long long*>(next_bbox + 4), (unsigned long long)nset);
+    }
   }
 }
 
@@ -300,10 +335,11 @@ static unsigned grid_for(long long items) {
 }
 
 static int launch_scatter(const DmFuseSource* sources, int n_sources, int b, int C, const DmFuseTarget& tgt,
-                          float* topdown, uint8_t* mask, float* height, int mask_inline, cudaStream_t stream) {
+                          float* topdown, uint8_t* mask, float* height, int mask_inline, cudaStream_t stream,
+                          long long* next_bbox = nullptr) {
   for (int i = 0; i < n_sources; ++i) {
     fuse_scatter_kernel<<<plane_grid(sources[i], b * C), kScanThreads, 0, stream>>>(sources[i], b * C, C, tgt, topdown,
-                                                                                  height, mask, mask_inline);
+                                                                                  height, mask, mask_inline, next_bbox);
     DM_LAUNCHED();
   }
   return DM_OK;
@@ -315,11 +351,19 @@ using namespace dm;
 
 extern "C" int dm_fuse_bbox_i64(const DmFuseSource* sources, int32_t n_sources, int32_t b, int32_t C,
                                 float target_res, int64_t* out, void* stream_) {
+  return dm_fuse_bbox_seeded_i64(sources, n_sources, b, C, target_res, nullptr, out, stream_);
+}
+
+extern "C" int dm_fuse_bbox_seeded_i64(const DmFuseSource* sources, int32_t n_sources, int32_t b, int32_t C,
+                                       float target_res, const int64_t* seed, int64_t* out, void* stream_) {
   if (!out) return DM_EINVAL;
-  const int rc = check_sources(sources, n_sources, b, C);
-  if (rc != DM_OK) return rc;
+  if (n_sources == 0 && !seed) return DM_EINVAL;
+  if (n_sources != 0) {
+    const int rc = check_sources(sources, n_sources, b, C);
+    if (rc != DM_OK) return rc;
+  }
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  fuse_bbox_init<<<1, 1, 0, stream>>>(reinterpret_cast<long long*>(out));
+  fuse_bbox_init<<<1, 1, 0, stream>>>(reinterpret_cast<long long*>(out), reinterpret_cast<const long long*>(seed));
   DM_LAUNCHED();
   for (int i = 0; i < n_sources; ++i) {
     // (fewer, longer blocks that walk several planes each were tried for the five same-address atomics at the end of
@@ -334,6 +378,12 @@ extern "C" int dm_fuse_bbox_i64(const DmFuseSource* sources, int32_t n_sources, 
 extern "C" int dm_fuse_scatter_f32(const DmFuseSource* sources, int32_t n_sources, int32_t b, int32_t C,
                                    const DmFuseTarget* target, float* topdown, uint8_t* mask, float* height,
                                    void* stream_) {
+  return dm_fuse_scatter_track_f32(sources, n_sources, b, C, target, topdown, mask, height, nullptr, stream_);
+}
+
+extern "C" int dm_fuse_scatter_track_f32(const DmFuseSource* sources, int32_t n_sources, int32_t b, int32_t C,
+                                         const DmFuseTarget* target, float* topdown, uint8_t* mask, float* height,
+                                         int64_t* next_bbox, void* stream_) {
   if (!target || !topdown || !mask || target->Mh <= 0 || target->Mw <= 0) return DM_EINVAL;
   if (target->reduction != 0 && target->reduction != 1) return DM_EINVAL;
   const int rc = check_sources(sources, n_sources, b, C);
@@ -347,7 +397,13 @@ extern "C" int dm_fuse_scatter_f32(const DmFuseSource* sources, int32_t n_source
   fuse_fill_kernel<<<grid_for((n_out + 3) / 4), kFuseThreads, 0, stream>>>(topdown, height, mask, n_out,
                                                                            target->fill_value, vec_ok);
   DM_LAUNCHED();
-  const int rs = launch_scatter(sources, n_sources, b, C, *target, topdown, mask, height, mask_inline, stream);
+  if (next_bbox) {
+    if (!mask_inline) return DM_EINVAL;  // NaN fill: the mask comes from the compare pass, nothing to track
+    fuse_bbox_init<<<1, 1, 0, stream>>>(reinterpret_cast<long long*>(next_bbox));
+    DM_LAUNCHED();
+  }
+  const int rs = launch_scatter(sources, n_sources, b, C, *target, topdown, mask, height, mask_inline, stream,
+                                reinterpret_cast<long long*>(next_bbox));
   if (rs != DM_OK) return rs;
   if (!mask_inline) {
     changed_mask_kernel<<<grid_for(n_out), kFuseThreads, 0, stream>>>(topdown, n_out, target->fill_value, mask);

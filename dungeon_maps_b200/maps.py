@@ -865,12 +865,21 @@ def fuse_topdown_maps(*maps: List[TopdownMap], map_projector: Optional[MapProjec
   C = max(s[1] for s in shapes)
   n_total = sum(C * s[2] * s[3] for s in shapes)
   keep: list = []
-  sources = (nat.DmFuseSource * len(live))(*[_fuse_source(m, proj, b, C, n_total, dev, keep) for m in live])
+  # A map that an earlier call of this function produced carries the bounding box pass 1 would find for it
+  # (_TrackedBox); it then only seeds the box and pass 1 scans the other maps — for a MapBuilder that is the local
+  # map instead of the whole world map, ahead of the host sync below.
+  seed = next((m for m in live if _tracked_box_valid(m, proj, dev)), None)
+  scan = [m for m in live if m is not seed]
+  all_sources = [_fuse_source(m, proj, b, C, n_total, dev, keep) for m in live]
+  sources = (nat.DmFuseSource * len(live))(*all_sources)
+  scan_sources = (nat.DmFuseSource * max(len(scan), 1))(*[s for m, s in zip(live, all_sources) if m is not seed])
   lib = nat.lib()
   bbox = torch.empty((5,), dtype=torch.int64, device=dev)
   with torch.cuda.device(dev):
-    rc = lib.dm_fuse_bbox_i64(sources, len(live), b, C, proj.map_res, bbox.data_ptr(), nat.stream_ptr(dev))
-  nat.check(rc, "dm_fuse_bbox_i64")
+    rc = lib.dm_fuse_bbox_seeded_i64(scan_sources, len(scan), b, C, proj.map_res,
+                                     None if seed is None else seed._tracked_box.box.data_ptr(), bbox.data_ptr(),
+                                     nat.stream_ptr(dev))
+  nat.check(rc, "dm_fuse_bbox_seeded_i64")
   min_x, max_x, min_z, max_z, n_valid = (int(v) for v in bbox.cpu())  # the reference's .item() sync
   if n_valid == 0:  # maps.py:2217-2225
     last = maps[-1]
@@ -891,14 +900,47 @@ def fuse_topdown_maps(*maps: List[TopdownMap], map_projector: Optional[MapProjec
   topdown = torch.empty((b, C, map_height, map_width), dtype=torch.float32, device=dev)
   mask = torch.empty((b, C, map_height, map_width), dtype=torch.bool, device=dev)
   height = None if is_height_map else torch.empty_like(topdown)
+  # the new map is in the global frame when the target is: pass 2 then leaves its box for the next merge
+  track = bool(proj.to_global) and tgt.fill_value == tgt.fill_value
+  next_box = torch.empty((5,), dtype=torch.int64, device=dev) if track else None
   with torch.cuda.device(dev):
-    rc = lib.dm_fuse_scatter_f32(sources, len(live), b, C, tgt, topdown.data_ptr(), mask.data_ptr(),
-                                 nat.ptr(height), nat.stream_ptr(dev))
-  nat.check(rc, "dm_fuse_scatter_f32")
+    rc = lib.dm_fuse_scatter_track_f32(sources, len(live), b, C, tgt, topdown.data_ptr(), mask.data_ptr(),
+                                       nat.ptr(height), nat.ptr(next_box), nat.stream_ptr(dev))
+  nat.check(rc, "dm_fuse_scatter_track_f32")
   new_proj = proj.clone(width_offset=width_offset, height_offset=height_offset, map_width=map_width,
                         map_height=map_height)
-  return TopdownMap(topdown_map=topdown, mask=mask, height_map=topdown if is_height_map else height,
-                    map_projector=new_proj, is_height_map=is_height_map)
+  out = TopdownMap(topdown_map=topdown, mask=mask, height_map=topdown if is_height_map else height,
+                   map_projector=new_proj, is_height_map=is_height_map)
+  if track:
+    out._tracked_box = _TrackedBox(next_box, mask, new_proj)
+  return out
+
+
+class _TrackedBox():
+  """Bounding box (device, 5 x int64) that pass 1 of fuse_topdown_maps would compute for a map this module wrote,
+  with what it was derived from: the mask tensor (and its in-place version counter) and the projector's
+  dequantisation parameters.  Anything that no longer matches makes the map an ordinary, scanned source again."""
+
+  def __init__(self, box: torch.Tensor, mask: torch.Tensor, proj: MapProjector):
+    self.box = box
+    self.mask = mask
+    self.mask_version = mask._version
+    self.proj = proj
+    self.key = self.proj_key(proj)
+
+  @staticmethod
+  def proj_key(proj: MapProjector):
+    f = lambda x: None if x is None else tuple(float(v) for v in torch.as_tensor(x).reshape(-1))
+    return (f(proj.width_offset), f(proj.height_offset), float(proj.map_res), bool(proj.flip_h), bool(proj.to_global))
+
+
+def _tracked_box_valid(m: TopdownMap, target: MapProjector, dev: torch.device) -> bool:
+  tb = getattr(m, "_tracked_box", None)
+  if tb is None or not target.to_global:
+    return False
+  return (m.mask is tb.mask and tb.mask._version == tb.mask_version and tb.box.device == dev
+          and m.proj is tb.proj and tb.proj_key(m.proj) == tb.key and tb.key[4]
+          and float(target.map_res) == tb.key[2])
 
 
 def merge_into_canvas(world: TopdownMap, new_map: TopdownMap, canvas_shape: Tuple[int, int],

@@ -178,6 +178,13 @@ typedef struct DmFuseSource {
  * initialises nothing; the call overwrites all five. */
 int dm_fuse_bbox_i64(const DmFuseSource* sources, int32_t n_sources, int32_t b, int32_t C,
                      float target_res, int64_t* out, void* stream);
+/* The same, starting from `seed` (device, 5×int64, may be NULL) instead of an empty box: the bounding box that
+ * dm_fuse_scatter_track_f32 left for a map that would otherwise be one of the sources.  A MapBuilder's world map is
+ * by far the largest source of every merge (maps.py:2471-2508) and its contribution to the box is a function of
+ * the map alone, so it is reduced once, while the map is written, instead of by a scan before every host sync.
+ * n_sources may be 0 when seed is given. */
+int dm_fuse_bbox_seeded_i64(const DmFuseSource* sources, int32_t n_sources, int32_t b, int32_t C,
+                            float target_res, const int64_t* seed, int64_t* out, void* stream);
 
 /* Pass 2: re-quantise every valid point with the new offsets and scatter-max
  * it into the freshly sized canvases (maps.py:2232-2272).
@@ -194,6 +201,13 @@ typedef struct DmFuseTarget {
 int dm_fuse_scatter_f32(const DmFuseSource* sources, int32_t n_sources, int32_t b, int32_t C,
                         const DmFuseTarget* target, float* topdown, uint8_t* mask, float* height,
                         void* stream);
+/* The same, and next_bbox (device, 5×int64, overwritten; may be NULL) receives what dm_fuse_bbox_i64 would compute
+ * for the map written here when it is later passed as a global-frame source (identity steps) with the same
+ * map_res, offsets and flip_h as `target`: min_x, max_x, min_z, max_z over its valid cells, and a count that is
+ * zero iff the map has no valid cell (NOT the number of valid cells).  DM_EINVAL with a NaN fill_value. */
+int dm_fuse_scatter_track_f32(const DmFuseSource* sources, int32_t n_sources, int32_t b, int32_t C,
+                              const DmFuseTarget* target, float* topdown, uint8_t* mask, float* height,
+                              int64_t* next_bbox, void* stream);
 
 /* Opt-in fixed-canvas merge (no reference call does this — the closest is
  * project(..., canvas=, canvas_masks=), maps.py:1089-1173 with utils.py:462-491, whose semantics it keeps):

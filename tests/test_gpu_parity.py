@@ -516,6 +516,58 @@ def test_map_builder_config4_shapes_vs_oracle():
   assert wm.mask.any(dim=(1, 2, 3)).all()
 
 
+def test_fuse_tracked_box_equals_a_scan_and_yields_to_edits():
+  """fuse_topdown_maps leaves the bounding box of the map it writes for the next merge (dm_fuse_scatter_track_f32 /
+  dm_fuse_bbox_seeded_i64).  (1) The tracked box equals what a scan of that map finds; (2) a merge seeded with it
+  equals a merge that scans; (3) after an in-place edit of the mask the box is ignored and the result still equals
+  the oracle's."""
+  b, H, W = 2, 96, 128
+  proj = dmap.MapProjector(width=W, height=H, hfov=HFOV, cam_pose=[0., 0., 0.], width_offset=0., height_offset=0.,
+                           cam_pitch=PITCH, cam_height=0.88, map_res=0.05, map_width=120, map_height=120,
+                           trunc_depth_min=0.15, trunc_depth_max=5.05, clip_border=2, fill_value=dmap.NINF,
+                           to_global=True, device="cuda")
+  import sys
+  sys.path.insert(0, str(__import__("pathlib").Path(__file__).resolve().parents[1]))
+  from bench import BuilderWorkload
+  poses = BuilderWorkload.walk(b, 3, seed=5, half=2.0)
+  kw = dict(to_global=False, width_offset=60., height_offset=0., map_width=120, map_height=120)
+  depth = lambda t: synth.room_depth(b, H, W, HFOV, PITCH, 0.88, poses[t].cuda(), seed=5, half=4.0, device="cuda")
+  builder = dmap.MapBuilder(map_projector=proj)
+  builder.step(depth(0), cam_pose=poses[0], **kw)
+  builder.step(depth(1), cam_pose=poses[1], **kw)
+  wm = builder.world_map
+  assert getattr(wm, "_tracked_box", None) is not None
+  # (1) tracked box == scanned box of the same map
+  from dungeon_maps_b200 import maps as _maps, _native as nat
+  keep = []
+  src = (nat.DmFuseSource * 1)(_maps._fuse_source(wm, wm.proj, b, 1, int(np.prod(wm.mask.shape[1:])), torch.device("cuda", 0), keep))
+  scanned = torch.empty((5,), dtype=torch.int64, device="cuda")
+  nat.check(nat.lib().dm_fuse_bbox_i64(src, 1, b, 1, wm.proj.map_res, scanned.data_ptr(), nat.stream_ptr(torch.device("cuda", 0))), "bbox")
+  assert scanned[:4].tolist() == wm._tracked_box.box[:4].tolist()
+  assert int(scanned[4]) == int(wm.mask.sum()) and int(wm._tracked_box.box[4]) > 0
+  # (2) seeded merge == scanning merge
+  local = builder.plot(depth(2), cam_pose=poses[2], **kw)
+  tgt = builder.proj.clone(cam_pose=poses[2])
+  seeded = dmap.fuse_topdown_maps(wm, local, map_projector=tgt)
+  plain_wm = dmap.TopdownMap(topdown_map=wm.topdown_map, mask=wm.mask, height_map=wm.height_map, map_projector=wm.proj)
+  plain = dmap.fuse_topdown_maps(plain_wm, local, map_projector=tgt)
+  assert seeded.mask.shape == plain.mask.shape
+  assert_same(npy(seeded.topdown_map), npy(plain.topdown_map), "seeded vs scanned topdown")
+  assert_same(npy(seeded.mask), npy(plain.mask), "seeded vs scanned mask")
+  # (3) the caller marks a far-away cell valid in place: the stale box must not be used
+  wm.topdown_map[0, 0, 0, 0] = 1.25
+  wm.mask[0, 0, 0, 0] = True
+  edited = dmap.fuse_topdown_maps(wm, local, map_projector=tgt)
+  p = poses[2].numpy()
+  want = orc.fuse([orc.FuseSource(npy(wm.height_map), npy(wm.mask), None, float(wm.proj.width_offset), float(wm.proj.height_offset),
+                                  0.05, True, True, p),
+                   orc.FuseSource(npy(local.height_map), npy(local.mask), None, 60., 0., 0.05, True, False, p)],
+                  True, p, 0.05, True)
+  assert [edited.proj.map_height, edited.proj.map_width] == [want["map_height"], want["map_width"]]
+  assert_same(npy(edited.topdown_map), want["topdown"], "edited world")
+  assert_same(npy(edited.mask), want["mask"], "edited world mask")
+
+
 def test_crop_matches_reference():
   g = Golden("crop")
   h, w = g.meta["h"], g.meta["w"]
