@@ -163,7 +163,9 @@ def ptr(t) -> int:
 
 
 def stream_ptr(device: torch.device) -> int:
-  return torch.cuda.current_stream(device).cuda_stream
+  """cudaStream_t of torch's current stream on `device` (the raw getter: torch.cuda.current_stream builds a Stream
+  object, ~10 us a call, and a MapBuilder step asks a dozen times)."""
+  return torch._C._cuda_getCurrentRawStream(device.index if device.index is not None else torch.cuda.current_device())
 
 
 def launch_count() -> int:

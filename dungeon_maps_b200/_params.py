@@ -14,6 +14,8 @@ from typing import Optional, Sequence
 import numpy as np
 import torch
 
+from . import _native as nat
+
 ANGLE_EPS = 0.001
 
 STEP_NONE, STEP_ROT_THEN_ADD, STEP_ADD_THEN_ROT, STEP_ADD, STEP_ROT = 0, 1, 2, 3, 4
@@ -236,7 +238,7 @@ class _DeviceCache:
 
   def get(self, host: torch.Tensor, device: torch.device) -> torch.Tensor:
     host = host.contiguous()
-    key = (str(device), torch.cuda.current_stream(device).cuda_stream, host.dtype, tuple(host.shape),
+    key = (device.index, nat.stream_ptr(device), host.dtype, tuple(host.shape),
            host.numpy().tobytes())
     hit = self._d.get(key)
     if hit is not None:

@@ -63,7 +63,7 @@ _workspaces: Dict[Tuple[int, int], torch.Tensor] = {}
 
 def _workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
   """Zero-initialised accumulation ring, one per (device, stream); the kernels leave it zeroed."""
-  key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+  key = (dev.index, nat.stream_ptr(dev))
   ws = _workspaces.get(key)
   if ws is None or ws.numel() < nbytes:
     ws = torch.zeros(max(nbytes, 16), dtype=torch.uint8, device=dev)
