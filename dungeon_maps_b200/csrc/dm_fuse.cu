@@ -236,9 +236,11 @@ fuse_scatter_kernel(const __grid_constant__ DmFuseSource src, int planes, int C,
   __shared__ PlaneCtx ctx;
   // next_bbox: what pass 1 of a FOLLOWING merge would find for the map written here, taken as a global-frame
   // source of the same resolution: min / max over its valid cells of quantize0(dequantize(cell)) (maps.py:1081-1086,
-  // 2159-2165) — a function of the cell and this target's offsets only.  Bins are whole numbers held in floats.
-  float nmnx = INFINITY, nmxx = -INFINITY, nmnz = INFINITY, nmxz = -INFINITY;
-  unsigned nset = 0;
+  // 2159-2165) — a function of the cell and this target's offsets only, and non-decreasing in the column and in the
+  // (flipped) row: every float step (int → float, − offset, × res, / res, + 0.5, floor) is weakly monotone.  So the
+  // extreme columns / rows that were marked valid are all that is tracked per cell (whole numbers held in floats);
+  // the four bins are evaluated once per block.
+  float cmin = INFINITY, cmax = -INFINITY, rmin = INFINITY, rmax = -INFINITY;
   const long long M = (long long)tgt.Mh * tgt.Mw;
   const int n = src.h * src.w;
   int loaded = -1;
@@ -261,33 +263,40 @@ fuse_scatter_kernel(const __grid_constant__ DmFuseSource src, int planes, int C,
         if (tgt.reduction) atomic_min_f32(tplane + o, v); else atomic_max_f32(tplane + o, v);
         if (mask_inline && better(v, tgt.fill_value, tgt.reduction)) {
           mplane[o] = 1;
-          if (next_bbox) {
-            float zb = zf;
-            if (tgt.flip_h) zb = __fsub_rn((float)(tgt.Mh - 1), zb);
-            const float pz = __fmul_rn(__fsub_rn(zb, tgt.height_offset), tgt.map_res);
-            const float px = __fmul_rn(__fsub_rn(xf, tgt.width_offset), tgt.map_res);
-            float qx, qz;
-            quantize_f(px, pz, 0.0f, 0.0f, tgt.map_res, 0, 0, &qx, &qz);
-            nmnx = fminf(nmnx, qx); nmxx = fmaxf(nmxx, qx);
-            nmnz = fminf(nmnz, qz); nmxz = fmaxf(nmxz, qz);
-            ++nset;
-          }
+          cmin = fminf(cmin, xf); cmax = fmaxf(cmax, xf);
+          rmin = fminf(rmin, zf); rmax = fmaxf(rmax, zf);
         }
       }
       if (oplane && p.y == p.y) atomic_max_f32(oplane + o, p.y);  // maps.py:2258-2271
     });
   }
-  if (next_bbox) {  // warp reduction, one set of atomics per warp that set a cell
+  if (next_bbox) {  // warp, then block reduction; one set of atomics per block that marked a cell
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      nmnx = fminf(nmnx, __shfl_xor_sync(0xffffffffu, nmnx, o)); nmxx = fmaxf(nmxx, __shfl_xor_sync(0xffffffffu, nmxx, o));
-      nmnz = fminf(nmnz, __shfl_xor_sync(0xffffffffu, nmnz, o)); nmxz = fmaxf(nmxz, __shfl_xor_sync(0xffffffffu, nmxz, o));
-      nset += __shfl_xor_sync(0xffffffffu, nset, o);
+      cmin = fminf(cmin, __shfl_xor_sync(0xffffffffu, cmin, o)); cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+      rmin = fminf(rmin, __shfl_xor_sync(0xffffffffu, rmin, o)); rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
     }
-    if ((threadIdx.x & 31) == 0 && nset) {
-      atomicMin(next_bbox + 0, f2i64(nmnx)); atomicMax(next_bbox + 1, f2i64(nmxx));
-      atomicMin(next_bbox + 2, f2i64(nmnz)); atomicMax(next_bbox + 3, f2i64(nmxz));
-      atomicAdd(reinterpret_cast<unsigned long long*>(next_bbox + 4), (unsigned long long)nset);
+    __shared__ float red[kScanThreads / 32][4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { red[warp][0] = cmin; red[warp][1] = cmax; red[warp][2] = rmin; red[warp][3] = rmax; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < kScanThreads / 32; ++w) {
+        cmin = fminf(cmin, red[w][0]); cmax = fmaxf(cmax, red[w][1]);
+        rmin = fminf(rmin, red[w][2]); rmax = fmaxf(rmax, red[w][3]);
+      }
+      if (cmin <= cmax) {
+        // rows: the dequantised z falls with the row when the map is flipped (maps.py:1081-1083)
+        const float zlo = tgt.flip_h ? __fsub_rn((float)(tgt.Mh - 1), rmax) : rmin;
+        const float zhi = tgt.flip_h ? __fsub_rn((float)(tgt.Mh - 1), rmin) : rmax;
+        auto deq = [&](float bin, float off) { return __fmul_rn(__fsub_rn(bin, off), tgt.map_res); };
+        float qx0, qx1, qz0, qz1;
+        quantize_f(deq(cmin, tgt.width_offset), deq(zlo, tgt.height_offset), 0.0f, 0.0f, tgt.map_res, 0, 0, &qx0, &qz0);
+        quantize_f(deq(cmax, tgt.width_offset), deq(zhi, tgt.height_offset), 0.0f, 0.0f, tgt.map_res, 0, 0, &qx1, &qz1);
+        atomicMin(next_bbox + 0, f2i64(qx0)); atomicMax(next_bbox + 1, f2i64(qx1));
+        atomicMin(next_bbox + 2, f2i64(qz0)); atomicMax(next_bbox + 3, f2i64(qz1));
+        atomicAdd(reinterpret_cast<unsigned long long*>(next_bbox + 4), 1ull);
+      }
     }
   }
 }
