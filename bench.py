@@ -421,6 +421,14 @@ def make_workload(args):
 
 # ================================================================================================
 
+_RESULT_LINE = []
+
+
+def _emit(line: str) -> None:
+  """The JSON line of this process (printed by main() once fd 1 is the real stdout again)."""
+  _RESULT_LINE[:] = [line]
+
+
 def cpu_baseline(wl, threads: int, budget_s: float = 20.0):
   """The oracle port on the same workload: bounded sample (≈10-20 s of CPU work)."""
   wl.cpu_setup(threads)
@@ -441,7 +449,7 @@ def run_reference(args):
     return
   wl = make_workload(args)
   if wl.key == "builder_fixed":
-    print(json.dumps({"impl": "reference", "unavailable": "the fixed-canvas merge has no reference implementation"}))
+    _emit(json.dumps({"impl": "reference", "unavailable": "the fixed-canvas merge has no reference implementation"}))
     return
   threads = os.cpu_count() or 1
   wl.cpu_setup(threads)
@@ -456,7 +464,7 @@ def run_reference(args):
     wl.cpu_fn()
   el = time.perf_counter() - t0
   value = wl.cpu_units * steps / el
-  print(json.dumps({
+  _emit(json.dumps({
     "impl": "reference", "metric": wl.metric, "value": value, "unit": wl.unit, "n_gpus": args.gpus, "steps": steps,
     "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * el / steps, "higher_is_better": True, "scaling": "weak",
     "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -551,7 +559,7 @@ def run_ours(args):
               "kernel": wl.kernel}
   if isinstance(wl, BuilderWorkload):
     roofline["kernel_ms_per_step"] = kernel_ms
-  print(json.dumps({
+  _emit(json.dumps({
     "metric": wl.metric, "value": value, "unit": wl.unit, "n_gpus": world, "steps": args.steps,
     "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
     "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -576,10 +584,22 @@ def main():
   ap.add_argument("--e2e-steps", type=int, default=5)
   ap.add_argument("--no-cpu-baseline", action="store_true")
   args = ap.parse_args()
-  if args.impl == "reference":
-    run_reference(args)
-  else:
-    run_ours(args)
+  # stdout carries the one JSON line and nothing else: libraries that print from C (NCCL's version banner ignores
+  # NCCL_DEBUG_FILE on some boxes) get stderr as their fd 1 while the run lasts
+  sys.stdout.flush()
+  real_stdout = os.dup(1)
+  os.dup2(2, 1)
+  try:
+    if args.impl == "reference":
+      run_reference(args)
+    else:
+      run_ours(args)
+  finally:
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    os.close(real_stdout)
+  if _RESULT_LINE:
+    print(_RESULT_LINE[0], flush=True)
 
 
 if __name__ == "__main__":

@@ -64,7 +64,7 @@ def raw_rows(rep):
 
 traffic_path = os.path.join(P, "traffic.json")
 traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
-for what, pattern, n_kernels in (("proj", "proj_ws", 1), ("flow", "flow_", 1), ("fuse", "fuse_|changed_", 7)):
+for what, pattern, n_kernels in (("proj", "proj_ws", 1), ("flow", "flow_", 1), ("fuse", "fuse_|changed_", 6)):
   rep = os.path.join(G, f"prof_{what}_{run}.ncu-rep")
   if not os.path.exists(rep):
     continue
@@ -85,8 +85,10 @@ for what, pattern, n_kernels in (("proj", "proj_ws", 1), ("flow", "flow_", 1), (
                        "duration_us_under_ncu": r["us"]}
   else:  # one merge = bbox_init + bbox + fill + scatter: sum the consecutive kernels of one step
     names = [r["kernel"] for r in rows]
-    inits = [i for i, k in enumerate(names) if k == "fuse_bbox_init"]
-    if len(inits) >= 2:  # one complete merge: everything between two bbox_init launches
+    # a merge starts with the bbox_init of pass 1 (followed by a bbox kernel; the second bbox_init of a merge
+    # arms the tracked box of pass 2 and is followed by a scatter kernel)
+    inits = [i for i, k in enumerate(names[:-1]) if k == "fuse_bbox_init" and names[i + 1] == "fuse_bbox_kernel"]
+    if len(inits) >= 2:  # one complete merge: everything between two pass-1 bbox_init launches
       step = rows[inits[0]:inits[1]]
       traffic["builder"] = {"kernels": [r["kernel"] for r in step], "run": run,
                             "dram_bytes_per_step": sum(r["rd"] + r["wr"] for r in step),
