@@ -14,7 +14,9 @@ want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'launch__grid_size', 'launch__block_size', 'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'smsp__inst_executed.sum',
         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
         'l1tex__throughput.avg.pct_of_peak_sustained_elapsed', 'lts__t_sector_hit_rate.pct',
-        'lts__t_sectors_op_red.sum', 'lts__t_sectors_op_atom.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
+        'lts__t_sectors_srcunit_tex_op_red.sum', 'lts__t_sectors_srcunit_tex_op_red.sum.pct_of_peak_sustained_elapsed',
+        'lts__d_atomic_input_cycles_active.avg.pct_of_peak_sustained_elapsed', 'lts__d_atomic_input_cycles_active.max.pct_of_peak_sustained_elapsed',
+        'smsp__inst_executed_op_global_red.sum', 'l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_red.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'lts__t_requests_srcunit_tex_op_red.sum',
         'sm__inst_executed_pipe_lsu.sum', 'l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed']
 want += [h for h in H if h.startswith('smsp__average_warps_issue_stalled') and h.endswith('per_issue_active.ratio')]
