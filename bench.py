@@ -437,7 +437,7 @@ def cpu_baseline(wl, threads: int, budget_s: float = 20.0):
     wl.cpu_fn()
     done += wl.cpu_units
     el = time.perf_counter() - t0
-    if el > budget_s / 2 or done >= 8 * max(wl.units_per_step, wl.cpu_units):
+    if el > budget_s / 2 or (el >= 5.0 and done >= 8 * max(wl.units_per_step, wl.cpu_units)):
       break
   return {"value": done / el, "unit": wl.unit, "cores": threads, "kind": "port",
           "sample": f"{wl.cpu_sample}; {done} units in {el:.1f} s"}
