@@ -119,3 +119,34 @@ def test_host_parameter_blocks_equal_the_oracles(n_points):
     for f in ("R", "t", "kind", "fused"):
       assert np.array_equal(ours[f], np.asarray(theirs)[f]), f
   assert _params.fused_for(45) and not _params.fused_for(44)   # 9*n >= 400 → MKL sgemm FMA chain
+
+
+def test_tracked_box_guard_host_logic():
+  """The bounding box fuse_topdown_maps keeps next to a map it wrote is only trusted while everything it was derived
+  from is unchanged (maps._tracked_box_valid): same mask tensor at the same in-place version, same projector object
+  with the same offsets / resolution / flip, global-frame map and target.  Pure host logic, no kernels."""
+  import math
+  import dungeon_maps_b200 as dmap
+  from dungeon_maps_b200 import maps as M
+  cpu = torch.device("cpu")
+  proj = dmap.MapProjector(width=64, height=48, hfov=math.radians(70), cam_pose=[0., 0., 0.],
+                           width_offset=torch.tensor([3.5]), height_offset=torch.tensor([2.0]), cam_pitch=0.,
+                           cam_height=0.88, map_res=0.05, map_width=20, map_height=20, to_global=True)
+  mask = torch.zeros((1, 1, 20, 20), dtype=torch.bool)
+  hm = torch.zeros((1, 1, 20, 20))
+  m = dmap.TopdownMap(topdown_map=hm, mask=mask, height_map=hm, map_projector=proj)
+  assert not M._tracked_box_valid(m, proj, cpu)                       # nothing tracked yet
+  m._tracked_box = M._TrackedBox(torch.zeros(5, dtype=torch.int64), mask, proj)
+  assert M._tracked_box_valid(m, proj.clone(cam_pose=[1., 0., 0.5]), cpu)   # the target's pose does not matter
+  assert not M._tracked_box_valid(m, proj.clone(to_global=False), cpu)     # local target: points get rotated
+  assert not M._tracked_box_valid(m, proj.clone(map_res=0.1), cpu)         # other bin size
+  assert not M._tracked_box_valid(m, proj, torch.device("cuda", 0))        # box lives on another device
+  other = dmap.TopdownMap(topdown_map=hm, mask=mask.clone(), height_map=hm, map_projector=proj)
+  other._tracked_box = m._tracked_box
+  assert not M._tracked_box_valid(other, proj, cpu)                        # not the mask the box was derived from
+  proj.width_offset = torch.tensor([4.5])                                  # projector edited in place
+  assert not M._tracked_box_valid(m, proj, cpu)
+  proj.width_offset = torch.tensor([3.5])
+  assert M._tracked_box_valid(m, proj, cpu)
+  mask[0, 0, 0, 0] = True                                                  # mask edited in place
+  assert not M._tracked_box_valid(m, proj, cpu)
