@@ -36,6 +36,20 @@ __global__ void __launch_bounds__(128) k(uint32_t* acc, uint32_t ncell, int cp, 
                    ::"l"(acc + (size_t)cell * cp), "r"(smem_u32(mine + lane * 32)), "r"(bytes) : "memory");
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       asm volatile("cp.async.bulk.wait_group.read 4;" ::: "memory");
+    } else if (MODE == 3) {  // lane = channel, ONE runlet per instruction: lanes 16-31 idle
+      const uint32_t r = hash(gw * 65536u + it);
+      const uint32_t cell = local ? (base + (r % local)) % ncell : r % ncell;
+      if (lane < 16)
+        asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(acc + (size_t)cell * cp + lane), "r"(r | 1u) : "memory");
+    } else if (MODE == 4) {  // 32 lanes on 32 consecutive words of ONE cell (128 B)
+      const uint32_t r = hash(gw * 65536u + it);
+      const uint32_t cell = local ? (base + (r % local)) % ncell : r % ncell;
+      asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(acc + (size_t)cell * cp + lane), "r"(r | 1u) : "memory");
+    } else if (MODE == 5) {  // 4 runlets x 8 channels per instruction
+      const int s = lane >> 3, c = lane & 7;
+      const uint32_t r = hash(gw * 65536u + it * 4 + s);
+      const uint32_t cell = local ? (base + (r % local)) % ncell : r % ncell;
+      asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(acc + (size_t)cell * cp + c), "r"(r | 1u) : "memory");
     } else {
       const uint32_t r = hash(gw * 65536u + it * 32 + lane);
       const uint32_t cell = local ? (base + (r % local)) % ncell : r % ncell;
@@ -61,6 +75,9 @@ int main() {
       if (mode == 0) k<0><<<grid, 128, smem>>>(acc, ncell, cp, iters, bytes, local);
       if (mode == 1) k<1><<<grid, 128, smem>>>(acc, ncell, cp, iters, bytes, local);
       if (mode == 2) k<2><<<grid, 128, smem>>>(acc, ncell, cp, iters, bytes, local);
+      if (mode == 3) k<3><<<grid, 128, smem>>>(acc, ncell, cp, iters, bytes, local);
+      if (mode == 4) k<4><<<grid, 128, smem>>>(acc, ncell, cp, iters, bytes, local);
+      if (mode == 5) k<5><<<grid, 128, smem>>>(acc, ncell, cp, iters, bytes, local);
       cudaEventRecord(e1);
       CK(cudaEventSynchronize(e1));
     }
@@ -76,6 +93,9 @@ int main() {
       run("RED lane=channel (2 runlets/instr)", 0, 17, c, 2000, 0, local, 2);
       run("RED lane=channel (2 runlets/instr)", 0, 16, c, 2000, 0, local, 2);
       run("RED lane=runlet (32 cells/instr)", 2, 17, c, 500, 0, local, 32);
+      run("RED lane=channel, 1 runlet x 16 ch/instr", 3, 17, c, 2000, 0, local, 1);
+      run("RED 1 cell x 32 words/instr (128 B)", 4, 32, c, 2000, 0, local, 1);
+      run("RED 4 runlets x 8 ch/instr", 5, 9, c, 2000, 0, local, 4);
       run("bulk reduce 64 B/runlet (32 runlets/instr)", 1, 16, c, 500, 64, local, 32);
       run("bulk reduce 80 B/runlet (32 runlets/instr)", 1, 20, c, 500, 80, local, 32);
       run("bulk reduce 128 B/runlet (32 runlets/instr)", 1, 32, c, 500, 128, local, 32);
