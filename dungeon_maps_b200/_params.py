@@ -200,6 +200,16 @@ class _PinnedRing:
   def __init__(self, slots: int = 64, slot_bytes: int = 1 << 16):
     self.slots, self.slot_bytes = slots, slot_bytes
     self._bufs, self._events, self._next = {}, {}, {}
+    self._streams = {}
+
+  def _stream(self, device: torch.device):
+    """torch Stream object of the current stream, looked up by its raw handle (torch.cuda.current_stream builds a
+    new object per call, ~10 us)."""
+    raw = nat.stream_ptr(device)
+    hit = self._streams.get((device.index, raw))
+    if hit is None:
+      hit = self._streams[(device.index, raw)] = torch.cuda.current_stream(device)
+    return hit
 
   def to_device(self, host: torch.Tensor, device: torch.device) -> torch.Tensor:
     nbytes = host.numel() * host.element_size()
@@ -221,7 +231,7 @@ class _PinnedRing:
     staged.copy_(host)
     dev = torch.empty(host.shape, dtype=host.dtype, device=device)
     dev.copy_(staged, non_blocking=True)
-    self._events[key][i].record(torch.cuda.current_stream(device))
+    self._events[key][i].record(self._stream(device))
     return dev
 
 

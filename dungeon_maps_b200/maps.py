@@ -829,17 +829,21 @@ def _fuse_source(m: TopdownMap, target: MapProjector, b: int, C: int, n_total: i
   # maps.py:2116-2117: everything goes to the target's local space if the target is local
   s0 = prm.identity(b) if m.proj.to_global else prm.local_to_global(pose, C * h * w)
   s1 = prm.identity(b) if target.to_global else prm.global_to_local(tpose, n_total)
-  steps = prm.upload(torch.cat((s0, s1), dim=1), dev)
-  woff = prm.upload(prm.per_sample(get(m.proj.width_offset, 0.), b).contiguous(), dev)
-  hoff = prm.upload(prm.per_sample(get(m.proj.height_offset, 0.), b).contiguous(), dev)
-  keep.extend((hm, mask, values, steps, woff, hoff))
+  # one parameter block per source: [steps (b, 2, 16 words) | width offsets (b,) | height offsets (b,)], one upload
+  params = torch.cat((torch.cat((s0, s1), dim=1).reshape(-1),
+                      prm.per_sample(get(m.proj.width_offset, 0.), b).reshape(-1),
+                      prm.per_sample(get(m.proj.height_offset, 0.), b).reshape(-1)))
+  params_dev = prm.upload(params, dev)
+  n_step_words = b * 2 * prm.STEP_WORDS
+  keep.extend((hm, mask, values, params_dev))
   src = nat.DmFuseSource()
   src.height, src.values, src.mask = hm.data_ptr(), nat.ptr(values), mask.data_ptr()
   src.height_bstride, src.height_cstride = hm.stride(0), hm.stride(1)
   src.h, src.w = h, w
   src.flip_h = bool(m.proj.flip_h)
   src.map_res = m.proj.map_res
-  src.width_offset, src.height_offset, src.steps = woff.data_ptr(), hoff.data_ptr(), steps.data_ptr()
+  base = params_dev.data_ptr()
+  src.steps, src.width_offset, src.height_offset = base, base + 4 * n_step_words, base + 4 * (n_step_words + b)
   return src
 
 
