@@ -244,13 +244,12 @@ class FlowWorkload:
     self.o_grid = torch.empty((self.B, 1, self.H, self.W, 2), dtype=torch.float32).pin_memory()
     self.h2d = self.h_depth.numel() * 4 + self.B * 192
     self.d2h = self.o_grid.numel() * 4
-    self.e2e_path = "MapProjector.camera_affine_grid on pinned host tensors (H2D copy, kernel, D2H copy of the grid)"
+    self.e2e_path = ("hostapi.camera_affine_grid_host -> MapProjector.camera_affine_grid on pinned host tensors "
+                     "(32-frame chunks: H2D copy, kernel, D2H copy of the grid on three streams)")
 
   def e2e_step(self):
-    d = self.h_depth.to(self.dev, non_blocking=True)
-    g = self.proj.camera_affine_grid(d, self.delta_host)
-    self.o_grid.copy_(g, non_blocking=True)
-    torch.cuda.current_stream(self.dev).synchronize()
+    from dungeon_maps_b200 import hostapi
+    hostapi.camera_affine_grid_host(self.proj, self.h_depth, self.delta_host, out=self.o_grid)
 
   def e2e_check(self):
     assert torch.equal(self.o_grid.nan_to_num(), self.out.cpu().nan_to_num()), "host path and device path disagree"

@@ -74,3 +74,43 @@ def orth_project_host(depth_map, value_map, valid_map, cam_pose, width_offset, h
   if not get_height_map:
     return top, mask_b
   return top, mask_b, (top if C == 0 else hgt)
+
+
+_flow_streams = {}
+
+
+def camera_affine_grid_host(proj, depth_map: torch.Tensor, trans_pose, out: Optional[torch.Tensor] = None,
+                            chunk: int = 32, **kwargs) -> torch.Tensor:
+  """MapProjector.camera_affine_grid (maps.py:353-460) for HOST depth maps: the batch goes through the device in
+  chunks of `chunk` frames — host→device copy, kernel, device→host copy of the grid on three streams — so that both
+  PCIe directions and the kernel overlap (the grid is twice the size of the depth: one blocking round trip is
+  copy-out bound and leaves the copy-in engine idle two thirds of the time).
+  depth_map: (b, 1, H, W) float32 CPU tensor (pinned for full-rate copies); trans_pose: (b, 3) or (3,);
+  out: optional (b, 1, H, W, 2) float32 CPU tensor (pinned).  Returns `out`."""
+  dev = nat.require_cuda(proj.device)
+  depth = depth_map if torch.is_tensor(depth_map) else torch.as_tensor(np.asarray(depth_map, dtype=np.float32))
+  assert depth.dim() == 4 and depth.shape[1] == 1 and depth.dtype is torch.float32 and depth.device.type == "cpu", \
+      "depth_map must be a (b, 1, H, W) float32 CPU tensor"
+  b, _, H, W = depth.shape
+  pose = prm.per_sample(trans_pose, b, (3,), "trans_pose")
+  if out is None:
+    out = torch.empty((b, 1, H, W, 2), dtype=torch.float32).pin_memory()
+  streams = _flow_streams.get(dev.index)
+  if streams is None:
+    streams = _flow_streams[dev.index] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+  s_in, s_out = streams
+  cur = torch.cuda.current_stream(dev)
+  s_in.wait_stream(cur)  # nothing the caller queued is overtaken
+  for i0 in range(0, b, max(int(chunk), 1)):
+    i1 = min(b, i0 + max(int(chunk), 1))
+    with torch.cuda.stream(s_in):
+      d = depth[i0:i1].to(dev, non_blocking=True)
+    d.record_stream(cur)
+    cur.wait_stream(s_in)
+    grid = proj.camera_affine_grid(d, pose[i0:i1], **kwargs)
+    grid.record_stream(s_out)
+    s_out.wait_stream(cur)
+    with torch.cuda.stream(s_out):
+      out[i0:i1].copy_(grid, non_blocking=True)
+  s_out.synchronize()
+  return out

@@ -287,6 +287,25 @@ def test_camera_affine_grid_480x640_and_flow():
   assert_same(npy(flow), g2["out_flow"], "ego flow")
 
 
+def test_camera_affine_grid_host_pipeline():
+  """hostapi.camera_affine_grid_host: host depth in, host grid out through the chunked three-stream pipeline —
+  ragged last chunk, more chunks than streams, repeated calls — equals the oracle bit for bit."""
+  from dungeon_maps_b200 import hostapi
+  b, H, W = 11, 48, 64
+  depth = synth.iid_depth(b, H, W, seed=31)
+  pose = synth.uniform((b, 3), 32, -0.3, 0.3)
+  intr = orc.intrinsics(W, H, HFOV)
+  proj = dmap.MapProjector(width=W, height=H, hfov=HFOV, cam_pitch=PITCH, cam_height=0.88, device="cuda")
+  want = orc.camera_affine_grid(depth.numpy(), pose.numpy(), PITCH, 0.88, intr["fx"], intr["fy"], intr["cx"], intr["cy"])
+  out = torch.empty((b, 1, H, W, 2), dtype=torch.float32).pin_memory()
+  for chunk in (3, 4, 32):
+    out.fill_(-7.0)
+    got = hostapi.camera_affine_grid_host(proj, depth.pin_memory(), pose, out=out, chunk=chunk)
+    assert got is out
+    assert_same(got.numpy(), want, f"grid chunk={chunk}")
+  assert_same(hostapi.camera_affine_grid_host(proj, depth, pose, chunk=5).numpy(), want, "grid (pageable in, fresh out)")
+
+
 def test_camera_affine_grid_full_config3():
   """BASELINE config 3 at full size (256 x 480x640, random pose deltas): frames bit-exact against the oracle —
   among them frames salted with NaN / inf / zero / negative / huge depths, which leave the packed straight-line
