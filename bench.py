@@ -13,8 +13,8 @@ Other workloads (BASELINE.json configs 3, 4, 5; results kept under profiles/):
   builder        MapBuilder.step (plot + reference-parity merge), 32 environments walking for 100 steps
   builder_fixed  the same walk merged in place into fixed 2400x2400 world canvases (opt-in mode)
   proj5          the projection at 1280x720 with 40 semantic channels, one 64-frame chunk per step
-N > 1: one process per GPU (torchrun), every rank works on its own environments, no collective on
-the data path (weak scaling).  Prints ONE JSON line on rank 0.
+N > 1: one process per GPU (torchrun; `python bench.py --gpus N` on its own re-launches itself that way), every
+rank works on its own environments, no collective on the data path (weak scaling).  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -599,6 +599,15 @@ def main():
   ap.add_argument("--e2e-steps", type=int, default=5)
   ap.add_argument("--no-cpu-baseline", action="store_true")
   args = ap.parse_args()
+  if args.gpus > 1 and args.impl == "ours" and "WORLD_SIZE" not in os.environ:
+    # called directly with --gpus N: become the torchrun launch the driver would have made (one rank per GPU)
+    import socket
+    with socket.socket() as sock:
+      sock.bind(("127.0.0.1", 0))
+      port = sock.getsockname()[1]
+    os.execv(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                              f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port", str(port),
+                              os.path.abspath(__file__)] + sys.argv[1:])
   # stdout carries the one JSON line and nothing else: libraries that print from C (NCCL's version banner ignores
   # NCCL_DEBUG_FILE on some boxes) get stderr as their fd 1 while the run lasts
   sys.stdout.flush()
