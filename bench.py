@@ -127,6 +127,8 @@ class ProjWorkload:
 
   def __init__(self, args, key="proj"):
     self.key, self.scene = key, args.scene
+    self.labels = key.endswith("_labels")
+    key = key.replace("_labels", "")
     if key == "proj":
       self.B, self.H, self.W, self.C = 64, 480, 640, 16
       self.metric = "top-down maps/sec (batch 64, 640x480 depth + 16 semantic channels -> 400x400 maps)"
@@ -139,8 +141,14 @@ class ProjWorkload:
                    "40-channel one-hot semantics -> 400x400 maps per step, per GPU; every GPU streams 4096/N frames")
     self.units_per_step = self.B
     # read 4*N*(1+C) input bytes, write Mh*Mw*(4C + C + 4) output bytes per frame
-    self.algo_bytes_per_step = self.B * (4 * self.H * self.W * (1 + self.C) + MH * MW * (4 * self.C + self.C + 4))
-    self.l2_note = f"inputs ({4 * self.B * self.H * self.W * (1 + self.C) / 1e9:.2f} GB per step) are larger than the 126 MB L2; no flush needed"
+    in_bytes = self.H * self.W * (5 if self.labels else 4 * (1 + self.C))
+    self.algo_bytes_per_step = self.B * (in_bytes + MH * MW * (4 * self.C + self.C + 4))
+    self.l2_note = (f"{self.algo_bytes_per_step / 1e9:.2f} GB move per step (inputs {self.B * in_bytes / 1e9:.2f} GB), larger than "
+                    "the 126 MB L2; no flush needed")
+    if self.labels:
+      self.kernel = "dm::proj_lbl_kernel (one step = ONE persistent launch of dm_orth_project_labels_f32)"
+      self.metric += " [semantics given as uint8 class ids]"
+      self.name += "; semantics enter as (b,1,H,W) uint8 class ids (label_map=, num_classes=16): bit-identical outputs"
 
   def kwargs(self):
     fx, fy, cx, cy = intrinsics(self.W, self.H)
@@ -162,26 +170,40 @@ class ProjWorkload:
                                   map_height=MH, trunc_depth_min=0.15, trunc_depth_max=5.05, clip_border=10,
                                   to_global=False, fill_value=dmap.NINF, device=dev)
     self.pose_host = pose.cpu()
+    self.label_ids = self.values.argmax(1, keepdim=True).to(torch.uint8)
 
   def step(self):
-    self.out = self.proj.orth_project(self.depth, self.values, cam_pose=self.pose_host, get_height_map=True)
+    if self.labels:
+      self.out = self.proj.orth_project(self.depth, cam_pose=self.pose_host, get_height_map=True,
+                                        label_map=self.label_ids, num_classes=self.C)
+    else:
+      self.out = self.proj.orth_project(self.depth, self.values, cam_pose=self.pose_host, get_height_map=True)
     return self.out
 
   def e2e_setup(self):
     B, C = self.B, self.C
     self.h_depth = self.depth.cpu().pin_memory().numpy()
-    self.h_values = self.values.cpu().pin_memory().numpy()
+    if self.labels:
+      self.h_values = self.label_ids.cpu().pin_memory().numpy()
+    else:
+      self.h_values = self.values.cpu().pin_memory().numpy()
     self.o_top = torch.empty((B, C, MH, MW), dtype=torch.float32).pin_memory().numpy()
     self.o_mask = torch.empty((B, C, MH, MW), dtype=torch.uint8).pin_memory().numpy()
     self.o_hgt = torch.empty((B, 1, MH, MW), dtype=torch.float32).pin_memory().numpy()
     self.h2d = self.h_depth.nbytes + self.h_values.nbytes + B * 192
     self.d2h = self.o_top.nbytes + self.o_mask.nbytes + self.o_hgt.nbytes
-    self.e2e_path = "hostapi.orth_project_host -> dm_orth_project_host_f32 (pinned host buffers)"
+    self.e2e_path = ("hostapi.orth_project_host -> dm_orth_project_labels_host_f32 (pinned host buffers)" if self.labels
+                     else "hostapi.orth_project_host -> dm_orth_project_host_f32 (pinned host buffers)")
 
   def e2e_step(self):
     from dungeon_maps_b200 import hostapi
-    hostapi.orth_project_host(self.h_depth, self.h_values, None, self.pose_host, 200., 0., PITCH, CAM_H,
-                              device=self.dev.index, out=(self.o_top, self.o_mask, self.o_hgt), **self.kwargs())
+    if self.labels:
+      hostapi.orth_project_host(self.h_depth, None, None, self.pose_host, 200., 0., PITCH, CAM_H,
+                                device=self.dev.index, out=(self.o_top, self.o_mask, self.o_hgt),
+                                label_map=self.h_values, num_classes=self.C, **self.kwargs())
+    else:
+      hostapi.orth_project_host(self.h_depth, self.h_values, None, self.pose_host, 200., 0., PITCH, CAM_H,
+                                device=self.dev.index, out=(self.o_top, self.o_mask, self.o_hgt), **self.kwargs())
 
   def e2e_check(self):
     assert np.array_equal(self.o_top, self.out[0].cpu().numpy()) and \
@@ -414,7 +436,7 @@ class BuilderWorkload:
 
 
 def make_workload(args):
-  if args.workload in ("proj", "proj5"):
+  if args.workload in ("proj", "proj5", "proj_labels", "proj5_labels"):
     return ProjWorkload(args, args.workload)
   if args.workload == "flow":
     return FlowWorkload(args)
@@ -594,7 +616,8 @@ def main():
   ap.add_argument("--steps", type=int, default=200)
   ap.add_argument("--warmup", type=int, default=10)
   ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
-  ap.add_argument("--workload", choices=("proj", "flow", "builder", "builder_fixed", "proj5"), default="proj")
+  ap.add_argument("--workload", choices=("proj", "flow", "builder", "builder_fixed", "proj5", "proj_labels", "proj5_labels"),
+                  default="proj")
   ap.add_argument("--scene", choices=("room", "iid"), default="room")
   ap.add_argument("--e2e-steps", type=int, default=5)
   ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -74,6 +74,14 @@ _SIGNATURES = {
                                          c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
   "dm_orth_project_host_f32": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(DmProjCfg), c_int32,
                                               c_void_p, c_void_p, c_void_p, c_int32]),
+  "dm_orth_project_labels_workspace_bytes": (c_size_t, [POINTER(DmProjCfg), c_int32]),
+  "dm_orth_project_labels_f32": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(DmProjCfg), c_int32,
+                                                c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+  "dm_orth_project_labels_host_f32": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(DmProjCfg),
+                                                     c_int32, c_void_p, c_void_p, c_void_p, c_int32]),
+  "dm_device_status": (ctypes.c_int, [c_int32]),
+  "dm_debug_set_wait_guard": (None, [ctypes.c_uint64, ctypes.c_uint32]),
+  "dm_debug_set_host_chunk": (None, [c_int32]),
   "dm_affine_grid_f32": (ctypes.c_int, [c_void_p, c_void_p, POINTER(DmFlowCfg), c_int32, c_void_p, c_void_p]),
   "dm_fuse_bbox_i64": (ctypes.c_int, [POINTER(DmFuseSource), c_int32, c_int32, c_int32, c_float, c_void_p, c_void_p]),
   "dm_fuse_scatter_f32": (ctypes.c_int, [POINTER(DmFuseSource), c_int32, c_int32, c_int32, POINTER(DmFuseTarget),
@@ -140,7 +148,9 @@ def check(rc: int, what: str) -> None:
     return
   if rc > 0:
     raise NativeError(f"{what}: CUDA error {rc}")
-  names = {-1: "invalid argument", -2: "workspace too small", -3: "device-side wait timed out"}
+  names = {-1: "invalid argument", -2: "workspace too small",
+           -3: "a device-side dependency wait timed out in an earlier launch on this device (its outputs are invalid; "
+               "the workspace was re-zeroed, the call can be repeated)"}
   raise NativeError(f"{what}: {names.get(rc, rc)}")
 
 
@@ -166,6 +176,13 @@ def stream_ptr(device: torch.device) -> int:
   """cudaStream_t of torch's current stream on `device` (the raw getter: torch.cuda.current_stream builds a Stream
   object, ~10 us a call, and a MapBuilder step asks a dozen times)."""
   return torch._C._cuda_getCurrentRawStream(device.index if device.index is not None else torch.cuda.current_device())
+
+
+def device_status(device=None) -> None:
+  """Raises NativeError if a projection launch on `device` ran into the dependency-wait guard since the last check
+  (include/dungeon_maps_b200.h: dm_device_status).  Synchronise the stream first."""
+  dev = require_cuda(device)
+  check(lib().dm_device_status(dev.index), "dm_device_status")
 
 
 def launch_count() -> int:

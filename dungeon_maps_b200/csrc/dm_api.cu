@@ -1,21 +1,38 @@
-// Library-level entry points: ABI introspection, launch accounting and the HOST-buffer
-// variant of the projection (host→device copy, kernels, device→host copy as a three-stream
+// Library-level entry points: ABI introspection, launch accounting, the device-side wait guard / status word, and
+// the HOST-buffer variants of the projection (host→device copy, kernels, device→host copy as a three-stream
 // pipeline over a ring of staging slots, so that both PCIe directions and the kernels overlap).
 #include <cstdlib>
 #include <mutex>
 
-#include "dm_common.cuh"
+#include "dm_project.cuh"
 
 namespace dm {
 int64_t g_launches = 0;
 
 namespace {
-// Pipeline of the HOST-buffer entry: three streams (host→device, kernels, device→host) and a ring of
+constexpr int kMaxDevices = 64;
+
+// ---- dependency-wait guard: one mapped pinned status word per device (ProjGuard, dm_project.cuh) ----------------
+struct StatusWord {
+  volatile uint32_t* host = nullptr;
+  uint32_t* dev = nullptr;
+  bool tried = false;
+};
+StatusWord g_status[kMaxDevices];
+std::mutex g_status_mu;
+unsigned long long g_spin_ns = kSpinLimitNs;
+uint32_t g_dep_bias = 0;
+int g_host_chunk = 0;  // test hook (dm_debug_set_host_chunk): frames per chunk of the host-buffer pipeline, 0 = automatic
+
+// Pipeline of the HOST-buffer entries: three streams (host→device, kernels, device→host) and a ring of
 // kSlots staging slots, chained with events.  The copy engine of each PCIe direction always has the next
 // chunk queued (a two-stream A/B scheme left the H2D engine idle while the same stream's D2H ran).
+// One Scratch per device, each behind its own mutex: two host threads on two devices do not serialise, and
+// switching devices does not free anything.
 constexpr int kSlots = 4;
 struct Scratch {
-  int device = -1;
+  std::mutex mu;
+  bool ready = false;
   cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
   cudaEvent_t ev_in[kSlots] = {}, ev_run[kSlots] = {}, ev_out[kSlots] = {};
   void* buf[kSlots] = {};   // staging: inputs + outputs of one chunk
@@ -23,31 +40,82 @@ struct Scratch {
   void* ws = nullptr;       // accumulation ring (kept zeroed by the kernel); kernels run on ONE stream
   size_t ws_bytes = 0;
 };
-Scratch g_scratch;
-std::mutex g_mu;
+Scratch g_scratch[kMaxDevices];
 
-void release_locked() {
+// caller holds sc.mu and has made `device` current
+void release_locked(Scratch& sc) {
   for (int i = 0; i < kSlots; ++i) {
-    if (g_scratch.buf[i]) cudaFree(g_scratch.buf[i]);
-    if (g_scratch.ev_in[i]) cudaEventDestroy(g_scratch.ev_in[i]);
-    if (g_scratch.ev_run[i]) cudaEventDestroy(g_scratch.ev_run[i]);
-    if (g_scratch.ev_out[i]) cudaEventDestroy(g_scratch.ev_out[i]);
-    g_scratch.buf[i] = nullptr;
-    g_scratch.buf_bytes[i] = 0;
-    g_scratch.ev_in[i] = g_scratch.ev_run[i] = g_scratch.ev_out[i] = nullptr;
+    if (sc.buf[i]) cudaFree(sc.buf[i]);
+    if (sc.ev_in[i]) cudaEventDestroy(sc.ev_in[i]);
+    if (sc.ev_run[i]) cudaEventDestroy(sc.ev_run[i]);
+    if (sc.ev_out[i]) cudaEventDestroy(sc.ev_out[i]);
+    sc.buf[i] = nullptr;
+    sc.buf_bytes[i] = 0;
+    sc.ev_in[i] = sc.ev_run[i] = sc.ev_out[i] = nullptr;
   }
-  if (g_scratch.ws) cudaFree(g_scratch.ws);
-  g_scratch.ws = nullptr;
-  g_scratch.ws_bytes = 0;
-  if (g_scratch.s_in) cudaStreamDestroy(g_scratch.s_in);
-  if (g_scratch.s_run) cudaStreamDestroy(g_scratch.s_run);
-  if (g_scratch.s_out) cudaStreamDestroy(g_scratch.s_out);
-  g_scratch.s_in = g_scratch.s_run = g_scratch.s_out = nullptr;
-  g_scratch.device = -1;
+  if (sc.ws) cudaFree(sc.ws);
+  sc.ws = nullptr;
+  sc.ws_bytes = 0;
+  if (sc.s_in) cudaStreamDestroy(sc.s_in);
+  if (sc.s_run) cudaStreamDestroy(sc.s_run);
+  if (sc.s_out) cudaStreamDestroy(sc.s_out);
+  sc.s_in = sc.s_run = sc.s_out = nullptr;
+  sc.ready = false;
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Restores the caller's current device on every exit path of the host entries.
+struct DeviceScope {
+  int prev = -1;
+  bool changed = false;
+  cudaError_t enter(int device) {
+    cudaError_t e = cudaGetDevice(&prev);
+    if (e != cudaSuccess) return e;
+    if (prev != device) {
+      e = cudaSetDevice(device);
+      changed = e == cudaSuccess;
+    }
+    return e;
+  }
+  ~DeviceScope() {
+    if (changed) cudaSetDevice(prev);
+  }
+};
 }  // namespace
+
+ProjGuard proj_guard(int device) {
+  ProjGuard g{g_spin_ns, g_dep_bias, nullptr};
+  if (device < 0 || device >= kMaxDevices) return g;
+  std::lock_guard<std::mutex> lk(g_status_mu);
+  StatusWord& s = g_status[device];
+  if (!s.tried) {  // the caller has made `device` current
+    s.tried = true;
+    void* h = nullptr;
+    if (cudaHostAlloc(&h, 64, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) {
+      *static_cast<volatile uint32_t*>(h) = 0u;
+      void* d = nullptr;
+      if (cudaHostGetDevicePointer(&d, h, 0) == cudaSuccess) {
+        s.host = static_cast<volatile uint32_t*>(h);
+        s.dev = static_cast<uint32_t*>(d);
+      } else {
+        cudaFreeHost(h);
+      }
+    }
+    cudaGetLastError();  // without mapped memory the guard still skips the item and scrubs the workspace
+  }
+  g.status = s.dev;
+  return g;
+}
+
+bool take_timeout(int device) {
+  if (device < 0 || device >= kMaxDevices) return false;
+  std::lock_guard<std::mutex> lk(g_status_mu);
+  StatusWord& s = g_status[device];
+  if (!s.host || *s.host == 0u) return false;
+  *s.host = 0u;
+  return true;
+}
 }  // namespace dm
 
 using namespace dm;
@@ -60,114 +128,167 @@ extern "C" const char* dm_build_info(void) {
 
 extern "C" int64_t dm_launch_count(void) { return g_launches; }
 
-extern "C" void dm_release_scratch(void) {
-  std::lock_guard<std::mutex> lk(g_mu);
-  release_locked();
+extern "C" int dm_device_status(int32_t device) { return take_timeout(device) ? DM_ETIMEOUT : DM_OK; }
+
+extern "C" void dm_debug_set_wait_guard(uint64_t spin_ns, uint32_t dep_bias) {
+  g_spin_ns = spin_ns ? spin_ns : kSpinLimitNs;
+  g_dep_bias = dep_bias;
 }
 
-extern "C" int dm_orth_project_host_f32(const float* depth, const float* values, const uint8_t* valid,
-                                        const DmProjSample* samples, const DmProjCfg* cfg, int32_t b,
-                                        float* topdown, uint8_t* mask, float* height, int32_t device) {
+extern "C" void dm_debug_set_host_chunk(int32_t frames) { g_host_chunk = frames > 0 ? frames : 0; }
+
+extern "C" void dm_release_scratch(void) {
+  int prev = -1;
+  cudaGetDevice(&prev);
+  for (int d = 0; d < kMaxDevices; ++d) {
+    Scratch& sc = g_scratch[d];
+    std::lock_guard<std::mutex> lk(sc.mu);
+    if (!sc.ready) continue;
+    if (cudaSetDevice(d) == cudaSuccess) release_locked(sc);
+  }
+  if (prev >= 0) cudaSetDevice(prev);
+  cudaGetLastError();
+}
+
+namespace {
+// Shared body of dm_orth_project_host_f32 (values: (b, C, H, W) f32 planes) and dm_orth_project_labels_host_f32
+// (labels: (b, 1, H, W) u8 class ids, cfg->C classes).
+int orth_project_host(const float* depth, const float* values, const uint8_t* labels, const uint8_t* valid,
+                      const DmProjSample* samples, const DmProjCfg* cfg, int32_t b, float* topdown, uint8_t* mask,
+                      float* height, int32_t device) {
   if (!cfg || b < 0) return DM_EINVAL;
   if (b == 0) return DM_OK;
   if (!depth || !samples || !topdown || !mask) return DM_EINVAL;
-  if (cfg->C > 0 && !values) return DM_EINVAL;
-  std::lock_guard<std::mutex> lk(g_mu);
-  DM_CUDA_OK(cudaSetDevice(device));
-  if (g_scratch.device != device) {
-    release_locked();
-    g_scratch.device = device;
-    DM_CUDA_OK(cudaStreamCreateWithFlags(&g_scratch.s_in, cudaStreamNonBlocking));
-    DM_CUDA_OK(cudaStreamCreateWithFlags(&g_scratch.s_run, cudaStreamNonBlocking));
-    DM_CUDA_OK(cudaStreamCreateWithFlags(&g_scratch.s_out, cudaStreamNonBlocking));
+  if (cfg->C > 0 && !values && !labels) return DM_EINVAL;
+  if (device < 0 || device >= kMaxDevices) return DM_EINVAL;
+  DeviceScope scope;
+  DM_CUDA_OK(scope.enter(device));
+  Scratch& sc = g_scratch[device];
+  std::lock_guard<std::mutex> lk(sc.mu);
+  if (!sc.ready) {
+    DM_CUDA_OK(cudaStreamCreateWithFlags(&sc.s_in, cudaStreamNonBlocking));
+    DM_CUDA_OK(cudaStreamCreateWithFlags(&sc.s_run, cudaStreamNonBlocking));
+    DM_CUDA_OK(cudaStreamCreateWithFlags(&sc.s_out, cudaStreamNonBlocking));
     for (int i = 0; i < kSlots; ++i) {
-      DM_CUDA_OK(cudaEventCreateWithFlags(&g_scratch.ev_in[i], cudaEventDisableTiming));
-      DM_CUDA_OK(cudaEventCreateWithFlags(&g_scratch.ev_run[i], cudaEventDisableTiming));
-      DM_CUDA_OK(cudaEventCreateWithFlags(&g_scratch.ev_out[i], cudaEventDisableTiming));
+      DM_CUDA_OK(cudaEventCreateWithFlags(&sc.ev_in[i], cudaEventDisableTiming));
+      DM_CUDA_OK(cudaEventCreateWithFlags(&sc.ev_run[i], cudaEventDisableTiming));
+      DM_CUDA_OK(cudaEventCreateWithFlags(&sc.ev_out[i], cudaEventDisableTiming));
     }
+    sc.ready = true;
   }
   const size_t N = (size_t)cfg->H * cfg->W, M = (size_t)cfg->Mh * cfg->Mw;
   const int Cv = cfg->C > 0 ? cfg->C : 1;
   const bool want_h = cfg->C > 0 && cfg->want_height && height;
+  const size_t value_bytes = labels ? N : N * 4 * (size_t)cfg->C;  // per frame
   // chunk: ≈ 80 MB of traffic per chunk — large enough for full-rate PCIe copies, small enough that the fill
   // (first chunk in) and drain (last chunk out) of the pipeline stay a few per cent of a 64-frame call
-  // (DM_HOST_CHUNK overrides, for experiments)
-  const size_t frame_bytes = N * 4 * (1 + (size_t)cfg->C) + (valid ? N : 0) + M * (5 * (size_t)Cv + (want_h ? 4 : 0));
+  const size_t frame_bytes = N * 4 + value_bytes + (valid ? N : 0) + M * (5 * (size_t)Cv + (want_h ? 4 : 0));
   int chunk = (int)((80u << 20) / (frame_bytes ? frame_bytes : 1));
-  if (const char* e = getenv("DM_HOST_CHUNK")) chunk = atoi(e);
+  if (g_host_chunk > 0) chunk = g_host_chunk;
   if (chunk < 1) chunk = 1;
   if (chunk > 16) chunk = 16;
   if (chunk > b) chunk = b;
   // staging layout of one chunk (every section 256-byte aligned)
   const size_t o_depth = 0;
   const size_t o_values = align_up(o_depth + chunk * N * 4, 256);
-  const size_t o_valid = align_up(o_values + (size_t)chunk * cfg->C * N * 4, 256);
+  const size_t o_valid = align_up(o_values + (size_t)chunk * value_bytes, 256);
   const size_t o_samples = align_up(o_valid + (valid ? chunk * N : 0), 256);
   const size_t o_top = align_up(o_samples + chunk * sizeof(DmProjSample), 256);
   const size_t o_mask = align_up(o_top + (size_t)chunk * Cv * M * 4, 256);
   const size_t o_height = align_up(o_mask + (size_t)chunk * Cv * M, 256);
   const size_t total = align_up(o_height + (want_h ? chunk * M * 4 : 0), 256);
-  const size_t ws_need = dm_orth_project_workspace_bytes(cfg, chunk);
+  const size_t ws_need = labels ? dm_orth_project_labels_workspace_bytes(cfg, chunk)
+                                : dm_orth_project_workspace_bytes(cfg, chunk);
+  if (ws_need == 0) return DM_EINVAL;
   for (int i = 0; i < kSlots; ++i) {
-    if (g_scratch.buf_bytes[i] < total) {
-      if (g_scratch.buf[i]) DM_CUDA_OK(cudaFree(g_scratch.buf[i]));
-      g_scratch.buf[i] = nullptr; g_scratch.buf_bytes[i] = 0;
-      DM_CUDA_OK(cudaMalloc(&g_scratch.buf[i], total));
-      g_scratch.buf_bytes[i] = total;
+    if (sc.buf_bytes[i] < total) {
+      if (sc.buf[i]) DM_CUDA_OK(cudaFree(sc.buf[i]));
+      sc.buf[i] = nullptr; sc.buf_bytes[i] = 0;
+      DM_CUDA_OK(cudaMalloc(&sc.buf[i], total));
+      sc.buf_bytes[i] = total;
     }
   }
-  if (g_scratch.ws_bytes < ws_need) {
-    if (g_scratch.ws) DM_CUDA_OK(cudaFree(g_scratch.ws));
-    g_scratch.ws = nullptr; g_scratch.ws_bytes = 0;
-    DM_CUDA_OK(cudaMalloc(&g_scratch.ws, ws_need));
-    DM_CUDA_OK(cudaMemset(g_scratch.ws, 0, ws_need));
-    g_scratch.ws_bytes = ws_need;
+  if (sc.ws_bytes < ws_need) {
+    if (sc.ws) DM_CUDA_OK(cudaFree(sc.ws));
+    sc.ws = nullptr; sc.ws_bytes = 0;
+    DM_CUDA_OK(cudaMalloc(&sc.ws, ws_need));
+    DM_CUDA_OK(cudaMemset(sc.ws, 0, ws_need));
+    sc.ws_bytes = ws_need;
   }
   int rc = DM_OK;
   int it = 0;
+#define DM_STEP(expr)                                            \
+  {                                                              \
+    const cudaError_t e_ = (expr);                               \
+    if (e_ != cudaSuccess) { rc = static_cast<int>(e_); break; } \
+  }
   for (int f0 = 0; f0 < b && rc == DM_OK; f0 += chunk, ++it) {
     const int nf = (b - f0) < chunk ? (b - f0) : chunk;
     const int k = it % kSlots;
-    char* base = static_cast<char*>(g_scratch.buf[k]);
+    char* base = static_cast<char*>(sc.buf[k]);
     float* d_depth = reinterpret_cast<float*>(base + o_depth);
-    float* d_values = cfg->C > 0 ? reinterpret_cast<float*>(base + o_values) : nullptr;
+    void* d_values = cfg->C > 0 ? static_cast<void*>(base + o_values) : nullptr;
     uint8_t* d_valid = valid ? reinterpret_cast<uint8_t*>(base + o_valid) : nullptr;
     DmProjSample* d_samples = reinterpret_cast<DmProjSample*>(base + o_samples);
     float* d_top = reinterpret_cast<float*>(base + o_top);
     uint8_t* d_mask = reinterpret_cast<uint8_t*>(base + o_mask);
     float* d_height = want_h ? reinterpret_cast<float*>(base + o_height) : nullptr;
     // host → device (the slot is free once its previous results have left)
-    cudaStream_t si = g_scratch.s_in;
-    if (it >= kSlots) DM_CUDA_OK(cudaStreamWaitEvent(si, g_scratch.ev_out[k], 0));
-    DM_CUDA_OK(cudaMemcpyAsync(d_depth, depth + (size_t)f0 * N, (size_t)nf * N * 4, cudaMemcpyHostToDevice, si));
-    if (d_values)
-      DM_CUDA_OK(cudaMemcpyAsync(d_values, values + (size_t)f0 * cfg->C * N, (size_t)nf * cfg->C * N * 4,
-                                 cudaMemcpyHostToDevice, si));
-    if (d_valid)
-      DM_CUDA_OK(cudaMemcpyAsync(d_valid, valid + (size_t)f0 * N, (size_t)nf * N, cudaMemcpyHostToDevice, si));
-    DM_CUDA_OK(cudaMemcpyAsync(d_samples, samples + f0, (size_t)nf * sizeof(DmProjSample), cudaMemcpyHostToDevice, si));
-    DM_CUDA_OK(cudaEventRecord(g_scratch.ev_in[k], si));
+    cudaStream_t si = sc.s_in;
+    if (it >= kSlots) DM_STEP(cudaStreamWaitEvent(si, sc.ev_out[k], 0));
+    DM_STEP(cudaMemcpyAsync(d_depth, depth + (size_t)f0 * N, (size_t)nf * N * 4, cudaMemcpyHostToDevice, si));
+    if (d_values) {
+      const char* src = labels ? reinterpret_cast<const char*>(labels) : reinterpret_cast<const char*>(values);
+      DM_STEP(cudaMemcpyAsync(d_values, src + (size_t)f0 * value_bytes, (size_t)nf * value_bytes,
+                              cudaMemcpyHostToDevice, si));
+    }
+    if (d_valid) DM_STEP(cudaMemcpyAsync(d_valid, valid + (size_t)f0 * N, (size_t)nf * N, cudaMemcpyHostToDevice, si));
+    DM_STEP(cudaMemcpyAsync(d_samples, samples + f0, (size_t)nf * sizeof(DmProjSample), cudaMemcpyHostToDevice, si));
+    DM_STEP(cudaEventRecord(sc.ev_in[k], si));
     // kernels
-    cudaStream_t sr = g_scratch.s_run;
-    DM_CUDA_OK(cudaStreamWaitEvent(sr, g_scratch.ev_in[k], 0));
+    cudaStream_t sr = sc.s_run;
+    DM_STEP(cudaStreamWaitEvent(sr, sc.ev_in[k], 0));
     DmProjCfg c = *cfg;
     if (!want_h) c.want_height = 0;
-    rc = dm_orth_project_f32(d_depth, d_values, d_valid, d_samples, &c, nf, d_top, d_mask, d_height,
-                             g_scratch.ws, g_scratch.ws_bytes, sr);
+    if (labels)
+      rc = dm_orth_project_labels_f32(d_depth, static_cast<const uint8_t*>(d_values), d_valid, d_samples, &c, nf, d_top,
+                                      d_mask, d_height, sc.ws, sc.ws_bytes, sr);
+    else
+      rc = dm_orth_project_f32(d_depth, static_cast<const float*>(d_values), d_valid, d_samples, &c, nf, d_top, d_mask,
+                               d_height, sc.ws, sc.ws_bytes, sr);
     if (rc != DM_OK) break;
-    DM_CUDA_OK(cudaEventRecord(g_scratch.ev_run[k], sr));
+    DM_STEP(cudaEventRecord(sc.ev_run[k], sr));
     // device → host
-    cudaStream_t so = g_scratch.s_out;
-    DM_CUDA_OK(cudaStreamWaitEvent(so, g_scratch.ev_run[k], 0));
-    DM_CUDA_OK(cudaMemcpyAsync(topdown + (size_t)f0 * Cv * M, d_top, (size_t)nf * Cv * M * 4, cudaMemcpyDeviceToHost, so));
-    DM_CUDA_OK(cudaMemcpyAsync(mask + (size_t)f0 * Cv * M, d_mask, (size_t)nf * Cv * M, cudaMemcpyDeviceToHost, so));
+    cudaStream_t so = sc.s_out;
+    DM_STEP(cudaStreamWaitEvent(so, sc.ev_run[k], 0));
+    DM_STEP(cudaMemcpyAsync(topdown + (size_t)f0 * Cv * M, d_top, (size_t)nf * Cv * M * 4, cudaMemcpyDeviceToHost, so));
+    DM_STEP(cudaMemcpyAsync(mask + (size_t)f0 * Cv * M, d_mask, (size_t)nf * Cv * M, cudaMemcpyDeviceToHost, so));
     if (d_height)
-      DM_CUDA_OK(cudaMemcpyAsync(height + (size_t)f0 * M, d_height, (size_t)nf * M * 4, cudaMemcpyDeviceToHost, so));
-    DM_CUDA_OK(cudaEventRecord(g_scratch.ev_out[k], so));
+      DM_STEP(cudaMemcpyAsync(height + (size_t)f0 * M, d_height, (size_t)nf * M * 4, cudaMemcpyDeviceToHost, so));
+    DM_STEP(cudaEventRecord(sc.ev_out[k], so));
   }
-  for (cudaStream_t st : {g_scratch.s_in, g_scratch.s_run, g_scratch.s_out}) {
+#undef DM_STEP
+  // every exit path drains the three streams: no copy into the caller's buffers is in flight after the return
+  for (cudaStream_t st : {sc.s_in, sc.s_run, sc.s_out}) {
     const cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess && rc == DM_OK) rc = static_cast<int>(e);
   }
+  // (always consumed here, after the streams are drained: no stale flag is left for an unrelated later call)
+  if (take_timeout(device) && rc == DM_OK) rc = DM_ETIMEOUT;  // the results in the caller's buffers are not valid
   return rc;
+}
+}  // namespace
+
+extern "C" int dm_orth_project_host_f32(const float* depth, const float* values, const uint8_t* valid,
+                                        const DmProjSample* samples, const DmProjCfg* cfg, int32_t b,
+                                        float* topdown, uint8_t* mask, float* height, int32_t device) {
+  if (cfg && cfg->C > 0 && !values) return DM_EINVAL;
+  return orth_project_host(depth, values, nullptr, valid, samples, cfg, b, topdown, mask, height, device);
+}
+
+extern "C" int dm_orth_project_labels_host_f32(const float* depth, const uint8_t* labels, const uint8_t* valid,
+                                               const DmProjSample* samples, const DmProjCfg* cfg, int32_t b,
+                                               float* topdown, uint8_t* mask, float* height, int32_t device) {
+  if (!cfg || cfg->C <= 0 || !labels) return DM_EINVAL;
+  return orth_project_host(depth, nullptr, labels, valid, samples, cfg, b, topdown, mask, height, device);
 }

@@ -27,28 +27,17 @@
 //    resolve_kernel, chunked over the ring) — same device functions, same results.
 #include <cstdlib>
 
-#include "dm_common.cuh"
+#include "dm_project.cuh"
 
 namespace dm {
 
 constexpr int kProjThreads = 256;
 constexpr int kResolveCells = 256;
-constexpr int kSliceCells = 64;                  // cells per sparse-ring flag (one resolve slice of a warp)
-#ifndef DM_FLAG_STRIDE
-#define DM_FLAG_STRIDE 8
-#endif
-constexpr int kFlagStride = DM_FLAG_STRIDE;      // words between two flags: every tile of a frame stores into the
-                                                 // same few hundred flags, so each gets its own 32-byte sector
 #ifndef DM_MAX_RING
 #define DM_MAX_RING 10  // measured at config 2 (room / iid ms): 6: 0.573 / 0.656, 8: 0.496 / 0.586, 10: 0.469 / 0.563, 14: 0.476 / 0.579, 20: 0.480 / 0.614
 #endif
 constexpr int kMaxRing = DM_MAX_RING;                     // frame slots of the accumulation ring
 constexpr size_t kRingBudgetBytes = (size_t)1 << 30;  // ... unless that exceeds 1 GiB of workspace
-#ifndef DM_SUSPEND_NS
-#define DM_SUSPEND_NS 20000u
-#endif
-constexpr int kCtrlWords = 512;                  // control block at the head of the workspace
-constexpr unsigned long long kSpinLimitNs = 4000000000ull;  // dependency wait guard (bug → no hang)
 
 struct ProjPlan {
   int Cv;     // value channels produced (C, or 1 when the heights are the values)
@@ -120,7 +109,8 @@ static ProjPlan make_plan(const DmProjCfg& cfg, int b) {
     p.ws_groups = (cfg.C + 23) / 24;
     p.ws_warps = 2;
   }
-  if (const char* e = getenv("DM_WS_WARPS")) {  // kernel experiments only (scripts/time_proj.py)
+#ifdef DM_EXPERIMENT_KNOBS  // kernel experiments only (scripts/exp_build.sh builds with -DDM_EXPERIMENT_KNOBS)
+  if (const char* e = getenv("DM_WS_WARPS")) {
     const int ww = atoi(e);
     if (ww == 2 || ww == 4) p.ws_warps = ww;
   }
@@ -128,6 +118,7 @@ static ProjPlan make_plan(const DmProjCfg& cfg, int b) {
     const int g = atoi(e);
     if (g >= 1 && g <= 8) p.ws_groups = g;
   }
+#endif
   if (cfg.C <= 0) p.ws_groups = 1;
   p.ws_cg = cfg.C > 0 ? (cfg.C + p.ws_groups - 1) / p.ws_groups : 0;
   p.ws_groups = cfg.C > 0 ? (cfg.C + p.ws_cg - 1) / p.ws_cg : 1;
@@ -141,27 +132,9 @@ struct ProjDims {
   unsigned long long slot_words;
   unsigned long long stage_bytes;
   int groups = 1, cg = 0;  // warp-specialised kernel: channel groups per frame, channels per group
+  unsigned long long ws_words = 0;  // 32-bit words of the workspace behind the control block (flags + ring)
 };
 
-// One pixel: validity, cell index (or -1) and the height that goes into the height map.
-__device__ __forceinline__ int pixel_cell(const DmProjCfg& cfg, const DmProjSample& sp, int r, int c,
-                                          float z, bool ok, float* y_out) {
-  if (cfg.has_trunc_depth_max) ok = ok && (z <= cfg.trunc_depth_max);  // maps.py:539-542
-  if (cfg.has_trunc_depth_min) ok = ok && (z >= cfg.trunc_depth_min);
-  if (cfg.clip_border > 0) {  // maps.py:48-70
-    const int k = cfg.clip_border;
-    ok = ok && (r >= k) && (r < cfg.H - k) && (c >= k) && (c < cfg.W - k);
-  }
-  V3 p = unproject(r, c, z, cfg.H, cfg.fx, cfg.fy, cfg.cx, cfg.cy, cfg.flip_h);
-  p = apply_step(sp.to_local, p);                                                  // maps.py:279-284
-  if (cfg.has_trunc_height_max) ok = ok && (p.y <= cfg.trunc_height_max);          // maps.py:286-288
-  p = apply_step(sp.to_global, p);                                                 // maps.py:290-295
-  float xf, zf;
-  quantize_f(p.x, p.z, sp.width_offset, sp.height_offset, cfg.map_res, cfg.Mh, cfg.flip_h, &xf, &zf);
-  ok = ok && (xf >= 0.0f) && (xf < (float)cfg.Mw) && (zf >= 0.0f) && (zf < (float)cfg.Mh);  // maps.py:1155-1158
-  *y_out = p.y;
-  return ok ? ((int)zf * cfg.Mw + (int)xf) : -1;  // utils.py:332-370
-}
 
 // ---- phase A: cells + heights of one staged tile ------------------------------------------
 // The depth row of the stage is overwritten in place by the heights (it becomes the height
@@ -340,63 +313,6 @@ resolve_kernel(uint32_t* __restrict__ acc, const DmProjCfg cfg, const ProjDims d
 
 // ================= persistent TMA kernel =======================================================
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// The suspend-time hint lets the hardware park the warp until the phase completes (or the hint expires)
-// instead of re-issuing the try_wait every few cycles: waiting warps must not eat the issue slots of working ones.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "DM_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-      "@p bra DM_DONE;\n\t"
-      "bra DM_WAIT;\n\t"
-      "DM_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(DM_SUSPEND_NS) : "memory");
-}
-// TMA bulk copy global → shared, completion on an mbarrier, L2 evict-first (inputs are read once).
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
-}
-__device__ __forceinline__ uint64_t policy_evict_first() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ uint32_t ld_relaxed(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ unsigned long long globaltimer() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-// thread 0 only.  Returns false on timeout (a scheduling bug, never expected) after raising ctrl[2].
-__device__ __forceinline__ bool wait_count(const uint32_t* counter, uint32_t target, uint32_t* ctrl) {
-  if (ld_acquire(counter) >= target) return true;
-  const unsigned long long t0 = globaltimer();
-  while (ld_acquire(counter) < target) {
-    __nanosleep(64);
-    if (globaltimer() - t0 > kSpinLimitNs) {
-      atomicExch(ctrl + 2, 1u);
-      return false;
-    }
-  }
-  return true;
-}
 
 // ---- warp-specialised persistent kernel -----------------------------------------------------
 // CTA = 1 producer warp + kWsWarps consumer warps, two smem stages.
@@ -430,114 +346,12 @@ constexpr int kWsMaxWarps = 4;
 #define DM_RES_K 2  // 64-cell slices a consumer warp resolves per resolve ticket (measured: 1: 0.494, 2: 0.470, 3: 0.473, 4: 0.485 ms)
 #endif
 constexpr int kResK = DM_RES_K;
-enum { kItemProj = 0, kItemResolve = 1, kItemNone = 2, kItemExit = 3 };
 
 struct WsItem {
   int kind, frame, idx, tile0, r0, c0, ok, _pad;
 };
 
-// ticket → work item.  Step s holds the P projection tiles of frame s and the R resolve tiles
-// of frame s - lag, interleaved evenly so HBM reads and writes mix.
-__device__ __forceinline__ void decode_ticket(unsigned t, int b, int P, int R, int lag, int* kind, int* frame,
-                                              int* idx) {
-  const unsigned per = (unsigned)(P + R);
-  const int s = (int)(t / per);
-  const int j = (int)(t - (unsigned)s * per);
-  // the R resolve tickets are spread evenly among the P projection tickets of the step (HBM reads and writes
-  // stay mixed whatever the ratio): ticket j is a resolve ticket when floor((j + 1) R / per) steps up
-  const unsigned rb0 = (unsigned)(((unsigned long long)j * (unsigned)R) / per);
-  const unsigned rb1 = (unsigned)(((unsigned long long)(j + 1) * (unsigned)R) / per);
-  if (rb1 > rb0) {
-    *kind = kItemResolve;
-    *idx = (int)rb0;
-  } else {
-    *kind = kItemProj;
-    *idx = j - (int)rb0;
-  }
-  *frame = *kind == kItemProj ? s : s - lag;
-  if (*frame < 0 || *frame >= b) *kind = kItemNone;
-}
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// sparse-ring slice flag: plain idempotent store, published with the tile's REDs
-__device__ __forceinline__ void st_flag(uint32_t* p) {
-  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(1u) : "memory");
-}
-// fire-and-forget reduction (RED, never the returning ATOM form)
-__device__ __forceinline__ void red_max_u32(uint32_t* p, uint32_t v) {
-#ifdef DM_ABL_NORED  // ablation build (wrong results): what the kernel costs without its REDs
-  asm volatile("" ::"l"(p), "r"(v) : "memory");
-#else
-  asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-#endif
-}
-// Predicated reduction: no branch, no reconvergence bookkeeping around the RED.
-__device__ __forceinline__ void red_max_u32_if(bool pred, uint32_t* p, uint32_t v) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %0, 0;\n\t"
-      "@p red.global.max.u32 [%1], %2;\n\t}" ::"r"((int)pred), "l"(p), "r"(v) : "memory");
-}
-
-// One pixel on the straight-line path (cfg.fast_steps): xn = rn(rn(c - cx) / fx), yn likewise.
-// x / res with one IEEE rounding, through rres = rn(1 / res): product, then two exact-residual corrections
-// (Markstein).  Equal to __fdiv_rn(x, res) whenever the quotient is a normal number (checked exhaustively-ish on
-// the host, 4e9 random operands over 200 divisors: no mismatch); a non-finite x gives NaN instead of inf, a
-// quotient in the denormal range may differ in its last bit — neither can change a bin: the pixel is off the
-// map either way, or the difference vanishes in the offset addition that follows (maps.py:1004-1013).
-__device__ __forceinline__ float div_by_rcp(float x, float res, float rres) {
-  const float q0 = __fmul_rn(x, rres);
-  const float q1 = __fmaf_rn(__fmaf_rn(-q0, res, x), rres, q0);
-  return __fmaf_rn(__fmaf_rn(-q1, res, x), rres, q1);
-}
-
-template <bool GLOBAL, bool RCP_DIV = false>
-__device__ __forceinline__ int pixel_cell_fast(const DmProjCfg& cfg, const DmProjSample& sp, float xn, float yn,
-                                               float z, bool ok, float* y_out, float rres = 0.0f) {
-  if (cfg.has_trunc_depth_max) ok = ok && (z <= cfg.trunc_depth_max);
-  if (cfg.has_trunc_depth_min) ok = ok && (z >= cfg.trunc_depth_min);
-  const float X = __fmul_rn(xn, z), Y = __fmul_rn(yn, z);
-  // pitch about x: R[0] = 1, R[1] = R[2] = R[3] = R[6] = 0 (x passes through), then + (0, h, 0)
-  const float* Rl = sp.to_local.R;
-  float ly = __fmaf_rn(Rl[7], z, __fmul_rn(Rl[4], Y));
-  float lz = __fmaf_rn(Rl[8], z, __fmul_rn(Rl[5], Y));
-  ly = __fadd_rn(ly, sp.to_local.t[1]);
-  if (cfg.has_trunc_height_max) ok = ok && (ly <= cfg.trunc_height_max);
-  float gx = X, gz = lz;
-  if (GLOBAL) {  // yaw about y: R[4] = 1, R[1] = R[3] = R[5] = R[7] = 0 (y passes through), + (x, 0, z)
-    const float* Rg = sp.to_global.R;
-    gx = __fadd_rn(__fmaf_rn(Rg[6], lz, __fmul_rn(Rg[0], X)), sp.to_global.t[0]);
-    gz = __fadd_rn(__fmaf_rn(Rg[8], lz, __fmul_rn(Rg[2], X)), sp.to_global.t[2]);
-  }
-  float xf, zf;
-  if (RCP_DIV) {
-    const float res = cfg.map_res;
-    const float xb = __fadd_rn(div_by_rcp(gx, res, rres), sp.width_offset);
-    float zb = __fadd_rn(div_by_rcp(gz, res, rres), sp.height_offset);
-    if (cfg.flip_h) zb = __fsub_rn((float)(cfg.Mh - 1), zb);
-    xf = floorf(__fadd_rn(xb, 0.5f));
-    zf = floorf(__fadd_rn(zb, 0.5f));
-  } else {
-    quantize_f(gx, gz, sp.width_offset, sp.height_offset, cfg.map_res, cfg.Mh, cfg.flip_h, &xf, &zf);
-  }
-  ok = ok && (xf >= 0.0f) && (xf < (float)cfg.Mw) && (zf >= 0.0f) && (zf < (float)cfg.Mh);
-  *y_out = ly;
-  return ok ? ((int)zf * cfg.Mw + (int)xf) : -1;
-}
-
-template <bool IS_MIN>
-__device__ __forceinline__ float red2(float a, float b) { return IS_MIN ? fminf(a, b) : fmaxf(a, b); }
-template <bool IS_MIN>
-__device__ __forceinline__ bool beats(float v, float fill) { return IS_MIN ? (v < fill) : (v > fill); }
-template <bool IS_MIN>
-__device__ __forceinline__ uint32_t key_of(float v) { return IS_MIN ? ~enc(v) : enc(v); }
-
-struct Rcps {
-  float res, fx, fy;  // rn(1 / map_res), rn(1 / fx), rn(1 / fy)
-};
 
 // FAST: 0 generic steps, 1 local only, 2 local + global.  IS_MIN: reduction of the value channels.
 template <int FAST, bool IS_MIN, int WW>
@@ -855,7 +669,7 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
                const uint8_t* __restrict__ valid, const DmProjSample* __restrict__ samples,
                const DmProjCfg cfg, const ProjDims d, int b, uint32_t* __restrict__ ctrl,
                uint32_t* __restrict__ flags, uint32_t* __restrict__ acc, float* __restrict__ topdown,
-               uint8_t* __restrict__ mask, float* __restrict__ height) {
+               uint8_t* __restrict__ mask, float* __restrict__ height, const ProjGuard guard) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int kWsWarps = WW, kWsTile = 128 * WW, kWsResolveCells = 64 * WW * kResK;
   constexpr int RS = kWsTile + 4;
@@ -947,17 +761,19 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
         it.tile0 = (it.idx / d.groups) * kWsTile;
         it.r0 = it.tile0 / cfg.W;
         it.c0 = it.tile0 - it.r0 * cfg.W;
-        if (it.frame >= ring) { dep = resolve_done + (it.frame - ring); dep_target = (uint32_t)R; }
+        if (it.frame >= ring) { dep = resolve_done + (it.frame - ring); dep_target = (uint32_t)R + guard.dep_bias; }
         const uint32_t* sw = reinterpret_cast<const uint32_t*>(samples + it.frame);
         spw0 = sw[lane];
         if (lane < 16) spw1 = sw[32 + lane];
       } else if (it.kind == kItemResolve) {
         dep = proj_done + it.frame;
-        dep_target = (uint32_t)P;
+        dep_target = (uint32_t)P + guard.dep_bias;
       }
-      // relaxed load, evaluated after the wait below (ordering: everything that depends on it is issued after a branch on the loaded value and bypasses L1 — RED, ld.cg, st.cg, TMA through L2)
+      // acquire load (pairs with the red.release of publish_prev in the CTA that completed the frame), issued here and
+      // evaluated after the wait below, so its round trip is never waited for.  The consumers inherit the ordering
+      // through the mbarrier hand-off of the item (release.cta by this warp, acquire.cta by theirs).
       uint32_t dep_seen = 0;
-      if (dep && lane == 0) dep_seen = ld_relaxed(dep);
+      if (dep && lane == 0) dep_seen = ld_acquire(dep);
       // ---- the stage is free once the consumers released the previous item
       [[maybe_unused]] const long long tq1 = DM_CLK();
       mbar_wait(empty, (fills & 1u) ^ 1u);
@@ -967,16 +783,13 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
       pending = __shfl_sync(0xffffffffu, pending, 0);
       const int prev_kind = pend_kind, prev_frame = pend_frame;
       auto publish_prev = [&]() {  // the release of the stage also completes the previous item
-        if (lane == 0 && prev_kind != kItemNone) {
-          asm volatile("fence.acq_rel.gpu;" ::: "memory");
-          asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;"
-                       ::"l"((prev_kind == kItemProj ? proj_done : resolve_done) + prev_frame) : "memory");
-        }
+        if (lane == 0 && prev_kind != kItemNone)
+          red_release_add1((prev_kind == kItemProj ? proj_done : resolve_done) + prev_frame);
       };
       if (pending) {
         // rare: must block.  Publish first — the frame we wait for may need this very tile.
         publish_prev();
-        if (lane == 0) it.ok = wait_count(dep, dep_target, ctrl);
+        if (lane == 0) it.ok = wait_count(dep, dep_target, ctrl, guard.spin_ns);
         it.ok = __shfl_sync(0xffffffffu, it.ok, 0);
       }
       [[maybe_unused]] const long long tq3 = DM_CLK();
@@ -1021,18 +834,27 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
     // the consumers have added their flagged-slice counts; the last CTA out re-arms the control block for
     // the next call and leaves it the density of this call's maps
     mbar_wait(empty, (fills & 1u) ^ 1u);
+    uint32_t last = 0;
     if (lane == 0) {
       atomicAdd(ctrl + 5, *reinterpret_cast<volatile uint32_t*>(occ_count));
       __threadfence();
-      const uint32_t prev = atomicAdd(ctrl + 3, 1u);
-      if (prev == gridDim.x - 1) {
+      last = atomicAdd(ctrl + 3, 1u) == gridDim.x - 1 ? 1u : 0u;
+      if (last) __threadfence();
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {  // every other CTA has left: a timed-out launch re-zeroes its workspace and tells the host
+      scrub_after_timeout(ctrl, flags, d.ws_words, lane, 32, guard.status);
+      __syncwarp();
+    }
+    if (lane == 0) {
+      if (last) {
         const unsigned long long flagged = atomicAdd(ctrl + 5, 0u);
         const unsigned long long slices = (unsigned long long)b * (unsigned long long)d.nsl;
         const unsigned long long f16 = slices ? (flagged << 16) / slices : 0ull;
         ctrl[4] = 1u + (uint32_t)(f16 < 65535ull ? f16 : 65535ull);
         ctrl[5] = 0;
         for (int i = 0; i < 2 * b; ++i) proj_done[i] = 0;
-        ctrl[0] = 0; ctrl[1] = 0; ctrl[3] = 0;
+        ctrl[0] = 0; ctrl[1] = 0; ctrl[2] = 0; ctrl[3] = 0;
         __threadfence();
       }
     }
@@ -1126,6 +948,9 @@ extern "C" int dm_orth_project_f32(const float* depth, const float* values, cons
   int dev = 0;
   DM_CUDA_OK(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) return DM_EINVAL;
+  // an earlier launch on this device ran into the dependency-wait guard: its outputs are garbage (it re-zeroed
+  // its workspace itself); report it once, launch nothing
+  if (take_timeout(dev)) return DM_ETIMEOUT;
   if (!g_dev[dev].ready) {
     DM_CUDA_OK(cudaFuncSetAttribute(proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     DM_CUDA_OK(cudaFuncSetAttribute(resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -1163,8 +988,9 @@ extern "C" int dm_orth_project_f32(const float* depth, const float* values, cons
     dw.groups = p.ws_groups;
     dw.cg = p.ws_cg;
     dw.stage_bytes = p.ws_stage_bytes;
+    dw.ws_words = (p.workspace_bytes() - p.ctrl_bytes) / 4;
     void (*kern)(const float*, const float*, const uint8_t*, const DmProjSample*, DmProjCfg, ProjDims, int,
-                 uint32_t*, uint32_t*, uint32_t*, float*, uint8_t*, float*) = nullptr;
+                 uint32_t*, uint32_t*, uint32_t*, float*, uint8_t*, float*, ProjGuard) = nullptr;
     const bool mn = cfg->reduction != 0;
 #define DM_WS_PICK(WW)                                                                         \
     switch (cfg->fast_steps) {                                                                 \
@@ -1180,7 +1006,7 @@ extern "C" int dm_orth_project_f32(const float* depth, const float* values, cons
     long long grid = (long long)g_dev[dev].sms * per_sm;
     if (grid > ws_total) grid = ws_total;
     kern<<<(unsigned)grid, ws_threads, p.smem_ws, stream>>>(depth, values, valid, samples, *cfg, dw, b, ctrl, flags,
-                                                            acc, topdown, mask, height);
+                                                            acc, topdown, mask, height, proj_guard(dev));
     DM_LAUNCHED();
     return DM_OK;
   }

@@ -21,18 +21,45 @@ def _host(a, dtype):
   return np.ascontiguousarray(a, dtype=dtype)
 
 
+def _batch_of(a: np.ndarray, b: int, what: str) -> np.ndarray:
+  """A batch-1 image array is shared by all b frames (the kernels index every plane by frame)."""
+  if a.shape[0] == b:
+    return a
+  if a.shape[0] == 1:
+    return np.ascontiguousarray(np.broadcast_to(a, (b,) + a.shape[1:]))
+  raise RuntimeError(f"{what} has batch {a.shape[0]}, depth_map has batch {b}")
+
+
 def orth_project_host(depth_map, value_map, valid_map, cam_pose, width_offset, height_offset, cam_pitch,
                       cam_height, map_res, map_width, map_height, focal_x, focal_y, center_x, center_y,
                       trunc_depth_min, trunc_depth_max, trunc_height_max, clip_border, to_global, flip_h=True,
-                      fill_value=None, reduction=None, get_height_map=False, device: int = 0, out=None):
+                      fill_value=None, reduction=None, get_height_map=False, device: Optional[int] = None, out=None,
+                      label_map=None, num_classes: Optional[int] = None):
   """Same arguments as maps.orth_project with (b,1,H,W) / (b,C,H,W) HOST arrays; returns numpy
-  (topdown, mask[, height]).  `out` may carry preallocated (pinned) result arrays."""
-  nat.require_cuda(device)
+  (topdown, mask[, height]).  `out` may carry preallocated (pinned) result arrays.  `label_map` (b,1,H,W) uint8
+  class ids + `num_classes` instead of `value_map`: the result of value_map = one_hot(label_map) with 5 instead
+  of 4 * (C + 1) bytes per pixel crossing PCIe (dm_orth_project_labels_host_f32).  `device` defaults to the
+  current CUDA device; the caller's current device is left as it was."""
+  device = nat.require_cuda(device).index
   depth = _host(depth_map, np.float32)
   values = _host(value_map, np.float32)
   valid = None if valid_map is None else _host(np.asarray(valid_map).astype(bool), np.uint8)
   b, _, H, W = depth.shape
-  C = 0 if values is None else values.shape[1]
+  labels = None
+  if label_map is not None:
+    if values is not None or num_classes is None or not 1 <= int(num_classes) <= 63:
+      raise ValueError("label_map excludes value_map and needs num_classes in 1..63")
+    labels = label_map.detach().cpu().numpy() if torch.is_tensor(label_map) else np.asarray(label_map)
+    if labels.dtype != np.uint8:
+      if labels.dtype.kind not in "iu":
+        raise TypeError(f"label_map must hold integer class ids, got {labels.dtype}")
+      labels = np.where((labels < 0) | (labels >= int(num_classes)), 255, labels).astype(np.uint8)
+    labels = _batch_of(np.ascontiguousarray(labels).reshape((-1, 1, H, W)), b, "label_map")
+  if values is not None:
+    values = _batch_of(values, b, "value_map")
+  if valid is not None:
+    valid = _batch_of(valid.reshape((-1, 1, H, W)), b, "valid_map")
+  C = int(num_classes) if labels is not None else (0 if values is None else values.shape[1])
   n_points = H * W
   pose = prm.per_sample(cam_pose, b, (3,), "cam_pose")
   pitch, camh = prm.per_sample(cam_pitch, b), prm.per_sample(cam_height, b)
@@ -67,9 +94,14 @@ def orth_project_host(depth_map, value_map, valid_map, cam_pose, width_offset, h
   else:
     top, mask, hgt = out
   p = lambda a: None if a is None else a.ctypes.data
-  rc = nat.lib().dm_orth_project_host_f32(p(depth), p(values), p(valid), p(samples), cfg, b, p(top), p(mask),
-                                          p(hgt), int(device))
-  nat.check(rc, "dm_orth_project_host_f32")
+  if labels is not None:
+    rc = nat.lib().dm_orth_project_labels_host_f32(p(depth), p(labels), p(valid), p(samples), cfg, b, p(top), p(mask),
+                                                   p(hgt), int(device))
+    nat.check(rc, "dm_orth_project_labels_host_f32")
+  else:
+    rc = nat.lib().dm_orth_project_host_f32(p(depth), p(values), p(valid), p(samples), cfg, b, p(top), p(mask),
+                                            p(hgt), int(device))
+    nat.check(rc, "dm_orth_project_host_f32")
   mask_b = mask.view(np.bool_)
   if not get_height_map:
     return top, mask_b

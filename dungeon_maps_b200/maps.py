@@ -43,7 +43,7 @@ __all__ = [
   'height_map_to_point_cloud', 'image_to_camera_space', 'camera_to_image_space', 'camera_to_local_space',
   'local_to_camera_space', 'local_to_global_space', 'global_to_local_space', 'map_quantize',
   'map_dequantize', 'project', 'compute_center_offsets', 'MapProjector', 'TopdownMap', 'crop_topdown_map',
-  'fuse_topdown_maps', 'merge_into_canvas', 'MapBuilder', 'Reduction', 'CameraIntrinsics', 'NINF', 'Float3D',
+  'fuse_topdown_maps', 'merge_into_canvas', 'MapBuilder', 'release_workspaces', 'Reduction', 'CameraIntrinsics', 'NINF', 'Float3D',
 ]
 
 
@@ -69,6 +69,13 @@ def _workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
     ws = torch.zeros(max(nbytes, 16), dtype=torch.uint8, device=dev)
     _workspaces[key] = ws
   return ws
+
+
+def release_workspaces() -> None:
+  """Frees the cached accumulation rings (one per device and stream that projected something) and the library's
+  own scratch of the host-buffer entries."""
+  _workspaces.clear()
+  nat.lib().dm_release_scratch()
 
 
 def _pick_device(device, *tensors) -> torch.device:
@@ -136,7 +143,9 @@ def orth_project(
   reduction: Optional[Reduction] = None,
   get_height_map: bool = False,
   device: Optional[torch.device] = None,
-  _validate_args: bool = True
+  _validate_args: bool = True,
+  label_map: Optional[torch.Tensor] = None,
+  num_classes: Optional[int] = None
 ) -> Union[Tuple[torch.Tensor, torch.Tensor], Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
   """Orthographic projection of UNNORMALIZED depth maps (and optional per-pixel value maps)
   onto top-down maps: one fused kernel pass + one resolve pass (csrc/dm_project.cu) in place of
@@ -147,20 +156,37 @@ def orth_project(
   hold `fill_value` (0 when None) and are False in `masks`; `height_map` is the same tensor as
   `topdown_map` when `value_map` is None, otherwise a stride-0 expand of the (b,1,mh,mw)
   max-height map with -inf in empty cells.
+
+  Addition to the reference's signature: `label_map` (b, 1, h, w) integer class ids with `num_classes` = C gives,
+  bit for bit, the result of value_map = one_hot(label_map, C) as float32 planes (what the reference's object-map
+  demo builds, demos/object_map/run.py:117-124) without ever materialising those planes — csrc/dm_labels.cu.
   """
+  if label_map is not None:
+    if value_map is not None:
+      raise ValueError("pass either `value_map` or `label_map`, not both")
+    if num_classes is None:
+      raise ValueError("`label_map` needs `num_classes` (the C of one_hot(label_map, C))")
+    if not 1 <= int(num_classes) <= 63:
+      raise ValueError(f"num_classes must be in 1..63, got {num_classes}")
   if utils._reduction_code(reduction, fused=False) > 1:
+    if label_map is not None:  # rarely used reductions: materialise the one-hot planes and take the composed path
+      value_map = _one_hot_planes(label_map, int(num_classes), _pick_device(device, depth_map, label_map))
     return _orth_project_composed(
       depth_map, value_map, valid_map, cam_pose, width_offset, height_offset, cam_pitch, cam_height, map_res,
       map_width, map_height, focal_x, focal_y, center_x, center_y, trunc_depth_min, trunc_depth_max,
       trunc_height_max, clip_border, to_global, flip_h, fill_value, reduction, get_height_map, device)
   red = utils._reduction_code(reduction)
-  dev = _pick_device(device, depth_map, value_map)
+  dev = _pick_device(device, depth_map, value_map, label_map)
   depth = _image(depth_map, dev, torch.float32)
   b, dc, H, W = depth.shape
-  values = None if value_map is None else _image(value_map, dev, torch.float32)
-  valid = None if valid_map is None else _image(valid_map, dev, torch.bool)
-  if values is not None and values.shape[-2:] != depth.shape[-2:]:
-    raise RuntimeError(f"value_map {tuple(values.shape)} does not match depth_map {tuple(depth.shape)}")
+  values = None if value_map is None else _batch_of(_image(value_map, dev, torch.float32), b, "value_map")
+  valid = None if valid_map is None else _batch_of(_image(valid_map, dev, torch.bool), b, "valid_map")
+  labels = None if label_map is None else _batch_of(_label_ids(label_map, int(num_classes), dev), b, "label_map")
+  for name, t in (("value_map", values), ("valid_map", valid), ("label_map", labels)):
+    if t is not None and t.shape[-2:] != depth.shape[-2:]:
+      raise RuntimeError(f"{name} {tuple(t.shape)} does not match depth_map {tuple(depth.shape)}")
+  if labels is not None and (dc != 1 or labels.shape[1] != 1):
+    raise RuntimeError("label_map needs single-channel depth and label maps: (b, 1, h, w)")
   # per-sample host parameters
   pose = prm.per_sample(cam_pose, b, (3,), "cam_pose")
   pitch = prm.per_sample(cam_pitch, b, (), "cam_pitch")
@@ -168,7 +194,7 @@ def orth_project(
   woff = prm.per_sample(width_offset, b, (), "width_offset")
   hoff = prm.per_sample(height_offset, b, (), "height_offset")
   frames = b
-  C = 0 if values is None else values.shape[1]
+  C = int(num_classes) if labels is not None else (0 if values is None else values.shape[1])
   if dc != 1:
     # one index set per depth channel (maps.py:298-318 keeps the channel dim): fold it into the batch
     if values is not None and values.shape[1] != dc:
@@ -217,11 +243,18 @@ def orth_project(
   height = torch.empty((frames, 1, cfg.Mh, cfg.Mw), dtype=torch.float32, device=dev) if want_height else None
   lib = nat.lib()
   with torch.cuda.device(dev):
-    ws = _workspace(dev, lib.dm_orth_project_workspace_bytes(cfg, frames))
-    rc = lib.dm_orth_project_f32(depth.data_ptr(), nat.ptr(values), nat.ptr(valid), samples_dev.data_ptr(),
-                                 cfg, frames, topdown.data_ptr(), masks.data_ptr(), nat.ptr(height),
-                                 ws.data_ptr(), ws.numel(), nat.stream_ptr(dev))
-  nat.check(rc, "dm_orth_project_f32")
+    if labels is not None:
+      ws = _workspace(dev, lib.dm_orth_project_labels_workspace_bytes(cfg, frames))
+      rc = lib.dm_orth_project_labels_f32(depth.data_ptr(), labels.data_ptr(), nat.ptr(valid), samples_dev.data_ptr(),
+                                          cfg, frames, topdown.data_ptr(), masks.data_ptr(), nat.ptr(height),
+                                          ws.data_ptr(), ws.numel(), nat.stream_ptr(dev))
+      nat.check(rc, "dm_orth_project_labels_f32")
+    else:
+      ws = _workspace(dev, lib.dm_orth_project_workspace_bytes(cfg, frames))
+      rc = lib.dm_orth_project_f32(depth.data_ptr(), nat.ptr(values), nat.ptr(valid), samples_dev.data_ptr(),
+                                   cfg, frames, topdown.data_ptr(), masks.data_ptr(), nat.ptr(height),
+                                   ws.data_ptr(), ws.numel(), nat.stream_ptr(dev))
+      nat.check(rc, "dm_orth_project_f32")
   if dc != 1:
     topdown = topdown.reshape(b, dc, cfg.Mh, cfg.Mw)
     masks = masks.reshape(b, dc, cfg.Mh, cfg.Mw)
@@ -229,9 +262,37 @@ def orth_project(
       height = height.reshape(b, dc, cfg.Mh, cfg.Mw)
   if not get_height_map:
     return topdown, masks
-  if value_map is None:
+  if C == 0:
     return topdown, masks, topdown          # maps.py:333-334: the very same tensor
   return topdown, masks, torch.broadcast_to(height, topdown.shape)  # maps.py:349
+
+
+def _batch_of(t: torch.Tensor, b: int, what: str) -> torch.Tensor:
+  """A per-frame image tensor with batch 1 is shared by all b frames (the reference's ops broadcast it); the kernels
+  index every plane by frame, so it is expanded here."""
+  if t.shape[0] == b:
+    return t
+  if t.shape[0] == 1:
+    return t.expand((b,) + tuple(t.shape[1:])).contiguous()
+  raise RuntimeError(f"{what} has batch {t.shape[0]}, depth_map has batch {b}")
+
+
+def _label_ids(label_map, num_classes: int, dev: torch.device) -> torch.Tensor:
+  """Class ids as the kernels take them: contiguous (b, 1, h, w) uint8 on `dev`; ids outside [0, num_classes)
+  become 255 ("no class": an all-zero one-hot row).  uint8 input is used as it is."""
+  t = utils.to_4D_image(utils.to_tensor(label_map))
+  if t.dtype is not torch.uint8:
+    if t.dtype.is_floating_point or t.dtype is torch.bool:
+      raise TypeError(f"label_map must hold integer class ids, got {t.dtype}")
+    t = t.to(dev)
+    t = torch.where((t < 0) | (t >= num_classes), torch.full_like(t, 255), t).to(torch.uint8)
+  return t.to(dev).contiguous()
+
+
+def _one_hot_planes(label_map, num_classes: int, dev: torch.device) -> torch.Tensor:
+  ids = _label_ids(label_map, num_classes, dev)[:, 0].to(torch.int64)               # (b, h, w)
+  planes = torch.arange(num_classes, device=dev).view(1, -1, 1, 1) == ids.unsqueeze(1)
+  return planes.to(torch.float32)
 
 
 def _orth_project_composed(depth_map, value_map, valid_map, cam_pose, width_offset, height_offset, cam_pitch,
@@ -555,7 +616,7 @@ _ATTR_DEFAULTS = (
   "map_height", "trunc_depth_min", "trunc_depth_max", "trunc_height_max", "clip_border", "to_global",
   "flip_h", "fill_value", "reduction", "device", "height",
 )
-_OPTIONAL_DATA = ("value_map", "valid_map")
+_OPTIONAL_DATA = ("value_map", "valid_map", "label_map", "num_classes")
 _CTOR_ARGS = (
   "width", "height", "hfov", "vfov", "cam_pose", "width_offset", "height_offset", "cam_pitch", "cam_height",
   "map_res", "map_width", "map_height", "trunc_depth_min", "trunc_depth_max", "trunc_height_max",
@@ -1059,7 +1120,7 @@ class MapBuilder():
     clone_kwargs = {k: v for k, v in kwargs.items() if k in _CTOR_ARGS}
     return TopdownMap(topdown_map=topdown_map, mask=mask, height_map=height_map,
                       map_projector=self.proj.clone(cam_pose=cam_pose, **clone_kwargs),
-                      is_height_map=(value_map is None))
+                      is_height_map=(value_map is None and kwargs.get('label_map') is None))
 
   def merge(self, topdown_map: TopdownMap, keep_pose: bool = False, fill_value: Optional[float] = None,
             reduction: Optional[Reduction] = None) -> TopdownMap:

@@ -128,6 +128,38 @@ int dm_orth_project_host_f32(const float* depth, const float* values, const uint
                              float* topdown, uint8_t* mask, float* height, int32_t device);
 void dm_release_scratch(void);
 
+/* Class-id form of the projection, for the reference's semantic usage: demos/object_map/run.py:117-124 feeds
+ * orth_project with value_map = one_hot(segmentation, num_classes).float().  This entry takes the ids themselves,
+ *   labels (b, 1, H, W) u8, cfg->C = num_classes (1..63),
+ * and writes exactly (bit for bit) what dm_orth_project_f32 writes for values[b][c][p] = (labels[b][p] == c) ? 1 : 0
+ * (an id >= num_classes is an all-zero row): same outputs, same mask rule, same fill_value / reduction (max, min) /
+ * want_height semantics, any H, W and alignment.  A pixel costs 5 input bytes instead of 4 * (C + 1) and a run of
+ * pixels in one cell two atomic reductions (height key, class-presence word) instead of C + 1.
+ * The workspace follows the rules of dm_orth_project_f32 (zero before first use, left zeroed) and may be the same
+ * buffer, provided it is large enough for both. */
+size_t dm_orth_project_labels_workspace_bytes(const DmProjCfg* cfg, int32_t b);
+int dm_orth_project_labels_f32(const float* depth, const uint8_t* labels, const uint8_t* valid,
+                               const DmProjSample* samples, const DmProjCfg* cfg, int32_t b,
+                               float* topdown, uint8_t* mask, float* height,
+                               void* workspace, size_t workspace_bytes, void* stream);
+/* HOST-buffer variant (see dm_orth_project_host_f32): 5 bytes per pixel cross PCIe instead of 4 * (C + 1). */
+int dm_orth_project_labels_host_f32(const float* depth, const uint8_t* labels, const uint8_t* valid,
+                                    const DmProjSample* samples, const DmProjCfg* cfg, int32_t b,
+                                    float* topdown, uint8_t* mask, float* height, int32_t device);
+
+/* Device-side wait guard.  The projection kernels are persistent launches whose CTAs wait on one another's
+ * per-frame completion counters; a wait that exceeds 4 s (a scheduling bug, never expected) does not hang the GPU:
+ * the item is skipped, the launch re-zeroes its workspace before it ends, and DM_ETIMEOUT is reported ONCE by
+ * whichever comes first of: the next dm_orth_project*_f32 call on that device (which then launches nothing), the
+ * final synchronisation of a *_host entry, or dm_device_status(device) (reads and clears the flag; call it after
+ * synchronising the stream).  The outputs of the timed-out call are undefined. */
+int dm_device_status(int32_t device);
+/* Test hook: spin_ns = guard time of the waits (0: the 4 s default); dep_bias is added to every dependency target
+ * (non-zero: no dependency is ever satisfied, every dependent item times out). */
+void dm_debug_set_wait_guard(uint64_t spin_ns, uint32_t dep_bias);
+/* Test hook: frames per chunk of the *_host entries' copy / kernel / copy pipeline (0: chosen from the frame size). */
+void dm_debug_set_host_chunk(int32_t frames);
+
 /* Per-sample parameters of camera_affine_grid (maps.py:353-460). */
 typedef struct DmFlowSample {
   DmStep to_local;   /* pitch, +cam_height                    maps.py:428-433 */

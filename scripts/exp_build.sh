@@ -6,6 +6,6 @@ cd "$(dirname "$0")/.."
 NAME=$1; shift
 mkdir -p build/exp
 nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo --fmad=false -Xcompiler -fPIC -shared \
-  -cudart static "$@" -o build/exp/lib_${NAME}.so dungeon_maps_b200/csrc/dm_api.cu dungeon_maps_b200/csrc/dm_project.cu \
+  -cudart static "$@" -o build/exp/lib_${NAME}.so dungeon_maps_b200/csrc/dm_api.cu dungeon_maps_b200/csrc/dm_project.cu dungeon_maps_b200/csrc/dm_labels.cu \
   dungeon_maps_b200/csrc/dm_flow.cu dungeon_maps_b200/csrc/dm_fuse.cu dungeon_maps_b200/csrc/dm_points.cu
 echo build/exp/lib_${NAME}.so

@@ -31,8 +31,13 @@ def _no_device_side_timeouts():
   """After every test: the persistent kernel's dependency waits never timed out (sticky flag,
   word 2 of the workspace control block) and the control block was re-armed."""
   yield
-  from dungeon_maps_b200 import maps as _maps
+  assert_workspaces_clean()
+
+
+def assert_workspaces_clean():
+  from dungeon_maps_b200 import _native as nat, maps as _maps
   torch.cuda.synchronize()
+  nat.device_status()  # raises if a dependency wait timed out (DM_ETIMEOUT through the mapped status word)
   for ws in _maps._workspaces.values():
     ctrl = ws[:16].view(torch.int32).cpu()
     assert int(ctrl[2]) == 0, "a device-side dependency wait timed out"
@@ -229,11 +234,7 @@ def test_orth_project_full_config2_properties():
   assert_same(npy(top[sel]), want[0], "topdown slice")
   assert_same(npy(mask[sel]), want[1], "mask slice")
   assert_same(npy(hgt[sel][:, :1]), want[2], "height slice")
-  # the persistent kernel's dependency waits never timed out (sticky flag, word 2 of the control block)
-  from dungeon_maps_b200 import maps as _maps
-  for ws in _maps._workspaces.values():
-    assert int(ws[:16].view(torch.int32)[2]) == 0
-    assert int(ws[:16].view(torch.int32)[0]) == 0 and int(ws[:16].view(torch.int32)[3]) == 0   # re-armed
+  assert_workspaces_clean()
 
 
 def test_orth_project_host_buffer_entry():
@@ -247,11 +248,12 @@ def test_orth_project_host_buffer_entry():
 
 
 @pytest.mark.parametrize("chunk", ["1", "2", "3"])
-def test_orth_project_host_buffer_pipeline_reuses_slots(chunk, monkeypatch):
+def test_orth_project_host_buffer_pipeline_reuses_slots(chunk):
   """More chunks than staging slots (4): every slot of the three-stream pipeline is re-used, with ragged last
   chunks; results (heights included) must equal the oracle's, call after call."""
   from dungeon_maps_b200 import hostapi
-  monkeypatch.setenv("DM_HOST_CHUNK", chunk)
+  from dungeon_maps_b200 import _native as nat
+  nat.lib().dm_debug_set_host_chunk(int(chunk))
   b, H, W, C = 11, 48, 64, 3
   depth = synth.iid_depth(b, H, W, seed=77).numpy()
   values = synth.uniform((b, C, H, W), 78, -2., 2.).numpy()
@@ -261,11 +263,14 @@ def test_orth_project_host_buffer_pipeline_reuses_slots(chunk, monkeypatch):
             center_y=intr["cy"], trunc_depth_min=0.15, trunc_depth_max=5.05, trunc_height_max=None, clip_border=2,
             to_global=False, fill_value=-np.inf, get_height_map=True)
   want = orc.orth_project(depth, values, None, pose, 20., 0., PITCH, 0.88, **kw)
-  for rep in range(2):
-    got = hostapi.orth_project_host(depth, values, None, pose, 20., 0., PITCH, 0.88, **kw)
-    assert_same(got[0], want[0], f"topdown rep{rep}")
-    assert_same(got[1], want[1], f"mask rep{rep}")
-    assert_same(got[2][:, :1], want[2][:, :1], f"height rep{rep}")
+  try:
+    for rep in range(2):
+      got = hostapi.orth_project_host(depth, values, None, pose, 20., 0., PITCH, 0.88, **kw)
+      assert_same(got[0], want[0], f"topdown rep{rep}")
+      assert_same(got[1], want[1], f"mask rep{rep}")
+      assert_same(got[2][:, :1], want[2][:, :1], f"height rep{rep}")
+  finally:
+    nat.lib().dm_debug_set_host_chunk(0)
 
 
 @pytest.mark.parametrize("name", ["flow_small", "flow_small_noflip_vfov"])
