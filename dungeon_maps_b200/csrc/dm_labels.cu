@@ -39,6 +39,12 @@ constexpr int kLblMaxRing = DM_LBL_RING;            // slots are small (8 or 12 
 constexpr int kLblList = 128 + 4;                   // runlet list entries per worker warp
 constexpr uint32_t kKeyNegInf = 0x007fffffu;        // enc(-inf); smaller non-zero keys only mark "hit" (NaN height)
 
+// CTA-wide hand-off between the scheduler warp and the worker warps (they reach it from different code paths,
+// each warp converged): a named barrier over all kLblThreads threads.
+__device__ __forceinline__ void lbl_cta_sync() {
+  asm volatile("bar.sync 1, %0;" ::"n"(kLblThreads) : "memory");
+}
+
 struct LblPlan {
   int C, W2, CP, ring, lag, nsl;
   size_t slot_words, ctrl_bytes, flag_bytes;
@@ -403,7 +409,7 @@ proj_lbl_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ lab
         // rare: must block.  The frame we wait for may need the very item our workers are finishing, so a bubble
         // goes through the barrier first and everything this CTA completed is published before the wait.
         if (lane == 0) s_item[slot] = LblItem{kItemNone, 0, 0, 1};
-        __syncthreads();
+        lbl_cta_sync();
         publish_prev();
         slot ^= 1;
         if (lane == 0) it.ok = wait_count(dep, dep_target, ctrl, guard.spin_ns);
@@ -414,7 +420,7 @@ proj_lbl_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ lab
         if (lane < 16) reinterpret_cast<uint32_t*>(&s_sample[slot])[32 + lane] = spw1;
       }
       if (lane == 0) s_item[slot] = it;
-      __syncthreads();  // the workers are done with the previous item and see this one
+      lbl_cta_sync();  // the workers are done with the previous item and see this one
       publish_prev();
       if (it.kind == kItemExit) break;
       if (it.kind == kItemProj || it.kind == kItemResolve) { prev_kind = it.kind; prev_frame = it.frame; }
@@ -441,7 +447,7 @@ proj_lbl_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ lab
     // ===================== workers =====================
     const Rcps rcp{__frcp_rn(cfg.map_res), __frcp_rn(cfg.fx), __frcp_rn(cfg.fy)};
     while (true) {
-      __syncthreads();
+      lbl_cta_sync();
       const LblItem it = s_item[slot];
       if (it.kind == kItemExit) break;
       if (it.ok) {

@@ -899,6 +899,10 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
           cp[5] += tc1 - tc0; cp[6] += DM_CLK() - tc1;
 #endif
         }
+      } else if (it.kind == kItemProj) {
+        // skipped after a dependency timeout: the tile's copies are in flight all the same, and the stage (and the
+        // phase of its barrier) may only be handed back once they have landed
+        mbar_wait(full_vals, (uses - 1u) & 1u);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(empty);
