@@ -16,8 +16,9 @@
 // tiles of frame f over a sparse ring of accumulation slots, per-frame completion counters), but with nothing to
 // transpose there is nothing to stage: a CTA is one scheduler warp (claims tickets two ahead, acquires the
 // dependency, fetches the sample block, publishes completions) and eight worker warps that load their 4 pixels per
-// lane straight into registers (one 128-bit depth load + one 32-bit label load, coalesced) and hand over through ONE
-// CTA barrier per ticket.
+// lane straight into registers (one 128-bit depth load + one 32-bit label load, coalesced; the scheduler prefetches
+// the lines into L2).  Items travel through two mbarrier-guarded slots, so a worker warp that finishes its part early
+// starts on the next item instead of waiting for the slowest warp of the CTA.
 #include <type_traits>
 
 #include "dm_project.cuh"
@@ -38,12 +39,6 @@ constexpr int kLblResCells = 64 * kLblWarps * kLblResK;
 constexpr int kLblMaxRing = DM_LBL_RING;            // slots are small (8 or 12 bytes per cell): a deep ring is cheap
 constexpr int kLblList = 128 + 4;                   // runlet list entries per worker warp
 constexpr uint32_t kKeyNegInf = 0x007fffffu;        // enc(-inf); smaller non-zero keys only mark "hit" (NaN height)
-
-// CTA-wide hand-off between the scheduler warp and the worker warps (they reach it from different code paths,
-// each warp converged): a named barrier over all kLblThreads threads.
-__device__ __forceinline__ void lbl_cta_sync() {
-  asm volatile("bar.sync 1, %0;" ::"n"(kLblThreads) : "memory");
-}
 
 struct LblPlan {
   int C, W2, CP, ring, lag, nsl;
@@ -71,7 +66,8 @@ static LblPlan make_lbl_plan(const DmProjCfg& cfg, int b) {
 struct LblDims {
   int C, CP, ring, lag, nsl, hasH;
   int vec_in;   // depth 16-byte / labels and valid 4-byte aligned for every frame: vector loads
-  int vec_out;  // output planes 16-byte aligned for every (frame, channel): vector stores
+  int vec_out;  // 0: scalar stores; 1: float planes 16-byte and mask planes 4-byte aligned for every (frame, channel)
+                // (M % 4 == 0); 2: mask planes 16-byte aligned as well (M % 16 == 0)
   unsigned long long slot_words, ws_words;
 };
 
@@ -92,6 +88,9 @@ __device__ __forceinline__ void st_stream_f2(float* p, float a, float b) {
 }
 __device__ __forceinline__ void st_stream_u16(uint8_t* p, uint32_t v) {
   asm volatile("st.global.cs.u16 [%0], %1;" ::"l"(p), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ void st_stream_u32(void* p, uint32_t v) {
+  asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void st_stream_u4(void* p, uint32_t v) {
   asm volatile("st.global.cs.v4.u32 [%0], {%1,%1,%1,%1};" ::"l"(p), "r"(v) : "memory");
@@ -255,7 +254,7 @@ __device__ __forceinline__ float lbl_channel(uint32_t key, LblBits<W2> bits, int
 // ---- resolve of one 64-cell slice by one warp -----------------------------------------------------------------
 template <int W2>
 __device__ __forceinline__ void lbl_resolve_slice(uint32_t* __restrict__ acc_slot, const DmProjCfg& cfg,
-                                                  const LblDims& d, uint32_t* __restrict__ slot_flags, int frame,
+                                                  const LblDims& d, uint32_t flagged, int frame,
                                                   int slice, int lane, float* __restrict__ topdown,
                                                   uint8_t* __restrict__ mask, float* __restrict__ height) {
   using Bits = LblBits<W2>;
@@ -265,13 +264,6 @@ __device__ __forceinline__ void lbl_resolve_slice(uint32_t* __restrict__ acc_slo
   const int ncell = min(64, M - cell0);
   if (ncell <= 0) return;
   const int C = cfg.C;
-  uint32_t* slice_flag = slot_flags + (size_t)slice * kFlagStride;
-  uint32_t flagged = 0;
-  if (lane == 0) {
-    flagged = __ldcg(slice_flag);
-    if (flagged) __stcg(slice_flag, 0u);
-  }
-  flagged = __shfl_sync(0xffffffffu, flagged, 0);
   const bool vec = d.vec_out && ncell == 64;
   const size_t plane0 = (size_t)frame * C * M + cell0;
   const float fill = cfg.fill_value;
@@ -279,7 +271,11 @@ __device__ __forceinline__ void lbl_resolve_slice(uint32_t* __restrict__ acc_slo
     if (vec) {
       const float4 f4 = make_float4(fill, fill, fill, fill);
       for (int c = lane >> 4; c < C; c += 2) st_stream_f4(topdown + plane0 + (size_t)c * M + (lane & 15) * 4, f4);
-      for (int c = lane >> 2; c < C; c += 8) st_stream_u4(mask + plane0 + (size_t)c * M + (lane & 3) * 16, 0u);
+      if (d.vec_out > 1) {  // mask planes 16-byte aligned (M % 16 == 0): 4 lanes cover a channel's 64 bytes
+        for (int c = lane >> 2; c < C; c += 8) st_stream_u4(mask + plane0 + (size_t)c * M + (lane & 3) * 16, 0u);
+      } else {              // 4-byte aligned (M % 4 == 0): 16 lanes per channel
+        for (int c = lane >> 4; c < C; c += 2) st_stream_u32(mask + plane0 + (size_t)c * M + (lane & 15) * 4, 0u);
+      }
       if (d.hasH && lane < 16)
         st_stream_f4(height + (size_t)frame * M + cell0 + lane * 4, make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY));
     } else {
@@ -346,14 +342,19 @@ __device__ __forceinline__ void lbl_resolve_slice(uint32_t* __restrict__ acc_slo
 }
 
 template <int FAST, int W2>
-__global__ void __launch_bounds__(kLblThreads)
+__global__ void __launch_bounds__(kLblThreads, 4)
 proj_lbl_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ labels, const uint8_t* __restrict__ valid,
                 const DmProjSample* __restrict__ samples, const DmProjCfg cfg, const LblDims d, int b,
                 uint32_t* __restrict__ ctrl, uint32_t* __restrict__ flags, uint32_t* __restrict__ acc,
                 float* __restrict__ topdown, uint8_t* __restrict__ mask, float* __restrict__ height,
                 const ProjGuard guard) {
-  __shared__ LblItem s_item[2];
+  // Two item slots per CTA.  The scheduler posts item k into slot k & 1 (full[slot]) as soon as the workers have
+  // released item k - 2 (empty[slot], one arrival per worker warp); a worker warp that finishes its part of item k
+  // early starts on item k + 1 instead of waiting for the slowest warp of the CTA (a CTA-wide barrier per item cost
+  // 27 % of the warp samples in stall_barrier, ncu r02a).
+  __shared__ __align__(16) LblItem s_item[2];
   __shared__ __align__(16) DmProjSample s_sample[2];
+  __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
   __shared__ uint32_t s_list[kLblWarps][(2 + W2) * kLblList];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = cfg.H * cfg.W, M = cfg.Mh * cfg.Mw;
@@ -363,15 +364,28 @@ proj_lbl_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ lab
   uint32_t* proj_done = ctrl + kCtrlWords;
   uint32_t* resolve_done = proj_done + b;
   const unsigned total = (unsigned)(b + lag) * (unsigned)(P + R);
-  int slot = 0;
+  if (tid == 0) {
+    mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
+    mbar_init(&s_empty[0], kLblWarps); mbar_init(&s_empty[1], kLblWarps);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
 
   if (warp == kLblWarps) {
     // ===================== scheduler =====================
-    int prev_kind = kItemNone, prev_frame = 0;
-    auto publish_prev = [&]() {  // after a CTA barrier: the workers' part of the previous item is complete
-      if (lane == 0 && prev_kind != kItemNone)
-        red_release_add1((prev_kind == kItemProj ? proj_done : resolve_done) + prev_frame);
-      prev_kind = kItemNone;
+    // items are numbered in posting order; `posted` items have been handed to the workers, the first `published`
+    // of them have been waited for (all worker warps released them) and their completion counters incremented
+    unsigned posted = 0, published = 0;
+    int kind0 = kItemNone, kind1 = kItemNone, frame0 = 0, frame1 = 0;  // kind / frame of the item in slot 0 / 1
+    auto ensure_published = [&](unsigned upto) {
+      while (published < upto) {
+        const unsigned s = published & 1u;
+        mbar_wait(&s_empty[s], (published >> 1) & 1u);
+        const int kd = s ? kind1 : kind0, fr = s ? frame1 : frame0;
+        if (lane == 0 && (kd == kItemProj || kd == kItemResolve))
+          red_release_add1((kd == kItemProj ? proj_done : resolve_done) + fr);
+        ++published;
+      }
     };
     // tickets are claimed two ahead so that the round trip of the atomic is never waited for
     unsigned raw0 = 0, raw1 = 0;
@@ -387,6 +401,7 @@ proj_lbl_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ lab
       }
       LblItem it{kItemExit, 0, 0, 1};
       if (t < total) decode_ticket(t, b, P, R, lag, &it.kind, &it.frame, &it.idx);
+      if (it.kind == kItemNone) continue;  // a ticket outside the batch (pipeline fill / drain): nothing to hand over
       // dependency: ring slot resolved by its previous tenant / frame fully projected
       const uint32_t* dep = nullptr;
       uint32_t dep_target = 0;
@@ -396,36 +411,55 @@ proj_lbl_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ lab
         const uint32_t* sw = reinterpret_cast<const uint32_t*>(samples + it.frame);
         spw0 = sw[lane];
         if (lane < 16) spw1 = sw[32 + lane];
+        // the tile's input lines on their way into L2 while the workers finish what they have
+        const int n0 = it.idx * kLblTile;
+        const char* dp = reinterpret_cast<const char*>(depth + (size_t)it.frame * N + n0) + lane * 128;
+        if (n0 + lane * 32 < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(dp));
+        if (lane < kLblTile / 128 && n0 + lane * 128 < N)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(labels + (size_t)it.frame * N + n0 + lane * 128));
       } else if (it.kind == kItemResolve) {
         dep = proj_done + it.frame;
         dep_target = (uint32_t)P + guard.dep_bias;
       }
       // acquire load: pairs with the red.release of the CTAs that completed the frame; the workers inherit the
-      // ordering through the CTA barrier below
+      // ordering through the mbarrier hand-off of the item (release.cta here, acquire.cta there)
       int pending = 0;
       if (dep && lane == 0) pending = ld_acquire(dep) < dep_target;
       pending = __shfl_sync(0xffffffffu, pending, 0);
+      // slot `posted & 1` is free once item posted - 2 has been released by every worker warp
+      if (posted >= 1) ensure_published(posted - 1);
       if (pending) {
-        // rare: must block.  The frame we wait for may need the very item our workers are finishing, so a bubble
-        // goes through the barrier first and everything this CTA completed is published before the wait.
-        if (lane == 0) s_item[slot] = LblItem{kItemNone, 0, 0, 1};
-        lbl_cta_sync();
-        publish_prev();
-        slot ^= 1;
+        // rare: must block.  The frame we wait for may need the very items our workers are finishing: everything
+        // this CTA was handed is completed and published before the wait.
+        ensure_published(posted);
         if (lane == 0) it.ok = wait_count(dep, dep_target, ctrl, guard.spin_ns);
         it.ok = __shfl_sync(0xffffffffu, it.ok, 0);
       }
-      if (it.kind == kItemProj) {
-        reinterpret_cast<uint32_t*>(&s_sample[slot])[lane] = spw0;
-        if (lane < 16) reinterpret_cast<uint32_t*>(&s_sample[slot])[32 + lane] = spw1;
+      const unsigned s = posted & 1u;
+      if (it.kind == kItemResolve && it.ok) {
+        // the slice flags of the item, read (and cleared) here: a worker then needs one L2 round trip per flagged
+        // slice (its keys) instead of two.  lane = slice of the item; the ballot travels in it.idx's companion word
+        const int slice = it.idx * (kLblWarps * kLblResK) + lane;
+        uint32_t f = 0;
+        if (lane < kLblWarps * kLblResK && slice < d.nsl) {
+          uint32_t* fp = flags + ((size_t)(it.frame % ring) * d.nsl + slice) * kFlagStride;
+          f = __ldcg(fp);
+          if (f) __stcg(fp, 0u);
+        }
+        it.ok = 1 | (int)(__ballot_sync(0xffffffffu, f != 0u) << 1);  // bit 0: run it, bits 1..: flagged slices
       }
-      if (lane == 0) s_item[slot] = it;
-      lbl_cta_sync();  // the workers are done with the previous item and see this one
-      publish_prev();
+      if (it.kind == kItemProj) {
+        reinterpret_cast<uint32_t*>(&s_sample[s])[lane] = spw0;
+        if (lane < 16) reinterpret_cast<uint32_t*>(&s_sample[s])[32 + lane] = spw1;
+      }
+      if (lane == 0) s_item[s] = it;
+      if (s) { kind1 = it.kind; frame1 = it.frame; } else { kind0 = it.kind; frame0 = it.frame; }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_full[s]);
+      ++posted;
       if (it.kind == kItemExit) break;
-      if (it.kind == kItemProj || it.kind == kItemResolve) { prev_kind = it.kind; prev_frame = it.frame; }
-      slot ^= 1;
     }
+    ensure_published(posted - 1);  // everything but the exit item, which nobody releases
     // the last CTA out re-arms the control block for the next call (and scrubs the workspace after a timeout)
     uint32_t last = 0;
     if (lane == 0) {
@@ -446,26 +480,28 @@ proj_lbl_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ lab
   } else {
     // ===================== workers =====================
     const Rcps rcp{__frcp_rn(cfg.map_res), __frcp_rn(cfg.fx), __frcp_rn(cfg.fy)};
-    while (true) {
-      lbl_cta_sync();
-      const LblItem it = s_item[slot];
+    for (unsigned k = 0;; ++k) {
+      const unsigned s = k & 1u;
+      mbar_wait(&s_full[s], (k >> 1) & 1u);
+      const LblItem it = s_item[s];
       if (it.kind == kItemExit) break;
       if (it.ok) {
         const int rslot = it.frame % ring;
         uint32_t* slot_flags = flags + (size_t)rslot * d.nsl * kFlagStride;
         if (it.kind == kItemProj) {
           const int n0 = it.idx * kLblTile + warp * 128 + lane * 4;
-          lbl_proj_warp<FAST, W2>(cfg, d, s_sample[slot], rcp, depth + (size_t)it.frame * N,
+          lbl_proj_warp<FAST, W2>(cfg, d, s_sample[s], rcp, depth + (size_t)it.frame * N,
                                   labels + (size_t)it.frame * N, valid ? valid + (size_t)it.frame * N : nullptr, n0,
                                   lane, s_list[warp], acc, (uint32_t)rslot * (uint32_t)d.slot_words, slot_flags);
         } else if (it.kind == kItemResolve) {
 #pragma unroll 1
-          for (int k = 0; k < kLblResK; ++k)
-            lbl_resolve_slice<W2>(acc + (size_t)rslot * d.slot_words, cfg, d, slot_flags, it.frame,
-                                  (it.idx * kLblWarps + warp) * kLblResK + k, lane, topdown, mask, height);
+          for (int q = 0; q < kLblResK; ++q)
+            lbl_resolve_slice<W2>(acc + (size_t)rslot * d.slot_words, cfg, d, ((unsigned)it.ok >> (1 + warp * kLblResK + q)) & 1u,
+                                  it.frame, (it.idx * kLblWarps + warp) * kLblResK + q, lane, topdown, mask, height);
         }
       }
-      slot ^= 1;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[s]);
     }
   }
 }
@@ -508,6 +544,7 @@ extern "C" int dm_orth_project_labels_f32(const float* depth, const uint8_t* lab
   d.hasH = cfg->want_height ? 1 : 0;
   d.vec_in = (N % 4 == 0) && lbl_aligned(depth, 16) && lbl_aligned(labels, 4) && (!valid || lbl_aligned(valid, 4));
   d.vec_out = (M % 4 == 0) && lbl_aligned(topdown, 16) && lbl_aligned(mask, 16) && (!d.hasH || lbl_aligned(height, 16));
+  if (d.vec_out && M % 16 == 0) d.vec_out = 2;
   d.slot_words = p.slot_words;
   d.ws_words = (p.workspace_bytes() - p.ctrl_bytes) / 4;
   const long long tickets = (long long)(b + p.lag) * ((N + kLblTile - 1) / kLblTile + (M + kLblResCells - 1) / kLblResCells);

@@ -5,7 +5,7 @@
 TAG=${1:-r02x}
 mkdir -p gpurun_out
 if [ "$2" != notests ]; then
-  timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+  timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_${TAG}.log 2>&1; tail -15 gpurun_out/pytest_${TAG}.log | cut -c1-300
 fi
 show() {
   python - "$1" "$2" <<'PY'
