@@ -60,6 +60,25 @@ class DmFuseTarget(ctypes.Structure):
   ]
 
 
+class DmBuilderCfg(ctypes.Structure):
+  _fields_ = [
+    ("proj", DmProjCfg), ("b", c_int32), ("plot_to_global", c_int32), ("pitch_R", c_float * 9),
+    ("cam_height", c_float), ("width_offset", c_float), ("height_offset", c_float),
+    ("yaw_skew", c_float * 9), ("yaw_skew_sq", c_float * 9), ("merge_fill_value", c_float),
+    ("merge_reduction", c_int32), ("_pad", c_int32 * 2),
+  ]
+
+
+class DmMapRef(ctypes.Structure):
+  _fields_ = [("topdown", c_void_p), ("mask", c_void_p), ("h", c_int32), ("w", c_int32),
+              ("width_offset", c_float), ("height_offset", c_float), ("box", c_void_p)]
+
+
+class DmMergeShape(ctypes.Structure):
+  _fields_ = [("n_valid", c_int64), ("map_height", c_int32), ("map_width", c_int32),
+              ("width_offset", c_float), ("height_offset", c_float)]
+
+
 STEP_WORDS = ctypes.sizeof(DmStep) // 4          # 16
 PROJ_SAMPLE_WORDS = 48                           # DmProjSample: 2 steps + 2 offsets + pad
 FLOW_SAMPLE_WORDS = 48                           # DmFlowSample: 3 steps
@@ -68,6 +87,7 @@ _SIGNATURES = {
   "dm_abi_version": (ctypes.c_int, []),
   "dm_build_info": (ctypes.c_char_p, []),
   "dm_launch_count": (c_int64, []),
+  "dm_sizeof_struct": (c_int32, [c_int32]),
   "dm_release_scratch": (None, []),
   "dm_orth_project_workspace_bytes": (c_size_t, [POINTER(DmProjCfg), c_int32]),
   "dm_orth_project_f32": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(DmProjCfg), c_int32,
@@ -93,6 +113,13 @@ _SIGNATURES = {
   "dm_fuse_inplace_f32": (ctypes.c_int, [POINTER(DmFuseSource), c_int32, c_int32, c_int32, POINTER(DmFuseTarget),
                                          c_void_p, c_void_p, c_void_p, c_void_p]),
   "dm_fuse_canvas_init_f32": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_void_p]),
+  "dm_builder_create": (ctypes.c_int, [POINTER(DmBuilderCfg), c_int32, POINTER(c_void_p)]),
+  "dm_builder_destroy": (None, [c_void_p]),
+  "dm_builder_plot": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     POINTER(DmMapRef), POINTER(DmMergeShape), c_void_p]),
+  "dm_builder_merge": (ctypes.c_int, [c_void_p, POINTER(DmMapRef), c_void_p]),
+  "dm_builder_step_fixed": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                           POINTER(DmMapRef), c_void_p]),
   "dm_transform_points_f32": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int64, c_void_p, c_void_p]),
   "dm_image_camera_f32": (ctypes.c_int, [c_void_p, c_int64, c_float, c_float, c_float, c_float, c_int32, c_int32,
                                          c_int32, c_void_p, c_void_p]),

@@ -128,6 +128,22 @@ extern "C" const char* dm_build_info(void) {
 
 extern "C" int64_t dm_launch_count(void) { return g_launches; }
 
+extern "C" int32_t dm_sizeof_struct(int32_t id) {
+  switch (id) {
+    case 0: return sizeof(DmStep);
+    case 1: return sizeof(DmProjSample);
+    case 2: return sizeof(DmProjCfg);
+    case 3: return sizeof(DmFlowSample);
+    case 4: return sizeof(DmFlowCfg);
+    case 5: return sizeof(DmFuseSource);
+    case 6: return sizeof(DmFuseTarget);
+    case 7: return sizeof(DmBuilderCfg);
+    case 8: return sizeof(DmMapRef);
+    case 9: return sizeof(DmMergeShape);
+    default: return -1;
+  }
+}
+
 extern "C" int dm_device_status(int32_t device) { return take_timeout(device) ? DM_ETIMEOUT : DM_OK; }
 
 extern "C" void dm_debug_set_wait_guard(uint64_t spin_ns, uint32_t dep_bias) {

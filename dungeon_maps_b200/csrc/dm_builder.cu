@@ -1,0 +1,270 @@
+// MapBuilder.step with its host side in C: plot (orth_project with get_height_map, maps.py:2408-2469) + merge
+// (fuse_topdown_maps, maps.py:2181-2287) for the case a mapping loop runs thousands of times — height maps of b
+// environments, world map in the global frame.  The Python layer made ~1000 interpreter calls per step for a few
+// hundred bytes of parameters (0.73 ms per step around 0.25 ms of merge kernels, profiles/r01n); here a step is two
+// C calls: every parameter block (projection samples, the two fuse sources) is packed into ONE pinned staging slot,
+// uploaded with ONE copy, and the kernels are launched back to back.  Nothing about the arithmetic changes: the
+// rotation matrices are formed from sin / cos values the caller computes with the reference's own torch-CPU ops
+// (utils.py:303-327; the last ulp matters), by the same float32 operations in the same order.
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "dm_common.cuh"
+
+namespace dm {
+namespace {
+
+constexpr int kParamSlots = 4;
+constexpr int kStepWords = sizeof(DmStep) / 4;           // 16
+constexpr int kSampleWords = sizeof(DmProjSample) / 4;   // 48
+constexpr int kFuseWords = 2 * kStepWords + 2;           // per sample: two steps, width offset, height offset
+
+void put_step(float* w, int kind, const float* R, const float* t, int fused) {
+  memset(w, 0, sizeof(DmStep));
+  if (kind == DM_STEP_NONE) return;
+  if (R) memcpy(w, R, 9 * sizeof(float));
+  if (t) memcpy(w + 9, t, 3 * sizeof(float));
+  int32_t* iw = reinterpret_cast<int32_t*>(w);
+  iw[12] = kind;
+  iw[13] = fused;
+}
+
+}  // namespace
+}  // namespace dm
+
+using namespace dm;
+
+struct DmBuilder {
+  DmBuilderCfg cfg;
+  int device = 0;
+  int fused_proj = 0, fused_fuse = 0;
+  int local_fast = 0;  // the pitch step has the structure DmProjCfg.fast_steps >= 1 promises
+  char* h_params[kParamSlots] = {};
+  char* d_params[kParamSlots] = {};
+  cudaEvent_t ev[kParamSlots] = {};
+  size_t param_bytes = 0;
+  unsigned next = 0;
+  int64_t* d_bbox = nullptr;
+  int64_t* h_bbox = nullptr;
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  // what dm_builder_plot leaves for dm_builder_merge
+  DmFuseSource src[2];
+  int n_src = 0;
+};
+
+static void builder_free(DmBuilder* h) {
+  if (!h) return;
+  for (int i = 0; i < kParamSlots; ++i) {
+    if (h->h_params[i]) cudaFreeHost(h->h_params[i]);
+    if (h->d_params[i]) cudaFree(h->d_params[i]);
+    if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  }
+  if (h->d_bbox) cudaFree(h->d_bbox);
+  if (h->h_bbox) cudaFreeHost(h->h_bbox);
+  if (h->ws) cudaFree(h->ws);
+  delete h;
+}
+
+extern "C" int dm_builder_create(const DmBuilderCfg* cfg, int32_t device, DmBuilder** out) {
+  if (!cfg || !out || cfg->b <= 0 || cfg->proj.C != 0) return DM_EINVAL;
+  if (cfg->proj.H <= 0 || cfg->proj.W <= 0 || cfg->proj.Mh <= 0 || cfg->proj.Mw <= 0) return DM_EINVAL;
+  if (cfg->merge_reduction != 0 && cfg->merge_reduction != 1) return DM_EINVAL;
+  DmBuilder* h = new (std::nothrow) DmBuilder();
+  if (!h) return DM_EINVAL;
+  h->cfg = *cfg;
+  h->device = device;
+  const long long n_proj = (long long)cfg->proj.H * cfg->proj.W;            // points one bmm rotates (utils.py:329)
+  const long long n_fuse = (long long)cfg->proj.Mh * cfg->proj.Mw;          // C * h * w points of the local map
+  h->fused_proj = 9 * n_proj >= 400;
+  h->fused_fuse = 9 * n_fuse >= 400;
+  const float* R = cfg->pitch_R;
+  h->local_fast = h->fused_proj && R[0] == 1.0f && R[1] == 0.0f && R[2] == 0.0f && R[3] == 0.0f && R[6] == 0.0f;
+  h->param_bytes = ((size_t)cfg->b * (kSampleWords + 2 * kFuseWords) * 4 + 255) & ~(size_t)255;
+  int rc = DM_OK;
+#define DM_TRY(expr)                                                       \
+  if (rc == DM_OK) {                                                       \
+    const cudaError_t e_ = (expr);                                         \
+    if (e_ != cudaSuccess) rc = static_cast<int>(e_);                      \
+  }
+  for (int i = 0; i < kParamSlots; ++i) {
+    DM_TRY(cudaHostAlloc(reinterpret_cast<void**>(&h->h_params[i]), h->param_bytes, cudaHostAllocDefault));
+    DM_TRY(cudaMalloc(reinterpret_cast<void**>(&h->d_params[i]), h->param_bytes));
+    DM_TRY(cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming));
+  }
+  DM_TRY(cudaMalloc(reinterpret_cast<void**>(&h->d_bbox), 5 * sizeof(int64_t)));
+  DM_TRY(cudaHostAlloc(reinterpret_cast<void**>(&h->h_bbox), 5 * sizeof(int64_t), cudaHostAllocDefault));
+  h->ws_bytes = dm_orth_project_workspace_bytes(&cfg->proj, cfg->b);
+  if (h->ws_bytes == 0 && rc == DM_OK) rc = DM_EINVAL;
+  DM_TRY(cudaMalloc(&h->ws, h->ws_bytes));
+  DM_TRY(cudaMemset(h->ws, 0, h->ws_bytes));
+#undef DM_TRY
+  if (rc != DM_OK) {
+    builder_free(h);
+    return rc;
+  }
+  *out = h;
+  return DM_OK;
+}
+
+extern "C" void dm_builder_destroy(DmBuilder* h) { builder_free(h); }
+
+// Packs one step's parameter blocks into a pinned slot and queues their upload; returns the slot's device base.
+//   [DmProjSample x b | local fuse params (steps (b,2), woff (b), hoff (b)) | world fuse params (same layout)]
+static int upload_params(DmBuilder* h, const float* pose, const float* sin_yaw, const float* cos_yaw,
+                         const DmMapRef* world, cudaStream_t stream, char** d_base, int* fast_steps) {
+  const DmBuilderCfg& c = h->cfg;
+  const int b = c.b;
+  const unsigned slot = h->next++ % kParamSlots;
+  DM_CUDA_OK(cudaEventSynchronize(h->ev[slot]));  // the copy that last read this slot has run (it was queued long ago)
+  float* w = reinterpret_cast<float*>(h->h_params[slot]);
+  float* samples = w;
+  float* lsteps = w + (size_t)b * kSampleWords;
+  float* lwoff = lsteps + (size_t)b * 2 * kStepWords;
+  float* lhoff = lwoff + b;
+  float* wsteps = lhoff + b;
+  float* wwoff = wsteps + (size_t)b * 2 * kStepWords;
+  float* whoff = wwoff + b;
+  int fast = h->local_fast ? (c.plot_to_global ? 2 : 1) : 0;
+  for (int i = 0; i < b; ++i) {
+    // utils.py:303-327 for the axis (0, 1, 0): R = (I + sin(a) S) + (1 - cos(a)) S², float32, this operation order
+    float Ry[9];
+    const float s = sin_yaw[i], one_minus_cos = 1.0f - cos_yaw[i];
+    for (int k = 0; k < 9; ++k) {
+      const float eye = (k == 0 || k == 4 || k == 8) ? 1.0f : 0.0f;
+      const float a = s * c.yaw_skew[k];
+      const float e = eye + a;
+      const float q = one_minus_cos * c.yaw_skew_sq[k];
+      Ry[k] = e + q;
+    }
+    const float ty[3] = {pose[3 * i + 0], 0.0f, pose[3 * i + 1]};  // maps.py:889-891
+    const float tl[3] = {0.0f, c.cam_height, 0.0f};                // maps.py:795-797
+    float* sp = samples + (size_t)i * kSampleWords;
+    memset(sp, 0, sizeof(DmProjSample));
+    put_step(sp, DM_STEP_ROT_THEN_ADD, c.pitch_R, tl, h->fused_proj);
+    put_step(sp + kStepWords, c.plot_to_global ? DM_STEP_ROT_THEN_ADD : DM_STEP_NONE, Ry, ty, h->fused_proj);
+    sp[32] = c.width_offset;
+    sp[33] = c.height_offset;
+    if (fast == 2 && !(Ry[4] == 1.0f && Ry[1] == 0.0f && Ry[3] == 0.0f && Ry[5] == 0.0f && Ry[7] == 0.0f)) fast = 0;
+    // the local map as a source of the merge (maps.py:2059-2060): local → global with its own pose, unless it was
+    // plotted in the global frame; the target is global (maps.py:2116-2117: no second step)
+    put_step(lsteps + (size_t)i * 2 * kStepWords, c.plot_to_global ? DM_STEP_NONE : DM_STEP_ROT_THEN_ADD, Ry, ty,
+             h->fused_fuse);
+    put_step(lsteps + (size_t)i * 2 * kStepWords + kStepWords, DM_STEP_NONE, nullptr, nullptr, 0);
+    lwoff[i] = c.width_offset;
+    lhoff[i] = c.height_offset;
+    put_step(wsteps + (size_t)i * 2 * kStepWords, DM_STEP_NONE, nullptr, nullptr, 0);
+    put_step(wsteps + (size_t)i * 2 * kStepWords + kStepWords, DM_STEP_NONE, nullptr, nullptr, 0);
+    wwoff[i] = world ? world->width_offset : 0.0f;
+    whoff[i] = world ? world->height_offset : 0.0f;
+  }
+  DM_CUDA_OK(cudaMemcpyAsync(h->d_params[slot], h->h_params[slot], h->param_bytes, cudaMemcpyHostToDevice, stream));
+  DM_CUDA_OK(cudaEventRecord(h->ev[slot], stream));
+  *d_base = h->d_params[slot];
+  *fast_steps = fast;
+  return DM_OK;
+}
+
+static void make_sources(DmBuilder* h, char* d_base, float* local_topdown, uint8_t* local_mask, const DmMapRef* world) {
+  const DmBuilderCfg& c = h->cfg;
+  const int b = c.b;
+  float* w = reinterpret_cast<float*>(d_base);
+  float* lsteps = w + (size_t)b * kSampleWords;
+  float* lwoff = lsteps + (size_t)b * 2 * kStepWords;
+  float* lhoff = lwoff + b;
+  float* wsteps = lhoff + b;
+  float* wwoff = wsteps + (size_t)b * 2 * kStepWords;
+  float* whoff = wwoff + b;
+  h->n_src = 0;
+  if (world) {  // fuse_topdown_maps(world, new): the world map first (maps.py:2471-2508)
+    DmFuseSource& s = h->src[h->n_src++];
+    s.height = world->topdown; s.values = nullptr; s.mask = world->mask;
+    s.height_bstride = (int64_t)world->h * world->w; s.height_cstride = s.height_bstride;
+    s.h = world->h; s.w = world->w; s.flip_h = c.proj.flip_h; s.map_res = c.proj.map_res;
+    s.width_offset = wwoff; s.height_offset = whoff; s.steps = reinterpret_cast<const DmStep*>(wsteps);
+  }
+  DmFuseSource& s = h->src[h->n_src++];
+  s.height = local_topdown; s.values = nullptr; s.mask = local_mask;
+  s.height_bstride = (int64_t)c.proj.Mh * c.proj.Mw; s.height_cstride = s.height_bstride;
+  s.h = c.proj.Mh; s.w = c.proj.Mw; s.flip_h = c.proj.flip_h; s.map_res = c.proj.map_res;
+  s.width_offset = lwoff; s.height_offset = lhoff; s.steps = reinterpret_cast<const DmStep*>(lsteps);
+}
+
+extern "C" int dm_builder_plot(DmBuilder* h, const float* depth, const float* pose, const float* sin_yaw,
+                               const float* cos_yaw, float* local_topdown, uint8_t* local_mask, const DmMapRef* world,
+                               DmMergeShape* shape, void* stream_) {
+  if (!h || !depth || !pose || !sin_yaw || !cos_yaw || !local_topdown || !local_mask || !shape) return DM_EINVAL;
+  if (world && (!world->topdown || !world->mask || world->h <= 0 || world->w <= 0)) return DM_EINVAL;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  char* d_base = nullptr;
+  int fast = 0;
+  int rc = upload_params(h, pose, sin_yaw, cos_yaw, world, stream, &d_base, &fast);
+  if (rc != DM_OK) return rc;
+  DmProjCfg pc = h->cfg.proj;
+  pc.fast_steps = fast;
+  pc.want_height = 0;  // C == 0: the topdown map is the height map (maps.py:333-334)
+  rc = dm_orth_project_f32(depth, nullptr, nullptr, reinterpret_cast<const DmProjSample*>(d_base), &pc, h->cfg.b,
+                           local_topdown, local_mask, nullptr, h->ws, h->ws_bytes, stream);
+  if (rc != DM_OK) return rc;
+  make_sources(h, d_base, local_topdown, local_mask, world);
+  // pass 1 (maps.py:2146-2179): a world map that carries the box its own scatter pass tracked only seeds the reduction
+  const bool seeded = world && world->box;
+  const DmFuseSource* scan = seeded ? &h->src[h->n_src - 1] : h->src;
+  rc = dm_fuse_bbox_seeded_i64(scan, seeded ? 1 : h->n_src, h->cfg.b, 1, h->cfg.proj.map_res,
+                               seeded ? world->box : nullptr, h->d_bbox, stream);
+  if (rc != DM_OK) return rc;
+  DM_CUDA_OK(cudaMemcpyAsync(h->h_bbox, h->d_bbox, 5 * sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+  DM_CUDA_OK(cudaStreamSynchronize(stream));  // the reference's .item() sync (maps.py:2172-2173)
+  const int64_t min_x = h->h_bbox[0], max_x = h->h_bbox[1], min_z = h->h_bbox[2], max_z = h->h_bbox[3];
+  shape->n_valid = h->h_bbox[4];
+  if (shape->n_valid == 0) return DM_OK;  // maps.py:2217-2225: the caller keeps the last map
+  // maps.py:2171-2178: sizes as Python ints, offsets as float32 tensors
+  const int64_t map_width = (max_x - min_x) + 2, map_height = (max_z - min_z) + 2;
+  if (map_width <= 0 || map_height <= 0 || map_width >= (1ll << 31) || map_height >= (1ll << 31)) return DM_EINVAL;
+  shape->map_width = (int32_t)map_width;
+  shape->map_height = (int32_t)map_height;
+  shape->width_offset = (float)((double)map_width / 2.0) - (float)(max_x + min_x) / 2.0f;
+  shape->height_offset = (float)((double)map_height / 2.0) - (float)(max_z + min_z) / 2.0f;
+  return DM_OK;
+}
+
+extern "C" int dm_builder_merge(DmBuilder* h, const DmMapRef* out, void* stream_) {
+  if (!h || !out || !out->topdown || !out->mask || out->h <= 0 || out->w <= 0 || h->n_src <= 0) return DM_EINVAL;
+  const DmBuilderCfg& c = h->cfg;
+  DmFuseTarget tgt;
+  tgt.Mh = out->h; tgt.Mw = out->w; tgt.flip_h = c.proj.flip_h; tgt.map_res = c.proj.map_res;
+  tgt.width_offset = out->width_offset; tgt.height_offset = out->height_offset;
+  tgt.fill_value = c.merge_fill_value; tgt.reduction = c.merge_reduction;
+  const int rc = dm_fuse_scatter_track_f32(h->src, h->n_src, c.b, 1, &tgt, out->topdown, out->mask, nullptr, out->box,
+                                           stream_);
+  h->n_src = 0;
+  return rc;
+}
+
+extern "C" int dm_builder_step_fixed(DmBuilder* h, const float* depth, const float* pose, const float* sin_yaw,
+                                     const float* cos_yaw, float* local_topdown, uint8_t* local_mask,
+                                     const DmMapRef* canvas, void* stream_) {
+  if (!h || !depth || !pose || !sin_yaw || !cos_yaw || !local_topdown || !local_mask) return DM_EINVAL;
+  if (!canvas || !canvas->topdown || !canvas->mask || canvas->h <= 0 || canvas->w <= 0) return DM_EINVAL;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  char* d_base = nullptr;
+  int fast = 0;
+  int rc = upload_params(h, pose, sin_yaw, cos_yaw, nullptr, stream, &d_base, &fast);
+  if (rc != DM_OK) return rc;
+  DmProjCfg pc = h->cfg.proj;
+  pc.fast_steps = fast;
+  pc.want_height = 0;
+  rc = dm_orth_project_f32(depth, nullptr, nullptr, reinterpret_cast<const DmProjSample*>(d_base), &pc, h->cfg.b,
+                           local_topdown, local_mask, nullptr, h->ws, h->ws_bytes, stream);
+  if (rc != DM_OK) return rc;
+  make_sources(h, d_base, local_topdown, local_mask, nullptr);
+  const DmBuilderCfg& c = h->cfg;
+  DmFuseTarget tgt;
+  tgt.Mh = canvas->h; tgt.Mw = canvas->w; tgt.flip_h = c.proj.flip_h; tgt.map_res = c.proj.map_res;
+  tgt.width_offset = canvas->width_offset; tgt.height_offset = canvas->height_offset;
+  tgt.fill_value = c.merge_fill_value; tgt.reduction = c.merge_reduction;
+  rc = dm_fuse_inplace_f32(h->src, 1, c.b, 1, &tgt, canvas->topdown, canvas->mask, nullptr, stream);
+  h->n_src = 0;
+  return rc;
+}

@@ -341,6 +341,17 @@ __device__ __forceinline__ void lbl_resolve_slice(uint32_t* __restrict__ acc_slo
   }
 }
 
+// Item slots per CTA and tickets the scheduler prepares at a time (one lane each).  A ticket costs the scheduler an
+// acquire load of its dependency, a read of its slice flags and a release of its completion counter — three L2 round
+// trips that, taken one ticket at a time, are longer than the ~1.5 us the eight workers need for the item (ncu r02b:
+// 37 % of all warp samples were workers polling for the next item).  Taken for kLblBatch tickets by kLblBatch lanes
+// they are one round trip each per batch.
+constexpr int kLblSlots = 8;
+constexpr int kLblBatch = 4;
+constexpr int kLblItemSlices = kLblWarps * kLblResK;  // 64-cell slices of one resolve item
+static_assert(kLblItemSlices * kLblBatch <= 32, "one scheduler lane per slice of a batch");
+static_assert(kLblItemSlices <= 30, "slice flags travel in the item's ok word");
+
 template <int FAST, int W2>
 __global__ void __launch_bounds__(kLblThreads, 4)
 proj_lbl_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ labels, const uint8_t* __restrict__ valid,
@@ -348,13 +359,15 @@ proj_lbl_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ lab
                 uint32_t* __restrict__ ctrl, uint32_t* __restrict__ flags, uint32_t* __restrict__ acc,
                 float* __restrict__ topdown, uint8_t* __restrict__ mask, float* __restrict__ height,
                 const ProjGuard guard) {
-  // Two item slots per CTA.  The scheduler posts item k into slot k & 1 (full[slot]) as soon as the workers have
-  // released item k - 2 (empty[slot], one arrival per worker warp); a worker warp that finishes its part of item k
-  // early starts on item k + 1 instead of waiting for the slowest warp of the CTA (a CTA-wide barrier per item cost
+  // The scheduler posts item k into slot k % kLblSlots (full[slot]) once the workers have released item
+  // k - kLblSlots (empty[slot], one arrival per worker warp); a worker warp that finishes its part of an item early
+  // starts on the next one instead of waiting for the slowest warp of the CTA (a CTA-wide barrier per item cost
   // 27 % of the warp samples in stall_barrier, ncu r02a).
-  __shared__ __align__(16) LblItem s_item[2];
-  __shared__ __align__(16) DmProjSample s_sample[2];
-  __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
+  constexpr int S = kLblSlots, G = kLblBatch, SL = kLblItemSlices;
+  __shared__ __align__(16) LblItem s_item[S];
+  __shared__ __align__(16) DmProjSample s_sample[S];
+  __shared__ __align__(8) uint64_t s_full[S], s_empty[S];
+  __shared__ int2 s_meta[S];  // (kind, frame) of the item in a slot, for the scheduler's own bookkeeping
   __shared__ uint32_t s_list[kLblWarps][(2 + W2) * kLblList];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = cfg.H * cfg.W, M = cfg.Mh * cfg.Mw;
@@ -364,9 +377,9 @@ proj_lbl_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ lab
   uint32_t* proj_done = ctrl + kCtrlWords;
   uint32_t* resolve_done = proj_done + b;
   const unsigned total = (unsigned)(b + lag) * (unsigned)(P + R);
-  if (tid == 0) {
-    mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
-    mbar_init(&s_empty[0], kLblWarps); mbar_init(&s_empty[1], kLblWarps);
+  if (tid < S) {
+    mbar_init(&s_full[tid], 1);
+    mbar_init(&s_empty[tid], kLblWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -374,92 +387,123 @@ proj_lbl_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ lab
   if (warp == kLblWarps) {
     // ===================== scheduler =====================
     // items are numbered in posting order; `posted` items have been handed to the workers, the first `published`
-    // of them have been waited for (all worker warps released them) and their completion counters incremented
+    // of them have been waited for (every worker warp released them) and their completion counters incremented
     unsigned posted = 0, published = 0;
-    int kind0 = kItemNone, kind1 = kItemNone, frame0 = 0, frame1 = 0;  // kind / frame of the item in slot 0 / 1
     auto ensure_published = [&](unsigned upto) {
-      while (published < upto) {
-        const unsigned s = published & 1u;
-        mbar_wait(&s_empty[s], (published >> 1) & 1u);
-        const int kd = s ? kind1 : kind0, fr = s ? frame1 : frame0;
-        if (lane == 0 && (kd == kItemProj || kd == kItemResolve))
-          red_release_add1((kd == kItemProj ? proj_done : resolve_done) + fr);
-        ++published;
+      if ((int)(upto - published) <= 0) return;
+      for (unsigned j = published; j != upto; ++j) mbar_wait(&s_empty[j % S], (j / S) & 1u);
+      if (lane < upto - published) {  // one lane per completed item: one release fence + RED instruction for all
+        const int2 m = s_meta[(published + lane) % S];
+        if (m.x == kItemProj || m.x == kItemResolve)
+          red_release_add1((m.x == kItemProj ? proj_done : resolve_done) + m.y);
       }
+      published = upto;
     };
-    // tickets are claimed two ahead so that the round trip of the atomic is never waited for
-    unsigned raw0 = 0, raw1 = 0;
-    if (lane == 0) {
-      raw0 = atomicAdd(ctrl, 1u);
-      raw1 = atomicAdd(ctrl, 1u);
-    }
-    while (true) {
-      const unsigned t = __shfl_sync(0xffffffffu, raw0, 0);
-      if (lane == 0) {
-        raw0 = raw1;
-        if (t < total) raw1 = atomicAdd(ctrl, 1u);
+    auto slice_flags = [&](int frame, int idx, int q, bool on) -> uint32_t {  // reads and clears one slice flag
+      uint32_t f = 0;
+      const int slice = idx * SL + q;
+      if (on && slice < d.nsl) {
+        uint32_t* fp = flags + ((size_t)(frame % ring) * d.nsl + slice) * kFlagStride;
+        f = __ldcg(fp);
+        if (f) __stcg(fp, 0u);
       }
-      LblItem it{kItemExit, 0, 0, 1};
-      if (t < total) decode_ticket(t, b, P, R, lag, &it.kind, &it.frame, &it.idx);
-      if (it.kind == kItemNone) continue;  // a ticket outside the batch (pipeline fill / drain): nothing to hand over
-      // dependency: ring slot resolved by its previous tenant / frame fully projected
+      return f;
+    };
+    // tickets are claimed a batch ahead so that the round trip of the atomic is never waited for
+    unsigned next_batch = 0;
+    if (lane == 0) next_batch = atomicAdd(ctrl, (unsigned)G);
+    bool done = false;
+    while (!done) {
+      const unsigned t0 = __shfl_sync(0xffffffffu, next_batch, 0);
+      if (lane == 0 && t0 < total) next_batch = atomicAdd(ctrl, (unsigned)G);
+      // ---- lane g prepares ticket t0 + g
+      int kind = kItemNone, frame = 0, idx = 0, ok = 1;
       const uint32_t* dep = nullptr;
       uint32_t dep_target = 0;
-      uint32_t spw0 = 0, spw1 = 0;  // my two words of the sample block
-      if (it.kind == kItemProj) {
-        if (it.frame >= ring) { dep = resolve_done + (it.frame - ring); dep_target = (uint32_t)R + guard.dep_bias; }
-        const uint32_t* sw = reinterpret_cast<const uint32_t*>(samples + it.frame);
-        spw0 = sw[lane];
-        if (lane < 16) spw1 = sw[32 + lane];
-        // the tile's input lines on their way into L2 while the workers finish what they have
-        const int n0 = it.idx * kLblTile;
-        const char* dp = reinterpret_cast<const char*>(depth + (size_t)it.frame * N + n0) + lane * 128;
+      if (lane < G) {
+        const unsigned t = t0 + (unsigned)lane;
+        if (t >= total) kind = kItemExit;
+        else decode_ticket(t, b, P, R, lag, &kind, &frame, &idx);
+        // dependency: ring slot resolved by its previous tenant / frame fully projected
+        if (kind == kItemProj) {
+          if (frame >= ring) { dep = resolve_done + (frame - ring); dep_target = (uint32_t)R + guard.dep_bias; }
+        } else if (kind == kItemResolve) {
+          dep = proj_done + frame;
+          dep_target = (uint32_t)P + guard.dep_bias;
+        }
+      }
+      // acquire loads (one instruction for the batch): they pair with the red.release of the CTAs that completed
+      // the frames; the other lanes and the workers inherit the ordering through __syncwarp and the mbarrier hand-off
+      int pending = 0;
+      if (dep) pending = ld_acquire(dep) < dep_target;
+      __syncwarp();
+      // the sample blocks of the batch (48 words per item) and, for projection items, the input lines on their way
+      // into L2 while the workers finish what they have
+      uint32_t sw[(G * 48 + 31) / 32];
+#pragma unroll
+      for (int j = 0; j < (G * 48 + 31) / 32; ++j) {
+        const int w = lane + 32 * j, g = w / 48;
+        const int gk = __shfl_sync(0xffffffffu, kind, g & (G - 1)), gf = __shfl_sync(0xffffffffu, frame, g & (G - 1));
+        sw[j] = 0;
+        if (g < G && gk == kItemProj) sw[j] = reinterpret_cast<const uint32_t*>(samples + gf)[w - 48 * g];
+      }
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const int gk = __shfl_sync(0xffffffffu, kind, g), gf = __shfl_sync(0xffffffffu, frame, g);
+        const int gi = __shfl_sync(0xffffffffu, idx, g);
+        if (gk != kItemProj) continue;
+        const int n0 = gi * kLblTile;
+        const char* dp = reinterpret_cast<const char*>(depth + (size_t)gf * N + n0) + lane * 128;
         if (n0 + lane * 32 < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(dp));
         if (lane < kLblTile / 128 && n0 + lane * 128 < N)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(labels + (size_t)it.frame * N + n0 + lane * 128));
-      } else if (it.kind == kItemResolve) {
-        dep = proj_done + it.frame;
-        dep_target = (uint32_t)P + guard.dep_bias;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(labels + (size_t)gf * N + n0 + lane * 128));
       }
-      // acquire load: pairs with the red.release of the CTAs that completed the frame; the workers inherit the
-      // ordering through the mbarrier hand-off of the item (release.cta here, acquire.cta there)
-      int pending = 0;
-      if (dep && lane == 0) pending = ld_acquire(dep) < dep_target;
-      pending = __shfl_sync(0xffffffffu, pending, 0);
-      // slot `posted & 1` is free once item posted - 2 has been released by every worker warp
-      if (posted >= 1) ensure_published(posted - 1);
-      if (pending) {
-        // rare: must block.  The frame we wait for may need the very items our workers are finishing: everything
-        // this CTA was handed is completed and published before the wait.
-        ensure_published(posted);
-        if (lane == 0) it.ok = wait_count(dep, dep_target, ctrl, guard.spin_ns);
-        it.ok = __shfl_sync(0xffffffffu, it.ok, 0);
+      // the slice flags of the resolve items whose dependency is satisfied, read (and cleared) here: a worker then
+      // needs one L2 round trip per flagged slice (its keys) instead of two.  lane = (item, slice)
+      uint32_t fl_all;
+      {
+        const int g = lane / SL, q = lane - g * SL;
+        const int gk = __shfl_sync(0xffffffffu, kind, g & (G - 1)), gf = __shfl_sync(0xffffffffu, frame, g & (G - 1));
+        const int gi = __shfl_sync(0xffffffffu, idx, g & (G - 1)), gp = __shfl_sync(0xffffffffu, pending, g & (G - 1));
+        fl_all = __ballot_sync(0xffffffffu, slice_flags(gf, gi, q, g < G && gk == kItemResolve && !gp) != 0u);
       }
-      const unsigned s = posted & 1u;
-      if (it.kind == kItemResolve && it.ok) {
-        // the slice flags of the item, read (and cleared) here: a worker then needs one L2 round trip per flagged
-        // slice (its keys) instead of two.  lane = slice of the item; the ballot travels in it.idx's companion word
-        const int slice = it.idx * (kLblWarps * kLblResK) + lane;
-        uint32_t f = 0;
-        if (lane < kLblWarps * kLblResK && slice < d.nsl) {
-          uint32_t* fp = flags + ((size_t)(it.frame % ring) * d.nsl + slice) * kFlagStride;
-          f = __ldcg(fp);
-          if (f) __stcg(fp, 0u);
+      // ---- post the batch in ticket order
+      for (int g = 0; g < G; ++g) {
+        const int k_ = __shfl_sync(0xffffffffu, kind, g);
+        if (k_ == kItemNone) continue;  // a ticket outside the batch (pipeline fill / drain)
+        const int fr = __shfl_sync(0xffffffffu, frame, g), ix = __shfl_sync(0xffffffffu, idx, g);
+        uint32_t fbits = (fl_all >> (g * SL)) & ((1u << SL) - 1u);
+        int okg = 1;
+        if (__shfl_sync(0xffffffffu, pending, g)) {
+          // rare: must block.  The frame we wait for may need the very items our workers are finishing: everything
+          // this CTA was handed so far is completed and published before the wait.
+          ensure_published(posted);
+          if (lane == g) ok = wait_count(dep, dep_target, ctrl, guard.spin_ns) ? 1 : 0;
+          okg = __shfl_sync(0xffffffffu, ok, g);
+          __syncwarp();
+          fbits = __ballot_sync(0xffffffffu, slice_flags(fr, ix, lane, lane < SL && k_ == kItemResolve && okg) != 0u);
         }
-        it.ok = 1 | (int)(__ballot_sync(0xffffffffu, f != 0u) << 1);  // bit 0: run it, bits 1..: flagged slices
+        // slot posted % S is free once item posted - S has been released by every worker warp
+        ensure_published(posted + 1u - (unsigned)S);
+        const unsigned s = posted % S;
+        if (k_ == kItemProj) {
+#pragma unroll
+          for (int j = 0; j < (G * 48 + 31) / 32; ++j) {
+            const int w = lane + 32 * j;
+            if (w / 48 == g) reinterpret_cast<uint32_t*>(&s_sample[s])[w - 48 * g] = sw[j];
+          }
+        }
+        if (lane == 0) {
+          s_item[s] = LblItem{k_, fr, ix, okg ? (int)(1u | (fbits << 1)) : 0};
+          s_meta[s] = make_int2(k_, fr);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_full[s]);
+        ++posted;
+        if (k_ == kItemExit) { done = true; break; }
       }
-      if (it.kind == kItemProj) {
-        reinterpret_cast<uint32_t*>(&s_sample[s])[lane] = spw0;
-        if (lane < 16) reinterpret_cast<uint32_t*>(&s_sample[s])[32 + lane] = spw1;
-      }
-      if (lane == 0) s_item[s] = it;
-      if (s) { kind1 = it.kind; frame1 = it.frame; } else { kind0 = it.kind; frame0 = it.frame; }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_full[s]);
-      ++posted;
-      if (it.kind == kItemExit) break;
     }
-    ensure_published(posted - 1);  // everything but the exit item, which nobody releases
+    ensure_published(posted - 1u);  // everything but the exit item, which nobody releases
     // the last CTA out re-arms the control block for the next call (and scrubs the workspace after a timeout)
     uint32_t last = 0;
     if (lane == 0) {
@@ -481,23 +525,24 @@ proj_lbl_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ lab
     // ===================== workers =====================
     const Rcps rcp{__frcp_rn(cfg.map_res), __frcp_rn(cfg.fx), __frcp_rn(cfg.fy)};
     for (unsigned k = 0;; ++k) {
-      const unsigned s = k & 1u;
-      mbar_wait(&s_full[s], (k >> 1) & 1u);
+      const unsigned s = k % S;
+      mbar_wait(&s_full[s], (k / S) & 1u);
       const LblItem it = s_item[s];
       if (it.kind == kItemExit) break;
       if (it.ok) {
         const int rslot = it.frame % ring;
-        uint32_t* slot_flags = flags + (size_t)rslot * d.nsl * kFlagStride;
         if (it.kind == kItemProj) {
           const int n0 = it.idx * kLblTile + warp * 128 + lane * 4;
           lbl_proj_warp<FAST, W2>(cfg, d, s_sample[s], rcp, depth + (size_t)it.frame * N,
                                   labels + (size_t)it.frame * N, valid ? valid + (size_t)it.frame * N : nullptr, n0,
-                                  lane, s_list[warp], acc, (uint32_t)rslot * (uint32_t)d.slot_words, slot_flags);
+                                  lane, s_list[warp], acc, (uint32_t)rslot * (uint32_t)d.slot_words,
+                                  flags + (size_t)rslot * d.nsl * kFlagStride);
         } else if (it.kind == kItemResolve) {
 #pragma unroll 1
           for (int q = 0; q < kLblResK; ++q)
-            lbl_resolve_slice<W2>(acc + (size_t)rslot * d.slot_words, cfg, d, ((unsigned)it.ok >> (1 + warp * kLblResK + q)) & 1u,
-                                  it.frame, (it.idx * kLblWarps + warp) * kLblResK + q, lane, topdown, mask, height);
+            lbl_resolve_slice<W2>(acc + (size_t)rslot * d.slot_words, cfg, d,
+                                  ((unsigned)it.ok >> (1 + warp * kLblResK + q)) & 1u, it.frame,
+                                  (it.idx * kLblWarps + warp) * kLblResK + q, lane, topdown, mask, height);
         }
       }
       __syncwarp();
@@ -548,7 +593,7 @@ extern "C" int dm_orth_project_labels_f32(const float* depth, const uint8_t* lab
   d.slot_words = p.slot_words;
   d.ws_words = (p.workspace_bytes() - p.ctrl_bytes) / 4;
   const long long tickets = (long long)(b + p.lag) * ((N + kLblTile - 1) / kLblTile + (M + kLblResCells - 1) / kLblResCells);
-  if (tickets >= (1ll << 31) - 4096 || (unsigned long long)p.ring * p.slot_words >= (1ull << 31)) return DM_EINVAL;
+  if (tickets >= (1ll << 31) - (1 << 20) || (unsigned long long)p.ring * p.slot_words >= (1ull << 31)) return DM_EINVAL;
   uint32_t* ctrl = static_cast<uint32_t*>(workspace);
   uint32_t* flags = reinterpret_cast<uint32_t*>(static_cast<char*>(workspace) + p.ctrl_bytes);
   uint32_t* acc = reinterpret_cast<uint32_t*>(static_cast<char*>(workspace) + p.ctrl_bytes + p.flag_bytes);

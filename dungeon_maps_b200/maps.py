@@ -1061,18 +1061,68 @@ def merge_into_canvas(world: TopdownMap, new_map: TopdownMap, canvas_shape: Tupl
 
 # ======== MapBuilder (maps.py:2289-2550) ==========================================================
 
+class _NativeBuilder():
+  """Owner of one DmBuilder handle (csrc/dm_builder.cu): a MapBuilder's step configuration frozen into C."""
+
+  def __init__(self, proj: MapProjector, key: tuple, dev: torch.device):
+    (b, H, W, _, plot_global, woff, hoff, Mw, Mh, pitch, camh, res, _, _, tdmin, tdmax, thmax, clip, flip, fill,
+     red) = key
+    cfg = nat.DmBuilderCfg()
+    p = cfg.proj
+    p.H, p.W, p.C, p.Mh, p.Mw = H, W, 0, Mh, Mw
+    k = proj.cam_params
+    p.fx, p.fy, p.cx, p.cy = k.fx, k.fy, k.cx, k.cy
+    p.map_res = res
+    p.has_trunc_depth_min, p.has_trunc_depth_max = tdmin is not None, tdmax is not None
+    p.has_trunc_height_max = thmax is not None
+    p.trunc_depth_min, p.trunc_depth_max, p.trunc_height_max = tdmin or 0., tdmax or 0., thmax or 0.
+    p.clip_border = int(clip) if clip is not None else 0
+    p.flip_h = flip
+    p.fill_value = 0. if fill is None else fill      # utils.py:472-473
+    p.reduction = red
+    cfg.b, cfg.plot_to_global = b, plot_global
+    R = prm.rotation_matrices([1., 0., 0.], torch.tensor([pitch], dtype=torch.float32))  # maps.py:789-793
+    cfg.pitch_R[:] = [float(v) for v in R.reshape(-1)]
+    cfg.cam_height = camh
+    cfg.width_offset, cfg.height_offset = woff, hoff
+    skew, skew_sq, _ = prm._skew_terms([0., 1., 0.])
+    cfg.yaw_skew[:] = [float(v) for v in skew.reshape(-1)]
+    cfg.yaw_skew_sq[:] = [float(v) for v in skew_sq.reshape(-1)]
+    self.fill = get(fill, NINF)                       # maps.py:2246: get(fill_value, proj.fill_value, NINF)
+    cfg.merge_fill_value = self.fill
+    cfg.merge_reduction = red
+    self._lib = nat.lib()
+    handle = nat.ctypes.c_void_p()
+    with torch.cuda.device(dev):
+      nat.check(self._lib.dm_builder_create(cfg, dev.index, nat.ctypes.byref(handle)), "dm_builder_create")
+    self.handle = handle
+
+  def __del__(self):
+    try:
+      if self.handle:
+        self._lib.dm_builder_destroy(self.handle)
+        self.handle = None
+    except Exception:
+      pass
+
+
 class MapBuilder():
   """Plots a local top-down map per frame and merges it into a growing world map."""
 
   def __init__(self, map_projector: MapProjector, world_map: Optional[TopdownMap] = None,
-               fixed_canvas: Optional[Tuple[int, int]] = None):
+               fixed_canvas: Optional[Tuple[int, int]] = None, native_step: bool = True):
     """`fixed_canvas=(map_height, map_width)` opts into the in-place world map (not in the reference,
     SURVEY.md §8f-2): global canvases of that size are allocated at the first merge, the world origin sits
     at their centre, and every merge max-merges the new map's cells into them with one kernel launch —
-    no bounding box, no host sync, no reallocation.  Points that fall outside the canvas are dropped."""
+    no bounding box, no host sync, no reallocation.  Points that fall outside the canvas are dropped.
+    `native_step`: height-map steps of a global-frame builder (value_map / valid_map None, CenterMode.none, device
+    depth tensors) run with their host side in C (dm_builder_*, csrc/dm_builder.cu) — same kernels, same results,
+    two library calls per step instead of ~1000 interpreter calls; anything else takes the general path."""
     self._proj = map_projector
     self._world_map = world_map if world_map is not None else TopdownMap(map_projector=self.proj.clone())
     self._fixed = None if fixed_canvas is None else (int(fixed_canvas[0]), int(fixed_canvas[1]))
+    self._native = bool(native_step)
+    self._handles: Dict[tuple, "_NativeBuilder"] = {}
 
   @property
   def proj(self) -> MapProjector:
@@ -1098,6 +1148,10 @@ class MapBuilder():
            **kwargs: Dict[str, Any]) -> TopdownMap:
     """Plot the frame's local map and (by default) merge it into the world map
     (maps.py:2357-2406).  Returns the local map."""
+    if self._native and merge and not keep_pose and value_map is None and valid_map is None:
+      done = self._native_step(depth_map, cam_pose, center_mode, kwargs)
+      if done is not None:
+        return done
     topdown_map = self.plot(depth_map=depth_map, value_map=value_map, valid_map=valid_map, cam_pose=cam_pose,
                             center_mode=center_mode, **kwargs)
     if merge:
@@ -1138,6 +1192,136 @@ class MapBuilder():
                                         map_projector=self.proj.clone(cam_pose=cam_pose),
                                         fill_value=fill_value, reduction=reduction)
     return self._world_map
+
+  # ---- the step with its host side in C (csrc/dm_builder.cu) ----------------------------------------------------
+
+  _NATIVE_KW = frozenset(("to_global", "width_offset", "height_offset", "map_width", "map_height"))
+
+  def _native_step(self, depth_map, cam_pose, center_mode, kwargs) -> Optional[TopdownMap]:
+    """MapBuilder.step for the case dm_builder_* covers; None when the call needs the general path."""
+    proj = self.proj
+    if (CenterMode(center_mode) is not CenterMode.none or not set(kwargs) <= self._NATIVE_KW or not proj.to_global
+        or not torch.is_tensor(depth_map) or not depth_map.is_cuda or depth_map.dtype is not torch.float32
+        or depth_map.dim() != 4 or depth_map.shape[1] != 1 or not depth_map.is_contiguous()):
+      return None
+    get_kw = lambda name: get(kwargs.get(name), getattr(proj, name))
+    scalars = [proj.cam_pitch, proj.cam_height, proj.map_res, get_kw("width_offset"), get_kw("height_offset"),
+               get_kw("map_width"), get_kw("map_height")]
+    if any(v is None or torch.is_tensor(v) or isinstance(v, (np.ndarray, list, tuple)) for v in scalars):
+      return None
+    try:
+      red = utils._reduction_code(proj.reduction)
+    except NotImplementedError:
+      return None
+    dev = depth_map.device
+    b, _, H, W = depth_map.shape
+    if (H, W) != (int(proj.height), int(proj.width)):
+      return None
+    world = self._world_map
+    have_world = world is not None and not world.is_empty
+    if have_world and not self._native_world_ok(world, b, dev):
+      return None
+    cam_pose = get(cam_pose, proj.cam_pose, np.array([0., 0., 0.], dtype=np.float32))
+    plot_global = bool(get_kw("to_global"))
+    woff, hoff = float(scalars[3]), float(scalars[4])
+    Mw, Mh = int(scalars[5]), int(scalars[6])
+    fill = proj.fill_value
+    key = (b, H, W, dev.index, plot_global, woff, hoff, Mw, Mh, float(proj.cam_pitch), float(proj.cam_height),
+           float(proj.map_res), proj.hfov, proj.vfov, proj.trunc_depth_min, proj.trunc_depth_max,
+           proj.trunc_height_max, proj.clip_border, bool(proj.flip_h), fill, red)
+    nb = self._handles.get(key)
+    if nb is None:
+      nb = self._handles[key] = _NativeBuilder(proj, key, dev)
+    pose = prm.per_sample(cam_pose, b, (3,), "cam_pose").contiguous()
+    # utils.py:323-326 with the reference's own torch-CPU ops (the last ulp of sin / cos matters)
+    yaw = pose[:, 2]
+    yaw = torch.where(torch.abs(yaw) > prm.ANGLE_EPS, yaw, torch.zeros((), dtype=torch.float32))
+    sin, cos = torch.sin(yaw), torch.cos(yaw)
+    local_top = torch.empty((b, 1, Mh, Mw), dtype=torch.float32, device=dev)
+    local_mask = torch.empty((b, 1, Mh, Mw), dtype=torch.bool, device=dev)
+    lib = nat.lib()
+    stream = nat.stream_ptr(dev)
+    # the local map as plot() describes it (maps.py:2459-2469); offsets as compute_center_offsets returns them
+    local_kw = {k: v for k, v in kwargs.items() if k in _CTOR_ARGS}
+    local_kw["width_offset"] = torch.tensor([woff], dtype=torch.float32)
+    local_kw["height_offset"] = torch.tensor([hoff], dtype=torch.float32)
+    local = TopdownMap(topdown_map=local_top, mask=local_mask, height_map=local_top,
+                       map_projector=proj.clone(cam_pose=cam_pose, **local_kw), is_height_map=True)
+    target = proj.clone(cam_pose=cam_pose)
+    with torch.cuda.device(dev):
+      if self._fixed is not None:
+        Hc, Wc = self._fixed
+        if not have_world:
+          topdown = torch.empty((b, 1, Hc, Wc), dtype=torch.float32, device=dev)
+          mask = torch.empty((b, 1, Hc, Wc), dtype=torch.bool, device=dev)
+          nat.check(lib.dm_fuse_canvas_init_f32(topdown.data_ptr(), mask.data_ptr(), None, topdown.numel(),
+                                                get(fill, NINF), stream), "dm_fuse_canvas_init_f32")
+        else:
+          topdown, mask = world.topdown_map, world.mask
+        canvas = nat.DmMapRef(topdown.data_ptr(), mask.data_ptr(), Hc, Wc, Wc / 2., Hc / 2., None)
+        nat.check(lib.dm_builder_step_fixed(nb.handle, depth_map.data_ptr(), pose.data_ptr(), sin.data_ptr(),
+                                            cos.data_ptr(), local_top.data_ptr(), local_mask.data_ptr(), canvas,
+                                            stream), "dm_builder_step_fixed")
+        self._world_map = TopdownMap(
+          topdown_map=topdown, mask=mask, height_map=topdown, is_height_map=True,
+          map_projector=target.clone(to_global=True, width_offset=Wc / 2., height_offset=Hc / 2., map_width=Wc,
+                                     map_height=Hc))
+        return local
+      wref = None
+      if have_world:
+        box = world._tracked_box.box if _tracked_box_valid(world, target, dev) else None
+        wref = nat.DmMapRef(world.topdown_map.data_ptr(), world.mask.data_ptr(), world.mask.shape[-2],
+                            world.mask.shape[-1], float(world.proj.width_offset), float(world.proj.height_offset),
+                            nat.ptr(box))
+      shape = nat.DmMergeShape()
+      nat.check(lib.dm_builder_plot(nb.handle, depth_map.data_ptr(), pose.data_ptr(), sin.data_ptr(), cos.data_ptr(),
+                                    local_top.data_ptr(), local_mask.data_ptr(), wref, shape, stream),
+                "dm_builder_plot")
+      if shape.n_valid == 0:  # maps.py:2217-2225
+        self._world_map = TopdownMap(topdown_map=local.topdown_map, mask=local.mask, height_map=local.height_map,
+                                     map_projector=target)
+        return local
+      mh, mw = shape.map_height, shape.map_width
+      topdown = torch.empty((b, 1, mh, mw), dtype=torch.float32, device=dev)
+      mask = torch.empty((b, 1, mh, mw), dtype=torch.bool, device=dev)
+      track = nb.fill == nb.fill
+      next_box = torch.empty((5,), dtype=torch.int64, device=dev) if track else None
+      out = nat.DmMapRef(topdown.data_ptr(), mask.data_ptr(), mh, mw, shape.width_offset, shape.height_offset,
+                         nat.ptr(next_box))
+      nat.check(lib.dm_builder_merge(nb.handle, out, stream), "dm_builder_merge")
+    new_proj = target.clone(width_offset=torch.tensor([shape.width_offset], dtype=torch.float32),
+                            height_offset=torch.tensor([shape.height_offset], dtype=torch.float32),
+                            map_width=mw, map_height=mh)
+    merged = TopdownMap(topdown_map=topdown, mask=mask, height_map=topdown, map_projector=new_proj,
+                        is_height_map=True)
+    if track:
+      merged._tracked_box = _TrackedBox(next_box, mask, new_proj)
+    # (the scatter pass still reads the old world map and the local map on the stream: torch's caching allocator
+    # hands freed blocks to later work of the same stream only, so dropping the old map here is safe)
+    self._world_map = merged
+    return local
+
+  def _native_world_ok(self, world: TopdownMap, b: int, dev: torch.device) -> bool:
+    """The world map is one the C step can take as it is: a contiguous (b, 1, h, w) float32 height map + bool mask on
+    `dev`, in the global frame, with this builder's resolution / flip and scalar offsets."""
+    p, proj = world.proj, self.proj
+    top, mask = world.topdown_map, world.mask
+    if not (world.is_height_map and p is not None and p.to_global and torch.is_tensor(top) and torch.is_tensor(mask)):
+      return False
+    if self._fixed is not None and tuple(top.shape[-2:]) != self._fixed:
+      return False
+    ok_t = lambda t, dt: (t.device == dev and t.dtype is dt and t.dim() == 4 and t.shape[0] == b and t.shape[1] == 1
+                          and t.is_contiguous())
+    if not (ok_t(top, torch.float32) and ok_t(mask, torch.bool) and top.shape == mask.shape):
+      return False
+    def one(v):
+      if v is None:
+        return False
+      if torch.is_tensor(v):
+        return v.numel() == 1
+      return np.asarray(v).size == 1
+    return (float(p.map_res) == float(proj.map_res) and bool(p.flip_h) == bool(proj.flip_h)
+            and one(p.width_offset) and one(p.height_offset))
 
   def _compute_offsets(self, cam_pose: np.ndarray, width_offset: Optional[np.ndarray] = None,
                        height_offset: Optional[np.ndarray] = None, map_res: Optional[float] = None,

@@ -54,14 +54,20 @@ def poses(b: int, seed: int = 0, xz: float = 1.0, yaw: float = math.pi, device=N
   return u * torch.tensor([xz, xz, yaw], dtype=torch.float32, device=device)
 
 
-def block_onehot(b: int, C: int, H: int, W: int, seed: int = 0, block: int = 16,
-                 device=None) -> torch.Tensor:
-  """(b,C,H,W) float32 one-hot semantics, class ids constant on block×block px tiles."""
+def block_labels(b: int, C: int, H: int, W: int, seed: int = 0, block: int = 16, device=None) -> torch.Tensor:
+  """(b,1,H,W) int64 class ids in [0, C), constant on block×block px tiles."""
   hb, wb = (H + block - 1) // block, (W + block - 1) // block
   ids = (hash_u24(b * hb * wb, seed ^ 0xC1A55, device) % C).reshape(b, hb, wb)
-  ids = ids.repeat_interleave(block, 1).repeat_interleave(block, 2)[:, :H, :W]
+  return ids.repeat_interleave(block, 1).repeat_interleave(block, 2)[:, :H, :W].unsqueeze(1).contiguous()
+
+
+def block_onehot(b: int, C: int, H: int, W: int, seed: int = 0, block: int = 16,
+                 device=None) -> torch.Tensor:
+  """(b,C,H,W) float32 one-hot semantics of block_labels (the planes the reference's object-map demo builds from a
+  segmentation image, demos/object_map/run.py:117-124)."""
+  ids = block_labels(b, C, H, W, seed, block, device)
   out = torch.zeros((b, C, H, W), dtype=torch.float32, device=device)
-  out.scatter_(1, ids.unsqueeze(1), 1.0)
+  out.scatter_(1, ids, 1.0)
   return out
 
 

@@ -254,6 +254,64 @@ int dm_fuse_inplace_f32(const DmFuseSource* sources, int32_t n_sources, int32_t 
 int dm_fuse_canvas_init_f32(float* topdown, uint8_t* mask, float* height, int64_t n, float fill_value,
                             void* stream);
 
+/* ---- MapBuilder.step with the host side in C (maps.py:2357-2508) ----------------------------------------------
+ * The plot → merge loop of b environments for height maps (value_map None) and a world map in the global frame —
+ * the configuration a mapping loop runs thousands of times.  A step packs every parameter block (projection
+ * samples, the fuse sources of world and local map) into one pinned slot, uploads it with one copy and launches the
+ * kernels back to back; the caller allocates the map tensors.  Results are those of dm_orth_project_f32 +
+ * dm_fuse_bbox_seeded_i64 + dm_fuse_scatter_track_f32 called one by one (the functions used inside). */
+typedef struct DmBuilder DmBuilder; /* opaque */
+
+typedef struct DmBuilderCfg {
+  DmProjCfg proj;          /* projection of the local maps (maps.py:2447-2458); C must be 0; fast_steps, want_height
+                              are derived */
+  int32_t b;               /* environments */
+  int32_t plot_to_global;  /* the local maps are plotted in the global frame (to_global of the plot call) */
+  float pitch_R[9];        /* DmStep.R of camera_to_local_space: rotation about x by cam_pitch, built on the host by
+                              the reference's own ops (utils.py:303-327) */
+  float cam_height;
+  float width_offset, height_offset; /* of the local maps */
+  float yaw_skew[9], yaw_skew_sq[9]; /* S and S² of the axis (0, 1, 0) as utils.py:303-318 builds them: the yaw
+                              rotation of a step is (I + sin S) + (1 - cos) S², float32, in that order */
+  float merge_fill_value;  /* fill_value of the merged canvases (maps.py:2246-2254) */
+  int32_t merge_reduction; /* 0 max, 1 min */
+  int32_t _pad[2];
+} DmBuilderCfg;
+
+/* A (b, 1, h, w) height map in the global frame, tensors on the device. */
+typedef struct DmMapRef {
+  float* topdown;
+  uint8_t* mask;
+  int32_t h, w;
+  float width_offset, height_offset;
+  int64_t* box; /* device, 5 x int64: as a source, the box dm_fuse_scatter_track_f32 left for this map (NULL: scan
+                   it); as the output of dm_builder_merge, where that box is written (NULL: not tracked) */
+} DmMapRef;
+
+/* Size and offsets of the canvas the merge needs (_compute_new_shape_and_offsets, maps.py:2146-2179). */
+typedef struct DmMergeShape {
+  int64_t n_valid; /* 0: no valid point anywhere, the merge is skipped (maps.py:2217-2225) */
+  int32_t map_height, map_width;
+  float width_offset, height_offset;
+} DmMergeShape;
+
+int dm_builder_create(const DmBuilderCfg* cfg, int32_t device, DmBuilder** out);
+void dm_builder_destroy(DmBuilder* builder);
+/* Step, first half: plots the local maps of `depth` (b, 1, H, W) at `pose` (HOST, (b, 3) = x, z, yaw; sin_yaw /
+ * cos_yaw: HOST (b,), of the yaw after the |a| <= 0.001 clamp of utils.py:323-324) into local_topdown / local_mask
+ * (b, 1, Mh, Mw), reduces the bounding box of world ∪ local and BLOCKS until it is on the host (the reference's
+ * .item() sync): `shape` says what to allocate.  world may be NULL (empty world map). */
+int dm_builder_plot(DmBuilder* builder, const float* depth, const float* pose, const float* sin_yaw,
+                    const float* cos_yaw, float* local_topdown, uint8_t* local_mask, const DmMapRef* world,
+                    DmMergeShape* shape, void* stream);
+/* Step, second half: fills `out` (shape->map_height x map_width, offsets from `shape`) and scatters the world map
+ * and the local map of the preceding dm_builder_plot into it. */
+int dm_builder_merge(DmBuilder* builder, const DmMapRef* out, void* stream);
+/* Opt-in fixed-canvas step (dm_fuse_inplace_f32 semantics): plot, then merge in place into `canvas`; no host sync. */
+int dm_builder_step_fixed(DmBuilder* builder, const float* depth, const float* pose, const float* sin_yaw,
+                          const float* cos_yaw, float* local_topdown, uint8_t* local_mask, const DmMapRef* canvas,
+                          void* stream);
+
 /* ---- materialising primitives (the reference's public L0/L1 functions) ------ */
 
 /* points (b, n, 3) f32 → out (b, n, 3): applies steps[b][n_steps] in order.
@@ -309,6 +367,10 @@ int dm_crop_nearest_u8(const uint8_t* image, const float* center, int32_t b, int
 
 /* Library/ABI introspection. */
 int dm_abi_version(void);
+/* sizeof() of a struct of this header as the library was compiled, for bindings to check their mirror against:
+ * 0 DmStep, 1 DmProjSample, 2 DmProjCfg, 3 DmFlowSample, 4 DmFlowCfg, 5 DmFuseSource, 6 DmFuseTarget,
+ * 7 DmBuilderCfg, 8 DmMapRef, 9 DmMergeShape; -1 for an unknown id. */
+int32_t dm_sizeof_struct(int32_t id);
 const char* dm_build_info(void);
 /* Number of kernel launches issued by this library since load (bench "gpu_launches"). */
 int64_t dm_launch_count(void);

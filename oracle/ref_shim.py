@@ -1,6 +1,7 @@
-"""ORACLE — test infrastructure only.  Imports the UNMODIFIED reference from
-/root/reference in the authoring container (it does not exist on the GPU box;
-nothing that runs there may import this module).
+"""ORACLE — test infrastructure only.  Imports the UNMODIFIED reference: from /root/reference in the authoring
+container (fixture generation, oracle/make_golden.py), or from baseline/_ref — the `pip install --target` copy of the
+same tree that travels to the GPU box — for the `--impl reference` arm of bench.py, the only thing on that box that
+may import this module.
 
 The reference imports `torch_scatter` at module top (utils.py:16), which is not
 installed.  A stand-in is registered first: scatter_{max,min,add,mul} with an
@@ -14,7 +15,18 @@ import types
 
 import torch
 
+import os
+
 REFERENCE_ROOT = "/root/reference"
+INSTALLED_ROOT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+
+
+def reference_root():
+  """Where an importable copy of the reference lives, or None."""
+  for root in (REFERENCE_ROOT, INSTALLED_ROOT):
+    if os.path.isdir(os.path.join(root, "dungeon_maps")):
+      return root
+  return None
 
 
 def _make(reduce: str):
@@ -48,8 +60,11 @@ def load_reference():
     ts.scatter_mul = _make("prod")
     ts.scatter_mean = _mean
     sys.modules["torch_scatter"] = ts
-  if REFERENCE_ROOT not in sys.path:
-    sys.path.insert(0, REFERENCE_ROOT)
+  root = reference_root()
+  if root is None:
+    raise ImportError("the reference is neither at /root/reference nor installed under baseline/_ref")
+  if root not in sys.path:
+    sys.path.insert(0, root)
   import dungeon_maps  # noqa: E402
   return dungeon_maps
 

@@ -57,6 +57,13 @@ def test_struct_layouts_match_the_header():
     assert n1 == n2 and ctypes.sizeof(t1) == ctypes.sizeof(t2)
   assert ctypes.sizeof(nat.DmFuseSource) == 3 * 8 + 2 * 8 + 4 * 4 + 3 * 8
   assert ctypes.sizeof(nat.DmFuseTarget) == 8 * 4
+  # every mirrored struct against sizeof() inside the compiled library
+  lib = nat.lib()
+  sizes = [64, nat.PROJ_SAMPLE_WORDS * 4, ctypes.sizeof(nat.DmProjCfg), nat.FLOW_SAMPLE_WORDS * 4,
+           ctypes.sizeof(nat.DmFlowCfg), ctypes.sizeof(nat.DmFuseSource), ctypes.sizeof(nat.DmFuseTarget),
+           ctypes.sizeof(nat.DmBuilderCfg), ctypes.sizeof(nat.DmMapRef), ctypes.sizeof(nat.DmMergeShape)]
+  assert [lib.dm_sizeof_struct(i) for i in range(len(sizes))] == sizes
+  assert lib.dm_sizeof_struct(99) == -1
 
 
 def test_workspace_query_needs_no_device():
