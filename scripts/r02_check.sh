@@ -3,6 +3,7 @@
 # the label kernel, compute-sanitizer memcheck / racecheck of small parity cases.
 # Usage: scripts/r02_check.sh <tag> [notests] [nosan]       — outputs land in gpurun_out/
 TAG=${1:-r02x}
+export TAG
 mkdir -p gpurun_out
 if [ "$2" != notests ]; then
   timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_${TAG}.log 2>&1; tail -15 gpurun_out/pytest_${TAG}.log | cut -c1-300
@@ -27,23 +28,31 @@ run() {  # run <name> <bench args...>
   timeout 400 python bench.py "$@" > gpurun_out/bench_${name}_${TAG}.json 2> gpurun_out/bench_${name}_${TAG}.err
   show $name gpurun_out/bench_${name}_${TAG}.json
 }
-run room --no-cpu-baseline
-run room20 --steps 20 --warmup 5 --no-cpu-baseline --e2e-steps 2
-run iid --scene iid --no-cpu-baseline --e2e-steps 2
-run labels --workload proj_labels
+run default
+python - "$TAG" <<'PY'
+import json, sys
+try:
+  d = json.load(open(f"gpurun_out/bench_default_{sys.argv[1]}.json"))
+  print("  e2e", d["e2e"]["value"], "e2e_float32", (d.get("e2e_float32") or {}).get("value"), "pcie", d.get("pcie"))
+  for k, v in (d.get("extra") or {}).items():
+    print("  extra", k, {a: (round(b, 4) if isinstance(b, float) else b) for a, b in v.items() if a not in ("workload",)})
+except Exception as e:
+  print("default line unreadable:", e)
+PY
+run room20 --steps 20 --warmup 5 --no-cpu-baseline --no-extra --e2e-steps 2
+run iid --scene iid --no-cpu-baseline --no-extra --e2e-steps 2
 run labels20 --workload proj_labels --steps 20 --warmup 5 --no-cpu-baseline --e2e-steps 2
 run labels_iid --workload proj_labels --scene iid --no-cpu-baseline --e2e-steps 2
-run labels5 --workload proj5_labels --steps 30 --no-cpu-baseline --e2e-steps 2
 for wl in ${WORKLOADS}; do
   run $wl --workload $wl --no-cpu-baseline
 done
 NCU="ncu --metrics gpu__time_duration.sum --clock-control none --csv"
 timeout 300 $NCU -k regex:"proj_|resolve_" -c 40 --log-file gpurun_out/launches_labels_${TAG}.csv python bench.py --workload proj_labels --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 2 > gpurun_out/ncu_launches_labels_${TAG}.log 2>&1
-timeout 300 $NCU -k regex:"proj_|resolve_" -c 40 --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 2 > gpurun_out/ncu_launches_${TAG}.log 2>&1
+timeout 300 $NCU -k regex:"proj_|resolve_" -c 40 --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extra --e2e-steps 2 > gpurun_out/ncu_launches_${TAG}.log 2>&1
 FULL="ncu --set full --clock-control none --import-source on -f"
 timeout 600 $FULL -k regex:"proj_lbl" -s 4 -c 1 -o gpurun_out/prof_labels_${TAG} python bench.py --workload proj_labels --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 2 > gpurun_out/ncu_full_labels_${TAG}.log 2>&1
 tail -2 gpurun_out/ncu_full_labels_${TAG}.log
-timeout 600 $FULL -k regex:"proj_ws" -s 4 -c 1 -o gpurun_out/prof_proj_${TAG} python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 2 > gpurun_out/ncu_full_${TAG}.log 2>&1
+timeout 600 $FULL -k regex:"proj_ws" -s 4 -c 1 -o gpurun_out/prof_proj_${TAG} python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extra --e2e-steps 2 > gpurun_out/ncu_full_${TAG}.log 2>&1
 tail -2 gpurun_out/ncu_full_${TAG}.log
 if [ "$3" != nosan ]; then
   SMALL="tests/test_gpu_labels.py::test_labels_random_vs_oracle[0] tests/test_gpu_labels.py::test_labels_random_vs_oracle[1] tests/test_gpu_labels.py::test_labels_random_vs_oracle[2] tests/test_gpu_parity.py::test_orth_project_random_vs_oracle[0] tests/test_gpu_parity.py::test_orth_project_random_vs_oracle[3] tests/test_gpu_parity.py::test_orth_project_edge_shapes tests/test_gpu_labels.py::test_labels_equal_float_path_and_argument_checks"
