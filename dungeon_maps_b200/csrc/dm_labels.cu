@@ -34,7 +34,7 @@ constexpr int kLblTile = 128 * kLblWarps;           // pixels per projection tic
 constexpr int kLblResK = DM_LBL_RES_K;              // 64-cell slices per worker warp and resolve ticket
 constexpr int kLblResCells = 64 * kLblWarps * kLblResK;
 #ifndef DM_LBL_RING
-#define DM_LBL_RING 16
+#define DM_LBL_RING 32
 #endif
 constexpr int kLblMaxRing = DM_LBL_RING;            // slots are small (8 or 12 bytes per cell): a deep ring is cheap
 constexpr int kLblList = 128 + 4;                   // runlet list entries per worker warp
@@ -345,9 +345,18 @@ __device__ __forceinline__ void lbl_resolve_slice(uint32_t* __restrict__ acc_slo
 // acquire load of its dependency, a read of its slice flags and a release of its completion counter — three L2 round
 // trips that, taken one ticket at a time, are longer than the ~1.5 us the eight workers need for the item (ncu r02b:
 // 37 % of all warp samples were workers polling for the next item).  Taken for kLblBatch tickets by kLblBatch lanes
-// they are one round trip each per batch.
-constexpr int kLblSlots = 8;
-constexpr int kLblBatch = 4;
+// they are one round trip each per batch.  The other side of the trade: every CTA holds kLblSlots + kLblBatch
+// tickets, and all CTAs together must not span more frames than the resolve pass lags behind the projection, or
+// the dependency waits stop being rare (r02c, 8 slots + 4 + 4 claimed ahead at lag 8: 1.1 M spins per launch, 0.30 ms
+// instead of 0.25) — the host picks the lag from the number of tickets in flight (lbl_schedule).
+#ifndef DM_LBL_SLOTS
+#define DM_LBL_SLOTS 4
+#endif
+#ifndef DM_LBL_BATCH
+#define DM_LBL_BATCH 2
+#endif
+constexpr int kLblSlots = DM_LBL_SLOTS;
+constexpr int kLblBatch = DM_LBL_BATCH;
 constexpr int kLblItemSlices = kLblWarps * kLblResK;  // 64-cell slices of one resolve item
 static_assert(kLblItemSlices * kLblBatch <= 32, "one scheduler lane per slice of a batch");
 static_assert(kLblItemSlices <= 30, "slice flags travel in the item's ok word");
@@ -409,13 +418,13 @@ proj_lbl_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ lab
       }
       return f;
     };
-    // tickets are claimed a batch ahead so that the round trip of the atomic is never waited for
-    unsigned next_batch = 0;
-    if (lane == 0) next_batch = atomicAdd(ctrl, (unsigned)G);
+    // (tickets are NOT claimed ahead: the round trip of the atomic is paid once per batch, and the tickets a CTA
+    // holds without working on them would widen the window of frames in flight)
     bool done = false;
     while (!done) {
-      const unsigned t0 = __shfl_sync(0xffffffffu, next_batch, 0);
-      if (lane == 0 && t0 < total) next_batch = atomicAdd(ctrl, (unsigned)G);
+      unsigned t0 = 0;
+      if (lane == 0) t0 = atomicAdd(ctrl, (unsigned)G);
+      t0 = __shfl_sync(0xffffffffu, t0, 0);
       // ---- lane g prepares ticket t0 + g
       int kind = kItemNone, frame = 0, idx = 0, ok = 1;
       const uint32_t* dep = nullptr;
@@ -551,6 +560,18 @@ proj_lbl_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ lab
   }
 }
 
+// Lag (frames between the projection of a frame and its resolve) and ring slots in use for a launch of `grid` CTAs:
+// the CTAs together hold grid * (slots + batch) tickets; the lag covers 1.5x the frames those span, + 1, within
+// what the workspace (sized for `max_ring` slots) and the batch allow.  ring = 2 * lag as in dm_project.cu.
+static void lbl_schedule(long long grid, long long tickets_per_frame, int max_ring, int* lag, int* ring) {
+  const double span = (double)grid * (kLblSlots + kLblBatch) / (double)(tickets_per_frame > 0 ? tickets_per_frame : 1);
+  int l = (int)(span * 1.5) + 2;
+  if (l > max_ring / 2) l = max_ring / 2;
+  if (l < 1) l = 1;
+  *lag = l;
+  *ring = 2 * l;
+}
+
 static bool lbl_aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 }  // namespace dm
@@ -592,7 +613,8 @@ extern "C" int dm_orth_project_labels_f32(const float* depth, const uint8_t* lab
   if (d.vec_out && M % 16 == 0) d.vec_out = 2;
   d.slot_words = p.slot_words;
   d.ws_words = (p.workspace_bytes() - p.ctrl_bytes) / 4;
-  const long long tickets = (long long)(b + p.lag) * ((N + kLblTile - 1) / kLblTile + (M + kLblResCells - 1) / kLblResCells);
+  const long long per_frame = (N + kLblTile - 1) / kLblTile + (M + kLblResCells - 1) / kLblResCells;
+  const long long tickets = (long long)(b + p.lag) * per_frame;  // p.lag = ring / 2: the largest lag a launch uses
   if (tickets >= (1ll << 31) - (1 << 20) || (unsigned long long)p.ring * p.slot_words >= (1ull << 31)) return DM_EINVAL;
   uint32_t* ctrl = static_cast<uint32_t*>(workspace);
   uint32_t* flags = reinterpret_cast<uint32_t*>(static_cast<char*>(workspace) + p.ctrl_bytes);
@@ -609,6 +631,7 @@ extern "C" int dm_orth_project_labels_f32(const float* depth, const uint8_t* lab
   if (per_sm < 1) return DM_EINVAL;
   long long grid = (long long)sms[dev] * per_sm;  // persistent: every CTA is resident (the dependency waits rely on it)
   if (grid > tickets) grid = tickets;
+  lbl_schedule(grid, per_frame, p.ring, &d.lag, &d.ring);
   kern<<<(unsigned)grid, kLblThreads, 0, stream>>>(depth, labels, valid, samples, *cfg, d, b, ctrl, flags, acc, topdown,
                                                    mask, height, proj_guard(dev));
   DM_LAUNCHED();

@@ -475,35 +475,50 @@ def _n_points(points) -> Tuple[int, int]:
   return b, max(t.numel() // (3 * max(b, 1)), 1)
 
 
+def _per_sample_steps(points, build, *params):
+  """Step blocks for a transform whose per-sample parameters (pose, pitch, height) may carry a batch of their own:
+  like the reference's tensor ops, a single point set is broadcast over b parameter sets (TopdownMap.get_camera of
+  a batched map, maps.py:1824-1839) and a single parameter set over b point sets.  Returns (points, steps)."""
+  bp, n = _n_points(points)
+  tails = [(3,) if isinstance(p, tuple) else () for p in params]
+  vals = [prm.host_f32(p[0] if isinstance(p, tuple) else p, tail) for p, tail in zip(params, tails)]
+  b = max([bp] + [v.shape[0] for v in vals])
+  if bp != b:
+    t = utils.to_tensor(points)
+    if bp != 1:
+      raise ValueError(f"points have batch {bp}, the transform parameters {b}")
+    if t.dim() < 2:
+      t = t.view(1, -1, 3)
+    points = t.expand((b,) + tuple(t.shape[1:]))
+  args = [prm.per_sample(v, b, tail) for v, tail in zip(vals, tails)]
+  return points, build(*args, n)
+
+
 def camera_to_local_space(points: torch.Tensor, cam_pitch: torch.Tensor, cam_height: torch.Tensor,
                           device: Optional[torch.device] = None, _validate_args: bool = True) -> torch.Tensor:
   """Rotate by the camera pitch about x, lift by the camera height (maps.py:753-800)."""
-  b, n = _n_points(points)
-  st = prm.camera_to_local(prm.per_sample(cam_pitch, b), prm.per_sample(cam_height, b), n)
+  points, st = _per_sample_steps(points, prm.camera_to_local, cam_pitch, cam_height)
   return _run_steps(points, _pick_device(device, points), [st])
 
 
 def local_to_camera_space(points: torch.Tensor, cam_pitch: torch.Tensor, cam_height: torch.Tensor,
                           device: Optional[torch.device] = None, _validate_args: bool = True) -> torch.Tensor:
   """Inverse of camera_to_local_space (maps.py:802-848)."""
-  b, n = _n_points(points)
-  st = prm.local_to_camera(prm.per_sample(cam_pitch, b), prm.per_sample(cam_height, b), n)
+  points, st = _per_sample_steps(points, prm.local_to_camera, cam_pitch, cam_height)
   return _run_steps(points, _pick_device(device, points), [st])
 
 
 def local_to_global_space(points: torch.Tensor, cam_pose: torch.Tensor,
                           device: Optional[torch.device] = None, _validate_args: bool = True) -> torch.Tensor:
   """Rotate by yaw about y, translate by (x, 0, z) (maps.py:850-895)."""
-  b, n = _n_points(points)
-  st = prm.local_to_global(prm.per_sample(cam_pose, b, (3,)), n)
+  points, st = _per_sample_steps(points, prm.local_to_global, (cam_pose,))
   return _run_steps(points, _pick_device(device, points), [st])
 
 
 def global_to_local_space(points: torch.Tensor, cam_pose: torch.Tensor,
                           device: Optional[torch.device] = None, _validate_args: bool = True) -> torch.Tensor:
   """Inverse of local_to_global_space (maps.py:897-942)."""
-  b, n = _n_points(points)
-  st = prm.global_to_local(prm.per_sample(cam_pose, b, (3,)), n)
+  points, st = _per_sample_steps(points, prm.global_to_local, (cam_pose,))
   return _run_steps(points, _pick_device(device, points), [st])
 
 
