@@ -60,6 +60,11 @@ class DmFuseTarget(ctypes.Structure):
   ]
 
 
+class DmPoseCfg(ctypes.Structure):
+  _fields_ = [("pitch_R", c_float * 9), ("pitch_back_R", c_float * 9), ("cam_height", c_float),
+              ("yaw_skew", c_float * 9), ("yaw_skew_sq", c_float * 9), ("fused", c_int32), ("_pad", c_int32 * 2)]
+
+
 class DmBuilderCfg(ctypes.Structure):
   _fields_ = [
     ("proj", DmProjCfg), ("b", c_int32), ("plot_to_global", c_int32), ("pitch_R", c_float * 9),
@@ -113,6 +118,9 @@ _SIGNATURES = {
   "dm_fuse_inplace_f32": (ctypes.c_int, [POINTER(DmFuseSource), c_int32, c_int32, c_int32, POINTER(DmFuseTarget),
                                          c_void_p, c_void_p, c_void_p, c_void_p]),
   "dm_fuse_canvas_init_f32": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_void_p]),
+  "dm_pack_proj_samples": (ctypes.c_int, [POINTER(DmPoseCfg), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
+                                          c_int32, c_void_p, POINTER(c_int32)]),
+  "dm_pack_flow_samples": (ctypes.c_int, [POINTER(DmPoseCfg), c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
   "dm_builder_create": (ctypes.c_int, [POINTER(DmBuilderCfg), c_int32, POINTER(c_void_p)]),
   "dm_builder_destroy": (None, [c_void_p]),
   "dm_builder_plot": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

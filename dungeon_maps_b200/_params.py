@@ -191,6 +191,86 @@ def fast_steps(samples: torch.Tensor) -> int:
   return 2 if global_ok else 0
 
 
+# ---- the same blocks packed in C (csrc/dm_params.cu) ------------------------------------------------------------
+# For the common case — one cam_pitch / cam_height for the whole batch — the per-sample blocks are a function of the
+# poses alone, and building them with torch / numpy cost 0.1-0.25 ms of interpreter time per call.  The C packers form
+# the yaw rotation from torch's own sin / cos (computed here) with the reference's float32 operation order.
+
+_pose_cfgs = {}
+
+
+def _uniform(t: torch.Tensor) -> bool:
+  """All entries of a per-sample tensor are one value (a scalar that per_sample expanded, or b == 1)."""
+  return t.dim() == 1 and (t.shape[0] == 1 or t.stride(0) == 0)
+
+
+def pose_cfg(pitch: torch.Tensor, cam_h: torch.Tensor, n_points: int) -> "nat.DmPoseCfg":
+  key = (float(pitch[0]), float(cam_h[0]), fused_for(n_points))
+  cfg = _pose_cfgs.get(key)
+  if cfg is None:
+    cfg = nat.DmPoseCfg()
+    p1 = pitch[:1].contiguous()
+    cfg.pitch_R[:] = rotation_matrices([1., 0., 0.], p1).reshape(-1).tolist()        # maps.py:789-793
+    cfg.pitch_back_R[:] = rotation_matrices([1., 0., 0.], -p1).reshape(-1).tolist()  # maps.py:838-842
+    cfg.cam_height = float(cam_h[0])
+    skew, skew_sq, _ = _skew_terms([0., 1., 0.])
+    cfg.yaw_skew[:] = skew.reshape(-1).tolist()
+    cfg.yaw_skew_sq[:] = skew_sq.reshape(-1).tolist()
+    cfg.fused = int(fused_for(n_points))
+    if len(_pose_cfgs) > 64:
+      _pose_cfgs.clear()
+    _pose_cfgs[key] = cfg
+  return cfg
+
+
+def yaw_sin_cos(pose: torch.Tensor):
+  """sin / cos of the yaw column after the |a| <= ANGLE_EPS clamp, with the reference's torch-CPU ops
+  (utils.py:323-326); contiguous float32 CPU tensors."""
+  yaw = pose[:, 2]
+  yaw = torch.where(torch.abs(yaw) > ANGLE_EPS, yaw, torch.zeros((), dtype=torch.float32))
+  return torch.sin(yaw), torch.cos(yaw)
+
+
+def proj_samples(pose, pitch, cam_h, woff, hoff, to_global: bool, n_points: int):
+  """(b, 48) float32 DmProjSample words + DmProjCfg.fast_steps for orth_project."""
+  b = pose.shape[0]
+  if _uniform(pitch) and _uniform(cam_h):
+    out = torch.empty((b, nat.PROJ_SAMPLE_WORDS), dtype=torch.float32)
+    fast = nat.c_int32(0)
+    woff, hoff = woff.contiguous(), hoff.contiguous()
+    if to_global:
+      pose = pose.contiguous()
+      sin, cos = yaw_sin_cos(pose)
+      rc = nat.lib().dm_pack_proj_samples(pose_cfg(pitch, cam_h, n_points), pose.data_ptr(), sin.data_ptr(),
+                                          cos.data_ptr(), woff.data_ptr(), hoff.data_ptr(), 1, b, out.data_ptr(),
+                                          nat.ctypes.byref(fast))
+    else:
+      rc = nat.lib().dm_pack_proj_samples(pose_cfg(pitch, cam_h, n_points), None, None, None, woff.data_ptr(),
+                                          hoff.data_ptr(), 0, b, out.data_ptr(), nat.ctypes.byref(fast))
+    nat.check(rc, "dm_pack_proj_samples")
+    return out, fast.value
+  samples = torch.zeros((b, nat.PROJ_SAMPLE_WORDS), dtype=torch.float32)
+  samples[:, 0:16] = camera_to_local(pitch, cam_h, n_points)
+  samples[:, 16:32] = local_to_global(pose, n_points) if to_global else identity(b)
+  samples[:, 32] = woff
+  samples[:, 33] = hoff
+  return samples, fast_steps(samples)
+
+
+def flow_samples(pose, pitch, cam_h, n_points: int) -> torch.Tensor:
+  """(b, 48) float32 DmFlowSample words for camera_affine_grid."""
+  b = pose.shape[0]
+  if _uniform(pitch) and _uniform(cam_h):
+    out = torch.empty((b, nat.FLOW_SAMPLE_WORDS), dtype=torch.float32)
+    pose = pose.contiguous()
+    sin, cos = yaw_sin_cos(pose)
+    nat.check(nat.lib().dm_pack_flow_samples(pose_cfg(pitch, cam_h, n_points), pose.data_ptr(), sin.data_ptr(),
+                                             cos.data_ptr(), b, out.data_ptr()), "dm_pack_flow_samples")
+    return out
+  return torch.cat((camera_to_local(pitch, cam_h, n_points), local_to_global(pose, n_points),
+                    local_to_camera(pitch, cam_h, n_points)), dim=1)
+
+
 class _PinnedRing:
   """Pinned staging slots for the small per-call parameter blocks.  `tensor.to(device)` from pageable memory
   synchronises the stream (torch waits for the copy, i.e. for everything queued before it), which would

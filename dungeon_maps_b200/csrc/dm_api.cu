@@ -140,6 +140,7 @@ extern "C" int32_t dm_sizeof_struct(int32_t id) {
     case 7: return sizeof(DmBuilderCfg);
     case 8: return sizeof(DmMapRef);
     case 9: return sizeof(DmMergeShape);
+    case 10: return sizeof(DmPoseCfg);
     default: return -1;
   }
 }

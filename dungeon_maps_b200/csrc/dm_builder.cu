@@ -20,16 +20,6 @@ constexpr int kStepWords = sizeof(DmStep) / 4;           // 16
 constexpr int kSampleWords = sizeof(DmProjSample) / 4;   // 48
 constexpr int kFuseWords = 2 * kStepWords + 2;           // per sample: two steps, width offset, height offset
 
-void put_step(float* w, int kind, const float* R, const float* t, int fused) {
-  memset(w, 0, sizeof(DmStep));
-  if (kind == DM_STEP_NONE) return;
-  if (R) memcpy(w, R, 9 * sizeof(float));
-  if (t) memcpy(w + 9, t, 3 * sizeof(float));
-  int32_t* iw = reinterpret_cast<int32_t*>(w);
-  iw[12] = kind;
-  iw[13] = fused;
-}
-
 }  // namespace
 }  // namespace dm
 
@@ -38,7 +28,8 @@ using namespace dm;
 struct DmBuilder {
   DmBuilderCfg cfg;
   int device = 0;
-  int fused_proj = 0, fused_fuse = 0;
+  DmPoseCfg pose;      // the constants of the yaw / pitch steps, fused as the projection's rotations are
+  int fused_fuse = 0;  // DmStep.fused of the local map's local → global step in the merge
   int local_fast = 0;  // the pitch step has the structure DmProjCfg.fast_steps >= 1 promises
   char* h_params[kParamSlots] = {};
   char* d_params[kParamSlots] = {};
@@ -77,10 +68,14 @@ extern "C" int dm_builder_create(const DmBuilderCfg* cfg, int32_t device, DmBuil
   h->device = device;
   const long long n_proj = (long long)cfg->proj.H * cfg->proj.W;            // points one bmm rotates (utils.py:329)
   const long long n_fuse = (long long)cfg->proj.Mh * cfg->proj.Mw;          // C * h * w points of the local map
-  h->fused_proj = 9 * n_proj >= 400;
+  memset(&h->pose, 0, sizeof(h->pose));
+  memcpy(h->pose.pitch_R, cfg->pitch_R, sizeof(cfg->pitch_R));
+  memcpy(h->pose.yaw_skew, cfg->yaw_skew, sizeof(cfg->yaw_skew));
+  memcpy(h->pose.yaw_skew_sq, cfg->yaw_skew_sq, sizeof(cfg->yaw_skew_sq));
+  h->pose.cam_height = cfg->cam_height;
+  h->pose.fused = 9 * n_proj >= 400;
   h->fused_fuse = 9 * n_fuse >= 400;
-  const float* R = cfg->pitch_R;
-  h->local_fast = h->fused_proj && R[0] == 1.0f && R[1] == 0.0f && R[2] == 0.0f && R[3] == 0.0f && R[6] == 0.0f;
+  h->local_fast = local_step_is_fast(h->pose);
   h->param_bytes = ((size_t)cfg->b * (kSampleWords + 2 * kFuseWords) * 4 + 255) & ~(size_t)255;
   int rc = DM_OK;
 #define DM_TRY(expr)                                                       \
@@ -128,25 +123,17 @@ static int upload_params(DmBuilder* h, const float* pose, const float* sin_yaw, 
   float* whoff = wwoff + b;
   int fast = h->local_fast ? (c.plot_to_global ? 2 : 1) : 0;
   for (int i = 0; i < b; ++i) {
-    // utils.py:303-327 for the axis (0, 1, 0): R = (I + sin(a) S) + (1 - cos(a)) S², float32, this operation order
     float Ry[9];
-    const float s = sin_yaw[i], one_minus_cos = 1.0f - cos_yaw[i];
-    for (int k = 0; k < 9; ++k) {
-      const float eye = (k == 0 || k == 4 || k == 8) ? 1.0f : 0.0f;
-      const float a = s * c.yaw_skew[k];
-      const float e = eye + a;
-      const float q = one_minus_cos * c.yaw_skew_sq[k];
-      Ry[k] = e + q;
-    }
+    yaw_matrix(h->pose, sin_yaw[i], cos_yaw[i], Ry);  // utils.py:303-327 for the axis (0, 1, 0)
     const float ty[3] = {pose[3 * i + 0], 0.0f, pose[3 * i + 1]};  // maps.py:889-891
     const float tl[3] = {0.0f, c.cam_height, 0.0f};                // maps.py:795-797
     float* sp = samples + (size_t)i * kSampleWords;
     memset(sp, 0, sizeof(DmProjSample));
-    put_step(sp, DM_STEP_ROT_THEN_ADD, c.pitch_R, tl, h->fused_proj);
-    put_step(sp + kStepWords, c.plot_to_global ? DM_STEP_ROT_THEN_ADD : DM_STEP_NONE, Ry, ty, h->fused_proj);
+    put_step(sp, DM_STEP_ROT_THEN_ADD, c.pitch_R, tl, h->pose.fused);
+    put_step(sp + kStepWords, c.plot_to_global ? DM_STEP_ROT_THEN_ADD : DM_STEP_NONE, Ry, ty, h->pose.fused);
     sp[32] = c.width_offset;
     sp[33] = c.height_offset;
-    if (fast == 2 && !(Ry[4] == 1.0f && Ry[1] == 0.0f && Ry[3] == 0.0f && Ry[5] == 0.0f && Ry[7] == 0.0f)) fast = 0;
+    if (fast == 2 && !yaw_step_is_fast(Ry)) fast = 0;
     // the local map as a source of the merge (maps.py:2059-2060): local → global with its own pose, unless it was
     // plotted in the global frame; the target is global (maps.py:2116-2117: no second step)
     put_step(lsteps + (size_t)i * 2 * kStepWords, c.plot_to_global ? DM_STEP_NONE : DM_STEP_ROT_THEN_ADD, Ry, ty,

@@ -75,7 +75,7 @@ extern "C" int dm_pack_flow_samples(const DmPoseCfg* cfg, const float* pose, con
                                     int32_t b, DmFlowSample* out) {
   if (!cfg || !pose || !sin_yaw || !cos_yaw || !out || b < 0) return DM_EINVAL;
   const float tl[3] = {0.0f, cfg->cam_height, 0.0f};    // maps.py:795-797
-  const float tb[3] = {-0.0f, -cfg->cam_height, -0.0f};  // maps.py:843-845: translate(-[0, h, 0])
+  const float tb[3] = {0.0f, -cfg->cam_height, 0.0f};   // maps.py:843-845
   for (int i = 0; i < b; ++i) {
     float* sp = reinterpret_cast<float*>(out + i);
     float Ry[9];

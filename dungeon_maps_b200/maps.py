@@ -213,11 +213,7 @@ def orth_project(
   elif valid is not None and valid.shape[1] != 1:
     raise RuntimeError(f"valid_map has {valid.shape[1]} channels, depth_map has 1")
   n_points = dc * H * W  # points the reference rotates per sample in one bmm
-  samples = torch.zeros((frames, nat.PROJ_SAMPLE_WORDS), dtype=torch.float32)
-  samples[:, 0:16] = prm.camera_to_local(pitch, camh, n_points)
-  samples[:, 16:32] = prm.local_to_global(pose, n_points) if to_global else prm.identity(frames)
-  samples[:, 32] = woff
-  samples[:, 33] = hoff
+  samples, fast_steps = prm.proj_samples(pose, pitch, camh, woff, hoff, bool(to_global), n_points)
   samples_dev = prm.upload(samples, dev)
 
   cfg = nat.DmProjCfg()
@@ -236,7 +232,7 @@ def orth_project(
   want_height = bool(get_height_map) and C > 0
   cfg.want_height = want_height
   cfg.reduction = red
-  cfg.fast_steps = prm.fast_steps(samples)
+  cfg.fast_steps = fast_steps
   Cv = max(C, 1)
   topdown = torch.empty((frames, Cv, cfg.Mh, cfg.Mw), dtype=torch.float32, device=dev)
   masks = torch.empty((frames, Cv, cfg.Mh, cfg.Mw), dtype=torch.bool, device=dev)
@@ -359,9 +355,7 @@ def camera_affine_grid(
   pitch = prm.per_sample(cam_pitch, b, (), "cam_pitch")
   camh = prm.per_sample(cam_height, b, (), "cam_height")
   n_points = ch * H * W
-  samples = torch.cat((prm.camera_to_local(pitch, camh, n_points), prm.local_to_global(pose, n_points),
-                       prm.local_to_camera(pitch, camh, n_points)), dim=1)
-  samples_dev = prm.upload(samples, dev)
+  samples_dev = prm.upload(prm.flow_samples(pose, pitch, camh, n_points), dev)
   cfg = nat.DmFlowCfg()
   cfg.H, cfg.W, cfg.channels = H, W, ch
   cfg.fx, cfg.fy, cfg.cx, cfg.cy = focal_x, focal_y, center_x, center_y
@@ -938,7 +932,7 @@ def fuse_topdown_maps(*maps: List[TopdownMap], map_projector: Optional[MapProjec
   kinds = {bool(m.is_height_map) for m in live}
   assert len(kinds) == 1, "All maps must be the same type of maps (all height maps or all value maps)."
   is_height_map = kinds.pop()
-  red = utils._reduction_code(reduction)
+  red = utils._reduction_code(get(reduction, proj.reduction))  # MapProjector.project: get(reduction, self.reduction), maps.py:1720
   dev = _pick_device(proj.device, *[m.mask for m in live], *[m.height_map for m in live])
   shapes = [utils.to_4D_image(m.mask).shape for m in live]
   b = max(s[0] for s in shapes)
@@ -1033,7 +1027,7 @@ def merge_into_canvas(world: TopdownMap, new_map: TopdownMap, canvas_shape: Tupl
   place into `world`'s tensors, which are allocated on the first call.  One launch, no host sync.
   `world`'s tensors are updated in place and shared with the returned map."""
   Hc, Wc = int(canvas_shape[0]), int(canvas_shape[1])
-  red = utils._reduction_code(reduction)
+  red = utils._reduction_code(get(reduction, map_projector.reduction))
   if new_map.is_empty:
     return world
   dev = _pick_device(map_projector.device, new_map.mask, new_map.height_map)

@@ -254,6 +254,29 @@ int dm_fuse_inplace_f32(const DmFuseSource* sources, int32_t n_sources, int32_t 
 int dm_fuse_canvas_init_f32(float* topdown, uint8_t* mask, float* height, int64_t n, float fill_value,
                             void* stream);
 
+/* ---- per-sample parameter blocks packed on the host, in C ------------------------------------------------------
+ * What the kernels need per sample derives from a pose (x, z, yaw) and per-call constants.  These two functions are
+ * pure host code (no device work, no sin / cos): the caller supplies sin(yaw) / cos(yaw) computed with the
+ * reference's own torch-CPU ops after the |a| <= 0.001 clamp (utils.py:323-326), and the yaw rotation is formed as
+ * (I + sin S) + (1 - cos) S² in float32, the reference's operation order (utils.py:318-327). */
+typedef struct DmPoseCfg {
+  float pitch_R[9];      /* camera_to_local_space: rotation about x by cam_pitch (maps.py:789-793), host-built */
+  float pitch_back_R[9]; /* local_to_camera_space: rotation about x by -cam_pitch (maps.py:838-842); flow only */
+  float cam_height;
+  float yaw_skew[9], yaw_skew_sq[9]; /* S and S² of the axis (0, 1, 0) as utils.py:303-318 builds them */
+  int32_t fused;         /* DmStep.fused of every step: 9 * (points rotated per sample) >= 400 */
+  int32_t _pad[2];
+} DmPoseCfg;
+/* orth_project (maps.py:279-295): to_local = rot(pitch) + (0, h, 0); to_global = rot(yaw) + (x, 0, z), or none.
+ * pose (b, 3), sin_yaw / cos_yaw (b,) may be NULL unless to_global; width_offset / height_offset (b,).
+ * *fast_steps receives the DmProjCfg.fast_steps value these blocks allow. */
+int dm_pack_proj_samples(const DmPoseCfg* cfg, const float* pose, const float* sin_yaw, const float* cos_yaw,
+                         const float* width_offset, const float* height_offset, int32_t to_global, int32_t b,
+                         DmProjSample* out, int32_t* fast_steps);
+/* camera_affine_grid (maps.py:428-446): to_local, transition by trans_pose, to_camera. */
+int dm_pack_flow_samples(const DmPoseCfg* cfg, const float* pose, const float* sin_yaw, const float* cos_yaw,
+                         int32_t b, DmFlowSample* out);
+
 /* ---- MapBuilder.step with the host side in C (maps.py:2357-2508) ----------------------------------------------
  * The plot → merge loop of b environments for height maps (value_map None) and a world map in the global frame —
  * the configuration a mapping loop runs thousands of times.  A step packs every parameter block (projection
@@ -369,7 +392,7 @@ int dm_crop_nearest_u8(const uint8_t* image, const float* center, int32_t b, int
 int dm_abi_version(void);
 /* sizeof() of a struct of this header as the library was compiled, for bindings to check their mirror against:
  * 0 DmStep, 1 DmProjSample, 2 DmProjCfg, 3 DmFlowSample, 4 DmFlowCfg, 5 DmFuseSource, 6 DmFuseTarget,
- * 7 DmBuilderCfg, 8 DmMapRef, 9 DmMergeShape; -1 for an unknown id. */
+ * 7 DmBuilderCfg, 8 DmMapRef, 9 DmMergeShape, 10 DmPoseCfg; -1 for an unknown id. */
 int32_t dm_sizeof_struct(int32_t id);
 const char* dm_build_info(void);
 /* Number of kernel launches issued by this library since load (bench "gpu_launches"). */

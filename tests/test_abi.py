@@ -128,6 +128,32 @@ def test_host_parameter_blocks_equal_the_oracles(n_points):
   assert _params.fused_for(45) and not _params.fused_for(44)   # 9*n >= 400 → MKL sgemm FMA chain
 
 
+@pytest.mark.parametrize("n_points", [33, 45, 307200])
+def test_c_packers_equal_the_python_blocks(n_points):
+  """dm_pack_proj_samples / dm_pack_flow_samples (csrc/dm_params.cu, pure host code) against the torch / numpy
+  construction of _params.py, byte for byte — including the |yaw| <= 0.001 clamp, yaw = 0, +-pi, and fast_steps."""
+  rng = np.random.default_rng(7 + n_points)
+  b = 19
+  pose = torch.from_numpy(rng.normal(size=(b, 3)).astype(np.float32) * np.float32([2., 2., 1.5]))
+  pose[0, 2] = 0.0; pose[1, 2] = 0.0009; pose[2, 2] = -0.00099; pose[3, 2] = np.pi; pose[4, 2] = -np.pi
+  pose[5, 2] = 0.0010001; pose[6, 2] = np.pi / 2
+  woff = torch.from_numpy(rng.normal(size=b).astype(np.float32) * 50)
+  hoff = torch.from_numpy(rng.normal(size=b).astype(np.float32) * 50)
+  for pitch_v in (-0.17453292, 0.0, 0.0005, 0.6):
+    pitch = _params.per_sample(pitch_v, b)
+    camh = _params.per_sample(0.88, b)
+    assert _params._uniform(pitch) and _params._uniform(camh)
+    real = lambda t: t.expand(b).clone()  # same values, not recognisably uniform: the torch / numpy path
+    for to_global in (False, True):
+      got, fast = _params.proj_samples(pose, pitch, camh, woff, hoff, to_global, n_points)
+      want, fast_w = _params.proj_samples(pose, real(pitch), real(camh), woff, hoff, to_global, n_points)
+      assert got.numpy().tobytes() == want.numpy().tobytes(), (pitch_v, to_global)
+      assert fast == fast_w
+    got = _params.flow_samples(pose, pitch, camh, n_points)
+    want = _params.flow_samples(pose, real(pitch), real(camh), n_points)
+    assert got.numpy().tobytes() == want.numpy().tobytes(), pitch_v
+
+
 def test_tracked_box_guard_host_logic():
   """The bounding box fuse_topdown_maps keeps next to a map it wrote is only trusted while everything it was derived
   from is unchanged (maps._tracked_box_valid): same mask tensor at the same in-place version, same projector object

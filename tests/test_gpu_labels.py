@@ -111,6 +111,26 @@ def test_labels_random_vs_oracle(seed):
       assert_same(npy(got[2][:, :1]), want[2][:, :1], f"height rep{rep}")
 
 
+def test_labels_more_frames_than_ring_slots():
+  """b > 64 frames in one call: ring slots are reused inside the launch (projection items then wait for the resolve
+  of the slot's previous tenant, resolve completions are published) — b <= 64 gives every frame a slot of its own."""
+  b, H, W, C = 150, 24, 32, 7
+  depth = synth.iid_depth(b, H, W, seed=77, lo=0.2, hi=4.0).numpy()
+  labels = ((synth.hash_u24(b * H * W, 78).numpy().reshape(b, 1, H, W) // 3) % C).astype(np.uint8)
+  pose = synth.poses(b, 79).numpy()
+  intr = orc.intrinsics(W, H, HFOV)
+  kw = dict(map_res=0.1, map_width=40, map_height=36, focal_x=intr["fx"], focal_y=intr["fy"], center_x=intr["cx"],
+            center_y=intr["cy"], trunc_depth_min=0.15, trunc_depth_max=5.05, trunc_height_max=None, clip_border=1,
+            to_global=False, fill_value=0.0, get_height_map=True)
+  want = orc.orth_project(depth, one_hot(labels, C), None, pose, 20., 0., PITCH, 0.88, **kw)
+  for rep in range(2):
+    got = dmap.orth_project(torch.from_numpy(depth), None, None, pose, 20., 0., PITCH, 0.88, device="cuda",
+                            label_map=torch.from_numpy(labels), num_classes=C, **kw)
+    assert_same(npy(got[0]), want[0], f"topdown rep{rep}")
+    assert_same(npy(got[1]), want[1], f"mask rep{rep}")
+    assert_same(npy(got[2][:, :1]), want[2][:, :1], f"height rep{rep}")
+
+
 def test_labels_equal_float_path_and_argument_checks():
   """Same call with value_map = one_hot(labels): identical tensors; misuse raises like the rest of the API."""
   b, H, W, C = 3, 60, 80, 16
