@@ -853,9 +853,11 @@ def run_ours(args):
             "h2d_gbs_per_rank": wl.h2d * e2e_steps / secs / 1e9, "d2h_gbs_per_rank": wl.d2h * e2e_steps / secs / 1e9,
             "check": "outputs compared with the device-resident path / the oracle: identical"}
 
-  e2e = e2e_leg()
-  e2e_float32 = e2e_leg(float32=True) if (isinstance(wl, ProjWorkload) and not wl.labels) else None
-  pcie = pcie_rates(dev, barrier, gather)
+  skipped = {"value": None, "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "steps": 0,
+             "path": "not measured (--e2e-steps 0: kernel experiments)"}
+  e2e = e2e_leg() if args.e2e_steps > 0 else skipped
+  e2e_float32 = e2e_leg(float32=True) if (args.e2e_steps > 0 and isinstance(wl, ProjWorkload) and not wl.labels) else None
+  pcie = pcie_rates(dev, barrier, gather) if args.e2e_steps > 0 else None
   peak, peak_src = measured_peak()
 
   extra = None

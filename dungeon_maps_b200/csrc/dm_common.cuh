@@ -38,6 +38,14 @@ void put_step(float* words, int kind, const float* R, const float* t, int fused)
 bool local_step_is_fast(const DmPoseCfg& c);  // the pitch step has the structure DmProjCfg.fast_steps >= 1 promises
 bool yaw_step_is_fast(const float* R);
 
+// ---- ordered scatter-reduce for sum / mean / prod (dm_ordered.cu) ---------------------------------
+// keys[i] = output cell of point i (or ~0: dropped), consumed; values[i]; canvas holds the starting values and
+// receives the cells folded in ascending point index (the reference's CPU order).  n < 2^31.
+// mask_or (optional): set to 1 where the fold changed the cell (utils.py:489-491).
+int ordered_reduce(unsigned long long* keys, const float* values, long long n, int key_bits, int reduction,
+                   float* canvas, uint8_t* mask_or, cudaStream_t stream);
+int bits_for(unsigned long long max_key_exclusive);
+
 // ---- reference arithmetic ------------------------------------------------------
 struct V3 {
   float x, y, z;

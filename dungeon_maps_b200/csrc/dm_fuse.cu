@@ -301,6 +301,75 @@ fuse_scatter_kernel(const __grid_constant__ DmFuseSource src, int planes, int C,
   }
 }
 
+static dim3 plane_grid(const DmFuseSource& s, int planes);
+
+// sum / mean / prod (utils.py:70-76): the merged value of a cell depends on the order of its hits, which is the
+// order of the reference's concatenated point cloud (_merge_point_clouds, maps.py:2071-2127: per (sample, channel)
+// row the cells of source 0 in row-major order, then those of source 1, ...).  Every point gets the key of its target
+// cell at position plane * points_per_plane + source offset + cell, and dm_ordered.cu folds each cell's hits in
+// ascending position.  The height map of a value-map merge stays an (order-independent) atomic max.
+__global__ void __launch_bounds__(kScanThreads)
+fuse_keys_kernel(const __grid_constant__ DmFuseSource src, int planes, int C, const DmFuseTarget tgt, long long off,
+                 long long points_per_plane, unsigned long long* __restrict__ keys, float* __restrict__ vals,
+                 float* __restrict__ height) {
+  __shared__ PlaneCtx ctx;
+  const long long M = (long long)tgt.Mh * tgt.Mw;
+  const int n = src.h * src.w;
+  int loaded = -1;
+  for (int plane = blockIdx.y; plane < planes; plane += gridDim.y) {
+    const int smp = plane / C, ch = plane - smp * C;
+    if (smp != loaded) { load_plane_ctx(src, smp, &ctx); loaded = smp; }
+    const float* hplane = src.height + (long long)smp * src.height_bstride + (long long)ch * src.height_cstride;
+    const float* vplane = src.values ? src.values + (long long)plane * n : nullptr;
+    const uint8_t* mplane = src.mask + (long long)plane * n;
+    for (int cell = blockIdx.x * kScanThreads + threadIdx.x; cell < n; cell += gridDim.x * kScanThreads) {
+      const long long pos = (long long)plane * points_per_plane + off + cell;
+      unsigned long long key = ~0ull;
+      float v = 0.0f;
+      if (mplane[cell]) {
+        const int r = cell / src.w;
+        const V3 p = source_point(src, ctx, hplane, cell, r, cell - r * src.w);
+        float xf, zf;  // maps.py:2232-2238
+        quantize_f(p.x, p.z, tgt.width_offset, tgt.height_offset, tgt.map_res, tgt.Mh, tgt.flip_h, &xf, &zf);
+        if (xf >= 0.0f && xf < (float)tgt.Mw && zf >= 0.0f && zf < (float)tgt.Mh) {
+          const long long o = (long long)plane * M + (long long)zf * tgt.Mw + (long long)xf;
+          key = (unsigned long long)o;
+          v = vplane ? vplane[cell] : p.y;  // maps.py:2214-2216
+          if (height && p.y == p.y) atomic_max_f32(height + o, p.y);  // maps.py:2258-2271
+        }
+      }
+      keys[pos] = key;
+      vals[pos] = v;
+    }
+  }
+}
+
+static int launch_ordered(const DmFuseSource* sources, int n_sources, int b, int C, const DmFuseTarget& tgt,
+                          float* topdown, uint8_t* mask, float* height, cudaStream_t stream) {
+  const long long planes = (long long)b * C, M = (long long)tgt.Mh * tgt.Mw;
+  long long per_plane = 0;
+  for (int i = 0; i < n_sources; ++i) per_plane += (long long)sources[i].h * sources[i].w;
+  const long long total = planes * per_plane;
+  if (total >= (1ll << 31)) return DM_EINVAL;
+  if (total == 0) return DM_OK;
+  unsigned long long* keys = nullptr;
+  float* vals = nullptr;
+  DM_CUDA_OK(cudaMallocAsync(&keys, (size_t)total * 8, stream));
+  DM_CUDA_OK(cudaMallocAsync(&vals, (size_t)total * 4, stream));
+  long long off = 0;
+  for (int i = 0; i < n_sources; ++i) {
+    fuse_keys_kernel<<<plane_grid(sources[i], (int)planes), kScanThreads, 0, stream>>>(sources[i], (int)planes, C, tgt, off,
+                                                                                        per_plane, keys, vals, height);
+    DM_LAUNCHED();
+    off += (long long)sources[i].h * sources[i].w;
+  }
+  const int rc = ordered_reduce(keys, vals, total, bits_for((unsigned long long)(planes * M)), tgt.reduction, topdown,
+                                mask, stream);
+  DM_CUDA_OK(cudaFreeAsync(keys, stream));
+  DM_CUDA_OK(cudaFreeAsync(vals, stream));
+  return rc;
+}
+
 __global__ void __launch_bounds__(kFuseThreads)
 changed_mask_kernel(const float* __restrict__ canvas, long long n, float fill, uint8_t* __restrict__ mask) {
   for (long long i = (long long)blockIdx.x * kFuseThreads + threadIdx.x; i < n;
@@ -394,7 +463,8 @@ extern "C" int dm_fuse_scatter_track_f32(const DmFuseSource* sources, int32_t n_
                                          const DmFuseTarget* target, float* topdown, uint8_t* mask, float* height,
                                          int64_t* next_bbox, void* stream_) {
   if (!target || !topdown || !mask || target->Mh <= 0 || target->Mw <= 0) return DM_EINVAL;
-  if (target->reduction != 0 && target->reduction != 1) return DM_EINVAL;
+  if (target->reduction < 0 || target->reduction > 4) return DM_EINVAL;
+  if (target->reduction >= 2 && next_bbox) return DM_EINVAL;  // the tracked box assumes "mask = value beats fill"
   const int rc = check_sources(sources, n_sources, b, C);
   if (rc != DM_OK) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -406,6 +476,8 @@ extern "C" int dm_fuse_scatter_track_f32(const DmFuseSource* sources, int32_t n_
   fuse_fill_kernel<<<grid_for((n_out + 3) / 4), kFuseThreads, 0, stream>>>(topdown, height, mask, n_out,
                                                                            target->fill_value, vec_ok);
   DM_LAUNCHED();
+  if (target->reduction >= 2)  // order-dependent reductions: the reference's point order, bit for bit
+    return launch_ordered(sources, n_sources, b, C, *target, topdown, mask, height, stream);
   if (next_bbox) {
     if (!mask_inline) return DM_EINVAL;  // NaN fill: the mask comes from the compare pass, nothing to track
     fuse_bbox_init<<<1, 1, 0, stream>>>(reinterpret_cast<long long*>(next_bbox));
@@ -429,11 +501,13 @@ extern "C" int dm_fuse_inplace_f32(const DmFuseSource* sources, int32_t n_source
                                    const DmFuseTarget* target, float* topdown, uint8_t* mask, float* height,
                                    void* stream_) {
   if (!target || !topdown || !mask || target->Mh <= 0 || target->Mw <= 0) return DM_EINVAL;
-  if (target->reduction != 0 && target->reduction != 1) return DM_EINVAL;
+  if (target->reduction < 0 || target->reduction > 4) return DM_EINVAL;
   if (!(target->fill_value == target->fill_value)) return DM_EINVAL;  // NaN fill has no in-place mask rule
   const int rc = check_sources(sources, n_sources, b, C);
   if (rc != DM_OK) return rc;
   if ((long long)target->Mh * target->Mw >= (1ll << 31)) return DM_EINVAL;
+  if (target->reduction >= 2)  // sum / mean / prod into the existing canvases: mask |= "cell changed" (utils.py:489-491)
+    return launch_ordered(sources, n_sources, b, C, *target, topdown, mask, height, static_cast<cudaStream_t>(stream_));
   return launch_scatter(sources, n_sources, b, C, *target, topdown, mask, height, 1, static_cast<cudaStream_t>(stream_));
 }
 

@@ -27,7 +27,11 @@ namespace dm {
 
 constexpr int kLblWarps = 8;                        // worker warps per CTA
 constexpr int kLblThreads = 32 * (kLblWarps + 1);   // + the scheduler warp
-constexpr int kLblTile = 128 * kLblWarps;           // pixels per projection ticket
+#ifndef DM_LBL_PROJ_J
+#define DM_LBL_PROJ_J 1
+#endif
+constexpr int kLblProjJ = DM_LBL_PROJ_J;            // 128-pixel sub-tiles per worker warp and projection ticket
+constexpr int kLblTile = 128 * kLblWarps * kLblProjJ;  // pixels per projection ticket
 #ifndef DM_LBL_RES_K
 #define DM_LBL_RES_K 1
 #endif
@@ -103,36 +107,52 @@ __device__ __forceinline__ void st_stream_u4(void* p, uint32_t v) {
 template <int W2>
 using LblBits = std::conditional_t<W2 == 1, uint32_t, unsigned long long>;
 
+// The 4 pixels of a lane as they come from memory: depth, class ids, valid bytes (0x01 each when there is no valid
+// map).  Loaded for all sub-tiles of a ticket before the first is worked on, so the latencies overlap.
+struct LblQuad {
+  float z[4];
+  uint32_t lab, vm;
+};
+
+__device__ __forceinline__ LblQuad lbl_load_quad(const LblDims& d, const float* __restrict__ dframe,
+                                                 const uint8_t* __restrict__ lframe, const uint8_t* __restrict__ vframe,
+                                                 int n0, int N) {
+  LblQuad q;
+  q.z[0] = q.z[1] = q.z[2] = q.z[3] = 0.0f;
+  q.lab = 0;
+  q.vm = 0;
+  if (n0 >= N) return q;
+  if (d.vec_in && n0 + 3 < N) {
+    const float4 z4 = ld_stream_f4(dframe + n0);
+    q.z[0] = z4.x; q.z[1] = z4.y; q.z[2] = z4.z; q.z[3] = z4.w;
+    q.lab = ld_stream_u32(lframe + n0);
+    q.vm = vframe ? ld_stream_u32(vframe + n0) : 0x01010101u;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const bool in = n0 + k < N;
+      q.z[k] = in ? ld_stream_f1(dframe + n0 + k) : 0.0f;
+      q.lab |= (in ? (uint32_t)lframe[n0 + k] : 0u) << (8 * k);
+      q.vm |= (in ? (vframe ? (uint32_t)(vframe[n0 + k] != 0) : 1u) : 0u) << (8 * k);
+    }
+  }
+  return q;
+}
+
 // ---- projection of 128 pixels by one warp (lane = 4 consecutive pixels) ---------------------------------------
 template <int FAST, int W2>
 __device__ __forceinline__ void lbl_proj_warp(const DmProjCfg& cfg, const LblDims& d, const DmProjSample& sp,
-                                              const Rcps& rcp, const float* __restrict__ dframe,
-                                              const uint8_t* __restrict__ lframe, const uint8_t* __restrict__ vframe,
-                                              int n0, int lane, uint32_t* list, uint32_t* __restrict__ acc,
-                                              uint32_t slot_off, uint32_t* __restrict__ slot_flags) {
+                                              const Rcps& rcp, const LblQuad& quad, int n0, int lane, uint32_t* list,
+                                              uint32_t* __restrict__ acc, uint32_t slot_off,
+                                              uint32_t* __restrict__ slot_flags) {
   using Bits = LblBits<W2>;
   const int N = cfg.H * cfg.W;
   int cl[4] = {-1, -1, -1, -1};
   float y[4] = {0.f, 0.f, 0.f, 0.f};
   Bits bt[4] = {0, 0, 0, 0};
   if (n0 < N) {
-    float z[4];
-    uint32_t lab = 0, vm = 0x01010101u;
-    if (d.vec_in && n0 + 3 < N) {
-      const float4 z4 = ld_stream_f4(dframe + n0);
-      z[0] = z4.x; z[1] = z4.y; z[2] = z4.z; z[3] = z4.w;
-      lab = ld_stream_u32(lframe + n0);
-      if (vframe) vm = ld_stream_u32(vframe + n0);
-    } else {
-      vm = 0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const bool in = n0 + k < N;
-        z[k] = in ? ld_stream_f1(dframe + n0 + k) : 0.0f;
-        lab |= (in ? (uint32_t)lframe[n0 + k] : 0u) << (8 * k);
-        vm |= (in ? (vframe ? (uint32_t)(vframe[n0 + k] != 0) : 1u) : 0u) << (8 * k);
-      }
-    }
+    const float* z = quad.z;
+    const uint32_t lab = quad.lab, vm = quad.vm;
     const int r = n0 / cfg.W, c = n0 - r * cfg.W;
     if (FAST && c + 3 < cfg.W) {
       // maps.py:677-678 column / row factors rn(rn(c - cx) / fx), rn(rn(yy - cy) / fy): exact division through the
@@ -255,11 +275,45 @@ __device__ __forceinline__ float lbl_channel(uint32_t key, LblBits<W2> bits, int
   return win ? v : fill;
 }
 
+// The keys of the two cells a lane owns in a flagged, fully vectorisable 64-cell slice (cells 2 * lane, 2 * lane + 1):
+// loaded with ld.cg, re-zeroed where set.  Issued for all slices of a ticket before the first is decoded.
+template <int W2>
+struct LblKeys {
+  uint32_t k0, k1;
+  LblBits<W2> b0, b1;
+};
+
+template <int W2>
+__device__ __forceinline__ LblKeys<W2> lbl_load_keys(uint32_t* __restrict__ acc_slot, const DmProjCfg& cfg,
+                                                     const LblDims& d, uint32_t flagged, int slice, int lane) {
+  using Bits = LblBits<W2>;
+  constexpr int CP = 1 + W2;
+  LblKeys<W2> out{0u, 0u, (Bits)0, (Bits)0};
+  const int M = cfg.Mh * cfg.Mw;
+  const int cell0 = slice * 64;
+  if (!flagged || !d.vec_out || M - cell0 < 64) return out;
+  uint32_t* src = acc_slot + (size_t)cell0 * CP;  // 16-byte aligned: cell0 % 64 == 0
+  if (W2 == 1) {
+    const uint4 v = __ldcg(reinterpret_cast<const uint4*>(src) + lane);
+    if (v.x | v.y | v.z | v.w) __stcg(reinterpret_cast<uint4*>(src) + lane, make_uint4(0u, 0u, 0u, 0u));
+    out.k0 = v.x; out.b0 = (Bits)v.y; out.k1 = v.z; out.b1 = (Bits)v.w;
+  } else {
+    uint2* s2 = reinterpret_cast<uint2*>(src) + lane * 3;
+    const uint2 a = __ldcg(s2), bq = __ldcg(s2 + 1), cq = __ldcg(s2 + 2);
+    if (a.x | a.y | bq.x | bq.y | cq.x | cq.y) {
+      __stcg(s2, make_uint2(0u, 0u)); __stcg(s2 + 1, make_uint2(0u, 0u)); __stcg(s2 + 2, make_uint2(0u, 0u));
+    }
+    out.k0 = a.x; out.b0 = (Bits)((unsigned long long)a.y | ((unsigned long long)bq.x << 32));
+    out.k1 = bq.y; out.b1 = (Bits)((unsigned long long)cq.x | ((unsigned long long)cq.y << 32));
+  }
+  return out;
+}
+
 // ---- resolve of one 64-cell slice by one warp -----------------------------------------------------------------
 template <int W2>
 __device__ __forceinline__ void lbl_resolve_slice(uint32_t* __restrict__ acc_slot, const DmProjCfg& cfg,
-                                                  const LblDims& d, uint32_t flagged, int frame,
-                                                  int slice, int lane, float* __restrict__ topdown,
+                                                  const LblDims& d, uint32_t flagged, const LblKeys<W2>& pre,
+                                                  int frame, int slice, int lane, float* __restrict__ topdown,
                                                   uint8_t* __restrict__ mask, float* __restrict__ height) {
   using Bits = LblBits<W2>;
   constexpr int CP = 1 + W2;
@@ -294,22 +348,9 @@ __device__ __forceinline__ void lbl_resolve_slice(uint32_t* __restrict__ acc_slo
     return;
   }
   uint32_t* src = acc_slot + (size_t)cell0 * CP;  // 16-byte aligned: cell0 % 64 == 0
-  if (vec) {  // lane owns cells 2 * lane and 2 * lane + 1
-    uint32_t k0, k1;
-    Bits b0, b1;
-    if (W2 == 1) {
-      const uint4 v = __ldcg(reinterpret_cast<const uint4*>(src) + lane);
-      if (v.x | v.y | v.z | v.w) __stcg(reinterpret_cast<uint4*>(src) + lane, make_uint4(0u, 0u, 0u, 0u));
-      k0 = v.x; b0 = (Bits)v.y; k1 = v.z; b1 = (Bits)v.w;
-    } else {
-      uint2* s2 = reinterpret_cast<uint2*>(src) + lane * 3;
-      const uint2 a = __ldcg(s2), bq = __ldcg(s2 + 1), cq = __ldcg(s2 + 2);
-      if (a.x | a.y | bq.x | bq.y | cq.x | cq.y) {
-        __stcg(s2, make_uint2(0u, 0u)); __stcg(s2 + 1, make_uint2(0u, 0u)); __stcg(s2 + 2, make_uint2(0u, 0u));
-      }
-      k0 = a.x; b0 = (Bits)((unsigned long long)a.y | ((unsigned long long)bq.x << 32));
-      k1 = bq.y; b1 = (Bits)((unsigned long long)cq.x | ((unsigned long long)cq.y << 32));
-    }
+  if (vec) {  // lane owns cells 2 * lane and 2 * lane + 1: their keys were loaded (and re-zeroed) by lbl_load_keys
+    const uint32_t k0 = pre.k0, k1 = pre.k1;
+    const Bits b0 = pre.b0, b1 = pre.b1;
     float* tp = topdown + plane0 + 2 * lane;
     uint8_t* mp = mask + plane0 + 2 * lane;
     for (int c = 0; c < C; ++c) {
@@ -466,8 +507,11 @@ proj_lbl_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ lab
         const int gi = __shfl_sync(0xffffffffu, idx, g);
         if (gk != kItemProj) continue;
         const int n0 = gi * kLblTile;
-        const char* dp = reinterpret_cast<const char*>(depth + (size_t)gf * N + n0) + lane * 128;
-        if (n0 + lane * 32 < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(dp));
+#pragma unroll
+        for (int j = 0; j < kLblTile / 1024; ++j) {  // 32 lanes x 128 bytes = 1024 pixels of depth per round
+          const int nj = n0 + j * 1024 + lane * 32;
+          if (nj < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(depth + (size_t)gf * N + nj));
+        }
         if (lane < kLblTile / 128 && n0 + lane * 128 < N)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(labels + (size_t)gf * N + n0 + lane * 128));
       }
@@ -545,17 +589,33 @@ proj_lbl_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ lab
       if (it.ok) {
         const int rslot = it.frame % ring;
         if (it.kind == kItemProj) {
-          const int n0 = it.idx * kLblTile + warp * 128 + lane * 4;
-          lbl_proj_warp<FAST, W2>(cfg, d, s_sample[s], rcp, depth + (size_t)it.frame * N,
-                                  labels + (size_t)it.frame * N, valid ? valid + (size_t)it.frame * N : nullptr, n0,
-                                  lane, s_list[warp], acc, (uint32_t)rslot * (uint32_t)d.slot_words,
-                                  flags + (size_t)rslot * d.nsl * kFlagStride);
+#ifndef DM_LBL_ABL_NOPROJ  // ablation builds (wrong results): what the kernel costs without one of its halves
+          const float* dframe = depth + (size_t)it.frame * N;
+          const uint8_t* lframe = labels + (size_t)it.frame * N;
+          const uint8_t* vframe = valid ? valid + (size_t)it.frame * N : nullptr;
+          const int n0 = it.idx * kLblTile + warp * 128 + lane * 4;  // sub-tile j: + j * 128 * kLblWarps
+          LblQuad quads[kLblProjJ];
+#pragma unroll
+          for (int j = 0; j < kLblProjJ; ++j) quads[j] = lbl_load_quad(d, dframe, lframe, vframe, n0 + j * 128 * kLblWarps, N);
+#pragma unroll
+          for (int j = 0; j < kLblProjJ; ++j)
+            lbl_proj_warp<FAST, W2>(cfg, d, s_sample[s], rcp, quads[j], n0 + j * 128 * kLblWarps, lane, s_list[warp], acc,
+                                    (uint32_t)rslot * (uint32_t)d.slot_words, flags + (size_t)rslot * d.nsl * kFlagStride);
+#endif
         } else if (it.kind == kItemResolve) {
-#pragma unroll 1
+#ifndef DM_LBL_ABL_NORESOLVE
+          uint32_t* acc_slot = acc + (size_t)rslot * d.slot_words;
+          const int slice0 = (it.idx * kLblWarps + warp) * kLblResK;
+          LblKeys<W2> keys[kLblResK];
+#pragma unroll
           for (int q = 0; q < kLblResK; ++q)
-            lbl_resolve_slice<W2>(acc + (size_t)rslot * d.slot_words, cfg, d,
-                                  ((unsigned)it.ok >> (1 + warp * kLblResK + q)) & 1u, it.frame,
-                                  (it.idx * kLblWarps + warp) * kLblResK + q, lane, topdown, mask, height);
+            keys[q] = lbl_load_keys<W2>(acc_slot, cfg, d, ((unsigned)it.ok >> (1 + warp * kLblResK + q)) & 1u,
+                                        slice0 + q, lane);
+#pragma unroll
+          for (int q = 0; q < kLblResK; ++q)
+            lbl_resolve_slice<W2>(acc_slot, cfg, d, ((unsigned)it.ok >> (1 + warp * kLblResK + q)) & 1u, keys[q],
+                                  it.frame, slice0 + q, lane, topdown, mask, height);
+#endif
         }
       }
       __syncwarp();

@@ -112,47 +112,34 @@ copy_kernel(const float* __restrict__ a, float* __restrict__ b, long long n) {
   DM_GRID_STRIDE(i, n) b[i] = a[i];
 }
 
-// reduction: 0 max, 1 min (torch_scatter: `src > out` / `src < out`, NaN never wins), 2 sum, 3 mean (sum here, the
-// division by the hit count follows), 4 prod (utils.py:70-76).  sum / mean / prod accumulate with float atomics: the
-// order of the hits is not the reference's index order, so results agree to rounding, not bit for bit.
-__device__ __forceinline__ void atomic_mul_f32(float* addr, float v) {
-  unsigned int* a = reinterpret_cast<unsigned int*>(addr);
-  unsigned int old = *a, assumed;
-  do {
-    assumed = old;
-    old = atomicCAS(a, assumed, __float_as_uint(__fmul_rn(__uint_as_float(assumed), v)));
-  } while (old != assumed);
-}
-
+// reduction: 0 max, 1 min (torch_scatter: `src > out` / `src < out`, NaN never wins): order-independent atomics.
 __global__ void __launch_bounds__(kThreads)
 scatter_kernel(const float* __restrict__ values, const long long* __restrict__ coords,
                const uint8_t* __restrict__ valid, long long N, long long total, int Mh, int Mw, int reduction,
-               float* __restrict__ canvas, int* __restrict__ count) {
+               float* __restrict__ canvas) {
   const long long M = (long long)Mh * Mw;
   DM_GRID_STRIDE(i, total) {
     if (valid && !valid[i]) continue;
     const long long r = coords[i * 2], c = coords[i * 2 + 1];
     if (r < 0 || r >= Mh || c < 0 || c >= Mw) continue;  // utils.py:448-453
     const float v = values[i];
-    const long long o = (i / N) * M + r * Mw + c;
-    float* dst = canvas + o;
-    if (reduction >= 2) {
-      if (reduction == 4) atomic_mul_f32(dst, v); else atomicAdd(dst, v);
-      if (count) atomicAdd(count + o, 1);
-      continue;
-    }
     if (v != v) continue;
+    float* dst = canvas + ((i / N) * M + r * Mw + c);
     if (reduction) atomic_min_f32(dst, v); else atomic_max_f32(dst, v);
   }
 }
 
-// scatter_mean: out / max(count, 1) with the count as a float (torch_scatter: ones of src's dtype are summed,
-// clamped to >= 1, out.true_divide_(count)); the canvas' starting value is part of the sum but not of the count.
+// 2 sum, 3 mean, 4 prod (utils.py:70-76) depend on the order of the hits: the points get the key of their cell and
+// dm_ordered.cu folds them in the reference's index order (bit-identical, deterministic).
 __global__ void __launch_bounds__(kThreads)
-mean_divide_kernel(float* __restrict__ canvas, const int* __restrict__ count, long long n) {
-  DM_GRID_STRIDE(i, n) {
-    const int k = count[i];
-    canvas[i] = __fdiv_rn(canvas[i], (float)(k < 1 ? 1 : k));
+scatter_keys_kernel(const long long* __restrict__ coords, const uint8_t* __restrict__ valid, long long N,
+                    long long total, int Mh, int Mw, unsigned long long* __restrict__ keys) {
+  const long long M = (long long)Mh * Mw;
+  DM_GRID_STRIDE(i, total) {
+    unsigned long long k = ~0ull;
+    const long long r = coords[i * 2], c = coords[i * 2 + 1];
+    if ((!valid || valid[i]) && r >= 0 && r < Mh && c >= 0 && c < Mw) k = (unsigned long long)((i / N) * M + r * Mw + c);
+    keys[i] = k;
   }
 }
 
@@ -298,20 +285,20 @@ extern "C" int dm_scatter_f32(const float* values, const int64_t* coords, const 
     copy_kernel<<<grid_for(n_out), kThreads, 0, stream>>>(canvas_in, canvas_out, n_out);
   DM_LAUNCHED();
   const long long total = (long long)B * N;
-  int* count = nullptr;
-  if (reduction == 3) {  // hit counts of scatter_mean: stream-ordered scratch, freed below
-    DM_CUDA_OK(cudaMallocAsync(&count, (size_t)n_out * sizeof(int), stream));
-    DM_CUDA_OK(cudaMemsetAsync(count, 0, (size_t)n_out * sizeof(int), stream));
-  }
-  if (total > 0) {
+  if (total > 0 && reduction < 2) {
     scatter_kernel<<<grid_for(total), kThreads, 0, stream>>>(values, reinterpret_cast<const long long*>(coords),
-                                                             valid, N, total, Mh, Mw, reduction, canvas_out, count);
+                                                             valid, N, total, Mh, Mw, reduction, canvas_out);
     DM_LAUNCHED();
-  }
-  if (count) {
-    mean_divide_kernel<<<grid_for(n_out), kThreads, 0, stream>>>(canvas_out, count, n_out);
+  } else if (total > 0) {
+    if (total >= (1ll << 31)) return DM_EINVAL;
+    unsigned long long* keys = nullptr;  // stream-ordered scratch
+    DM_CUDA_OK(cudaMallocAsync(&keys, (size_t)total * 8, stream));
+    scatter_keys_kernel<<<grid_for(total), kThreads, 0, stream>>>(reinterpret_cast<const long long*>(coords), valid, N,
+                                                                  total, Mh, Mw, keys);
     DM_LAUNCHED();
-    DM_CUDA_OK(cudaFreeAsync(count, stream));
+    const int rc = ordered_reduce(keys, values, total, bits_for((unsigned long long)n_out), reduction, canvas_out, nullptr, stream);
+    DM_CUDA_OK(cudaFreeAsync(keys, stream));
+    if (rc != DM_OK) return rc;
   }
   if (has_fill)
     changed_fill_kernel<<<grid_for(n_out), kThreads, 0, stream>>>(canvas_out, fill_value, n_out, mask);

@@ -41,6 +41,18 @@ def orth_project_host(depth_map, value_map, valid_map, cam_pose, width_offset, h
   of 4 * (C + 1) bytes per pixel crossing PCIe (dm_orth_project_labels_host_f32).  `device` defaults to the
   current CUDA device; the caller's current device is left as it was."""
   device = nat.require_cuda(device).index
+  if utils._reduction_code(reduction, fused=False) > 1:
+    # sum / mean / prod: the composed path on device tensors (maps.orth_project), results copied back
+    from . import maps
+    dev = torch.device("cuda", device)
+    up = lambda a, dt: None if a is None else torch.as_tensor(np.asarray(a)).to(device=dev, dtype=dt)
+    res = maps.orth_project(up(depth_map, torch.float32), up(value_map, torch.float32), up(valid_map, torch.bool),
+                            cam_pose, width_offset, height_offset, cam_pitch, cam_height, map_res, map_width,
+                            map_height, focal_x, focal_y, center_x, center_y, trunc_depth_min, trunc_depth_max,
+                            trunc_height_max, clip_border, to_global, flip_h, fill_value, reduction, get_height_map,
+                            device=dev, label_map=None if label_map is None else up(label_map, torch.int64),
+                            num_classes=num_classes)
+    return tuple(r.contiguous().cpu().numpy() for r in res)
   depth = _host(depth_map, np.float32)
   values = _host(value_map, np.float32)
   valid = None if valid_map is None else _host(np.asarray(valid_map).astype(bool), np.uint8)

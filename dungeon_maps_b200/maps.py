@@ -932,7 +932,9 @@ def fuse_topdown_maps(*maps: List[TopdownMap], map_projector: Optional[MapProjec
   kinds = {bool(m.is_height_map) for m in live}
   assert len(kinds) == 1, "All maps must be the same type of maps (all height maps or all value maps)."
   is_height_map = kinds.pop()
-  red = utils._reduction_code(get(reduction, proj.reduction))  # MapProjector.project: get(reduction, self.reduction), maps.py:1720
+  # MapProjector.project: get(reduction, self.reduction), maps.py:1720.  All five reductions: max / min through the
+  # atomic scatter, sum / mean / prod through the ordered fold (csrc/dm_ordered.cu: the reference's point order)
+  red = utils._reduction_code(get(reduction, proj.reduction), fused=False)
   dev = _pick_device(proj.device, *[m.mask for m in live], *[m.height_map for m in live])
   shapes = [utils.to_4D_image(m.mask).shape for m in live]
   b = max(s[0] for s in shapes)
@@ -975,7 +977,7 @@ def fuse_topdown_maps(*maps: List[TopdownMap], map_projector: Optional[MapProjec
   mask = torch.empty((b, C, map_height, map_width), dtype=torch.bool, device=dev)
   height = None if is_height_map else torch.empty_like(topdown)
   # the new map is in the global frame when the target is: pass 2 then leaves its box for the next merge
-  track = bool(proj.to_global) and tgt.fill_value == tgt.fill_value
+  track = bool(proj.to_global) and tgt.fill_value == tgt.fill_value and red < 2
   next_box = torch.empty((5,), dtype=torch.int64, device=dev) if track else None
   with torch.cuda.device(dev):
     rc = lib.dm_fuse_scatter_track_f32(sources, len(live), b, C, tgt, topdown.data_ptr(), mask.data_ptr(),
@@ -1027,7 +1029,7 @@ def merge_into_canvas(world: TopdownMap, new_map: TopdownMap, canvas_shape: Tupl
   place into `world`'s tensors, which are allocated on the first call.  One launch, no host sync.
   `world`'s tensors are updated in place and shared with the returned map."""
   Hc, Wc = int(canvas_shape[0]), int(canvas_shape[1])
-  red = utils._reduction_code(get(reduction, map_projector.reduction))
+  red = utils._reduction_code(get(reduction, map_projector.reduction), fused=False)
   if new_map.is_empty:
     return world
   dev = _pick_device(map_projector.device, new_map.mask, new_map.height_map)

@@ -7,7 +7,8 @@ Differences from the reference, all consequences of "CUDA only, no fallback":
   * tensors that are not on a CUDA device are moved to one (`device=` or the
     current CUDA device) and results live there;
   * batch > 1 works (the reference raises, utils.py:311-316);
-  * Reduction.sum / mean / prod are not implemented yet (NotImplementedError).
+  * Reduction.sum / mean / prod fold the hits of a cell in the reference's CPU order (ascending point index,
+    csrc/dm_ordered.cu): bit-identical to the reference's CPU path and deterministic; max / min are atomics.
 """
 import enum
 from dataclasses import dataclass
@@ -50,14 +51,15 @@ _RED_CODES = {Reduction.max: 0, Reduction.min: 1, Reduction.sum: 2, Reduction.me
 
 
 def _reduction_code(reduction, fused: bool = True) -> int:
-  """Kernel code of a Reduction.  The fused kernels (projection, map fusion) implement max and min;
-  scatter_tensor / project implement all five (fused=False)."""
+  """Kernel code of a Reduction.  The single-pass projection kernels implement max and min (fused=True raises for the
+  others: orth_project then takes its composed path); scatter_tensor / project / fuse_topdown_maps /
+  merge_into_canvas implement all five (fused=False)."""
   red = Reduction(reduction)
   code = _RED_CODES[red]
   if fused and code > 1:
     raise NotImplementedError(
-      f"Reduction.{red.value} is not implemented by this fused kernel (max and min are); "
-      "scatter_tensor / project / orth_project handle it through the scatter kernel")
+      f"Reduction.{red.value} is not implemented by the single-pass projection kernel (max and min are); "
+      "orth_project / scatter_tensor / project / fuse_topdown_maps handle it through the ordered scatter")
   return code
 
 

@@ -209,11 +209,11 @@ def flow_cases():
 def builder_cases():
   H, W = 60, 80
 
-  def run(name, to_global, C, center_mode, steps, keep_pose=False, fill_value=dm.NINF):
+  def run(name, to_global, C, center_mode, steps, keep_pose=False, fill_value=dm.NINF, reduction=None):
     proj = dm.MapProjector(width=W, height=H, hfov=HFOV, cam_pose=[0., 0., 0.], width_offset=0., height_offset=0.,
                            cam_pitch=PITCH, cam_height=0.88, map_res=0.1, map_width=60, map_height=60,
                            trunc_depth_min=0.15, trunc_depth_max=5.05, clip_border=3, to_global=to_global,
-                           fill_value=fill_value)
+                           fill_value=fill_value, reduction=reduction)
     builder = dm.MapBuilder(map_projector=proj)
     pose = torch.zeros(1, 3)
     arrays = {}
@@ -223,6 +223,8 @@ def builder_cases():
       pose = pose + step
       depth = synth.room_depth(1, H, W, HFOV, PITCH, 0.88, pose, seed=7)
       vals = synth.block_onehot(1, C, H, W, seed=200 + t, block=8) if C > 0 else None
+      if reduction is not None and C > 0:  # order-dependent reductions: values whose sums / products round
+        vals = synth.uniform((1, C, H, W), 200 + t, 0.25, 1.75)
       cam_pose = pose[0].numpy().copy()
       local = builder.step(depth_map=depth[0].numpy(), value_map=None if vals is None else vals[0].numpy(),
                            cam_pose=cam_pose, center_mode=center_mode, keep_pose=keep_pose)
@@ -247,12 +249,18 @@ def builder_cases():
         arrays["world_origin"] = wm.get_origin()
     save(name, dict(kind="map_builder", to_global=to_global, C=C, center_mode=center_mode, steps=steps,
                     keep_pose=keep_pose, fill_value=None if fill_value is None else float(fill_value),
+                    reduction=reduction,
                     world_shapes=shapes, H=H, W=W), **arrays)
 
   run("builder_global_height", True, 0, "none", 4)
   run("builder_local_height_camera", False, 0, "camera", 4)
   run("builder_global_values_origin", True, 3, "origin", 3, fill_value=0.)
   run("builder_local_values_keep_pose", False, 2, "none", 3, keep_pose=True)
+  # Reduction.sum / mean / prod through plot AND merge (MapProjector.project falls back to the projector's reduction,
+  # maps.py:1720): order-dependent float results, pinned bit for bit
+  run("builder_global_values_sum", True, 2, "none", 3, fill_value=0., reduction="sum")
+  run("builder_local_values_mean", False, 2, "none", 3, fill_value=0., reduction="mean")
+  run("builder_global_height_prod", True, 0, "none", 3, fill_value=1., reduction="prod")
 
 
 # ------------------------------------------------------------------ fixed-canvas merge

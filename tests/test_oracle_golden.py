@@ -164,7 +164,7 @@ def test_fuse_topdown_maps_matches_reference(name):
   for t in range(g.meta["steps"]):
     srcs = _builder_sources(g, t, C, to_global)
     tgt_pose = np.zeros(3, np.float32) if g.meta["keep_pose"] else g[f"pose_{t}"]
-    out = orc.fuse(srcs, to_global, tgt_pose, 0.1, True, None, fill, None)
+    out = orc.fuse(srcs, to_global, tgt_pose, 0.1, True, None, fill, g.meta.get("reduction"))
     assert [out["map_height"], out["map_width"]] == g.meta["world_shapes"][t], f"step {t} shape"
     assert_same(np.float32(out["width_offset"]), g[f"world_woff_{t}"].reshape(()), f"step {t} woff")
     assert_same(np.float32(out["height_offset"]), g[f"world_hoff_{t}"].reshape(()), f"step {t} hoff")
