@@ -41,6 +41,91 @@ __device__ __forceinline__ uint32_t bits_of(const uint4 v) {
   return bits;
 }
 
+// The same walk restricted to the plane's bounding box of valid cells (rows r0..r1, columns c0..c1), as the scatter
+// pass that wrote the map tracked it (DmFuseSource.plane_box).  A grown world map is mostly empty canvas: every
+// environment's explored region is a small rectangle of the batch-wide canvas, and scanning the whole 155 MB of masks
+// to find it again was the largest merge kernel after the fill (ncu r01m: 90 us at 25 % DRAM throughput).  Work item =
+// (row of the box, 16-byte group of that row's column range); groups stay aligned to the plane's 16-byte grid, so a
+// group may reach outside the box — where the mask is zero by construction.
+template <typename F>
+__device__ __forceinline__ void for_valid_cells_of_box(const DmFuseSource& src, long long plane, int r0, int r1, int c0,
+                                                       int c1, F&& visit) {
+  constexpr int kAhead = 4;
+  if (r1 < r0 || c1 < c0) return;  // no valid cell in this plane
+  const int n = src.h * src.w, w = src.w;
+  const uint8_t* base = src.mask + plane * n;
+  const int a0 = (int)(reinterpret_cast<uintptr_t>(base) & 15);
+  const int gpr = ((c1 - c0 + 15) >> 4) + 1;            // groups per row, upper bound
+  const long long items = (long long)(r1 - r0 + 1) * gpr;
+  const int stride = gridDim.x * kScanThreads;
+  const int lane = threadIdx.x & 31;
+  auto group_offset = [&](long long item) -> int {       // plane-relative byte offset of the item's group, or INT_MIN
+    if (item >= items) return INT_MIN;
+    const int ri = (int)(item / gpr), gi = (int)(item - (long long)ri * gpr);
+    const int r = r0 + ri;
+    const int g = ((r * w + c0 + a0) >> 4) + gi;
+    if (g > ((r * w + c1 + a0) >> 4)) return INT_MIN;    // past the row's last group
+    if (ri > 0 && g <= (((r - 1) * w + c1 + a0) >> 4)) return INT_MIN;  // the previous row's item already took it
+    return g * kGroup - a0;
+  };
+  for (long long iw = blockIdx.x * kScanThreads + (threadIdx.x & ~31); iw < items; iw += (long long)kAhead * stride) {
+    int o[kAhead];
+    uint4 v[kAhead];
+#pragma unroll
+    for (int k = 0; k < kAhead; ++k) {
+      o[k] = group_offset(iw + lane + (long long)k * stride);
+      v[k] = make_uint4(0u, 0u, 0u, 0u);
+      if (o[k] != INT_MIN && o[k] >= 0 && o[k] + kGroup <= n) v[k] = __ldg(reinterpret_cast<const uint4*>(base + o[k]));
+    }
+    unsigned long long bits = 0;
+#pragma unroll
+    for (int k = 0; k < kAhead; ++k) {
+      uint32_t bk = 0;
+      if (o[k] != INT_MIN) {
+        if (o[k] >= 0 && o[k] + kGroup <= n) {
+          if (v[k].x | v[k].y | v[k].z | v[k].w) bk = bits_of(v[k]);
+        } else {
+          for (int j = 0; j < kGroup; ++j)
+            if (o[k] + j >= 0 && o[k] + j < n && base[o[k] + j]) bk |= 1u << j;
+        }
+      }
+      bits |= (unsigned long long)bk << (16 * k);
+    }
+    if (!__any_sync(0xffffffffu, bits != 0ull)) continue;
+    const int cnt = __popcll(bits);
+    int incl = cnt;
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, dd);
+      if (lane >= dd) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const uint32_t blo = (uint32_t)bits, bhi = (uint32_t)(bits >> 32);
+    for (int first = 0; first < total; first += 32) {
+      const int idx = first + lane;
+      int L = 0;
+#pragma unroll
+      for (int step = 16; step >= 1; step >>= 1) {
+        const int t = __shfl_sync(0xffffffffu, incl, L + step - 1);
+        if (t <= idx) L += step;
+      }
+      L &= 31;
+      const uint32_t lo_own = __shfl_sync(0xffffffffu, blo, L), hi_own = __shfl_sync(0xffffffffu, bhi, L);
+      const int excl_own = __shfl_sync(0xffffffffu, incl - cnt, L);
+      const int o0 = __shfl_sync(0xffffffffu, o[0], L), o1 = __shfl_sync(0xffffffffu, o[1], L);
+      const int o2 = __shfl_sync(0xffffffffu, o[2], L), o3 = __shfl_sync(0xffffffffu, o[3], L);
+      if (idx < total) {
+        const int rank = idx - excl_own, nlo = __popc(lo_own);
+        const int bit = rank < nlo ? (int)__fns(lo_own, 0, rank + 1) : 32 + (int)__fns(hi_own, 0, rank - nlo + 1);
+        const int k = bit >> 4;
+        const int cell = (k == 0 ? o0 : k == 1 ? o1 : k == 2 ? o2 : o3) + (bit & 15);
+        const int r = cell / w;
+        visit(cell, r, cell - r * w);
+      }
+    }
+  }
+}
+
 template <typename F>
 __device__ __forceinline__ void for_valid_cells_of_plane(const DmFuseSource& src, long long plane, F&& visit) {
   constexpr int kAhead = 4;  // groups per lane and round: 64 cells, one bit each in a 64-bit word
@@ -113,6 +198,18 @@ __device__ __forceinline__ void for_valid_cells_of_plane(const DmFuseSource& src
   }
 }
 
+// Walks the valid cells of a plane: inside its tracked bounding box when the source carries one, else all of it.
+template <typename F>
+__device__ __forceinline__ void for_valid_cells(const DmFuseSource& src, long long plane, F&& visit) {
+  if (src.plane_box) {
+    const int4 bx = __ldg(reinterpret_cast<const int4*>(src.plane_box) + plane);  // rmin, rmax, cmin, cmax
+    const int r0 = max(bx.x, 0), r1 = min(bx.y, src.h - 1), c0 = max(bx.z, 0), c1 = min(bx.w, src.w - 1);
+    for_valid_cells_of_box(src, plane, r0, r1, c0, c1, visit);
+  } else {
+    for_valid_cells_of_plane(src, plane, visit);
+  }
+}
+
 // Loads the plane's sample parameters into shared memory (block-uniform), once per sample change.
 __device__ __forceinline__ void load_plane_ctx(const DmFuseSource& src, int smp, PlaneCtx* ctx) {
   __syncthreads();
@@ -166,7 +263,7 @@ fuse_bbox_kernel(const __grid_constant__ DmFuseSource src, int planes, int C, fl
     const int smp = plane / C, ch = plane - smp * C;
     if (smp != loaded) { load_plane_ctx(src, smp, &ctx); loaded = smp; }
     const float* hplane = src.height + (long long)smp * src.height_bstride + (long long)ch * src.height_cstride;
-    for_valid_cells_of_plane(src, plane, [&](int cell, int r, int c) {
+    for_valid_cells(src, plane, [&](int cell, int r, int c) {
       const V3 p = source_point(src, ctx, hplane, cell, r, c);
       // maps.py:2159-2165: map_quantize(width_offset=0., height_offset=0., flip_h=False)
       float xf, zf;

@@ -33,7 +33,7 @@ constexpr int kLblThreads = 32 * (kLblWarps + 1);   // + the scheduler warp
 constexpr int kLblProjJ = DM_LBL_PROJ_J;            // 128-pixel sub-tiles per worker warp and projection ticket
 constexpr int kLblTile = 128 * kLblWarps * kLblProjJ;  // pixels per projection ticket
 #ifndef DM_LBL_RES_K
-#define DM_LBL_RES_K 1
+#define DM_LBL_RES_K 2  // measured (room / iid ms per 64 frames): 1: 0.259 / 0.391, 2: 0.252 / 0.352
 #endif
 constexpr int kLblResK = DM_LBL_RES_K;              // 64-cell slices per worker warp and resolve ticket
 constexpr int kLblResCells = 64 * kLblWarps * kLblResK;
@@ -390,7 +390,7 @@ __device__ __forceinline__ void lbl_resolve_slice(uint32_t* __restrict__ acc_slo
 // acquire load of its dependency, a read of its slice flags and a release of its completion counter — three L2 round
 // trips that, taken one ticket at a time, are longer than the ~1.5 us the eight workers need for the item (ncu r02b:
 // 37 % of all warp samples were workers polling for the next item).  Taken for kLblBatch tickets by kLblBatch lanes
-// they are one round trip each per batch.  The other side of the trade: every CTA holds kLblSlots + kLblBatch
+// they are one round trip each per batch (the slice flags are read by the workers: eight warps at a time).  The other side of the trade: every CTA holds kLblSlots + kLblBatch
 // tickets, and all CTAs together must not span more frames than the resolve pass lags behind the projection, or
 // the dependency waits stop being rare (r02c, 8 slots + 4 + 4 claimed ahead at lag 8: 1.1 M spins per launch, 0.30 ms
 // instead of 0.25) — the host picks the lag from the number of tickets in flight (lbl_schedule).
@@ -403,8 +403,6 @@ __device__ __forceinline__ void lbl_resolve_slice(uint32_t* __restrict__ acc_slo
 constexpr int kLblSlots = DM_LBL_SLOTS;
 constexpr int kLblBatch = DM_LBL_BATCH;
 constexpr int kLblItemSlices = kLblWarps * kLblResK;  // 64-cell slices of one resolve item
-static_assert(kLblItemSlices * kLblBatch <= 32, "one scheduler lane per slice of a batch");
-static_assert(kLblItemSlices <= 30, "slice flags travel in the item's ok word");
 
 template <int FAST, int W2>
 __global__ void __launch_bounds__(kLblThreads, 4)
@@ -417,7 +415,7 @@ proj_lbl_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ lab
   // k - kLblSlots (empty[slot], one arrival per worker warp); a worker warp that finishes its part of an item early
   // starts on the next one instead of waiting for the slowest warp of the CTA (a CTA-wide barrier per item cost
   // 27 % of the warp samples in stall_barrier, ncu r02a).
-  constexpr int S = kLblSlots, G = kLblBatch, SL = kLblItemSlices;
+  constexpr int S = kLblSlots, G = kLblBatch;
   __shared__ __align__(16) LblItem s_item[S];
   __shared__ __align__(16) DmProjSample s_sample[S];
   __shared__ __align__(8) uint64_t s_full[S], s_empty[S];
@@ -453,23 +451,14 @@ proj_lbl_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ lab
       }
       published = upto;
     };
-    auto slice_flags = [&](int frame, int idx, int q, bool on) -> uint32_t {  // reads and clears one slice flag
-      uint32_t f = 0;
-      const int slice = idx * SL + q;
-      if (on && slice < d.nsl) {
-        uint32_t* fp = flags + ((size_t)(frame % ring) * d.nsl + slice) * kFlagStride;
-        f = __ldcg(fp);
-        if (f) __stcg(fp, 0u);
-      }
-      return f;
-    };
-    // (tickets are NOT claimed ahead: the round trip of the atomic is paid once per batch, and the tickets a CTA
-    // holds without working on them would widen the window of frames in flight)
+    // tickets are claimed one batch ahead: every L2 round trip the scheduler waits for is a round trip of a memory
+    // system that the workers keep saturated (2-3 us each under load), and they add up per batch
+    unsigned next_batch = 0;
+    if (lane == 0) next_batch = atomicAdd(ctrl, (unsigned)G);
     bool done = false;
     while (!done) {
-      unsigned t0 = 0;
-      if (lane == 0) t0 = atomicAdd(ctrl, (unsigned)G);
-      t0 = __shfl_sync(0xffffffffu, t0, 0);
+      const unsigned t0 = __shfl_sync(0xffffffffu, next_batch, 0);
+      if (lane == 0 && t0 < total) next_batch = atomicAdd(ctrl, (unsigned)G);
       // ---- lane g prepares ticket t0 + g
       int kind = kItemNone, frame = 0, idx = 0, ok = 1;
       const uint32_t* dep = nullptr;
@@ -486,13 +475,8 @@ proj_lbl_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ lab
           dep_target = (uint32_t)P + guard.dep_bias;
         }
       }
-      // acquire loads (one instruction for the batch): they pair with the red.release of the CTAs that completed
-      // the frames; the other lanes and the workers inherit the ordering through __syncwarp and the mbarrier hand-off
-      int pending = 0;
-      if (dep) pending = ld_acquire(dep) < dep_target;
-      __syncwarp();
       // the sample blocks of the batch (48 words per item) and, for projection items, the input lines on their way
-      // into L2 while the workers finish what they have
+      // into L2 while the workers finish what they have — issued BEFORE the acquire loads, which would hold them back
       uint32_t sw[(G * 48 + 31) / 32];
 #pragma unroll
       for (int j = 0; j < (G * 48 + 31) / 32; ++j) {
@@ -515,21 +499,16 @@ proj_lbl_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ lab
         if (lane < kLblTile / 128 && n0 + lane * 128 < N)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(labels + (size_t)gf * N + n0 + lane * 128));
       }
-      // the slice flags of the resolve items whose dependency is satisfied, read (and cleared) here: a worker then
-      // needs one L2 round trip per flagged slice (its keys) instead of two.  lane = (item, slice)
-      uint32_t fl_all;
-      {
-        const int g = lane / SL, q = lane - g * SL;
-        const int gk = __shfl_sync(0xffffffffu, kind, g & (G - 1)), gf = __shfl_sync(0xffffffffu, frame, g & (G - 1));
-        const int gi = __shfl_sync(0xffffffffu, idx, g & (G - 1)), gp = __shfl_sync(0xffffffffu, pending, g & (G - 1));
-        fl_all = __ballot_sync(0xffffffffu, slice_flags(gf, gi, q, g < G && gk == kItemResolve && !gp) != 0u);
-      }
+      // acquire loads (one instruction for the batch): they pair with the red.release of the CTAs that completed
+      // the frames; the other lanes and the workers inherit the ordering through __syncwarp and the mbarrier hand-off
+      int pending = 0;
+      if (dep) pending = ld_acquire(dep) < dep_target;
+      __syncwarp();
       // ---- post the batch in ticket order
       for (int g = 0; g < G; ++g) {
         const int k_ = __shfl_sync(0xffffffffu, kind, g);
         if (k_ == kItemNone) continue;  // a ticket outside the batch (pipeline fill / drain)
         const int fr = __shfl_sync(0xffffffffu, frame, g), ix = __shfl_sync(0xffffffffu, idx, g);
-        uint32_t fbits = (fl_all >> (g * SL)) & ((1u << SL) - 1u);
         int okg = 1;
         if (__shfl_sync(0xffffffffu, pending, g)) {
           // rare: must block.  The frame we wait for may need the very items our workers are finishing: everything
@@ -538,7 +517,6 @@ proj_lbl_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ lab
           if (lane == g) ok = wait_count(dep, dep_target, ctrl, guard.spin_ns) ? 1 : 0;
           okg = __shfl_sync(0xffffffffu, ok, g);
           __syncwarp();
-          fbits = __ballot_sync(0xffffffffu, slice_flags(fr, ix, lane, lane < SL && k_ == kItemResolve && okg) != 0u);
         }
         // slot posted % S is free once item posted - S has been released by every worker warp
         ensure_published(posted + 1u - (unsigned)S);
@@ -551,7 +529,7 @@ proj_lbl_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ lab
           }
         }
         if (lane == 0) {
-          s_item[s] = LblItem{k_, fr, ix, okg ? (int)(1u | (fbits << 1)) : 0};
+          s_item[s] = LblItem{k_, fr, ix, okg};
           s_meta[s] = make_int2(k_, fr);
         }
         __syncwarp();
@@ -606,15 +584,22 @@ proj_lbl_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ lab
 #ifndef DM_LBL_ABL_NORESOLVE
           uint32_t* acc_slot = acc + (size_t)rslot * d.slot_words;
           const int slice0 = (it.idx * kLblWarps + warp) * kLblResK;
+          // sparse ring: lane q reads (and clears) the flag of slice q; a slice nobody flagged holds no key
+          uint32_t fl = 0;
+          if (lane < kLblResK && slice0 + lane < d.nsl) {
+            uint32_t* fp = flags + ((size_t)rslot * d.nsl + slice0 + lane) * kFlagStride;
+            fl = __ldcg(fp);
+            if (fl) __stcg(fp, 0u);
+          }
+          const uint32_t flagged = __ballot_sync(0xffffffffu, fl != 0u);
           LblKeys<W2> keys[kLblResK];
 #pragma unroll
           for (int q = 0; q < kLblResK; ++q)
-            keys[q] = lbl_load_keys<W2>(acc_slot, cfg, d, ((unsigned)it.ok >> (1 + warp * kLblResK + q)) & 1u,
-                                        slice0 + q, lane);
+            keys[q] = lbl_load_keys<W2>(acc_slot, cfg, d, (flagged >> q) & 1u, slice0 + q, lane);
 #pragma unroll
           for (int q = 0; q < kLblResK; ++q)
-            lbl_resolve_slice<W2>(acc_slot, cfg, d, ((unsigned)it.ok >> (1 + warp * kLblResK + q)) & 1u, keys[q],
-                                  it.frame, slice0 + q, lane, topdown, mask, height);
+            lbl_resolve_slice<W2>(acc_slot, cfg, d, (flagged >> q) & 1u, keys[q], it.frame, slice0 + q, lane, topdown,
+                                  mask, height);
 #endif
         }
       }
@@ -629,7 +614,7 @@ proj_lbl_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ lab
 // what the workspace (sized for `max_ring` slots) and the batch allow; ring = 2 * lag as in dm_project.cu when
 // slots have to be reused (b > max_ring).
 static void lbl_schedule(long long grid, long long tickets_per_frame, int b, int max_ring, int* lag, int* ring) {
-  const double span = (double)grid * (kLblSlots + kLblBatch) / (double)(tickets_per_frame > 0 ? tickets_per_frame : 1);
+  const double span = (double)grid * (kLblSlots + 2 * kLblBatch) / (double)(tickets_per_frame > 0 ? tickets_per_frame : 1);
   int l = (int)(span * 1.5) + 2;
   if (b <= max_ring) {  // a slot per frame: the lag is free (at most the batch)
     *lag = l < b ? l : b;
