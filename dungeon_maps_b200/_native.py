@@ -12,7 +12,7 @@ import torch
 
 from . import build as _build
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class NativeError(RuntimeError):
@@ -48,7 +48,7 @@ class DmFuseSource(ctypes.Structure):
     ("height", c_void_p), ("values", c_void_p), ("mask", c_void_p),
     ("height_bstride", c_int64), ("height_cstride", c_int64),
     ("h", c_int32), ("w", c_int32), ("flip_h", c_int32), ("map_res", c_float),
-    ("width_offset", c_void_p), ("height_offset", c_void_p), ("steps", c_void_p),
+    ("width_offset", c_void_p), ("height_offset", c_void_p), ("steps", c_void_p), ("plane_box", c_void_p),
   ]
 
 
@@ -76,7 +76,7 @@ class DmBuilderCfg(ctypes.Structure):
 
 class DmMapRef(ctypes.Structure):
   _fields_ = [("topdown", c_void_p), ("mask", c_void_p), ("h", c_int32), ("w", c_int32),
-              ("width_offset", c_float), ("height_offset", c_float), ("box", c_void_p)]
+              ("width_offset", c_float), ("height_offset", c_float), ("box", c_void_p), ("plane_box", c_void_p)]
 
 
 class DmMergeShape(ctypes.Structure):
@@ -114,7 +114,7 @@ _SIGNATURES = {
   "dm_fuse_bbox_seeded_i64": (ctypes.c_int, [POINTER(DmFuseSource), c_int32, c_int32, c_int32, c_float, c_void_p,
                                              c_void_p, c_void_p]),
   "dm_fuse_scatter_track_f32": (ctypes.c_int, [POINTER(DmFuseSource), c_int32, c_int32, c_int32, POINTER(DmFuseTarget),
-                                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
   "dm_fuse_inplace_f32": (ctypes.c_int, [POINTER(DmFuseSource), c_int32, c_int32, c_int32, POINTER(DmFuseTarget),
                                          c_void_p, c_void_p, c_void_p, c_void_p]),
   "dm_fuse_canvas_init_f32": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_void_p]),

@@ -170,12 +170,14 @@ static void make_sources(DmBuilder* h, char* d_base, float* local_topdown, uint8
     s.height_bstride = (int64_t)world->h * world->w; s.height_cstride = s.height_bstride;
     s.h = world->h; s.w = world->w; s.flip_h = c.proj.flip_h; s.map_res = c.proj.map_res;
     s.width_offset = wwoff; s.height_offset = whoff; s.steps = reinterpret_cast<const DmStep*>(wsteps);
+    s.plane_box = world->plane_box;
   }
   DmFuseSource& s = h->src[h->n_src++];
   s.height = local_topdown; s.values = nullptr; s.mask = local_mask;
   s.height_bstride = (int64_t)c.proj.Mh * c.proj.Mw; s.height_cstride = s.height_bstride;
   s.h = c.proj.Mh; s.w = c.proj.Mw; s.flip_h = c.proj.flip_h; s.map_res = c.proj.map_res;
   s.width_offset = lwoff; s.height_offset = lhoff; s.steps = reinterpret_cast<const DmStep*>(lsteps);
+  s.plane_box = nullptr;
 }
 
 extern "C" int dm_builder_plot(DmBuilder* h, const float* depth, const float* pose, const float* sin_yaw,
@@ -224,7 +226,7 @@ extern "C" int dm_builder_merge(DmBuilder* h, const DmMapRef* out, void* stream_
   tgt.width_offset = out->width_offset; tgt.height_offset = out->height_offset;
   tgt.fill_value = c.merge_fill_value; tgt.reduction = c.merge_reduction;
   const int rc = dm_fuse_scatter_track_f32(h->src, h->n_src, c.b, 1, &tgt, out->topdown, out->mask, nullptr, out->box,
-                                           stream_);
+                                           out->plane_box, stream_);
   h->n_src = 0;
   return rc;
 }

@@ -324,12 +324,42 @@ fuse_fill_kernel(float* __restrict__ topdown, float* __restrict__ height, uint8_
   }
 }
 
+// Block-wide min / max of four per-thread extremes (min, max, min, max); the result is valid in thread 0.
+__device__ __forceinline__ void block_reduce_box(float& amin, float& amax, float& bmin, float& bmax) {
+  __shared__ float red[kScanThreads / 32][4];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    amin = fminf(amin, __shfl_xor_sync(0xffffffffu, amin, o)); amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    bmin = fminf(bmin, __shfl_xor_sync(0xffffffffu, bmin, o)); bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();  // the previous use of `red` has been read
+  if (lane == 0) { red[warp][0] = amin; red[warp][1] = amax; red[warp][2] = bmin; red[warp][3] = bmax; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kScanThreads / 32; ++w) {
+      amin = fminf(amin, red[w][0]); amax = fmaxf(amax, red[w][1]);
+      bmin = fminf(bmin, red[w][2]); bmax = fmaxf(bmax, red[w][3]);
+    }
+  }
+}
+
+__global__ void fuse_plane_box_init(int* box, int planes) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < planes; i += gridDim.x * blockDim.x) {
+    box[4 * i + 0] = 0x7fffffff; box[4 * i + 1] = -1;  // rows:    min, max
+    box[4 * i + 2] = 0x7fffffff; box[4 * i + 3] = -1;  // columns: min, max
+  }
+}
+
 // mask_inline: the mask (utils.py:489-491: the cell differs from what the canvas was filled with) is
 // stored right where a value beats `fill`; with a NaN fill the generic pass below is used instead.
+// next_plane_box (optional, (planes, 4) int32 = row min / max, column min / max, initialised by fuse_plane_box_init):
+// the rectangle of every plane of the map written here that holds its valid cells — what a later merge needs to scan
+// when this map is one of its sources (DmFuseSource.plane_box).
 __global__ void __launch_bounds__(kScanThreads, 1024 / kScanThreads)
 fuse_scatter_kernel(const __grid_constant__ DmFuseSource src, int planes, int C, const DmFuseTarget tgt,
                     float* __restrict__ topdown, float* __restrict__ height, uint8_t* __restrict__ mask,
-                    int mask_inline, long long* __restrict__ next_bbox) {
+                    int mask_inline, long long* __restrict__ next_bbox, int* __restrict__ next_plane_box) {
   __shared__ PlaneCtx ctx;
   // next_bbox: what pass 1 of a FOLLOWING merge would find for the map written here, taken as a global-frame
   // source of the same resolution: min / max over its valid cells of quantize0(dequantize(cell)) (maps.py:1081-1086,
@@ -349,7 +379,8 @@ fuse_scatter_kernel(const __grid_constant__ DmFuseSource src, int planes, int C,
     float* tplane = topdown + (long long)plane * M;
     float* oplane = height ? height + (long long)plane * M : nullptr;
     uint8_t* mplane = mask + (long long)plane * M;
-    for_valid_cells_of_plane(src, plane, [&](int cell, int r, int c) {
+    float pcmin = INFINITY, pcmax = -INFINITY, prmin = INFINITY, prmax = -INFINITY;  // this plane's marked cells
+    for_valid_cells(src, plane, [&](int cell, int r, int c) {
       const V3 p = source_point(src, ctx, hplane, cell, r, c);
       float xf, zf;  // maps.py:2232-2238
       quantize_f(p.x, p.z, tgt.width_offset, tgt.height_offset, tgt.map_res, tgt.Mh, tgt.flip_h, &xf, &zf);
@@ -360,28 +391,25 @@ fuse_scatter_kernel(const __grid_constant__ DmFuseSource src, int planes, int C,
         if (tgt.reduction) atomic_min_f32(tplane + o, v); else atomic_max_f32(tplane + o, v);
         if (mask_inline && better(v, tgt.fill_value, tgt.reduction)) {
           mplane[o] = 1;
-          cmin = fminf(cmin, xf); cmax = fmaxf(cmax, xf);
-          rmin = fminf(rmin, zf); rmax = fmaxf(rmax, zf);
+          pcmin = fminf(pcmin, xf); pcmax = fmaxf(pcmax, xf);
+          prmin = fminf(prmin, zf); prmax = fmaxf(prmax, zf);
         }
       }
       if (oplane && p.y == p.y) atomic_max_f32(oplane + o, p.y);  // maps.py:2258-2271
     });
+    cmin = fminf(cmin, pcmin); cmax = fmaxf(cmax, pcmax);
+    rmin = fminf(rmin, prmin); rmax = fmaxf(rmax, prmax);
+    if (next_plane_box) {  // block-uniform branch: one set of atomics per block and plane it marked a cell in
+      block_reduce_box(prmin, prmax, pcmin, pcmax);
+      if (threadIdx.x == 0 && pcmin <= pcmax) {
+        atomicMin(next_plane_box + 4 * plane + 0, (int)prmin); atomicMax(next_plane_box + 4 * plane + 1, (int)prmax);
+        atomicMin(next_plane_box + 4 * plane + 2, (int)pcmin); atomicMax(next_plane_box + 4 * plane + 3, (int)pcmax);
+      }
+    }
   }
   if (next_bbox) {  // warp, then block reduction; one set of atomics per block that marked a cell
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      cmin = fminf(cmin, __shfl_xor_sync(0xffffffffu, cmin, o)); cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
-      rmin = fminf(rmin, __shfl_xor_sync(0xffffffffu, rmin, o)); rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
-    }
-    __shared__ float red[kScanThreads / 32][4];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) { red[warp][0] = cmin; red[warp][1] = cmax; red[warp][2] = rmin; red[warp][3] = rmax; }
-    __syncthreads();
+    block_reduce_box(cmin, cmax, rmin, rmax);
     if (threadIdx.x == 0) {
-      for (int w = 1; w < kScanThreads / 32; ++w) {
-        cmin = fminf(cmin, red[w][0]); cmax = fmaxf(cmax, red[w][1]);
-        rmin = fminf(rmin, red[w][2]); rmax = fmaxf(rmax, red[w][3]);
-      }
       if (cmin <= cmax) {
         // rows: the dequantised z falls with the row when the map is flipped (maps.py:1081-1083)
         const float zlo = tgt.flip_h ? __fsub_rn((float)(tgt.Mh - 1), rmax) : rmin;
@@ -511,10 +539,10 @@ static unsigned grid_for(long long items) {
 
 static int launch_scatter(const DmFuseSource* sources, int n_sources, int b, int C, const DmFuseTarget& tgt,
                           float* topdown, uint8_t* mask, float* height, int mask_inline, cudaStream_t stream,
-                          long long* next_bbox = nullptr) {
+                          long long* next_bbox = nullptr, int* next_plane_box = nullptr) {
   for (int i = 0; i < n_sources; ++i) {
-    fuse_scatter_kernel<<<plane_grid(sources[i], b * C), kScanThreads, 0, stream>>>(sources[i], b * C, C, tgt, topdown,
-                                                                                  height, mask, mask_inline, next_bbox);
+    fuse_scatter_kernel<<<plane_grid(sources[i], b * C), kScanThreads, 0, stream>>>(
+        sources[i], b * C, C, tgt, topdown, height, mask, mask_inline, next_bbox, next_plane_box);
     DM_LAUNCHED();
   }
   return DM_OK;
@@ -553,15 +581,15 @@ extern "C" int dm_fuse_bbox_seeded_i64(const DmFuseSource* sources, int32_t n_so
 extern "C" int dm_fuse_scatter_f32(const DmFuseSource* sources, int32_t n_sources, int32_t b, int32_t C,
                                    const DmFuseTarget* target, float* topdown, uint8_t* mask, float* height,
                                    void* stream_) {
-  return dm_fuse_scatter_track_f32(sources, n_sources, b, C, target, topdown, mask, height, nullptr, stream_);
+  return dm_fuse_scatter_track_f32(sources, n_sources, b, C, target, topdown, mask, height, nullptr, nullptr, stream_);
 }
 
 extern "C" int dm_fuse_scatter_track_f32(const DmFuseSource* sources, int32_t n_sources, int32_t b, int32_t C,
                                          const DmFuseTarget* target, float* topdown, uint8_t* mask, float* height,
-                                         int64_t* next_bbox, void* stream_) {
+                                         int64_t* next_bbox, int32_t* next_plane_box, void* stream_) {
   if (!target || !topdown || !mask || target->Mh <= 0 || target->Mw <= 0) return DM_EINVAL;
   if (target->reduction < 0 || target->reduction > 4) return DM_EINVAL;
-  if (target->reduction >= 2 && next_bbox) return DM_EINVAL;  // the tracked box assumes "mask = value beats fill"
+  if (target->reduction >= 2 && (next_bbox || next_plane_box)) return DM_EINVAL;  // tracking assumes "mask = beats fill"
   const int rc = check_sources(sources, n_sources, b, C);
   if (rc != DM_OK) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -575,13 +603,19 @@ extern "C" int dm_fuse_scatter_track_f32(const DmFuseSource* sources, int32_t n_
   DM_LAUNCHED();
   if (target->reduction >= 2)  // order-dependent reductions: the reference's point order, bit for bit
     return launch_ordered(sources, n_sources, b, C, *target, topdown, mask, height, stream);
-  if (next_bbox) {
+  if (next_bbox || next_plane_box) {
     if (!mask_inline) return DM_EINVAL;  // NaN fill: the mask comes from the compare pass, nothing to track
-    fuse_bbox_init<<<1, 1, 0, stream>>>(reinterpret_cast<long long*>(next_bbox));
-    DM_LAUNCHED();
+    if (next_bbox) {
+      fuse_bbox_init<<<1, 1, 0, stream>>>(reinterpret_cast<long long*>(next_bbox));
+      DM_LAUNCHED();
+    }
+    if (next_plane_box) {
+      fuse_plane_box_init<<<(b * C + 255) / 256, 256, 0, stream>>>(next_plane_box, b * C);
+      DM_LAUNCHED();
+    }
   }
   const int rs = launch_scatter(sources, n_sources, b, C, *target, topdown, mask, height, mask_inline, stream,
-                                reinterpret_cast<long long*>(next_bbox));
+                                reinterpret_cast<long long*>(next_bbox), next_plane_box);
   if (rs != DM_OK) return rs;
   if (!mask_inline) {
     changed_mask_kernel<<<grid_for(n_out), kFuseThreads, 0, stream>>>(topdown, n_out, target->fill_value, mask);

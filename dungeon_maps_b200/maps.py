@@ -914,6 +914,13 @@ def _fuse_source(m: TopdownMap, target: MapProjector, b: int, C: int, n_total: i
   src.map_res = m.proj.map_res
   base = params_dev.data_ptr()
   src.steps, src.width_offset, src.height_offset = base, base + 4 * n_step_words, base + 4 * (n_step_words + b)
+  # a map this module wrote carries, per plane, the rectangle that holds its valid cells: the passes scan that instead
+  # of the whole plane (a grown world map is mostly empty canvas)
+  tb = getattr(m, "_tracked_box", None)
+  if (tb is not None and tb.plane_box is not None and m.mask is tb.mask and tb.mask._version == tb.mask_version
+      and tb.plane_box.device == dev and tuple(m.mask.shape) == (b, C, h, w)):
+    src.plane_box = tb.plane_box.data_ptr()
+    keep.append(tb.plane_box)
   return src
 
 
@@ -979,16 +986,19 @@ def fuse_topdown_maps(*maps: List[TopdownMap], map_projector: Optional[MapProjec
   # the new map is in the global frame when the target is: pass 2 then leaves its box for the next merge
   track = bool(proj.to_global) and tgt.fill_value == tgt.fill_value and red < 2
   next_box = torch.empty((5,), dtype=torch.int64, device=dev) if track else None
+  # ... and, whatever the frame, the per-plane rectangles of its valid cells (cell coordinates: no projector involved)
+  track_planes = tgt.fill_value == tgt.fill_value and red < 2
+  plane_box = torch.empty((b * C, 4), dtype=torch.int32, device=dev) if track_planes else None
   with torch.cuda.device(dev):
     rc = lib.dm_fuse_scatter_track_f32(sources, len(live), b, C, tgt, topdown.data_ptr(), mask.data_ptr(),
-                                       nat.ptr(height), nat.ptr(next_box), nat.stream_ptr(dev))
+                                       nat.ptr(height), nat.ptr(next_box), nat.ptr(plane_box), nat.stream_ptr(dev))
   nat.check(rc, "dm_fuse_scatter_track_f32")
   new_proj = proj.clone(width_offset=width_offset, height_offset=height_offset, map_width=map_width,
                         map_height=map_height)
   out = TopdownMap(topdown_map=topdown, mask=mask, height_map=topdown if is_height_map else height,
                    map_projector=new_proj, is_height_map=is_height_map)
-  if track:
-    out._tracked_box = _TrackedBox(next_box, mask, new_proj)
+  if track or track_planes:
+    out._tracked_box = _TrackedBox(next_box, mask, new_proj, plane_box)
   return out
 
 
@@ -997,8 +1007,10 @@ class _TrackedBox():
   with what it was derived from: the mask tensor (and its in-place version counter) and the projector's
   dequantisation parameters.  Anything that no longer matches makes the map an ordinary, scanned source again."""
 
-  def __init__(self, box: torch.Tensor, mask: torch.Tensor, proj: MapProjector):
-    self.box = box
+  def __init__(self, box: Optional[torch.Tensor], mask: torch.Tensor, proj: MapProjector,
+               plane_box: Optional[torch.Tensor] = None):
+    self.box = box              # None: only the per-plane rectangles are tracked (local-frame target)
+    self.plane_box = plane_box  # (b*C, 4) int32 device: rows [min, max], columns [min, max] of every plane's valid cells
     self.mask = mask
     self.mask_version = mask._version
     self.proj = proj
@@ -1012,7 +1024,7 @@ class _TrackedBox():
 
 def _tracked_box_valid(m: TopdownMap, target: MapProjector, dev: torch.device) -> bool:
   tb = getattr(m, "_tracked_box", None)
-  if tb is None or not target.to_global:
+  if tb is None or tb.box is None or not target.to_global:
     return False
   return (m.mask is tb.mask and tb.mask._version == tb.mask_version and tb.box.device == dev
           and m.proj is tb.proj and tb.proj_key(m.proj) == tb.key and tb.key[4]
@@ -1269,7 +1281,7 @@ class MapBuilder():
                                                 get(fill, NINF), stream), "dm_fuse_canvas_init_f32")
         else:
           topdown, mask = world.topdown_map, world.mask
-        canvas = nat.DmMapRef(topdown.data_ptr(), mask.data_ptr(), Hc, Wc, Wc / 2., Hc / 2., None)
+        canvas = nat.DmMapRef(topdown.data_ptr(), mask.data_ptr(), Hc, Wc, Wc / 2., Hc / 2., None, None)
         nat.check(lib.dm_builder_step_fixed(nb.handle, depth_map.data_ptr(), pose.data_ptr(), sin.data_ptr(),
                                             cos.data_ptr(), local_top.data_ptr(), local_mask.data_ptr(), canvas,
                                             stream), "dm_builder_step_fixed")
@@ -1281,9 +1293,14 @@ class MapBuilder():
       wref = None
       if have_world:
         box = world._tracked_box.box if _tracked_box_valid(world, target, dev) else None
+        tb = getattr(world, "_tracked_box", None)
+        planes = None
+        if (tb is not None and tb.plane_box is not None and world.mask is tb.mask
+            and tb.mask._version == tb.mask_version and tb.plane_box.device == dev):
+          planes = tb.plane_box
         wref = nat.DmMapRef(world.topdown_map.data_ptr(), world.mask.data_ptr(), world.mask.shape[-2],
                             world.mask.shape[-1], float(world.proj.width_offset), float(world.proj.height_offset),
-                            nat.ptr(box))
+                            nat.ptr(box), nat.ptr(planes))
       shape = nat.DmMergeShape()
       nat.check(lib.dm_builder_plot(nb.handle, depth_map.data_ptr(), pose.data_ptr(), sin.data_ptr(), cos.data_ptr(),
                                     local_top.data_ptr(), local_mask.data_ptr(), wref, shape, stream),
@@ -1297,8 +1314,9 @@ class MapBuilder():
       mask = torch.empty((b, 1, mh, mw), dtype=torch.bool, device=dev)
       track = nb.fill == nb.fill
       next_box = torch.empty((5,), dtype=torch.int64, device=dev) if track else None
+      next_planes = torch.empty((b, 4), dtype=torch.int32, device=dev) if track else None
       out = nat.DmMapRef(topdown.data_ptr(), mask.data_ptr(), mh, mw, shape.width_offset, shape.height_offset,
-                         nat.ptr(next_box))
+                         nat.ptr(next_box), nat.ptr(next_planes))
       nat.check(lib.dm_builder_merge(nb.handle, out, stream), "dm_builder_merge")
     new_proj = target.clone(width_offset=torch.tensor([shape.width_offset], dtype=torch.float32),
                             height_offset=torch.tensor([shape.height_offset], dtype=torch.float32),
@@ -1306,7 +1324,7 @@ class MapBuilder():
     merged = TopdownMap(topdown_map=topdown, mask=mask, height_map=topdown, map_projector=new_proj,
                         is_height_map=True)
     if track:
-      merged._tracked_box = _TrackedBox(next_box, mask, new_proj)
+      merged._tracked_box = _TrackedBox(next_box, mask, new_proj, next_planes)
     # (the scatter pass still reads the old world map and the local map on the stream: torch's caching allocator
     # hands freed blocks to later work of the same stream only, so dropping the old map here is safe)
     self._world_map = merged

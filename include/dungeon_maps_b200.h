@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DM_ABI_VERSION 1
+#define DM_ABI_VERSION 2
 
 #define DM_OK 0
 #define DM_EINVAL (-1)     /* bad argument (null pointer, non-positive size, ...) */
@@ -201,6 +201,10 @@ typedef struct DmFuseSource {
   const float* height_offset; /* (b,) device */
   const DmStep* steps;   /* (b, 2) device: [source local→global or none, global→target local or none]
                             _flattened_topdown_map maps.py:2059-2060, _merge_point_clouds maps.py:2116-2117 */
+  const int32_t* plane_box; /* optional, (b*C, 4) int32 device, 16-byte aligned: per plane the rows [min, max] and
+                            columns [min, max] that hold all of its valid cells, as dm_fuse_scatter_track_f32 left
+                            them for a map it wrote (max < min: the plane has no valid cell).  The passes then scan
+                            that rectangle instead of the whole plane.  NULL: scan everything. */
 } DmFuseSource;
 
 /* Pass 1: bounding box of every valid point of every source in bins of the
@@ -237,9 +241,11 @@ int dm_fuse_scatter_f32(const DmFuseSource* sources, int32_t n_sources, int32_t 
  * for the map written here when it is later passed as a global-frame source (identity steps) with the same
  * map_res, offsets and flip_h as `target`: min_x, max_x, min_z, max_z over its valid cells, and a count that is
  * zero iff the map has no valid cell (NOT the number of valid cells).  DM_EINVAL with a NaN fill_value. */
+/* next_plane_box (device, (b*C, 4) int32, overwritten; may be NULL): per plane of the map written here, the rows and
+ * columns that hold its valid cells — DmFuseSource.plane_box of a later merge. */
 int dm_fuse_scatter_track_f32(const DmFuseSource* sources, int32_t n_sources, int32_t b, int32_t C,
                               const DmFuseTarget* target, float* topdown, uint8_t* mask, float* height,
-                              int64_t* next_bbox, void* stream);
+                              int64_t* next_bbox, int32_t* next_plane_box, void* stream);
 
 /* Opt-in fixed-canvas merge (no reference call does this — the closest is
  * project(..., canvas=, canvas_masks=), maps.py:1089-1173 with utils.py:462-491, whose semantics it keeps):
@@ -309,6 +315,7 @@ typedef struct DmMapRef {
   float width_offset, height_offset;
   int64_t* box; /* device, 5 x int64: as a source, the box dm_fuse_scatter_track_f32 left for this map (NULL: scan
                    it); as the output of dm_builder_merge, where that box is written (NULL: not tracked) */
+  int32_t* plane_box; /* device, (b, 4) int32: the per-plane rectangles of valid cells, same roles (NULL: none) */
 } DmMapRef;
 
 /* Size and offsets of the canvas the merge needs (_compute_new_shape_and_offsets, maps.py:2146-2179). */

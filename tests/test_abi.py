@@ -34,7 +34,7 @@ def test_library_loads_and_exports_every_declared_symbol():
   for name in _declared_functions():
     assert hasattr(handle, name), f"libdungeon_maps_b200.so does not export {name}"
   lib = nat.lib()
-  assert lib.dm_abi_version() == nat.ABI_VERSION == 1
+  assert lib.dm_abi_version() == nat.ABI_VERSION == 2
   assert b"sm_100a" in lib.dm_build_info()
   assert lib.dm_launch_count() >= 0
 
@@ -55,7 +55,7 @@ def test_struct_layouts_match_the_header():
   assert ctypes.sizeof(nat.DmFlowCfg) == ctypes.sizeof(orc.FlowCfg) == 15 * 4
   for (n1, t1), (n2, t2) in zip(nat.DmProjCfg._fields_, orc.ProjCfg._fields_):
     assert n1 == n2 and ctypes.sizeof(t1) == ctypes.sizeof(t2)
-  assert ctypes.sizeof(nat.DmFuseSource) == 3 * 8 + 2 * 8 + 4 * 4 + 3 * 8
+  assert ctypes.sizeof(nat.DmFuseSource) == 3 * 8 + 2 * 8 + 4 * 4 + 4 * 8
   assert ctypes.sizeof(nat.DmFuseTarget) == 8 * 4
   # every mirrored struct against sizeof() inside the compiled library
   lib = nat.lib()

@@ -123,3 +123,42 @@ def test_native_step_vs_oracle_and_fallbacks():
   nb.step(depth, cam_pose=poses[0], merge=False, **base)                                # plot only
   assert len(nb._handles) == n_handles, "a fallback case created a native handle"
   assert_workspaces_clean()
+
+
+def test_plane_boxes_equal_the_mask_extents_and_a_full_scan():
+  """The per-plane rectangles the scatter pass leaves next to a map it wrote (DmFuseSource.plane_box) are exactly the
+  extents of that plane's valid cells, a merge that scans only those rectangles equals a merge that scans whole
+  planes, and an in-place edit of the mask drops them."""
+  b, T, H, W = 3, 4, 120, 160
+  poses = _walk(b, T + 1, seed=11)
+  gb = _builder(False)   # general path: fuse_topdown_maps
+  kw = dict(to_global=False, width_offset=60., height_offset=0., map_width=120, map_height=120)
+  for t in range(T):
+    depth = synth.room_depth(b, H, W, HFOV, PITCH, 0.88, poses[t].cuda(), seed=11, half=6.0, device="cuda")
+    gb.step(depth, cam_pose=poses[t], **kw)
+  wm = gb.world_map
+  tb = wm._tracked_box
+  assert tb.plane_box is not None and tuple(tb.plane_box.shape) == (b, 4)
+  boxes = tb.plane_box.cpu().numpy()
+  mask = npy(wm.mask)
+  for p in range(b):
+    rows, cols = np.nonzero(mask[p, 0])
+    assert list(boxes[p]) == [rows.min(), rows.max(), cols.min(), cols.max()], f"plane {p}"
+  depth = synth.room_depth(b, H, W, HFOV, PITCH, 0.88, poses[T].cuda(), seed=11, half=6.0, device="cuda")
+  local = gb.plot(depth, cam_pose=poses[T], **kw)
+  target = gb.proj.clone(cam_pose=poses[T])
+  boxed = dmap.fuse_topdown_maps(wm, local, map_projector=target)
+  planes, tb.plane_box = tb.plane_box, None
+  full = dmap.fuse_topdown_maps(wm, local, map_projector=target)
+  tb.plane_box = planes
+  _same_map(boxed, full, "boxed scan vs full scan")
+  wm.mask[0, 0, 0, 0] = True          # in-place edit: the rectangles no longer describe the mask
+  edited = dmap.fuse_topdown_maps(wm, local, map_projector=target)
+  assert bool(edited.mask.any()) and edited.mask.sum() >= full.mask.sum()
+  # the same through the C step object: world maps of the native path carry the rectangles too
+  nb = _builder(True)
+  for t in range(T):
+    depth = synth.room_depth(b, H, W, HFOV, PITCH, 0.88, poses[t].cuda(), seed=11, half=6.0, device="cuda")
+    nb.step(depth, cam_pose=poses[t], **kw)
+  assert_same(npy(nb.world_map._tracked_box.plane_box), boxes, "native path plane boxes")
+  assert_workspaces_clean()
