@@ -36,7 +36,17 @@ def host_f32(x, shape_tail=()) -> torch.Tensor:
   return t.reshape(want)
 
 
+_scalar_rows = {}
+
+
 def per_sample(x, b: int, shape_tail=(), what: str = "argument") -> torch.Tensor:
+  if type(x) is float and shape_tail == ():  # projector defaults repeat call after call
+    hit = _scalar_rows.get((x, b))
+    if hit is None:
+      if len(_scalar_rows) > 256:
+        _scalar_rows.clear()
+      hit = _scalar_rows[(x, b)] = host_f32(x, ()).expand((b,))
+    return hit
   t = host_f32(x, shape_tail)
   if t.shape[0] == b:
     return t
@@ -224,10 +234,10 @@ def pose_cfg(pitch: torch.Tensor, cam_h: torch.Tensor, n_points: int) -> "nat.Dm
 
 
 def yaw_sin_cos(pose: torch.Tensor):
-  """sin / cos of the yaw column after the |a| <= ANGLE_EPS clamp, with the reference's torch-CPU ops
-  (utils.py:323-326); contiguous float32 CPU tensors."""
+  """sin / cos of the yaw column with the reference's torch-CPU ops (utils.py:325-326); contiguous float32 CPU tensors.
+  The |a| <= ANGLE_EPS → 0 clamp (utils.py:323-324) is applied by the C packers, which replace the pair by exactly
+  (0, 1) = (sin 0, cos 0) for such angles."""
   yaw = pose[:, 2]
-  yaw = torch.where(torch.abs(yaw) > ANGLE_EPS, yaw, torch.zeros((), dtype=torch.float32))
   return torch.sin(yaw), torch.cos(yaw)
 
 

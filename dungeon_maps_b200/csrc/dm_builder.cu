@@ -124,7 +124,7 @@ static int upload_params(DmBuilder* h, const float* pose, const float* sin_yaw, 
   int fast = h->local_fast ? (c.plot_to_global ? 2 : 1) : 0;
   for (int i = 0; i < b; ++i) {
     float Ry[9];
-    yaw_matrix(h->pose, sin_yaw[i], cos_yaw[i], Ry);  // utils.py:303-327 for the axis (0, 1, 0)
+    yaw_matrix(h->pose, pose[3 * i + 2], sin_yaw[i], cos_yaw[i], Ry);  // utils.py:303-327 for the axis (0, 1, 0)
     const float ty[3] = {pose[3 * i + 0], 0.0f, pose[3 * i + 1]};  // maps.py:889-891
     const float tl[3] = {0.0f, c.cam_height, 0.0f};                // maps.py:795-797
     float* sp = samples + (size_t)i * kSampleWords;

@@ -33,7 +33,7 @@ extern int64_t g_launches;  // defined in dm_api.cu
 constexpr int kNumSMs = 148;  // B200
 
 // ---- host-side parameter packing (dm_params.cu) --------------------------------------------------
-void yaw_matrix(const DmPoseCfg& c, float sin_a, float cos_a, float* R);  // utils.py:318-327 for the axis (0, 1, 0)
+void yaw_matrix(const DmPoseCfg& c, float yaw, float sin_yaw, float cos_yaw, float* R);  // utils.py:318-327, axis (0, 1, 0)
 void put_step(float* words, int kind, const float* R, const float* t, int fused);
 bool local_step_is_fast(const DmPoseCfg& c);  // the pitch step has the structure DmProjCfg.fast_steps >= 1 promises
 bool yaw_step_is_fast(const float* R);

@@ -2,17 +2,21 @@
 // same blocks with torch / numpy — correct, but 0.1-0.25 ms of interpreter time per call, which is what a caller
 // with a fresh pose every frame pays (bench.py rotates poses: the ego-flow step went from 0.19 ms, kernel-bound, to
 // 0.29 ms, host-bound).  Nothing here touches the device, and nothing here calls sin / cos: the yaw rotation is formed
-// from sin / cos values the caller computed with the reference's own torch-CPU ops (utils.py:323-326, the last ulp
-// matters), by the float32 operations of utils.py:318-327 in the reference's order:
+// from sin / cos values the caller computed with the reference's own torch-CPU ops (utils.py:325-326, the last ulp
+// matters; of the raw yaw — the |a| <= 0.001 clamp of utils.py:323-324 is applied here), by the float32 operations of
+// utils.py:318-327 in the reference's order:
 //     R = (I + sin(a) S) + (1 - cos(a)) S²        S, S² built by the caller exactly as utils.py:303-318 does.
 // tests/test_abi.py checks these blocks byte for byte against _params.py and the oracle.
+#include <cmath>
 #include <cstring>
 
 #include "dm_common.cuh"
 
 namespace dm {
 
-void yaw_matrix(const DmPoseCfg& c, float s, float cos_a, float* R) {
+void yaw_matrix(const DmPoseCfg& c, float yaw, float s, float cos_a, float* R) {
+  // utils.py:323-324: |angle| <= 0.001 rotates by exactly 0 — sin(0) = 0, cos(0) = 1, whatever the caller computed
+  if (!(fabsf(yaw) > 0.001f)) { s = 0.0f; cos_a = 1.0f; }
   const float one_minus_cos = 1.0f - cos_a;
   for (int k = 0; k < 9; ++k) {
     const float eye = (k == 0 || k == 4 || k == 8) ? 1.0f : 0.0f;
@@ -59,7 +63,7 @@ extern "C" int dm_pack_proj_samples(const DmPoseCfg* cfg, const float* pose, con
     put_step(sp, DM_STEP_ROT_THEN_ADD, cfg->pitch_R, tl, cfg->fused);
     if (to_global) {
       float Ry[9];
-      yaw_matrix(*cfg, sin_yaw[i], cos_yaw[i], Ry);
+      yaw_matrix(*cfg, pose[3 * i + 2], sin_yaw[i], cos_yaw[i], Ry);
       const float ty[3] = {pose[3 * i + 0], 0.0f, pose[3 * i + 1]};  // maps.py:889-891
       put_step(sp + 16, DM_STEP_ROT_THEN_ADD, Ry, ty, cfg->fused);
       if (fast == 2 && !yaw_step_is_fast(Ry)) fast = 0;
@@ -79,7 +83,7 @@ extern "C" int dm_pack_flow_samples(const DmPoseCfg* cfg, const float* pose, con
   for (int i = 0; i < b; ++i) {
     float* sp = reinterpret_cast<float*>(out + i);
     float Ry[9];
-    yaw_matrix(*cfg, sin_yaw[i], cos_yaw[i], Ry);
+    yaw_matrix(*cfg, pose[3 * i + 2], sin_yaw[i], cos_yaw[i], Ry);
     const float ty[3] = {pose[3 * i + 0], 0.0f, pose[3 * i + 1]};
     put_step(sp, DM_STEP_ROT_THEN_ADD, cfg->pitch_R, tl, cfg->fused);          // camera_to_local_space
     put_step(sp + 16, DM_STEP_ROT_THEN_ADD, Ry, ty, cfg->fused);               // local_to_global_space(trans_pose)

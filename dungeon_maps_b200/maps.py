@@ -1256,10 +1256,8 @@ class MapBuilder():
     if nb is None:
       nb = self._handles[key] = _NativeBuilder(proj, key, dev)
     pose = prm.per_sample(cam_pose, b, (3,), "cam_pose").contiguous()
-    # utils.py:323-326 with the reference's own torch-CPU ops (the last ulp of sin / cos matters)
-    yaw = pose[:, 2]
-    yaw = torch.where(torch.abs(yaw) > prm.ANGLE_EPS, yaw, torch.zeros((), dtype=torch.float32))
-    sin, cos = torch.sin(yaw), torch.cos(yaw)
+    # utils.py:325-326 with the reference's own torch-CPU ops (the last ulp of sin / cos matters)
+    sin, cos = prm.yaw_sin_cos(pose)
     local_top = torch.empty((b, 1, Mh, Mw), dtype=torch.float32, device=dev)
     local_mask = torch.empty((b, 1, Mh, Mw), dtype=torch.bool, device=dev)
     lib = nat.lib()

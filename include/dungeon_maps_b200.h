@@ -262,9 +262,10 @@ int dm_fuse_canvas_init_f32(float* topdown, uint8_t* mask, float* height, int64_
 
 /* ---- per-sample parameter blocks packed on the host, in C ------------------------------------------------------
  * What the kernels need per sample derives from a pose (x, z, yaw) and per-call constants.  These two functions are
- * pure host code (no device work, no sin / cos): the caller supplies sin(yaw) / cos(yaw) computed with the
- * reference's own torch-CPU ops after the |a| <= 0.001 clamp (utils.py:323-326), and the yaw rotation is formed as
- * (I + sin S) + (1 - cos) S² in float32, the reference's operation order (utils.py:318-327). */
+ * pure host code (no device work, no sin / cos): the caller supplies sin(yaw) / cos(yaw) of the raw yaw computed with
+ * the reference's own torch-CPU ops (utils.py:325-326; the |a| <= 0.001 → 0 clamp of utils.py:323-324 is applied
+ * here: sin = 0, cos = 1), and the yaw rotation is formed as (I + sin S) + (1 - cos) S² in float32, the reference's
+ * operation order (utils.py:318-327). */
 typedef struct DmPoseCfg {
   float pitch_R[9];      /* camera_to_local_space: rotation about x by cam_pitch (maps.py:789-793), host-built */
   float pitch_back_R[9]; /* local_to_camera_space: rotation about x by -cam_pitch (maps.py:838-842); flow only */
@@ -328,7 +329,7 @@ typedef struct DmMergeShape {
 int dm_builder_create(const DmBuilderCfg* cfg, int32_t device, DmBuilder** out);
 void dm_builder_destroy(DmBuilder* builder);
 /* Step, first half: plots the local maps of `depth` (b, 1, H, W) at `pose` (HOST, (b, 3) = x, z, yaw; sin_yaw /
- * cos_yaw: HOST (b,), of the yaw after the |a| <= 0.001 clamp of utils.py:323-324) into local_topdown / local_mask
+ * cos_yaw: HOST (b,), of the raw yaw: the |a| <= 0.001 clamp of utils.py:323-324 is applied inside) into local_topdown / local_mask
  * (b, 1, Mh, Mw), reduces the bounding box of world ∪ local and BLOCKS until it is on the host (the reference's
  * .item() sync): `shape` says what to allocate.  world may be NULL (empty world map). */
 int dm_builder_plot(DmBuilder* builder, const float* depth, const float* pose, const float* sin_yaw,
