@@ -386,6 +386,7 @@ class BuilderWorkload:
     return {"workload": self.name, "scene": "room (66 m hall, 32 walkers)", "envs_per_gpu": self.B,
             "episode_steps": self.EPISODE, "world_cells_at_end": getattr(self, "world_shape", None),
             "input_rotation": "every step has its own depth frames and poses (100-step walk)",
+            "warmup": "one whole episode (the allocator's cached blocks serve the timed one, like any episode after the first)",
             "parallelism": f"environment-sharded x{world}, no collective",
             "l2": "world maps (>1 GB per step) are larger than the 126 MB L2; no flush needed"}
 
@@ -743,7 +744,9 @@ def run_extras(args, dev, rank, world, barrier, max_over_ranks, peak):
         shared_frames = wl.frames
       else:
         wl.setup(dev, rank)
-      for _ in range(3):
+      # MapBuilder: one whole episode of warm-up — the timed episode then finds the allocator's cached blocks, as every
+      # episode after the first of a long-running mapping loop does
+      for _ in range(wl.EPISODE if isinstance(wl, BuilderWorkload) else 3):
         wl.step()
       ms, value, algo = time_steps(wl, steps, barrier, max_over_ranks, world)
       out[key] = {"value": value, "unit": wl.unit, "ms_per_step": ms, "steps": steps,
@@ -796,6 +799,8 @@ def run_ours(args):
     raise SystemExit("proj5_job is reported under `extra` of the default line (python bench.py)")
   wl.setup(dev, rank)  # every rank owns its own environments (weak scaling, no data-path collective)
   warmup = max(args.warmup, 3)
+  if isinstance(wl, BuilderWorkload):
+    warmup = max(warmup, wl.EPISODE)  # one whole episode: see run_extras
   for _ in range(warmup):
     wl.step()
   if hasattr(wl, "reset_counters"):

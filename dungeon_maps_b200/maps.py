@@ -71,6 +71,19 @@ def _workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
   return ws
 
 
+def _alloc_canvas(shape: Tuple[int, ...], dtype: torch.dtype, dev: torch.device) -> torch.Tensor:
+  """A fresh, contiguous tensor of `shape` for a map whose size is data dependent (the merged world map grows step by
+  step, maps.py:2171-2178).  The storage is rounded up to a size class (a quarter of a power of two apart): torch's
+  caching allocator can then hand the block a merge freed two steps ago to the next, slightly larger map instead of
+  going to cudaMalloc — a device-wide synchronising call, twice per step — for every new size."""
+  n = int(np.prod(shape))
+  if n < (1 << 18):
+    return torch.empty(shape, dtype=dtype, device=dev)
+  top = 1 << (n - 1).bit_length()          # smallest power of two >= n
+  cap = next(c for c in (top // 2 + k * (top // 8) for k in range(1, 5)) if c >= n)
+  return torch.empty((cap,), dtype=dtype, device=dev)[:n].view(shape)
+
+
 def release_workspaces() -> None:
   """Frees the cached accumulation rings (one per device and stream that projected something) and the library's
   own scratch of the host-buffer entries."""
@@ -980,9 +993,9 @@ def fuse_topdown_maps(*maps: List[TopdownMap], map_projector: Optional[MapProjec
   tgt.width_offset, tgt.height_offset = float(width_offset), float(height_offset)
   tgt.fill_value = get(fill_value, proj.fill_value, NINF)
   tgt.reduction = red
-  topdown = torch.empty((b, C, map_height, map_width), dtype=torch.float32, device=dev)
-  mask = torch.empty((b, C, map_height, map_width), dtype=torch.bool, device=dev)
-  height = None if is_height_map else torch.empty_like(topdown)
+  topdown = _alloc_canvas((b, C, map_height, map_width), torch.float32, dev)
+  mask = _alloc_canvas((b, C, map_height, map_width), torch.bool, dev)
+  height = None if is_height_map else _alloc_canvas((b, C, map_height, map_width), torch.float32, dev)
   # the new map is in the global frame when the target is: pass 2 then leaves its box for the next merge
   track = bool(proj.to_global) and tgt.fill_value == tgt.fill_value and red < 2
   next_box = torch.empty((5,), dtype=torch.int64, device=dev) if track else None
@@ -1308,8 +1321,8 @@ class MapBuilder():
                                      map_projector=target)
         return local
       mh, mw = shape.map_height, shape.map_width
-      topdown = torch.empty((b, 1, mh, mw), dtype=torch.float32, device=dev)
-      mask = torch.empty((b, 1, mh, mw), dtype=torch.bool, device=dev)
+      topdown = _alloc_canvas((b, 1, mh, mw), torch.float32, dev)
+      mask = _alloc_canvas((b, 1, mh, mw), torch.bool, dev)
       track = nb.fill == nb.fill
       next_box = torch.empty((5,), dtype=torch.int64, device=dev) if track else None
       next_planes = torch.empty((b, 4), dtype=torch.int32, device=dev) if track else None

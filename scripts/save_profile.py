@@ -7,6 +7,7 @@
 usage: scripts/save_profile.py <run-tag> [<profile-tag>]      e.g. save_profile.py r1a r01
 """
 import csv
+import glob
 import io
 import json
 import os
@@ -44,6 +45,8 @@ def save_launches(src, dst, cmd):
 
 save_launches(os.path.join(G, f"launches_{run}.csv"), os.path.join(P, f"{tag}_launches.csv"),
               "python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 2")
+save_launches(os.path.join(G, f"launches_labels_{run}.csv"), os.path.join(P, f"{tag}_launches_labels.csv"),
+              "python bench.py --workload proj_labels --steps 3 --warmup 3 --no-cpu-baseline --no-extra --e2e-steps 2")
 save_launches(os.path.join(G, f"launches_flow_{run}.csv"), os.path.join(P, f"{tag}_launches_flow.csv"),
               "python bench.py --workload flow --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 2")
 save_launches(os.path.join(G, f"launches_builder_{run}.csv"), os.path.join(P, f"{tag}_launches_builder.csv"),
@@ -64,7 +67,8 @@ def raw_rows(rep):
 
 traffic_path = os.path.join(P, "traffic.json")
 traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
-for what, pattern, n_kernels in (("proj", "proj_ws", 1), ("flow", "flow_", 1), ("fuse", "fuse_|changed_", 6)):
+for what, pattern, n_kernels in (("proj", "proj_ws", 1), ("labels", "proj_lbl", 1), ("flow", "flow_", 1),
+                                 ("fuse", "fuse_|changed_", 6)):
   rep = os.path.join(G, f"prof_{what}_{run}.ncu-rep")
   if not os.path.exists(rep):
     continue
@@ -79,6 +83,10 @@ for what, pattern, n_kernels in (("proj", "proj_ws", 1), ("flow", "flow_", 1), (
     r = rows[0]
     traffic.update({"kernel": r["kernel"], "run": run, "dram_bytes_read": r["rd"], "dram_bytes_write": r["wr"],
                     "dram_bytes_per_step": r["rd"] + r["wr"], "duration_us_under_ncu": r["us"]})
+  elif what == "labels":
+    r = rows[0]
+    traffic["proj_labels"] = {"kernel": r["kernel"], "run": run, "dram_bytes_read": r["rd"], "dram_bytes_write": r["wr"],
+                              "dram_bytes_per_step": r["rd"] + r["wr"], "duration_us_under_ncu": r["us"]}
   elif what == "flow":
     r = rows[0]
     traffic["flow"] = {"kernel": r["kernel"], "run": run, "dram_bytes_per_step": r["rd"] + r["wr"],
@@ -96,7 +104,17 @@ for what, pattern, n_kernels in (("proj", "proj_ws", 1), ("flow", "flow_", 1), (
   print(what, "traffic ok")
 json.dump(traffic, open(traffic_path, "w"), indent=1)
 
-for name in ("room", "iid", "flow", "builder", "builder_fixed", "proj5"):
+for name in ("default", "room", "room20", "iid", "labels", "labels20", "labels_iid", "flow", "builder", "builder_fixed",
+             "proj5", "n2", "ref"):
   b = os.path.join(G, f"bench_{name}_{run}.json")
   if os.path.exists(b) and os.path.getsize(b):
     shutil.copy(b, os.path.join(P, f"{tag}_bench_{name}.json"))
+
+# compute-sanitizer logs of the small parity cases, host backtraces dropped
+for tool in ("memcheck", "racecheck"):
+  src = os.path.join(G, f"sanitizer_{tool}_{run}.log")
+  if os.path.exists(src):
+    keep = [l for l in open(src, errors="replace") if "Host Frame" not in l and "frame #" not in l]
+    with open(os.path.join(P, f"{tag}_sanitizer_{tool}.log"), "w") as f:
+      f.write(f"# compute-sanitizer --tool {tool} --error-exitcode 9 python -m pytest <7 small parity cases, see scripts/r02_check.sh>  (run {run}; host frames dropped)\n")
+      f.writelines(keep[:400])
