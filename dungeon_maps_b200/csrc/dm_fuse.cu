@@ -616,39 +616,21 @@ fuse_translate_kernel(const __grid_constant__ DmFuseSource src, int planes, cons
       sc0 = max(sc0, c0); sc1 = min(sc1, c1); sr0 = max(sr0, r0); sr1 = min(sr1, r1);
       const int ww = sc1 - sc0 + 1, wh = sr1 - sr0 + 1;
       if (ww > 0 && wh > 0) {
-        // kTileBatch cells per thread and round, mask byte and height of all of them in flight before the first is
-        // looked at: one memory round trip per round (cell by cell the loop was latency-bound: 116 us, ncu r02i)
-        constexpr int kTileBatch = 8;
-        const int total_w = ww * wh;
-        for (int base = 0; base < total_w; base += kTileThreads * kTileBatch) {
-          uint8_t mk[kTileBatch];
-          float hv[kTileBatch];
-          int cells[kTileBatch];
-#pragma unroll
-          for (int k = 0; k < kTileBatch; ++k) {
-            const int i = base + k * kTileThreads + tid;
-            const bool in = i < total_w;
-            const int rr = sr0 + (in ? i / ww : 0), cc = sc0 + (in ? i - (i / ww) * ww : 0);
-            cells[k] = in ? rr * w + cc : -1;
-            mk[k] = in ? __ldg(mplane + cells[k]) : (uint8_t)0;
-            hv[k] = in ? __ldg(hplane + cells[k]) : 0.0f;
-          }
-#pragma unroll
-          for (int k = 0; k < kTileBatch; ++k) {
-            if (!mk[k]) continue;
-            const int rr = cells[k] / w, cc = cells[k] - rr * w;
-            float xf, zf;
-            target_of(rr, cc, &xf, &zf);
-            if (!(xf >= (float)C0 && xf <= (float)C1 && zf >= (float)R0 && zf <= (float)R1)) continue;  // another tile's
-            const float v = hv[k];  // a height map: the value is the point's y (maps.py:2214-2216)
-            if (v == v) {
-              const int o = ((int)zf - R0) * kTileW + ((int)xf - C0);
-              if (tgt.reduction) atomic_min_f32(s_val + o, v); else atomic_max_f32(s_val + o, v);
-              if (better(v, tgt.fill_value, tgt.reduction)) {
-                s_msk[o] = 1;
-                pcmin = fminf(pcmin, xf); pcmax = fmaxf(pcmax, xf);
-                prmin = fminf(prmin, zf); prmax = fmaxf(prmax, zf);
-              }
+        for (int i = tid; i < ww * wh; i += kTileThreads) {
+          const int rr = sr0 + i / ww, cc = sc0 + (i - (i / ww) * ww);
+          const int cell = rr * w + cc;
+          if (!mplane[cell]) continue;
+          float xf, zf;
+          target_of(rr, cc, &xf, &zf);
+          if (!(xf >= (float)C0 && xf <= (float)C1 && zf >= (float)R0 && zf <= (float)R1)) continue;  // another tile's
+          const float v = hplane[cell];  // a height map: the value is the point's y (maps.py:2214-2216)
+          if (v == v) {
+            const int o = ((int)zf - R0) * kTileW + ((int)xf - C0);
+            if (tgt.reduction) atomic_min_f32(s_val + o, v); else atomic_max_f32(s_val + o, v);
+            if (better(v, tgt.fill_value, tgt.reduction)) {
+              s_msk[o] = 1;
+              pcmin = fminf(pcmin, xf); pcmax = fmaxf(pcmax, xf);
+              prmin = fminf(prmin, zf); prmax = fmaxf(prmax, zf);
             }
           }
         }
@@ -727,7 +709,7 @@ static int launch_scatter(const DmFuseSource* sources, int n_sources, int b, int
     const DmFuseSource& s0 = sources[0];
     if (s0.translate_only && !s0.values && !height && s0.map_res == tgt.map_res && (s0.flip_h != 0) == (tgt.flip_h != 0) &&
         s0.height_cstride == (long long)s0.h * s0.w) {
-      dim3 grid(64, (unsigned)(b < 65535 ? b : 65535));  // CTAs per plane: each takes every 64th tile of the plane's region
+      dim3 grid(16, (unsigned)(b < 65535 ? b : 65535));
       fuse_translate_kernel<<<grid, kTileThreads, 0, stream>>>(s0, b, tgt, topdown, mask, next_bbox, next_plane_box);
       DM_LAUNCHED();
       first = 1;
