@@ -49,7 +49,6 @@ class DmFuseSource(ctypes.Structure):
     ("height_bstride", c_int64), ("height_cstride", c_int64),
     ("h", c_int32), ("w", c_int32), ("flip_h", c_int32), ("map_res", c_float),
     ("width_offset", c_void_p), ("height_offset", c_void_p), ("steps", c_void_p), ("plane_box", c_void_p),
-    ("translate_only", c_int32), ("_pad", c_int32),
   ]
 
 

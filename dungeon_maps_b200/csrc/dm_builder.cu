@@ -171,8 +171,6 @@ static void make_sources(DmBuilder* h, char* d_base, float* local_topdown, uint8
     s.h = world->h; s.w = world->w; s.flip_h = c.proj.flip_h; s.map_res = c.proj.map_res;
     s.width_offset = wwoff; s.height_offset = whoff; s.steps = reinterpret_cast<const DmStep*>(wsteps);
     s.plane_box = world->plane_box;
-    s.translate_only = 1;  // global-frame world map into a global-frame target: no transform step
-    s._pad = 0;
   }
   DmFuseSource& s = h->src[h->n_src++];
   s.height = local_topdown; s.values = nullptr; s.mask = local_mask;
@@ -180,8 +178,6 @@ static void make_sources(DmBuilder* h, char* d_base, float* local_topdown, uint8
   s.h = c.proj.Mh; s.w = c.proj.Mw; s.flip_h = c.proj.flip_h; s.map_res = c.proj.map_res;
   s.width_offset = lwoff; s.height_offset = lhoff; s.steps = reinterpret_cast<const DmStep*>(lsteps);
   s.plane_box = nullptr;
-  s.translate_only = c.plot_to_global ? 1 : 0;
-  s._pad = 0;
 }
 
 extern "C" int dm_builder_plot(DmBuilder* h, const float* depth, const float* pose, const float* sin_yaw,

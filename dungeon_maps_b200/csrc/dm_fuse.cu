@@ -537,185 +537,10 @@ static unsigned grid_for(long long items) {
   return (unsigned)blocks;
 }
 
-// ---- translate-only sources: gather by target tile -------------------------------------------------------------
-// A world map merged into the next world map (same frame, same resolution, no transform step: DmFuseSource.
-// translate_only) moves by a whole number of cells, give or take the rounding of the re-quantisation
-// (maps.py:1004-1013 after maps.py:1081-1086).  The generic scatter pass spends its time on where the cells LAND, not
-// on finding them: 1.6 M atomic maxima + mask bytes at the end of the config-4 walk, spread over a 0.72 GB canvas that
-// the fill kernel has just streamed through L2 (79 us with or without the per-plane rectangles, ncu r02h).  Here a
-// CTA owns a TARGET tile (kTileH x kTileW cells): it initialises the tile in shared memory (fill, mask 0), walks the
-// source window that can land in it (the tile moved back by the plane's offset difference, + a halo for the
-// rounding), computes every valid cell's target with the SAME per-cell arithmetic as the scatter kernel, folds the
-// ones that land inside with shared-memory atomics, and writes the whole tile once — coalesced.  Only tiles that
-// intersect the source's rectangle of valid cells (plane_box; the whole plane without one) are visited; the rest of
-// the canvas keeps what the fill kernel wrote.  Must run right after the fill kernel and before any other source.
-constexpr int kTileH = 32, kTileW = 128, kTileHalo = 2, kTileThreads = 256;
-
-__global__ void __launch_bounds__(kTileThreads)
-fuse_translate_kernel(const __grid_constant__ DmFuseSource src, int planes, const DmFuseTarget tgt,
-                      float* __restrict__ topdown, uint8_t* __restrict__ mask, long long* __restrict__ next_bbox,
-                      int* __restrict__ next_plane_box) {
-  __shared__ float s_val[kTileH * kTileW];
-  __shared__ uint8_t s_msk[kTileH * kTileW];
-  __shared__ PlaneCtx ctx;
-  __shared__ float s_red[kTileThreads / 32][4];
-  const long long M = (long long)tgt.Mh * tgt.Mw;
-  const int n = src.h * src.w, w = src.w, tid = threadIdx.x;
-  float cmin = INFINITY, cmax = -INFINITY, rmin = INFINITY, rmax = -INFINITY;  // over everything this CTA marks
-  for (int plane = blockIdx.y; plane < planes; plane += gridDim.y) {
-    __syncthreads();
-    if (tid < 32) reinterpret_cast<uint32_t*>(&ctx.step0)[tid] = 0u;  // translate_only: both steps are NONE
-    if (tid == 0) { ctx.woff = src.width_offset[plane]; ctx.hoff = src.height_offset[plane]; }  // C == 1: plane == sample
-    __syncthreads();
-    int r0 = 0, r1 = src.h - 1, c0 = 0, c1 = w - 1;
-    if (src.plane_box) {
-      const int4 bx = __ldg(reinterpret_cast<const int4*>(src.plane_box) + plane);
-      r0 = max(bx.x, 0); r1 = min(bx.y, src.h - 1); c0 = max(bx.z, 0); c1 = min(bx.w, w - 1);
-    }
-    if (r1 < r0 || c1 < c0) continue;  // block-uniform
-    // where the rectangle's corners land (exact per-cell arithmetic), widened by the halo: the target region
-    const float* hplane = src.height + (long long)plane * src.height_bstride;
-    const uint8_t* mplane = src.mask + (long long)plane * n;
-    auto target_of = [&](int r, int c, float* xf, float* zf) {
-      float zb = (float)r;  // maps.py:1081-1086 (source_point without the height)
-      if (src.flip_h) zb = __fsub_rn((float)(src.h - 1), zb);
-      const float pz = __fmul_rn(__fsub_rn(zb, ctx.hoff), src.map_res);
-      const float px = __fmul_rn(__fsub_rn((float)c, ctx.woff), src.map_res);
-      quantize_f(px, pz, tgt.width_offset, tgt.height_offset, tgt.map_res, tgt.Mh, tgt.flip_h, xf, zf);
-    };
-    float xa, za, xb, zb2;
-    target_of(r0, c0, &xa, &za);
-    target_of(r1, c1, &xb, &zb2);
-    if (!(xa == xa && xb == xb && za == za && zb2 == zb2)) continue;  // NaN offsets: nothing lands anywhere
-    // columns grow with c; rows grow with r when source and target flip alike, else they fall
-    const float tx0 = fminf(xa, xb) - kTileHalo, tx1 = fmaxf(xa, xb) + kTileHalo;
-    const float tz0 = fminf(za, zb2) - kTileHalo, tz1 = fmaxf(za, zb2) + kTileHalo;
-    const int tc0 = (int)fmaxf(tx0, 0.0f), tc1 = (int)fminf(tx1, (float)(tgt.Mw - 1));
-    const int tr0 = (int)fmaxf(tz0, 0.0f), tr1 = (int)fminf(tz1, (float)(tgt.Mh - 1));
-    if (tc1 < tc0 || tr1 < tr0) continue;
-    const int tiles_c = (tc1 - tc0) / kTileW + 1, tiles_r = (tr1 - tr0) / kTileH + 1;
-    // cell shift source → target (rounded; the halo absorbs the rest): dc = xa - c0 and dr likewise
-    const int dc = (int)(xa - (float)c0);
-    const bool rows_rise = zb2 >= za;
-    const int dr = rows_rise ? (int)(za - (float)r0) : 0;  // falling rows: handled through the window's other end
-    const float* tplane_dummy = nullptr; (void)tplane_dummy;
-    float pcmin = INFINITY, pcmax = -INFINITY, prmin = INFINITY, prmax = -INFINITY;
-    for (int t = blockIdx.x; t < tiles_c * tiles_r; t += gridDim.x) {
-      const int ty = t / tiles_c, tx = t - ty * tiles_c;
-      const int R0 = tr0 + ty * kTileH, C0 = tc0 + tx * kTileW;                       // tile origin (target cells)
-      const int R1 = min(R0 + kTileH - 1, tgt.Mh - 1), C1 = min(C0 + kTileW - 1, tgt.Mw - 1);
-      __syncthreads();  // the previous tile has been written out
-      for (int i = tid; i < kTileH * kTileW; i += kTileThreads) { s_val[i] = tgt.fill_value; s_msk[i] = 0; }
-      __syncthreads();
-      // source window of this tile
-      int sc0 = C0 - dc - kTileHalo, sc1 = C1 - dc + kTileHalo, sr0, sr1;
-      if (rows_rise) { sr0 = R0 - dr - kTileHalo; sr1 = R1 - dr + kTileHalo; }
-      else {  // zf = za - (r - r0) up to rounding
-        sr0 = r0 + (int)(za - (float)R1) - kTileHalo; sr1 = r0 + (int)(za - (float)R0) + kTileHalo;
-      }
-      sc0 = max(sc0, c0); sc1 = min(sc1, c1); sr0 = max(sr0, r0); sr1 = min(sr1, r1);
-      const int ww = sc1 - sc0 + 1, wh = sr1 - sr0 + 1;
-      if (ww > 0 && wh > 0) {
-        for (int i = tid; i < ww * wh; i += kTileThreads) {
-          const int rr = sr0 + i / ww, cc = sc0 + (i - (i / ww) * ww);
-          const int cell = rr * w + cc;
-          if (!mplane[cell]) continue;
-          float xf, zf;
-          target_of(rr, cc, &xf, &zf);
-          if (!(xf >= (float)C0 && xf <= (float)C1 && zf >= (float)R0 && zf <= (float)R1)) continue;  // another tile's
-          const float v = hplane[cell];  // a height map: the value is the point's y (maps.py:2214-2216)
-          if (v == v) {
-            const int o = ((int)zf - R0) * kTileW + ((int)xf - C0);
-            if (tgt.reduction) atomic_min_f32(s_val + o, v); else atomic_max_f32(s_val + o, v);
-            if (better(v, tgt.fill_value, tgt.reduction)) {
-              s_msk[o] = 1;
-              pcmin = fminf(pcmin, xf); pcmax = fmaxf(pcmax, xf);
-              prmin = fminf(prmin, zf); prmax = fmaxf(prmax, zf);
-            }
-          }
-        }
-      }
-      __syncthreads();
-      float* tplane = topdown + (long long)plane * M;
-      uint8_t* oplane = mask + (long long)plane * M;
-      const int tw = C1 - C0 + 1, th = R1 - R0 + 1;
-      for (int i = tid; i < tw * th; i += kTileThreads) {
-        const int rr = i / tw, cc = i - rr * tw;
-        const long long o = (long long)(R0 + rr) * tgt.Mw + (C0 + cc);
-        tplane[o] = s_val[rr * kTileW + cc];
-        oplane[o] = s_msk[rr * kTileW + cc];
-      }
-    }
-    cmin = fminf(cmin, pcmin); cmax = fmaxf(cmax, pcmax);
-    rmin = fminf(rmin, prmin); rmax = fmaxf(rmax, prmax);
-    if (next_plane_box) {
-      // block reduction of this plane's marked extents (block-uniform branch)
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        prmin = fminf(prmin, __shfl_xor_sync(0xffffffffu, prmin, o)); prmax = fmaxf(prmax, __shfl_xor_sync(0xffffffffu, prmax, o));
-        pcmin = fminf(pcmin, __shfl_xor_sync(0xffffffffu, pcmin, o)); pcmax = fmaxf(pcmax, __shfl_xor_sync(0xffffffffu, pcmax, o));
-      }
-      __syncthreads();
-      if ((tid & 31) == 0) { s_red[tid >> 5][0] = prmin; s_red[tid >> 5][1] = prmax; s_red[tid >> 5][2] = pcmin; s_red[tid >> 5][3] = pcmax; }
-      __syncthreads();
-      if (tid == 0) {
-        for (int q = 1; q < kTileThreads / 32; ++q) {
-          prmin = fminf(prmin, s_red[q][0]); prmax = fmaxf(prmax, s_red[q][1]);
-          pcmin = fminf(pcmin, s_red[q][2]); pcmax = fmaxf(pcmax, s_red[q][3]);
-        }
-        if (pcmin <= pcmax) {
-          atomicMin(next_plane_box + 4 * plane + 0, (int)prmin); atomicMax(next_plane_box + 4 * plane + 1, (int)prmax);
-          atomicMin(next_plane_box + 4 * plane + 2, (int)pcmin); atomicMax(next_plane_box + 4 * plane + 3, (int)pcmax);
-        }
-      }
-    }
-  }
-  if (next_bbox) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      cmin = fminf(cmin, __shfl_xor_sync(0xffffffffu, cmin, o)); cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
-      rmin = fminf(rmin, __shfl_xor_sync(0xffffffffu, rmin, o)); rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
-    }
-    __syncthreads();
-    if ((tid & 31) == 0) { s_red[tid >> 5][0] = cmin; s_red[tid >> 5][1] = cmax; s_red[tid >> 5][2] = rmin; s_red[tid >> 5][3] = rmax; }
-    __syncthreads();
-    if (tid == 0) {
-      for (int q = 1; q < kTileThreads / 32; ++q) {
-        cmin = fminf(cmin, s_red[q][0]); cmax = fmaxf(cmax, s_red[q][1]);
-        rmin = fminf(rmin, s_red[q][2]); rmax = fmaxf(rmax, s_red[q][3]);
-      }
-      if (cmin <= cmax) {  // as in fuse_scatter_kernel
-        const float zlo = tgt.flip_h ? __fsub_rn((float)(tgt.Mh - 1), rmax) : rmin;
-        const float zhi = tgt.flip_h ? __fsub_rn((float)(tgt.Mh - 1), rmin) : rmax;
-        auto deq = [&](float bin, float off) { return __fmul_rn(__fsub_rn(bin, off), tgt.map_res); };
-        float qx0, qx1, qz0, qz1;
-        quantize_f(deq(cmin, tgt.width_offset), deq(zlo, tgt.height_offset), 0.0f, 0.0f, tgt.map_res, 0, 0, &qx0, &qz0);
-        quantize_f(deq(cmax, tgt.width_offset), deq(zhi, tgt.height_offset), 0.0f, 0.0f, tgt.map_res, 0, 0, &qx1, &qz1);
-        atomicMin(next_bbox + 0, f2i64(qx0)); atomicMax(next_bbox + 1, f2i64(qx1));
-        atomicMin(next_bbox + 2, f2i64(qz0)); atomicMax(next_bbox + 3, f2i64(qz1));
-        atomicAdd(reinterpret_cast<unsigned long long*>(next_bbox + 4), 1ull);
-      }
-    }
-  }
-}
-
 static int launch_scatter(const DmFuseSource* sources, int n_sources, int b, int C, const DmFuseTarget& tgt,
                           float* topdown, uint8_t* mask, float* height, int mask_inline, cudaStream_t stream,
-                          long long* next_bbox = nullptr, int* next_plane_box = nullptr, bool fresh = false) {
-  // `fresh`: the canvases hold nothing but the fill.  The FIRST source may then go tile by tile (it overwrites its
-  // tiles) when it is a pure translation of a height map onto a canvas of the same resolution and orientation.
-  int first = 0;
-  if (fresh && n_sources > 0 && C == 1 && mask_inline) {
-    const DmFuseSource& s0 = sources[0];
-    if (s0.translate_only && !s0.values && !height && s0.map_res == tgt.map_res && (s0.flip_h != 0) == (tgt.flip_h != 0) &&
-        s0.height_cstride == (long long)s0.h * s0.w) {
-      dim3 grid(16, (unsigned)(b < 65535 ? b : 65535));
-      fuse_translate_kernel<<<grid, kTileThreads, 0, stream>>>(s0, b, tgt, topdown, mask, next_bbox, next_plane_box);
-      DM_LAUNCHED();
-      first = 1;
-    }
-  }
-  for (int i = first; i < n_sources; ++i) {
+                          long long* next_bbox = nullptr, int* next_plane_box = nullptr) {
+  for (int i = 0; i < n_sources; ++i) {
     fuse_scatter_kernel<<<plane_grid(sources[i], b * C), kScanThreads, 0, stream>>>(
         sources[i], b * C, C, tgt, topdown, height, mask, mask_inline, next_bbox, next_plane_box);
     DM_LAUNCHED();
@@ -790,7 +615,7 @@ extern "C" int dm_fuse_scatter_track_f32(const DmFuseSource* sources, int32_t n_
     }
   }
   const int rs = launch_scatter(sources, n_sources, b, C, *target, topdown, mask, height, mask_inline, stream,
-                                reinterpret_cast<long long*>(next_bbox), next_plane_box, /*fresh=*/true);
+                                reinterpret_cast<long long*>(next_bbox), next_plane_box);
   if (rs != DM_OK) return rs;
   if (!mask_inline) {
     changed_mask_kernel<<<grid_for(n_out), kFuseThreads, 0, stream>>>(topdown, n_out, target->fill_value, mask);

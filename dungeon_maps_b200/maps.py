@@ -927,7 +927,6 @@ def _fuse_source(m: TopdownMap, target: MapProjector, b: int, C: int, n_total: i
   src.map_res = m.proj.map_res
   base = params_dev.data_ptr()
   src.steps, src.width_offset, src.height_offset = base, base + 4 * n_step_words, base + 4 * (n_step_words + b)
-  src.translate_only = int(bool(m.proj.to_global) and bool(target.to_global))  # both steps are identity
   # a map this module wrote carries, per plane, the rectangle that holds its valid cells: the passes scan that instead
   # of the whole plane (a grown world map is mostly empty canvas)
   tb = getattr(m, "_tracked_box", None)

@@ -205,11 +205,6 @@ typedef struct DmFuseSource {
                             columns [min, max] that hold all of its valid cells, as dm_fuse_scatter_track_f32 left
                             them for a map it wrote (max < min: the plane has no valid cell).  The passes then scan
                             that rectangle instead of the whole plane.  NULL: scan everything. */
-  int32_t translate_only; /* caller's promise: both steps are NONE for every sample (a global-frame map merged into a
-                            global-frame target).  With the same map_res / flip_h as the target such a height map
-                            moves by whole cells, and dm_fuse_scatter_*_f32 gathers it tile by tile instead of
-                            scattering it cell by cell (results identical). */
-  int32_t _pad;
 } DmFuseSource;
 
 /* Pass 1: bounding box of every valid point of every source in bins of the

@@ -55,7 +55,7 @@ def test_struct_layouts_match_the_header():
   assert ctypes.sizeof(nat.DmFlowCfg) == ctypes.sizeof(orc.FlowCfg) == 15 * 4
   for (n1, t1), (n2, t2) in zip(nat.DmProjCfg._fields_, orc.ProjCfg._fields_):
     assert n1 == n2 and ctypes.sizeof(t1) == ctypes.sizeof(t2)
-  assert ctypes.sizeof(nat.DmFuseSource) == 3 * 8 + 2 * 8 + 4 * 4 + 4 * 8 + 2 * 4
+  assert ctypes.sizeof(nat.DmFuseSource) == 3 * 8 + 2 * 8 + 4 * 4 + 4 * 8
   assert ctypes.sizeof(nat.DmFuseTarget) == 8 * 4
   # every mirrored struct against sizeof() inside the compiled library
   lib = nat.lib()
