@@ -131,11 +131,11 @@ static ProjPlan make_plan(const DmProjCfg& cfg, int b) {
 
 struct ProjDims {
   int Cv, hasH, CU, CP, rows, tile, ring, lag, nsl;
+  int zw = 0;  // zero-presence words per cell, at word CU + group
   unsigned long long slot_words;
   unsigned long long stage_bytes;
   int groups = 1, cg = 0;  // warp-specialised kernel: channel groups per frame, channels per group
   unsigned long long ws_words = 0;  // 32-bit words of the workspace behind the control block (flags + ring)
-  int zw = 0;  // zero-presence words per cell, at word CU + group (warp-specialised kernel only)
 };
 
 
