@@ -43,7 +43,6 @@ struct ProjPlan {
   int Cv;     // value channels produced (C, or 1 when the heights are the values)
   int hasH;   // separate height channel accumulated after the values
   int CU;     // Cv + hasH: keys per cell
-  int ZW;     // zero-presence words per cell (one per channel group; sparse value planes, see ws_proj_slice)
   int CP;     // cell stride in words (odd → conflict-free transposed smem reads)
   int rows;   // staged rows per tile: C value planes + the depth/height row
   int tile;   // pixels per CTA tile
@@ -69,8 +68,7 @@ static ProjPlan make_plan(const DmProjCfg& cfg, int b) {
   p.Cv = cfg.C > 0 ? cfg.C : 1;
   p.hasH = (cfg.C > 0 && cfg.want_height) ? 1 : 0;
   p.CU = p.Cv + p.hasH;
-  p.ZW = cfg.C > 0 ? (cfg.C + 23) / 24 : 0;  // >= the number of channel groups any schedule below uses
-  p.CP = ((p.CU + p.ZW) & 1) ? p.CU + p.ZW : p.CU + p.ZW + 1;
+  p.CP = (p.CU & 1) ? p.CU : p.CU + 1;
   p.rows = cfg.C + 1;
   const size_t M = (size_t)cfg.Mh * cfg.Mw;
   p.slot_words = (M * p.CP + 3) & ~(size_t)3;
@@ -131,7 +129,6 @@ static ProjPlan make_plan(const DmProjCfg& cfg, int b) {
 
 struct ProjDims {
   int Cv, hasH, CU, CP, rows, tile, ring, lag, nsl;
-  int zw = 0;  // zero-presence words per cell, at word CU + group
   unsigned long long slot_words;
   unsigned long long stage_bytes;
   int groups = 1, cg = 0;  // warp-specialised kernel: channel groups per frame, channels per group
@@ -316,14 +313,6 @@ resolve_kernel(uint32_t* __restrict__ acc, const DmProjCfg cfg, const ProjDims d
 
 // ================= persistent TMA kernel =======================================================
 
-
-__device__ __forceinline__ void red_or_u32(uint32_t* p, uint32_t v) {
-#ifdef DM_ABL_NORED
-  asm volatile("" ::"l"(p), "r"(v) : "memory");
-#else
-  asm volatile("red.relaxed.gpu.global.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-#endif
-}
 
 // ---- warp-specialised persistent kernel -----------------------------------------------------
 // CTA = 1 producer warp + kWsWarps consumer warps, two smem stages.
@@ -512,31 +501,9 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
 #undef DM_B1_ROW
   __syncwarp();
   [[maybe_unused]] const long long tp2 = DM_CLK();
-  // ---- sparse value planes (round 2).  One-hot semantics — the reference's own use of value maps,
-  // demos/object_map/run.py:117-124 — are 0.0 in all channels but one, and with fill = -inf every one of those zeros is a
-  // RED of its own (it beats the fill): 17 REDs per runlet, the SM-side cost that separates this kernel from its load /
-  // store pipeline.  An exact 0.0 needs no key: a per-cell ZERO-PRESENCE word (bit c = "a 0.0 of
-  // channel c landed here", set only when 0.0 beats the fill) says the same, and the resolve pass folds it back in
-  // (max(key, 0) / min(key, 0)).  When the first 32 runlets of the slice carry at most two other values each, the
-  // slice goes lane = runlet: one RED.OR of the zero bits + one RED per non-zero value (+ the height) per runlet —
-  // 3 RED instructions per 32 runlets of one-hot data instead of 17.  Dense float planes keep the lane = channel path
-  // below; both may hit the same cell, the resolve combines them.  Exact for any input (-0.0 counts as 0.0: the
-  // reference's scatter_max cannot tell them apart either, `src > out` is false both ways).
-  const bool zero_beats = beats<IS_MIN>(0.0f, cfg.fill_value);
-  bool sparse = false;
-  if (cfg.C > 0 && d.zw > 0) {
-    int n = 0;
-    if (lane < total) {
-      for (int c = 0; c < nch; ++c) {
-        const float v = vals[c * RS + sb + lane];
-        n += (v != 0.0f && beats<IS_MIN>(v, cfg.fill_value)) ? 1 : 0;
-      }
-    }
-    sparse = __all_sync(0xffffffffu, n <= 2);
-  }
   // ---- B2: one RED per (runlet, channel); lane = channel keeps a runlet's keys in 1-2 lines
   const int total4 = total + padn;
-  if (cfg.C > 0 && !sparse) {
+  if (cfg.C > 0) {
     const int Cv = nch;  // this group's channels; their keys start at ch0
     const int cu_eff = Cv < 32 ? Cv : 32;
     const int streams = Cv <= 32 ? 32 / Cv : 1;
@@ -577,71 +544,25 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
   }
   // lane = runlet for the heights.  Neighbouring runlets of one cell are folded by a segmented scan over the
   // lanes and only the last one of a run issues its RED.
-  const bool with_h = (d.hasH || cfg.C == 0) && ch0 == 0;  // heights: once per tile, by the first channel group
-  if (with_h || sparse) {
+  if ((d.hasH || cfg.C == 0) && ch0 == 0) {  // once per tile: the first channel group
     const bool hmin = IS_MIN && cfg.C == 0;  // C == 0: the heights are the values (fill / reduction apply)
     const float hfill = cfg.C == 0 ? cfg.fill_value : -INFINITY;  // height channel: max against -inf (maps.py:340-348)
     const uint32_t hoff = slot_off + (cfg.C == 0 ? 0u : (uint32_t)d.Cv);
-    const uint32_t voff = slot_off + (uint32_t)ch0;                                   // this group's value keys
-    const uint32_t zoff = slot_off + (uint32_t)d.CU + (uint32_t)(d.cg > 0 ? ch0 / d.cg : 0);  // ... and zero word
-    const float fill = cfg.fill_value;
     for (int base = 0; base < total; base += 32) {
       const int i = base + lane;
       const bool active = i < total;
       const uint32_t cellv = active ? (uint32_t)lcell[sb + i] : 0xffffffffu;
       float v = active ? zrow[sb + i] : hfill;
-      // sparse value planes: my runlet's zero bits and its (at most two, else the overflow loop) other values
-      uint32_t zmask = 0;
-      int n = 0, c0 = 0, c1 = 0;
-      float v0 = fill, v1 = fill;
-      if (sparse && active) {
-        for (int c = 0; c < nch; ++c) {
-          const float x = vals[c * RS + sb + i];
-          if (x == 0.0f) {
-            zmask |= zero_beats ? (1u << c) : 0u;
-          } else if (beats<IS_MIN>(x, fill)) {
-            if (n == 0) { c0 = c; v0 = x; } else if (n == 1) { c1 = c; v1 = x; }
-            ++n;
-          }
-        }
-      }
-      // a run of one cell spans neighbouring runlets: heights and zero bits fold over the lanes (segmented scan), a
-      // single value folds when the neighbour carries the same single channel; the last runlet of a run issues
-      const uint32_t tag = n == 1 ? (uint32_t)c0 : 0x100u + (uint32_t)lane;  // foldable with an equal tag only
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const float pv = __shfl_up_sync(0xffffffffu, v, o);
         const uint32_t pc = __shfl_up_sync(0xffffffffu, cellv, o);
         if (lane >= o && pc == cellv) v = hmin ? fminf(v, pv) : fmaxf(v, pv);
-        if (sparse) {
-          const uint32_t pz = __shfl_up_sync(0xffffffffu, zmask, o);
-          const uint32_t pt = __shfl_up_sync(0xffffffffu, tag, o);
-          const float pv0 = __shfl_up_sync(0xffffffffu, v0, o);
-          if (lane >= o && pc == cellv) {
-            zmask |= pz;
-            if (pt == tag) v0 = red2<IS_MIN>(v0, pv0);
-          }
-        }
       }
       const uint32_t nc = __shfl_down_sync(0xffffffffu, cellv, 1);
       const bool last = lane == 31 || nc != cellv;
-      if (with_h) {
-        const bool win = hmin ? (v < hfill) : (v > hfill);
-        if (active && last && win) red_max_u32(acc + (hoff + cellv), hmin ? ~enc(v) : enc(v));
-      }
-      if (sparse) {
-        const uint32_t nt = __shfl_down_sync(0xffffffffu, tag, 1);
-        const bool vlast = last || nt != tag;  // the scan above is only complete at the last lane of an equal-tag run
-        if (active && last && zmask) red_or_u32(acc + (zoff + cellv), zmask);
-        if (active && n >= 1 && (n > 1 || vlast)) red_max_u32(acc + (voff + cellv + (uint32_t)c0), key_of<IS_MIN>(v0));
-        if (active && n >= 2) red_max_u32(acc + (voff + cellv + (uint32_t)c1), key_of<IS_MIN>(v1));
-        if (__any_sync(0xffffffffu, n > 2)) {  // overflow (the first block promised sparsity, this one is not): the rest
-          for (int c = c1 + 1; c < nch; ++c) {
-            const float x = (active && n > 2) ? vals[c * RS + sb + i] : 0.0f;
-            if (x != 0.0f && beats<IS_MIN>(x, fill)) red_max_u32(acc + (voff + cellv + (uint32_t)c), key_of<IS_MIN>(x));
-          }
-        }
-      }
+      const bool win = hmin ? (v < hfill) : (v > hfill);
+      if (active && last && win) red_max_u32(acc + (hoff + cellv), hmin ? ~enc(v) : enc(v));
     }
   }
 #ifdef DM_PROFILE
@@ -725,20 +646,13 @@ __device__ __forceinline__ bool ws_resolve_slice(uint32_t* __restrict__ acc_slot
     const uint32_t* mine = wres + j * d.CP;
     float* tp = topdown + plane0 + j;
     uint8_t* mp = mask + plane0 + j;
-    // zero-presence words (sparse value planes, ws_proj_slice): bit set = a 0.0 of that channel landed here and
-    // beats the fill; it is one more candidate of the channel's max / min
-    int g = 0, bit = 0;
-    uint32_t zw = d.zw ? mine[d.CU] : 0u;
     for (int c = 0; c < d.Cv; ++c) {
       const uint32_t k = mine[c];
-      const bool z = (zw >> bit) & 1u;
-      float out = k ? dec_red(k, cfg.reduction) : (z ? 0.0f : cfg.fill_value);  // utils.py:472-491
-      if (k && z) out = cfg.reduction ? fminf(out, 0.0f) : fmaxf(out, 0.0f);
+      const float out = k ? dec_red(k, cfg.reduction) : cfg.fill_value;  // utils.py:472-491
       st_stream_f1(tp, out);
-      st_stream_u8(mp, (k || z) ? 1 : 0);
+      st_stream_u8(mp, k ? 1 : 0);
       tp += M;
       mp += M;
-      if (++bit == d.cg && c + 1 < d.Cv) { bit = 0; ++g; zw = mine[d.CU + g]; }
     }
     if (d.hasH) {
       const uint32_t k = mine[d.Cv];
@@ -1079,7 +993,6 @@ extern "C" int dm_orth_project_f32(const float* depth, const float* values, cons
     dw.cg = p.ws_cg;
     dw.stage_bytes = p.ws_stage_bytes;
     dw.ws_words = (p.workspace_bytes() - p.ctrl_bytes) / 4;
-    dw.zw = p.ZW;
     void (*kern)(const float*, const float*, const uint8_t*, const DmProjSample*, DmProjCfg, ProjDims, int,
                  uint32_t*, uint32_t*, uint32_t*, float*, uint8_t*, float*, ProjGuard) = nullptr;
     const bool mn = cfg->reduction != 0;

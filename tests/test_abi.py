@@ -70,11 +70,10 @@ def test_workspace_query_needs_no_device():
   lib = nat.lib()
   cfg = nat.DmProjCfg(H=480, W=640, C=16, Mh=400, Mw=400, want_height=1)
   need = lib.dm_orth_project_workspace_bytes(ctypes.byref(cfg), 64)
-  # sparse ring of up to 10 frame slots of 400*400 cells x (17 keys + 1 zero-presence word, odd stride 19) + slice
-  # flags + control block
-  assert 4 * 160000 * 19 * 4 <= need <= 10 * 160000 * 19 * 4 + (2 << 20)
+  # sparse ring of up to 10 frame slots of 400*400 cells x 17 keys + slice flags + control block
+  assert 4 * 160000 * 17 * 4 <= need <= 10 * 160000 * 17 * 4 + (2 << 20)
   # a single frame still gets the two slots the schedule needs
-  assert lib.dm_orth_project_workspace_bytes(ctypes.byref(cfg), 1) >= 2 * 160000 * 19 * 4
+  assert lib.dm_orth_project_workspace_bytes(ctypes.byref(cfg), 1) >= 2 * 160000 * 17 * 4
   assert lib.dm_orth_project_workspace_bytes(None, 64) == 0
   assert lib.dm_orth_project_workspace_bytes(ctypes.byref(cfg), 0) == 0
 
