@@ -27,6 +27,8 @@
 //    resolve_kernel, chunked over the ring) — same device functions, same results.
 #include <cstdlib>
 
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link)
+
 #include "dm_project.cuh"
 
 namespace dm {
@@ -58,12 +60,20 @@ struct ProjPlan {
   int ws_warps;          // warp-specialised kernel: consumer warps per CTA (tile = 128 px each)
   int ws_groups;         // ... channel groups a frame's value planes are staged in (each group re-reads the depth row)
   int ws_cg;             // ... value channels per group
+  int ws_r2d;            // ... image rows per 2-D tile (tensor-map TMA), 0: tiles of 128 * ws_warps consecutive pixels
   size_t ws_stage_bytes; // warp-specialised kernel: one stage of 128 * ws_warps pixels
   size_t smem_ws;        // stage + barriers/item/sample block
   size_t workspace_bytes() const { return ctrl_bytes + flag_bytes + slot_words * 4 * (size_t)ring; }
 };
 
-static ProjPlan make_plan(const DmProjCfg& cfg, int b) {
+// Tile rows of the warp-specialised kernel: -1 automatic, 0 forces the 1-D row tiles, 4 / 8 force 2-D tiles of that
+// many image rows (test hook dm_debug_set_tile_rows; both layouts give identical results).
+static int g_tile_rows = -1;
+#ifndef DM_R2D_DEFAULT
+#define DM_R2D_DEFAULT 0  // measured (r02m-r02p): row tiles 0.455 ms, 4-row 2-D tiles 0.509 ms, 8-row 0.603 ms per config-2 step
+#endif
+
+static ProjPlan make_plan(const DmProjCfg& cfg, int b, int tile_rows = -1) {
   ProjPlan p{};
   p.Cv = cfg.C > 0 ? cfg.C : 1;
   p.hasH = (cfg.C > 0 && cfg.want_height) ? 1 : 0;
@@ -122,7 +132,24 @@ static ProjPlan make_plan(const DmProjCfg& cfg, int b) {
   if (cfg.C <= 0) p.ws_groups = 1;
   p.ws_cg = cfg.C > 0 ? (cfg.C + p.ws_groups - 1) / p.ws_groups : 0;
   p.ws_groups = cfg.C > 0 ? (cfg.C + p.ws_cg - 1) / p.ws_cg : 1;
-  p.ws_stage_bytes = ws_stage(p.ws_warps, p.ws_cg + 1);
+  p.ws_r2d = tile_rows >= 0 ? tile_rows : g_tile_rows >= 0 ? g_tile_rows : DM_R2D_DEFAULT;
+#ifdef DM_EXPERIMENT_KNOBS
+  if (const char* e = getenv("DM_R2D")) if (tile_rows < 0) p.ws_r2d = atoi(e);
+#endif
+  if (p.ws_r2d != 0 && p.ws_r2d != 4 && p.ws_r2d != 8) p.ws_r2d = 0;
+  // 8-row tiles: 8 x 64 pixels (2 consumer warps) keep the stage of a 4 x 128 tile; only without channel groups
+  if (p.ws_r2d == 8) {
+    if (p.ws_groups == 1 && p.ws_warps == 4) p.ws_warps = 2; else p.ws_r2d = 4;
+  }
+  if (p.ws_r2d) {
+    // (cg + 1) dense planes of R x 32 ww words + the runlet list; a tensor-map box dimension is at most 256
+    const size_t pw = (size_t)p.ws_r2d * 32 * p.ws_warps * 4;
+    const size_t ws = (size_t)(p.ws_cg + 2) * pw;
+    const size_t ws_res = ((size_t)p.ws_warps * 64 * p.CP * 4 + 127) & ~(size_t)127;
+    p.ws_stage_bytes = ws < ws_res ? ws_res : ws;
+    if (p.ws_cg > 256) p.ws_r2d = 0;
+  }
+  if (!p.ws_r2d) p.ws_stage_bytes = ws_stage(p.ws_warps, p.ws_cg + 1);
   p.smem_ws = p.ws_stage_bytes + 256;
   return p;
 }
@@ -416,7 +443,7 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
     if (lane >= o) incl += n;
   }
   const int total = __shfl_sync(0xffffffffu, incl, 31);
-  const int padn = (4 - (total & 3)) & 3;  // the runlet list is padded to a multiple of 4 with no-ops
+  const int padn = (4 - (total & 3)) & 3;  // B2 reads the list in quads; the stale tail of the last one is masked there
   // compacted positions of my runlets (word offsets inside a row); dead pixels park on a scratch
   // word past the slice so that stores need no predicate juggling
   const int o0 = sb + incl - cnt, o1 = o0 + (int)t0, o2 = o1 + (int)t1, o3 = o2 + (int)t2;
@@ -425,7 +452,6 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
   if (t1) lcell[o1] = cl[1] * d.CP;
   if (t2) lcell[o2] = cl[2] * d.CP;
   if (t3) lcell[o3] = cl[3] * d.CP;
-  if (lane < padn) lcell[sb + total + lane] = 0;
   {  // sparse ring: flag the 64-cell slices my runlets touch (one store per change of slice, not per runlet)
     const int s0 = cl[0] >> 6, s1 = cl[1] >> 6, s2 = cl[2] >> 6, s3 = cl[3] >> 6;
     const int lastv = t3 ? s3 : t2 ? s2 : t1 ? s1 : t0 ? s0 : -1;
@@ -457,7 +483,6 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
 #endif
   [[maybe_unused]] const long long tp1 = DM_CLK();
   // ---- B1: channel loop at full lane utilisation, compaction in place
-  const float neutral = cfg.fill_value;  // padding value: never beats fill → never emitted
 #define DM_B1_ROW(ROW)                                                     \
   {                                                                        \
     float* row_ = (ROW);                                                   \
@@ -470,7 +495,6 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
     if (t1) row_[o1] = a.y;                                                \
     if (t2) row_[o2] = a.z;                                                \
     if (t3) row_[o3] = a.w;                                                \
-    if (lane < padn) row_[sb + total + lane] = neutral;                    \
   }
   {
     int c = 0;
@@ -491,10 +515,6 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
       if (t1) { r0[o1] = a0.y; r0[RS + o1] = a1.y; r0[2 * RS + o1] = a2.y; r0[3 * RS + o1] = a3.y; }
       if (t2) { r0[o2] = a0.z; r0[RS + o2] = a1.z; r0[2 * RS + o2] = a2.z; r0[3 * RS + o2] = a3.z; }
       if (t3) { r0[o3] = a0.w; r0[RS + o3] = a1.w; r0[2 * RS + o3] = a2.w; r0[3 * RS + o3] = a3.w; }
-      if (lane < padn) {
-        const int pp = sb + total + lane;
-        r0[pp] = neutral; r0[RS + pp] = neutral; r0[2 * RS + pp] = neutral; r0[3 * RS + pp] = neutral;
-      }
     }
     for (; c < nch; ++c) DM_B1_ROW(vals + c * RS)
   }
@@ -525,21 +545,27 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
       uint32_t pc = 0xffffffffu;
       float pv = fill;
       for (int i = beg; i < end; i += 4) {
-        const uint4 c4 = *reinterpret_cast<const uint4*>(lc + i);
+        uint4 c4 = *reinterpret_cast<const uint4*>(lc + i);
         float4 v4 = *reinterpret_cast<const float4*>(row + i);
+        if (i + 4 > total) {  // the last quad of the list is partly stale: its tail continues the last entry with `fill`
+          const int n = total - i;
+          if (n < 2) { c4.y = c4.x; v4.y = fill; }
+          if (n < 3) { c4.z = c4.y; v4.z = fill; }
+          c4.w = c4.z; v4.w = fill;
+        }
         const bool mp = pc == c4.x, m01 = c4.x == c4.y, m12 = c4.y == c4.z, m23 = c4.z == c4.w;
-        if (!mp && beats<IS_MIN>(pv, fill)) red_max_u32(acc + (off_c + pc), key_of<IS_MIN>(pv));
+        red_key_if_run_ends<IS_MIN>(pc, c4.x, pv, fill, acc + (off_c + pc));
         v4.x = mp ? red2<IS_MIN>(pv, v4.x) : v4.x;
         v4.y = m01 ? red2<IS_MIN>(v4.x, v4.y) : v4.y;
         v4.z = m12 ? red2<IS_MIN>(v4.y, v4.z) : v4.z;
         v4.w = m23 ? red2<IS_MIN>(v4.z, v4.w) : v4.w;
-        if (!m01 && beats<IS_MIN>(v4.x, fill)) red_max_u32(acc + (off_c + c4.x), key_of<IS_MIN>(v4.x));
-        if (!m12 && beats<IS_MIN>(v4.y, fill)) red_max_u32(acc + (off_c + c4.y), key_of<IS_MIN>(v4.y));
-        if (!m23 && beats<IS_MIN>(v4.z, fill)) red_max_u32(acc + (off_c + c4.z), key_of<IS_MIN>(v4.z));
+        red_key_if_run_ends<IS_MIN>(c4.x, c4.y, v4.x, fill, acc + (off_c + c4.x));
+        red_key_if_run_ends<IS_MIN>(c4.y, c4.z, v4.y, fill, acc + (off_c + c4.y));
+        red_key_if_run_ends<IS_MIN>(c4.z, c4.w, v4.z, fill, acc + (off_c + c4.z));
         pc = c4.w;
         pv = v4.w;
       }
-      if (beats<IS_MIN>(pv, fill)) red_max_u32(acc + (off_c + pc), key_of<IS_MIN>(pv));
+      red_key_if_run_ends<IS_MIN>(pc, 0xfffffffeu, pv, fill, acc + (off_c + pc));
     }
   }
   // lane = runlet for the heights.  Neighbouring runlets of one cell are folded by a segmented scan over the
@@ -558,6 +584,232 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
         const float pv = __shfl_up_sync(0xffffffffu, v, o);
         const uint32_t pc = __shfl_up_sync(0xffffffffu, cellv, o);
         if (lane >= o && pc == cellv) v = hmin ? fminf(v, pv) : fmaxf(v, pv);
+      }
+      const uint32_t nc = __shfl_down_sync(0xffffffffu, cellv, 1);
+      const bool last = lane == 31 || nc != cellv;
+      const bool win = hmin ? (v < hfill) : (v > hfill);
+      if (active && last && win) red_max_u32(acc + (hoff + cellv), hmin ? ~enc(v) : enc(v));
+    }
+  }
+#ifdef DM_PROFILE
+  [[maybe_unused]] const long long tp3 = DM_CLK();
+  tprof[0] += tp1 - tp0; tprof[1] += tp2 - tp1; tprof[2] += tp3 - tp2; tprof[3] += total;
+#endif
+}
+
+// ---- 2-D tiles (round 2): R image rows x 32 WW columns, staged by ONE tensor-map TMA copy per tile ------------
+// A thread owns the R rows of ONE image column.  Vertical structure (walls, furniture) projects onto one map cell,
+// so runs fold in-thread down the column first and then across the lanes along each tile row: the runlet list holds
+// the runlets that END in tile row 0 (in lane = column order), then those of row 1, ... ("row streams"), neighbours
+// in the list that share the cell fold in B2.  Host model of the room frames (same folding rules): 65.5 k RED groups
+// per frame with 128 x 1 pixels per warp, 29.8 k with 32 x 4, 22.8 k with 32 x 8.
+// Stage layout: plane p (value channel of the group, then the depth plane at index d.cg) = R segments (tile rows) of
+// TW = 32 WW words, dense — exactly what cp.async.bulk.tensor.3d writes for a box (TW, R, planes).  Warp cw owns words
+// [32 cw, 32 cw + 32) of every segment, for its pixels and — in place — for its compacted runlet list (entry i at
+// segment i / 32, word i % 32).  Dense planes are a multiple of 32 words apart, which would make B2's transposed
+// reads (lane = channel, same list position) 8-way bank conflicts; the compacted entries of value plane c are
+// therefore XOR-swizzled by 4 (c & 3) words inside their 32-word segment (B1 writes, B2 reads them so).
+template <int FAST, bool IS_MIN, int WW, int R>
+__device__ __forceinline__ void ws_proj_slice2d(const DmProjCfg& cfg, const ProjDims& d, const WsItem& it,
+                                                const DmProjSample& sp, const Rcps& rcp,
+                                                const uint8_t* __restrict__ vplane, float* vals, int* lcell,
+                                                uint32_t* __restrict__ acc, uint32_t slot_off,
+                                                uint32_t* __restrict__ slot_flags, int cw, int lane,
+                                                uint64_t* full_vals, uint32_t phase, int ch0, int nch,
+                                                long long* tprof) {
+  [[maybe_unused]] const long long tp0 = DM_CLK();
+  constexpr int TW = 32 * WW;
+  constexpr int PW = R * TW;  // words per staged plane
+  const int colt = (cw << 5) + lane;  // my column inside the tile
+  const int wbase = cw << 5;
+  // word offset (inside a staged plane) of entry i of this warp's runlet list
+  auto pos = [&](int i) { return (i >> 5) * TW + wbase + (i & 31); };
+  float* zrow = vals + d.cg * PW;  // the depth plane follows the group's value planes (fixed place: the box is cg planes)
+  int cl[R];
+  float y[R];
+  // ---- A: cells and heights of my R pixels
+  {
+    const int c = it.c0 + colt;
+    const bool colok = c < cfg.W;
+    float z[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) z[k] = zrow[k * TW + colt];  // rows / columns beyond the image: zero-filled by the TMA
+    const int kb = cfg.clip_border;
+    bool ok[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const int r = it.r0 + k;
+      ok[k] = colok && r < cfg.H;
+      if (kb > 0) ok[k] = ok[k] && (r >= kb) && (r < cfg.H - kb) && (c >= kb) && (c < cfg.W - kb);
+      if (vplane && ok[k]) ok[k] = vplane[(size_t)r * cfg.W + c] != 0;
+    }
+    if (FAST) {
+      const float xn = div_by_rcp(__fsub_rn((float)c, cfg.cx), cfg.fx, rcp.fx);
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        const int r = it.r0 + k;
+        const float yy = cfg.flip_h ? __fsub_rn((float)(cfg.H - 1), (float)r) : (float)r;
+        const float yn = div_by_rcp(__fsub_rn(yy, cfg.cy), cfg.fy, rcp.fy);
+        cl[k] = pixel_cell_fast<FAST == 2, true>(cfg, sp, xn, yn, z[k], ok[k], &y[k], rcp.res);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        y[k] = 0.f;
+        cl[k] = ok[k] ? pixel_cell(cfg, sp, it.r0 + k, c, z[k], true, &y[k]) : -1;
+      }
+    }
+  }
+  // in-thread runs down the column: pixel k continues into k + 1 when both are valid and share the cell
+  bool p[R], t[R];
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    p[k] = (k + 1 < R) && (cl[k] >= 0) && (cl[k] == cl[k + 1 < R ? k + 1 : k]);
+    t[k] = (cl[k] >= 0) && !p[k];
+  }
+  // compacted positions: row streams
+  int o[R];
+  int total = 0;
+  {
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const unsigned bk = __ballot_sync(0xffffffffu, t[k]);
+      o[k] = pos(total + __popc(bk & lt));
+      total += __popc(bk);
+    }
+  }
+  const int padn = (4 - (total & 3)) & 3;  // B2 reads the list in quads; the stale tail of the last one is masked there
+  // the list holds word offsets of the cells in the accumulation slot (cell * CP)
+#pragma unroll
+  for (int k = 0; k < R; ++k)
+    if (t[k]) lcell[o[k]] = cl[k] * d.CP;
+  {  // sparse ring flags: one store per change of slice down my column and against my left neighbour's row
+    int prev = -1;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const int sk = cl[k] >> 6;
+      const int lk = __shfl_up_sync(0xffffffffu, t[k] ? sk : -1, 1);
+      if (t[k] && sk != prev && (lane == 0 || sk != lk)) st_flag(slot_flags + sk * kFlagStride);
+      prev = t[k] ? sk : prev;
+    }
+  }
+  {  // the depth plane becomes the (compacted) height list; C == 0: it is the value channel itself
+    const bool hmin = IS_MIN && cfg.C == 0;
+#pragma unroll
+    for (int k = 0; k + 1 < R; ++k) y[k + 1] = p[k] ? (hmin ? fminf(y[k], y[k + 1]) : fmaxf(y[k], y[k + 1])) : y[k + 1];
+    __syncwarp();  // every lane has read its depths
+#pragma unroll
+    for (int k = 0; k < R; ++k)
+      if (t[k]) zrow[o[k]] = y[k];
+  }
+  // phase A needed the depth plane only; the value planes (their own barrier) had this long to arrive
+  mbar_wait(full_vals, phase);
+#ifdef DM_ABL_NOB  // ablation build (wrong results): load pipeline + phase A + resolve only
+  return;
+#endif
+  [[maybe_unused]] const long long tp1 = DM_CLK();
+  // ---- B1: channel loop at full lane utilisation, vertical fold, compaction in place.  The entries of plane c are
+  // stored XOR-swizzled by 4 (c & 3) words: the planes of one pass (c, c + 4, c + 8, c + 12) share the swizzle, so it
+  // costs one LOP per stored row instead of address arithmetic per store, and B2's transposed 128-bit reads are at
+  // worst 2-way conflicts
+  {
+    constexpr int CB = R <= 4 ? 4 : 2;  // planes in flight per pass
+#pragma unroll 1
+    for (int s4 = 0; s4 < 4; ++s4) {
+      int os[R];
+#pragma unroll
+      for (int k = 0; k < R; ++k) os[k] = o[k] ^ (4 * s4);
+#pragma unroll 1
+      for (int c = s4; c < nch; c += 4 * CB) {
+        float* pl = vals + c * PW;
+        float a[CB][R];
+#pragma unroll
+        for (int u = 0; u < CB; ++u)
+          if (c + 4 * u < nch) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) a[u][k] = pl[4 * u * PW + k * TW + colt];
+          }
+#pragma unroll
+        for (int u = 0; u < CB; ++u)
+#pragma unroll
+          for (int k = 0; k + 1 < R; ++k) a[u][k + 1] = p[k] ? red2<IS_MIN>(a[u][k], a[u][k + 1]) : a[u][k + 1];
+        __syncwarp();  // loads of these planes are done before any lane compacts into them
+#pragma unroll
+        for (int u = 0; u < CB; ++u)
+          if (c + 4 * u < nch) {
+#pragma unroll
+            for (int k = 0; k < R; ++k)
+              if (t[k]) pl[4 * u * PW + os[k]] = a[u][k];
+          }
+      }
+    }
+  }
+  __syncwarp();
+  [[maybe_unused]] const long long tp2 = DM_CLK();
+  // ---- B2: one RED per (run, channel); lane = channel keeps a run's keys in 1-2 lines
+  const int total4 = total + padn;
+  if (cfg.C > 0) {
+    const int Cv = nch;  // this group's channels; their keys start at ch0
+    const int cu_eff = Cv < 32 ? Cv : 32;
+    const int streams = Cv <= 32 ? 32 / Cv : 1;
+    const int passes = Cv <= 32 ? 1 : (Cv + 31) / 32;
+    const int s = lane / cu_eff;
+    const int per = ((total4 / 4 + streams - 1) / streams) * 4;
+    const int beg = s * per;
+    const int end = min(beg + per, total4);
+    for (int pass = 0; pass < passes; ++pass) {
+      const int c = pass * 32 + (lane - s * cu_eff);
+      if (s >= streams || c >= Cv) continue;
+      const float* pl = vals + c * PW;
+      const int swz = 4 * (c & 3);
+      const uint32_t off_c = slot_off + (uint32_t)(ch0 + c);
+      const float fill = cfg.fill_value;
+      // neighbouring runlets of one cell (the same cell along a tile row) are folded, the RED goes out when the cell
+      // changes: (pc, pv) is the run that has not been issued yet
+      uint32_t pc = 0xffffffffu;
+      float pv = fill;
+      for (int i = beg; i < end; i += 4) {
+        const int pi = pos(i);
+        uint4 c4 = *reinterpret_cast<const uint4*>(lcell + pi);
+        float4 v4 = *reinterpret_cast<const float4*>(pl + (pi ^ swz));
+        if (i + 4 > total) {  // the last quad of the list is partly stale: its tail continues the last entry with `fill`
+          const int n = total - i;
+          if (n < 2) { c4.y = c4.x; v4.y = fill; }
+          if (n < 3) { c4.z = c4.y; v4.z = fill; }
+          c4.w = c4.z; v4.w = fill;
+        }
+        const bool mp = pc == c4.x, m01 = c4.x == c4.y, m12 = c4.y == c4.z, m23 = c4.z == c4.w;
+        red_key_if_run_ends<IS_MIN>(pc, c4.x, pv, fill, acc + (off_c + pc));
+        v4.x = mp ? red2<IS_MIN>(pv, v4.x) : v4.x;
+        v4.y = m01 ? red2<IS_MIN>(v4.x, v4.y) : v4.y;
+        v4.z = m12 ? red2<IS_MIN>(v4.y, v4.z) : v4.z;
+        v4.w = m23 ? red2<IS_MIN>(v4.z, v4.w) : v4.w;
+        red_key_if_run_ends<IS_MIN>(c4.x, c4.y, v4.x, fill, acc + (off_c + c4.x));
+        red_key_if_run_ends<IS_MIN>(c4.y, c4.z, v4.y, fill, acc + (off_c + c4.y));
+        red_key_if_run_ends<IS_MIN>(c4.z, c4.w, v4.z, fill, acc + (off_c + c4.z));
+        pc = c4.w;
+        pv = v4.w;
+      }
+      red_key_if_run_ends<IS_MIN>(pc, 0xfffffffeu, pv, fill, acc + (off_c + pc));
+    }
+  }
+  // lane = runlet for the heights: segmented scan over the lanes, the last runlet of a run issues
+  if ((d.hasH || cfg.C == 0) && ch0 == 0) {  // once per tile: the first channel group
+    const bool hmin = IS_MIN && cfg.C == 0;
+    const float hfill = cfg.C == 0 ? cfg.fill_value : -INFINITY;  // maps.py:340-348
+    const uint32_t hoff = slot_off + (cfg.C == 0 ? 0u : (uint32_t)d.Cv);
+    for (int base = 0; base < total; base += 32) {
+      const int i = base + lane;
+      const bool active = i < total;
+      const int pi = pos(i);
+      const uint32_t cellv = active ? (uint32_t)lcell[pi] : 0xffffffffu;
+      float v = active ? zrow[pi] : hfill;
+#pragma unroll
+      for (int o2 = 1; o2 < 32; o2 <<= 1) {
+        const float pv = __shfl_up_sync(0xffffffffu, v, o2);
+        const uint32_t pc = __shfl_up_sync(0xffffffffu, cellv, o2);
+        if (lane >= o2 && pc == cellv) v = hmin ? fminf(v, pv) : fmaxf(v, pv);
       }
       const uint32_t nc = __shfl_down_sync(0xffffffffu, cellv, 1);
       const bool last = lane == 31 || nc != cellv;
@@ -663,16 +915,23 @@ __device__ __forceinline__ bool ws_resolve_slice(uint32_t* __restrict__ acc_slot
   return flagged != 0;
 }
 
-template <int FAST, bool IS_MIN, int WW>
+// R2D = 0: tiles of 128 WW consecutive pixels, one bulk copy per plane row (any W % 4 == 0 layout).
+// R2D = 4 / 8: tiles of R2D image rows x 32 WW columns, one tensor-map copy (cp.async.bulk.tensor.3d, UTMALDG) for
+// the group's value planes and one for the depth plane; tmv / tmd are the tensor maps of `values` (W, H, b C) and
+// `depth` (W, H, b), encoded on the host per call.
+template <int FAST, bool IS_MIN, int WW, int R2D>
 __global__ void __launch_bounds__(32 * (WW + 1))
 proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values,
                const uint8_t* __restrict__ valid, const DmProjSample* __restrict__ samples,
                const DmProjCfg cfg, const ProjDims d, int b, uint32_t* __restrict__ ctrl,
                uint32_t* __restrict__ flags, uint32_t* __restrict__ acc, float* __restrict__ topdown,
-               uint8_t* __restrict__ mask, float* __restrict__ height, const ProjGuard guard) {
+               uint8_t* __restrict__ mask, float* __restrict__ height, const ProjGuard guard,
+               const __grid_constant__ CUtensorMap tmv, const __grid_constant__ CUtensorMap tmd) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int kWsWarps = WW, kWsTile = 128 * WW, kWsResolveCells = 64 * WW * kResK;
   constexpr int RS = kWsTile + 4;
+  constexpr int TW = 32 * WW;                    // 2-D tiles: columns per tile
+  constexpr int PW = (R2D ? R2D : 1) * TW;       // ... words per staged plane
   const Rcps rcp{__frcp_rn(cfg.map_res), __frcp_rn(cfg.fx), __frcp_rn(cfg.fy)};
   // one stage per CTA: latency is hidden by the 5-6 CTAs resident per SM, not by an in-CTA ring
   unsigned char* stage = smem;
@@ -685,7 +944,9 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = cfg.H * cfg.W, M = cfg.Mh * cfg.Mw;
-  const int P = ((N + kWsTile - 1) / kWsTile) * d.groups;  // projection tickets per frame: tiles x channel groups
+  const int CBk = (cfg.W + TW - 1) / TW;        // 2-D tiles: column blocks per row group
+  // projection tickets per frame: tiles x channel groups
+  const int P = (R2D ? ((cfg.H + R2D - 1) / (R2D ? R2D : 1)) * CBk : (N + kWsTile - 1) / kWsTile) * d.groups;
   const int R = (M + kWsResolveCells - 1) / kWsResolveCells;
   uint32_t* proj_done = ctrl + kCtrlWords;
   uint32_t* resolve_done = proj_done + b;
@@ -758,9 +1019,16 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
         const int grp = it.idx % d.groups;  // neighbouring tickets share the tile: its depth row is re-read from L2
         const int ch0 = grp * d.cg;
         it._pad = ch0 | (min(d.cg, cfg.C - ch0) << 16);
-        it.tile0 = (it.idx / d.groups) * kWsTile;
-        it.r0 = it.tile0 / cfg.W;
-        it.c0 = it.tile0 - it.r0 * cfg.W;
+        if (R2D) {
+          const int ti = it.idx / d.groups, rg = ti / CBk;
+          it.r0 = R2D * rg;
+          it.c0 = (ti - rg * CBk) * TW;
+          it.tile0 = it.r0 * cfg.W + it.c0;
+        } else {
+          it.tile0 = (it.idx / d.groups) * kWsTile;
+          it.r0 = it.tile0 / cfg.W;
+          it.c0 = it.tile0 - it.r0 * cfg.W;
+        }
         if (it.frame >= ring) { dep = resolve_done + (it.frame - ring); dep_target = (uint32_t)R + guard.dep_bias; }
         const uint32_t* sw = reinterpret_cast<const uint32_t*>(samples + it.frame);
         spw0 = sw[lane];
@@ -799,7 +1067,19 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
       }
       if (lane == 0) *item = it;
       __syncwarp();
-      if (it.kind == kItemProj) {
+      if (R2D && it.kind == kItemProj) {
+        // one tensor-map copy for the depth plane (completes `full`: phase A starts) and one for the group's d.cg value
+        // planes; rows / columns / planes beyond the tensor are zero-filled and count towards the transaction bytes
+        const int ch0 = it._pad & 0xffff, nch = it._pad >> 16;
+        if (lane == 0) {
+          float* vals = reinterpret_cast<float*>(stage);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_expect_tx(full, (uint32_t)PW * 4u);
+          if (nch > 0) mbar_expect_tx(full_vals, (uint32_t)PW * 4u * (uint32_t)d.cg); else mbar_arrive(full_vals);
+          tensor_g2s_3d(vals + d.cg * PW, &tmd, it.c0, it.r0, it.frame, full, policy);
+          if (nch > 0) tensor_g2s_3d(vals, &tmv, it.c0, it.r0, it.frame * cfg.C + ch0, full_vals, policy);
+        }
+      } else if (it.kind == kItemProj) {
         const int npx = min(kWsTile, N - it.tile0);
         const uint32_t row_bytes = (uint32_t)npx * 4u;
         const int ch0 = it._pad & 0xffff, nch = it._pad >> 16;
@@ -878,12 +1158,20 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
       if (it.ok) {
         if (it.kind == kItemProj) {
           float* vals = reinterpret_cast<float*>(stage);
-          int* lcell = reinterpret_cast<int*>(vals + d.rows * RS);
           const int slot = it.frame % ring;
-          ws_proj_slice<FAST, IS_MIN, WW>(cfg, d, it, *sps, rcp, valid ? valid + (size_t)it.frame * N : nullptr, vals,
-                                      lcell, acc, (uint32_t)slot * (uint32_t)d.slot_words,
-                                      flags + (size_t)slot * d.nsl * kFlagStride, warp, lane, full_vals,
-                                      (uses - 1u) & 1u, it._pad & 0xffff, it._pad >> 16, cp);
+          if constexpr (R2D != 0) {
+            int* lcell = reinterpret_cast<int*>(vals + d.rows * PW);
+            ws_proj_slice2d<FAST, IS_MIN, WW, (R2D ? R2D : 4)>(
+                cfg, d, it, *sps, rcp, valid ? valid + (size_t)it.frame * N : nullptr, vals, lcell, acc,
+                (uint32_t)slot * (uint32_t)d.slot_words, flags + (size_t)slot * d.nsl * kFlagStride, warp, lane,
+                full_vals, (uses - 1u) & 1u, it._pad & 0xffff, it._pad >> 16, cp);
+          } else {
+            int* lcell = reinterpret_cast<int*>(vals + d.rows * RS);
+            ws_proj_slice<FAST, IS_MIN, WW>(cfg, d, it, *sps, rcp, valid ? valid + (size_t)it.frame * N : nullptr, vals,
+                                        lcell, acc, (uint32_t)slot * (uint32_t)d.slot_words,
+                                        flags + (size_t)slot * d.nsl * kFlagStride, warp, lane, full_vals,
+                                        (uses - 1u) & 1u, it._pad & 0xffff, it._pad >> 16, cp);
+          }
 #ifdef DM_PROFILE
           cp[4] += tc1 - tc0; cp[7] += 1;
 #endif
@@ -923,9 +1211,42 @@ struct DeviceInfo {
 };
 static DeviceInfo g_dev[64];
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point query: the library keeps linking cudart only.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+#ifndef DM_TM_L2PROMO
+#define DM_TM_L2PROMO 3  // CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+#endif
+// float32 tensor (W, H, planes) of contiguous H x W planes, box (bw, bh, bp); false: not expressible as a tensor map
+static bool plane_tensor_map(CUtensorMap* tm, const float* base, int W, int H, long long planes, int bw, int bh, int bp) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc || planes <= 0 || planes > 0xffffffffll) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
+  const cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4};  // bytes, multiples of 16
+  const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bp};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, (CUtensorMapL2promotion)DM_TM_L2PROMO,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace dm
 
 using namespace dm;
+
+extern "C" void dm_debug_set_tile_rows(int32_t rows) { dm::g_tile_rows = rows; }
 
 extern "C" size_t dm_orth_project_workspace_bytes(const DmProjCfg* cfg, int32_t b) {
   if (!cfg || b <= 0 || cfg->Mh <= 0 || cfg->Mw <= 0) return 0;
@@ -947,7 +1268,7 @@ extern "C" int dm_orth_project_f32(const float* depth, const float* values, cons
   if (cfg->reduction != 0 && cfg->reduction != 1) return DM_EINVAL;
   if (!aligned(workspace, 256)) return DM_EINVAL;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const ProjPlan p = make_plan(*cfg, b);
+  ProjPlan p = make_plan(*cfg, b);
   if (workspace_bytes < p.workspace_bytes()) return DM_EWORKSPACE;
   int dev = 0;
   DM_CUDA_OK(cudaGetDevice(&dev));
@@ -959,8 +1280,11 @@ extern "C" int dm_orth_project_f32(const float* depth, const float* values, cons
     DM_CUDA_OK(cudaFuncSetAttribute(proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     DM_CUDA_OK(cudaFuncSetAttribute(resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
 #define DM_WS_ATTR(F, MN) \
-    DM_CUDA_OK(cudaFuncSetAttribute(proj_ws_kernel<F, MN, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); \
-    DM_CUDA_OK(cudaFuncSetAttribute(proj_ws_kernel<F, MN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    DM_CUDA_OK(cudaFuncSetAttribute(proj_ws_kernel<F, MN, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); \
+    DM_CUDA_OK(cudaFuncSetAttribute(proj_ws_kernel<F, MN, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); \
+    DM_CUDA_OK(cudaFuncSetAttribute(proj_ws_kernel<F, MN, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); \
+    DM_CUDA_OK(cudaFuncSetAttribute(proj_ws_kernel<F, MN, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); \
+    DM_CUDA_OK(cudaFuncSetAttribute(proj_ws_kernel<F, MN, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     DM_WS_ATTR(0, false) DM_WS_ATTR(1, false) DM_WS_ATTR(2, false)
     DM_WS_ATTR(0, true) DM_WS_ATTR(1, true) DM_WS_ATTR(2, true)
 #undef DM_WS_ATTR
@@ -977,8 +1301,22 @@ extern "C" int dm_orth_project_f32(const float* depth, const float* values, cons
   const int rtiles = (M + kResolveCells - 1) / kResolveCells;
   // the warp-specialised TMA kernel needs 16-byte aligned plane starts / row sizes, pixel quads
   // that do not straddle image rows, and two stages that fit in shared memory
+  // 2-D tiles need tensor maps of the inputs (16-byte aligned bases and row pitches); anything else takes row tiles
+  CUtensorMap tmv{}, tmd{};
+  int r2d = p.ws_r2d;
+  if (r2d) {
+    const int tw = 32 * p.ws_warps;
+    bool ok = cfg->W % 4 == 0 && aligned(depth, 16) && (!values || aligned(values, 16)) &&
+              plane_tensor_map(&tmd, depth, cfg->W, cfg->H, b, tw, r2d, 1);
+    if (ok && cfg->C > 0) ok = plane_tensor_map(&tmv, values, cfg->W, cfg->H, (long long)b * cfg->C, tw, r2d, p.ws_cg);
+    if (!ok) {
+      r2d = 0;
+      p = make_plan(*cfg, b, 0);  // same workspace layout, row tiles
+    }
+  }
   const int ws_tile = 128 * p.ws_warps, ws_threads = 32 * (p.ws_warps + 1);
-  const long long ws_tiles = (long long)((N + ws_tile - 1) / ws_tile) * p.ws_groups;
+  const long long ws_tiles = (r2d ? (long long)((cfg->H + r2d - 1) / r2d) * ((cfg->W + 32 * p.ws_warps - 1) / (32 * p.ws_warps))
+                                  : (long long)((N + ws_tile - 1) / ws_tile)) * p.ws_groups;
   const int ws_rtiles = (M + 64 * p.ws_warps * kResK - 1) / (64 * p.ws_warps * kResK);
   const long long ws_total = (long long)(b + p.lag) * (ws_tiles + ws_rtiles);
   const bool ws_ok = (N % 4 == 0) && (cfg->W % 4 == 0) && aligned(depth, 16) && (!values || aligned(values, 16)) &&
@@ -994,15 +1332,17 @@ extern "C" int dm_orth_project_f32(const float* depth, const float* values, cons
     dw.stage_bytes = p.ws_stage_bytes;
     dw.ws_words = (p.workspace_bytes() - p.ctrl_bytes) / 4;
     void (*kern)(const float*, const float*, const uint8_t*, const DmProjSample*, DmProjCfg, ProjDims, int,
-                 uint32_t*, uint32_t*, uint32_t*, float*, uint8_t*, float*, ProjGuard) = nullptr;
+                 uint32_t*, uint32_t*, uint32_t*, float*, uint8_t*, float*, ProjGuard, CUtensorMap, CUtensorMap) = nullptr;
     const bool mn = cfg->reduction != 0;
-#define DM_WS_PICK(WW)                                                                         \
-    switch (cfg->fast_steps) {                                                                 \
-      case 1: kern = mn ? proj_ws_kernel<1, true, WW> : proj_ws_kernel<1, false, WW>; break;   \
-      case 2: kern = mn ? proj_ws_kernel<2, true, WW> : proj_ws_kernel<2, false, WW>; break;   \
-      default: kern = mn ? proj_ws_kernel<0, true, WW> : proj_ws_kernel<0, false, WW>; break;  \
+#define DM_WS_PICK(WW, RR)                                                                             \
+    switch (cfg->fast_steps) {                                                                         \
+      case 1: kern = mn ? proj_ws_kernel<1, true, WW, RR> : proj_ws_kernel<1, false, WW, RR>; break;   \
+      case 2: kern = mn ? proj_ws_kernel<2, true, WW, RR> : proj_ws_kernel<2, false, WW, RR>; break;   \
+      default: kern = mn ? proj_ws_kernel<0, true, WW, RR> : proj_ws_kernel<0, false, WW, RR>; break;  \
     }
-    if (p.ws_warps == 4) { DM_WS_PICK(4) } else { DM_WS_PICK(2) }
+    if (r2d == 8) { DM_WS_PICK(2, 8) }
+    else if (r2d == 4) { if (p.ws_warps == 4) { DM_WS_PICK(4, 4) } else { DM_WS_PICK(2, 4) } }
+    else { if (p.ws_warps == 4) { DM_WS_PICK(4, 0) } else { DM_WS_PICK(2, 0) } }
 #undef DM_WS_PICK
     int per_sm = 0;
     DM_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ws_threads, p.smem_ws));
@@ -1010,7 +1350,7 @@ extern "C" int dm_orth_project_f32(const float* depth, const float* values, cons
     long long grid = (long long)g_dev[dev].sms * per_sm;
     if (grid > ws_total) grid = ws_total;
     kern<<<(unsigned)grid, ws_threads, p.smem_ws, stream>>>(depth, values, valid, samples, *cfg, dw, b, ctrl, flags,
-                                                            acc, topdown, mask, height, proj_guard(dev));
+                                                            acc, topdown, mask, height, proj_guard(dev), tmv, tmd);
     DM_LAUNCHED();
     return DM_OK;
   }

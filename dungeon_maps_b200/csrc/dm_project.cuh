@@ -76,6 +76,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
       ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
 }
+// TMA tensor copy global → shared (tile mode, 3-D box at element coordinates (x, y, z) of the tensor map `tm`, a
+// __grid_constant__ kernel parameter), completion on an mbarrier.  Out-of-bounds elements arrive as zeros.
+__device__ __forceinline__ void tensor_g2s_3d(void* dst, const void* tm, int x, int y, int z, uint64_t* bar,
+                                              uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%2, %3, %4}], [%5], %6;"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
 __device__ __forceinline__ uint64_t policy_evict_first() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
@@ -172,6 +181,29 @@ __device__ __forceinline__ void red_max_u32(uint32_t* p, uint32_t v) {
   asm volatile("" ::"l"(p), "r"(v) : "memory");
 #else
   asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#endif
+}
+// B2's RED sites: "the run that ends here (cell ca, next entry's cell cb differs) holds a value that beats the fill".
+// Both tests and the RED are predicated inside one asm block: no branch, no reconvergence bookkeeping, and the two
+// half-warp streams of a list no longer diverge at every site (ncu r02h: 9 instructions and a BSSY / BSYNC pair per site).
+template <bool IS_MIN>
+__device__ __forceinline__ void red_key_if_run_ends(uint32_t ca, uint32_t cb, float v, float fill, uint32_t* p) {
+  const uint32_t key = IS_MIN ? ~enc(v) : enc(v);
+#ifdef DM_ABL_NORED
+  asm volatile("" ::"r"(ca), "r"(cb), "f"(v), "f"(fill), "l"(p), "r"(key) : "memory");
+#else
+  if (IS_MIN)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.u32 p, %0, %1;\n\t"
+        "setp.lt.and.f32 p, %2, %3, p;\n\t"
+        "@p red.relaxed.gpu.global.max.u32 [%4], %5;\n\t}" ::"r"(ca), "r"(cb), "f"(v), "f"(fill), "l"(p), "r"(key) : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.u32 p, %0, %1;\n\t"
+        "setp.gt.and.f32 p, %2, %3, p;\n\t"
+        "@p red.relaxed.gpu.global.max.u32 [%4], %5;\n\t}" ::"r"(ca), "r"(cb), "f"(v), "f"(fill), "l"(p), "r"(key) : "memory");
 #endif
 }
 // Predicated reduction: no branch, no reconvergence bookkeeping around the RED.

@@ -159,6 +159,11 @@ int dm_device_status(int32_t device);
 void dm_debug_set_wait_guard(uint64_t spin_ns, uint32_t dep_bias);
 /* Test hook: frames per chunk of the *_host entries' copy / kernel / copy pipeline (0: chosen from the frame size). */
 void dm_debug_set_host_chunk(int32_t frames);
+/* Tile layout of the float projection kernel. -1: automatic (the fastest measured layout: tiles of 512 consecutive
+ * pixels staged by bulk copies), 0: the same, forced, 4 / 8: 2-D tiles of that many image rows x 128 / 64 columns staged
+ * by one tensor-map TMA copy per tile (cp.async.bulk.tensor.3d; folds vertical runs before they leave the SM — fewer
+ * REDs, more instructions: slower on the B200).  Every layout produces the same bits. */
+void dm_debug_set_tile_rows(int32_t rows);
 
 /* Per-sample parameters of camera_affine_grid (maps.py:353-460). */
 typedef struct DmFlowSample {

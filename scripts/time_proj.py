@@ -16,9 +16,12 @@ ap.add_argument("--fill", default="ninf")
 ap.add_argument("--b", type=int, default=64)
 ap.add_argument("--c", type=int, default=16)
 ap.add_argument("--hw", default="480x640")
+ap.add_argument("--rows", type=int, default=-1, help="tile layout (dm_debug_set_tile_rows): -1 auto, 0 row tiles, 4 / 8 2-D tiles")
 a = ap.parse_args()
 H, W = map(int, a.hw.split("x"))
 dev = torch.device("cuda", 0)
+from dungeon_maps_b200 import _native as _nat
+_nat.lib().dm_debug_set_tile_rows(a.rows)
 depth, values, pose = synth.frames(a.scene, a.b, H, W, a.c, seed=0, device=dev)
 proj = dmap.MapProjector(width=W, height=H, hfov=math.radians(70), cam_pose=[0., 0., 0.], width_offset=200.,
                          height_offset=0., cam_pitch=math.radians(-10), cam_height=0.88, map_res=0.03,
@@ -41,7 +44,7 @@ for _ in range(a.steps):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.steps
-out = {"lib": os.environ.get("DM_B200_LIB", "default"), "scene": a.scene, "fill": a.fill, "ms_per_step": round(ms, 4),
+out = {"lib": os.environ.get("DM_B200_LIB", "default"), "rows": a.rows, "hw": a.hw, "c": a.c, "scene": a.scene, "fill": a.fill, "ms_per_step": round(ms, 4),
        "maps_per_s": round(a.b / ms * 1e3)}
 if prof:
   c = ws[0].view(torch.int64)[160:184].cpu().tolist()

@@ -128,6 +128,66 @@ def test_orth_project_random_vs_oracle(seed):
       assert_same(npy(got[2][:, :1]), want[2][:, :1], f"height rep{rep}")
 
 
+def _tile_case(seed):
+  """Shapes the warp-specialised kernel takes (W % 4 == 0), with ragged tile edges in both directions."""
+  rng = np.random.default_rng(seed)
+  W = 4 * int(rng.integers(1, 80)); H = int(rng.integers(1, 40))
+  b = int(rng.integers(1, 14))
+  C = int(rng.choice([0, 1, 3, 16, 17, 25, 40, 49]))
+  Mh = int(rng.integers(3, 90)); Mw = int(rng.integers(3, 90))
+  intr = orc.intrinsics(W, H, HFOV)
+  kw = dict(map_res=float(rng.choice([0.05, 0.1, 0.25])), map_width=Mw, map_height=Mh, focal_x=intr["fx"],
+            focal_y=intr["fy"], center_x=intr["cx"], center_y=intr["cy"],
+            trunc_depth_min=None if rng.random() < 0.3 else 0.15, trunc_depth_max=None if rng.random() < 0.3 else 5.05,
+            trunc_height_max=None if rng.random() < 0.6 else 1.2,
+            clip_border=None if rng.random() < 0.5 else int(rng.integers(0, 3)),
+            to_global=bool(rng.random() < 0.5), flip_h=bool(rng.random() < 0.7),
+            fill_value=[None, -np.inf, 0.0, -1.0][int(rng.integers(0, 4))], reduction=None,
+            get_height_map=bool(rng.random() < 0.7))
+  if C > 0 and rng.random() < 0.25:
+    kw["reduction"], kw["fill_value"] = "min", [None, np.inf, 0.0][int(rng.integers(0, 3))]
+  # coherent depth (long runs down the columns and along the rows) or i.i.d. depth
+  if rng.random() < 0.5:
+    depth = synth.room_depth(b, H, W, HFOV, PITCH, 0.88, synth.poses(b, seed), seed).numpy()
+  else:
+    depth = synth.iid_depth(b, H, W, seed=seed).numpy()
+  if rng.random() < 0.3:
+    depth.reshape(-1)[::11] = np.nan
+  values = None
+  if C > 0:
+    values = (synth.block_onehot(b, C, H, W, seed=seed, block=3).numpy() if rng.random() < 0.5
+              else synth.uniform((b, C, H, W), seed + 7, -2., 2.).numpy())
+  valid = (synth.uniform((b, 1, H, W), seed + 9).numpy() > 0.3) if rng.random() < 0.3 else None
+  pose = synth.poses(b, seed).numpy()
+  woff = (Mw / 2 + rng.normal(size=b)).astype(np.float32)
+  hoff = rng.normal(size=b).astype(np.float32) + (Mh / 2 if kw["to_global"] else 0)
+  pitch = np.full(b, PITCH, np.float32)
+  camh = np.full(b, 0.88, np.float32)
+  return depth, values, valid, pose, woff, hoff, pitch, camh, kw
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_orth_project_tile_layouts_vs_oracle(seed):
+  """The float projection kernel has three tile layouts — 2-D tiles of 4 / 8 image rows staged by tensor-map TMA
+  copies, tiles of 512 consecutive pixels staged by bulk copies (dm_debug_set_tile_rows) — and every one of them must
+  give the oracle's bits."""
+  from dungeon_maps_b200 import _native as nat
+  depth, values, valid, pose, woff, hoff, pitch, camh, kw = _tile_case(5000 + seed)
+  want = orc.orth_project(depth, values, valid, pose, woff, hoff, pitch, camh, **kw)
+  try:
+    for rows in (4, 8, 0, -1):
+      nat.lib().dm_debug_set_tile_rows(rows)
+      got = dmap.orth_project(torch.from_numpy(depth), None if values is None else torch.from_numpy(values),
+                              None if valid is None else torch.from_numpy(valid), pose, woff, hoff, pitch, camh,
+                              device="cuda", **kw)
+      assert_same(npy(got[0]), want[0], f"topdown rows={rows}")
+      assert_same(npy(got[1]), want[1], f"mask rows={rows}")
+      if kw["get_height_map"]:
+        assert_same(npy(got[2][:, :1]), want[2][:, :1], f"height rows={rows}")
+  finally:
+    nat.lib().dm_debug_set_tile_rows(-1)
+
+
 def test_orth_project_edge_shapes():
   intr = orc.intrinsics(4, 4, HFOV)
   kw = dict(map_res=0.5, map_width=8, map_height=8, focal_x=intr["fx"], focal_y=intr["fy"], center_x=intr["cx"],
