@@ -165,6 +165,18 @@ __device__ __forceinline__ void st_stream_f4(float* p, float4 v) {
 __device__ __forceinline__ void st_stream_f1(float* p, float v) {
   asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
+__device__ __forceinline__ void st_stream_f2(float* p, float a, float b) {
+  asm volatile("st.global.cs.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void st_stream_u16(uint8_t* p, uint32_t v) {
+  asm volatile("st.global.cs.u16 [%0], %1;" ::"l"(p), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ void st_stream_u32(void* p, uint32_t v) {
+  asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_stream_u4(void* p, uint32_t v) {
+  asm volatile("st.global.cs.v4.u32 [%0], {%1,%1,%1,%1};" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void st_stream_u8(uint8_t* p, uint8_t v) {
   asm volatile("st.global.cs.u8 [%0], %1;" ::"l"(p), "r"((uint32_t)v) : "memory");
 }

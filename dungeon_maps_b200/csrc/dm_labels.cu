@@ -91,18 +91,6 @@ __device__ __forceinline__ uint32_t ld_stream_u32(const void* p) {
 __device__ __forceinline__ void red_or_u32(uint32_t* p, uint32_t v) {
   asm volatile("red.relaxed.gpu.global.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void st_stream_f2(float* p, float a, float b) {
-  asm volatile("st.global.cs.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(a), "f"(b) : "memory");
-}
-__device__ __forceinline__ void st_stream_u16(uint8_t* p, uint32_t v) {
-  asm volatile("st.global.cs.u16 [%0], %1;" ::"l"(p), "h"((unsigned short)v) : "memory");
-}
-__device__ __forceinline__ void st_stream_u32(void* p, uint32_t v) {
-  asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ void st_stream_u4(void* p, uint32_t v) {
-  asm volatile("st.global.cs.v4.u32 [%0], {%1,%1,%1,%1};" ::"l"(p), "r"(v) : "memory");
-}
 
 template <int W2>
 using LblBits = std::conditional_t<W2 == 1, uint32_t, unsigned long long>;

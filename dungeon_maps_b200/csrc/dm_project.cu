@@ -542,7 +542,12 @@ __device__ __forceinline__ void ws_proj_slice(const DmProjCfg& cfg, const ProjDi
       // runs longer than a pixel quad arrive as neighbouring runlets of one cell: they are folded and the RED goes
       // out when the cell changes; (pc, pv) is the runlet that has not been issued yet, carried across the quads of
       // the list (folding inside a quad only: 70 k REDs per room frame, carried: 56 k; 0.470 -> 0.457 ms)
+#ifdef DM_B2_BRANCHFREE
+      if (beg >= end) continue;
+      uint32_t pc = (uint32_t)lc[beg];
+#else
       uint32_t pc = 0xffffffffu;
+#endif
       float pv = fill;
       for (int i = beg; i < end; i += 4) {
         uint4 c4 = *reinterpret_cast<const uint4*>(lc + i);
@@ -879,15 +884,17 @@ __device__ __forceinline__ bool ws_resolve_slice(uint32_t* __restrict__ acc_slot
   const bool occupied = __any_sync(0xffffffffu, any != 0);
   const size_t plane0 = (size_t)frame * d.Cv * M + cell0;
   if (!occupied && ncell == 64 && (M & 3) == 0) {
-    // empty slice: 64 x fill per channel as 16 float4 stores, 64 x False as 16 u32 stores
+    // empty slice: 64 x fill per channel, 64 x False per channel.  Every store instruction is a full warp of 16-byte
+    // stores — two channels of values (512 B), eight channels of masks when the mask planes are 16-byte aligned —
+    // because what a global store costs on the SM is the instruction, not its bytes (r02q ablations): 11 store
+    // instructions per slice at C = 16 instead of 33.
     const float f = cfg.fill_value;
-    float* tp = topdown + plane0 + (lane & 15) * 4;
-    uint8_t* mp = mask + plane0 + (lane & 15) * 4;
-    for (int c = 0; c < d.Cv; ++c) {
-      if (lane < 16) st_stream_f4(tp, make_float4(f, f, f, f));
-      else asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(mp), "r"(0u) : "memory");
-      tp += M;
-      mp += M;
+    const float4 f4 = make_float4(f, f, f, f);
+    for (int c = lane >> 4; c < d.Cv; c += 2) st_stream_f4(topdown + plane0 + (size_t)c * M + (lane & 15) * 4, f4);
+    if ((M & 15) == 0) {
+      for (int c = lane >> 2; c < d.Cv; c += 8) st_stream_u4(mask + plane0 + (size_t)c * M + (lane & 3) * 16, 0u);
+    } else {
+      for (int c = lane >> 4; c < d.Cv; c += 2) st_stream_u32(mask + plane0 + (size_t)c * M + (lane & 15) * 4, 0u);
     }
     if (d.hasH && lane < 16)
       st_stream_f4(height + (size_t)frame * M + cell0 + lane * 4, make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY));
@@ -1321,7 +1328,7 @@ extern "C" int dm_orth_project_f32(const float* depth, const float* values, cons
   const long long ws_total = (long long)(b + p.lag) * (ws_tiles + ws_rtiles);
   const bool ws_ok = (N % 4 == 0) && (cfg->W % 4 == 0) && aligned(depth, 16) && (!values || aligned(values, 16)) &&
                      (!valid || aligned(valid, 4)) && p.smem_ws <= 220 * 1024 && ws_total < (1ll << 31) &&
-                     cfg->fast_steps >= 0 && cfg->fast_steps <= 2 &&
+                     cfg->fast_steps >= 0 && cfg->fast_steps <= 2 && p.ws_cg <= 32 &&
                      (unsigned long long)p.ring * p.slot_words < (1ull << 31);
   if (ws_ok) {
     ProjDims dw = d;

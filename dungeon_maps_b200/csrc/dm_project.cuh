@@ -191,6 +191,29 @@ __device__ __forceinline__ void red_key_if_run_ends(uint32_t ca, uint32_t cb, fl
   const uint32_t key = IS_MIN ? ~enc(v) : enc(v);
 #ifdef DM_ABL_NORED
   asm volatile("" ::"r"(ca), "r"(cb), "f"(v), "f"(fill), "l"(p), "r"(key) : "memory");
+#elif defined(DM_B2_BRANCHFREE)  // every site issues: a RED of key 0 changes nothing (the address must be a real cell)
+  {
+    const bool on = (ca != cb) && (IS_MIN ? (v < fill) : (v > fill));
+    asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(p), "r"(on ? key : 0u) : "memory");
+  }
+#elif defined(DM_ABL_REDVAR)  // ablation builds (wrong results): what exactly the REDs cost
+  {
+    const int ln = threadIdx.x & 31;
+    bool on = (ca != cb) && (IS_MIN ? (v < fill) : (v > fill));
+#if DM_ABL_REDVAR == 2      // half the lanes
+    on = on && ((ln & 1) == 0);
+#elif DM_ABL_REDVAR == 4    // one lane per run
+    on = on && ((ln & 15) == 0);
+#endif
+#if DM_ABL_REDVAR == 3      // every RED lands in a 1 MB window (L2-resident, no new lines)
+    p = reinterpret_cast<uint32_t*>((reinterpret_cast<unsigned long long>(p) & ~0xfffffffull) | (reinterpret_cast<unsigned long long>(p) & 0xffffcull));
+#endif
+#if DM_ABL_REDVAR == 1      // plain stores instead of reductions
+    if (on) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(key) : "memory");
+#else
+    if (on) asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(p), "r"(key) : "memory");
+#endif
+  }
 #else
   if (IS_MIN)
     asm volatile(
