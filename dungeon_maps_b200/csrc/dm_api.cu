@@ -9,6 +9,18 @@
 namespace dm {
 int64_t g_launches = 0;
 
+int sm_count() {
+  static int sms[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (sms[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    sms[dev] = n;
+  }
+  return sms[dev];
+}
+
 namespace {
 constexpr int kMaxDevices = 64;
 

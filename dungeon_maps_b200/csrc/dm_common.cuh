@@ -30,7 +30,8 @@ extern int64_t g_launches;  // defined in dm_api.cu
     if (_e != cudaSuccess) return static_cast<int>(_e);   \
   } while (0)
 
-constexpr int kNumSMs = 148;  // B200
+// SM count of the current device (148 on a B200), queried once per device: grids are sized in multiples of it.
+int sm_count();  // dm_api.cu
 
 // ---- host-side parameter packing (dm_params.cu) --------------------------------------------------
 void yaw_matrix(const DmPoseCfg& c, float yaw, float sin_yaw, float cos_yaw, float* R);  // utils.py:318-327, axis (0, 1, 0)

@@ -522,7 +522,7 @@ static dim3 plane_grid(const DmFuseSource& s, int planes) {
   constexpr int waves = 2, max_gy = 65535;
   const long long groups = ((long long)s.h * s.w + 2 * kGroup - 1) / kGroup;
   const int gy = planes < max_gy ? planes : max_gy;
-  long long gx = (((long long)kNumSMs * 8 * waves + gy - 1) / gy) * (256 / kScanThreads);
+  long long gx = (((long long)sm_count() * 8 * waves + gy - 1) / gy) * (256 / kScanThreads);
   const long long gx_max = (groups + kScanThreads - 1) / kScanThreads;
   if (gx > gx_max) gx = gx_max;
   if (gx < 1) gx = 1;
@@ -531,7 +531,7 @@ static dim3 plane_grid(const DmFuseSource& s, int planes) {
 
 static unsigned grid_for(long long items) {
   long long blocks = (items + kFuseThreads - 1) / kFuseThreads;
-  const long long cap = (long long)kNumSMs * 8 * 4;
+  const long long cap = (long long)sm_count() * 8 * 4;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (unsigned)blocks;

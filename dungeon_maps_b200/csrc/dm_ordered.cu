@@ -19,7 +19,7 @@ constexpr unsigned long long kNoCell = ~0ull;
 
 static unsigned ord_grid(long long items) {
   long long blocks = (items + kOrdThreads - 1) / kOrdThreads;
-  const long long cap = (long long)kNumSMs * 8 * 4;
+  const long long cap = (long long)sm_count() * 8 * 4;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (unsigned)blocks;

@@ -14,9 +14,11 @@ namespace dm {
 
 constexpr int kThreads = 256;
 
+static bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
 static unsigned grid_for(long long items) {
   long long blocks = (items + kThreads - 1) / kThreads;
-  const long long cap = (long long)kNumSMs * 8 * 2;
+  const long long cap = (long long)sm_count() * 8 * 2;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (unsigned)blocks;
@@ -25,54 +27,128 @@ static unsigned grid_for(long long items) {
 #define DM_GRID_STRIDE(i, n) \
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += (long long)gridDim.x * blockDim.x)
 
+// xyz point clouds are arrays of structures (n, 3): a thread takes FOUR consecutive points = 48 bytes = three
+// 128-bit accesses (the warp reads / writes 1.5 KB contiguous per instruction triple) instead of 3 stride-3 scalar
+// accesses per point, which left two thirds of every sector to the L1 (round 1).  `vec`: both arrays 16-byte aligned.
+struct P4 {
+  float v[12];
+};
+__device__ __forceinline__ P4 load_p4(const float* __restrict__ pts, long long i0, long long total, bool vec) {
+  P4 q;
+  if (vec && i0 + 3 < total) {
+    const float4* s4 = reinterpret_cast<const float4*>(pts + i0 * 3);
+    const float4 a = __ldg(s4), b = __ldg(s4 + 1), c = __ldg(s4 + 2);
+    q.v[0] = a.x; q.v[1] = a.y; q.v[2] = a.z; q.v[3] = a.w; q.v[4] = b.x; q.v[5] = b.y; q.v[6] = b.z; q.v[7] = b.w;
+    q.v[8] = c.x; q.v[9] = c.y; q.v[10] = c.z; q.v[11] = c.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) q.v[k] = (i0 * 3 + k < total * 3) ? pts[i0 * 3 + k] : 0.0f;
+  }
+  return q;
+}
+__device__ __forceinline__ void store_p4(float* __restrict__ out, long long i0, long long total, bool vec, const P4& q) {
+  if (vec && i0 + 3 < total) {
+    float4* d4 = reinterpret_cast<float4*>(out + i0 * 3);
+    d4[0] = make_float4(q.v[0], q.v[1], q.v[2], q.v[3]);
+    d4[1] = make_float4(q.v[4], q.v[5], q.v[6], q.v[7]);
+    d4[2] = make_float4(q.v[8], q.v[9], q.v[10], q.v[11]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 12; ++k)
+      if (i0 * 3 + k < total * 3) out[i0 * 3 + k] = q.v[k];
+  }
+}
+
 __global__ void __launch_bounds__(kThreads)
 transform_points_kernel(const float* __restrict__ pts, const DmStep* __restrict__ steps, int n_steps,
-                        long long n, long long total, float* __restrict__ out) {
-  DM_GRID_STRIDE(i, total) {
-    const int s = (int)(i / n);
-    V3 p{pts[i * 3], pts[i * 3 + 1], pts[i * 3 + 2]};
-    for (int k = 0; k < n_steps; ++k) p = apply_step(steps[s * n_steps + k], p);
-    out[i * 3] = p.x; out[i * 3 + 1] = p.y; out[i * 3 + 2] = p.z;
+                        long long n, long long total, float* __restrict__ out, int vec) {
+  DM_GRID_STRIDE(g, (total + 3) / 4) {
+    const long long i0 = g * 4;
+    P4 q = load_p4(pts, i0, total, vec);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (i0 + j >= total) break;
+      const int s = (int)((i0 + j) / n);
+      V3 p{q.v[3 * j], q.v[3 * j + 1], q.v[3 * j + 2]};
+      for (int k = 0; k < n_steps; ++k) p = apply_step(steps[s * n_steps + k], p);
+      q.v[3 * j] = p.x; q.v[3 * j + 1] = p.y; q.v[3 * j + 2] = p.z;
+    }
+    store_p4(out, i0, total, vec, q);
   }
 }
 
 __global__ void __launch_bounds__(kThreads)
 image_camera_kernel(const float* __restrict__ pts, long long n, float fx, float fy, float cx, float cy,
-                    int flip_h, int height, int to_image, float* __restrict__ out) {
-  DM_GRID_STRIDE(i, n) {
-    float x = pts[i * 3], y = pts[i * 3 + 1];
-    const float z = pts[i * 3 + 2];
-    if (!to_image) {  // maps.py:670-678
-      if (flip_h) y = __fsub_rn((float)(height - 1), y);
-      x = __fmul_rn(__fdiv_rn(__fsub_rn(x, cx), fx), z);
-      y = __fmul_rn(__fdiv_rn(__fsub_rn(y, cy), fy), z);
-    } else {  // maps.py:743-747
-      const float ze = __fadd_rn(z, 1e-7f);
-      x = __fadd_rn(__fmul_rn(__fdiv_rn(x, ze), fx), cx);
-      y = __fadd_rn(__fmul_rn(__fdiv_rn(y, ze), fy), cy);
-      if (flip_h) y = __fsub_rn((float)(height - 1), y);
+                    int flip_h, int height, int to_image, float* __restrict__ out, int vec) {
+  DM_GRID_STRIDE(g, (n + 3) / 4) {
+    const long long i0 = g * 4;
+    P4 q = load_p4(pts, i0, n, vec);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float x = q.v[3 * j], y = q.v[3 * j + 1];
+      const float z = q.v[3 * j + 2];
+      if (!to_image) {  // maps.py:670-678
+        if (flip_h) y = __fsub_rn((float)(height - 1), y);
+        x = __fmul_rn(__fdiv_rn(__fsub_rn(x, cx), fx), z);
+        y = __fmul_rn(__fdiv_rn(__fsub_rn(y, cy), fy), z);
+      } else {  // maps.py:743-747
+        const float ze = __fadd_rn(z, 1e-7f);
+        x = __fadd_rn(__fmul_rn(__fdiv_rn(x, ze), fx), cx);
+        y = __fadd_rn(__fmul_rn(__fdiv_rn(y, ze), fy), cy);
+        if (flip_h) y = __fsub_rn((float)(height - 1), y);
+      }
+      q.v[3 * j] = x; q.v[3 * j + 1] = y;
     }
-    out[i * 3] = x; out[i * 3 + 1] = y; out[i * 3 + 2] = z;
+    store_p4(out, i0, n, vec, q);
   }
 }
 
+// four consecutive pixels per thread: one 128-bit depth load, three 128-bit point stores, one 32-bit valid store
 __global__ void __launch_bounds__(kThreads)
 depth_to_points_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ valid_in, long long total,
                        int H, int W, float fx, float fy, float cx, float cy, int flip_h, int has_tmin,
                        float tmin, int has_tmax, float tmax, float* __restrict__ pts,
-                       uint8_t* __restrict__ valid_out) {
+                       uint8_t* __restrict__ valid_out, int vec) {
   const int N = H * W;
-  DM_GRID_STRIDE(i, total) {
-    const int n = (int)(i % N);
-    const int r = n / W, c = n - r * W;
-    const float z = depth[i];
-    const V3 p = unproject(r, c, z, H, fx, fy, cx, cy, flip_h);
-    pts[i * 3] = p.x; pts[i * 3 + 1] = p.y; pts[i * 3 + 2] = p.z;
-    bool ok = true;
-    if (has_tmax) ok = ok && (z <= tmax);
-    if (has_tmin) ok = ok && (z >= tmin);
-    if (valid_in) ok = ok && valid_in[i];
-    valid_out[i] = ok;
+  DM_GRID_STRIDE(g, (total + 3) / 4) {
+    const long long i0 = g * 4;
+    const bool full = vec && i0 + 3 < total;
+    float z[4];
+    uint32_t vin = 0x01010101u;
+    if (full) {
+      const float4 z4 = ld_stream_f4(depth + i0);
+      z[0] = z4.x; z[1] = z4.y; z[2] = z4.z; z[3] = z4.w;
+      if (valid_in) vin = *reinterpret_cast<const uint32_t*>(valid_in + i0);
+    } else {
+      vin = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        z[j] = i0 + j < total ? depth[i0 + j] : 0.0f;
+        if (i0 + j < total && (!valid_in || valid_in[i0 + j])) vin |= 1u << (8 * j);
+      }
+    }
+    int n = (int)(i0 % N);
+    int r = n / W, c = n - r * W;
+    P4 q;
+    uint32_t vout = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const V3 p = unproject(r, c, z[j], H, fx, fy, cx, cy, flip_h);
+      q.v[3 * j] = p.x; q.v[3 * j + 1] = p.y; q.v[3 * j + 2] = p.z;
+      bool ok = ((vin >> (8 * j)) & 0xffu) != 0;
+      if (has_tmax) ok = ok && (z[j] <= tmax);
+      if (has_tmin) ok = ok && (z[j] >= tmin);
+      vout |= (ok ? 1u : 0u) << (8 * j);
+      if (++c == W) { c = 0; if (++r == H) r = 0; }
+    }
+    store_p4(pts, i0, total, vec, q);
+    if (full) {
+      *reinterpret_cast<uint32_t*>(valid_out + i0) = vout;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (i0 + j < total) valid_out[i0 + j] = (uint8_t)((vout >> (8 * j)) & 1u);
+    }
   }
 }
 
@@ -210,8 +286,8 @@ extern "C" int dm_transform_points_f32(const float* points, const DmStep* steps,
   const long long total = (long long)b * n;
   if (total == 0) return DM_OK;
   if (!points || !out || (n_steps > 0 && !steps)) return DM_EINVAL;
-  transform_points_kernel<<<grid_for(total), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      points, steps, n_steps, n, total, out);
+  transform_points_kernel<<<grid_for((total + 3) / 4), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      points, steps, n_steps, n, total, out, aligned_to(points, 16) && aligned_to(out, 16));
   DM_LAUNCHED();
   return DM_OK;
 }
@@ -221,8 +297,8 @@ extern "C" int dm_image_camera_f32(const float* points, int64_t n, float fx, flo
   if (n < 0) return DM_EINVAL;
   if (n == 0) return DM_OK;
   if (!points || !out) return DM_EINVAL;
-  image_camera_kernel<<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      points, n, fx, fy, cx, cy, flip_h, height, to_image, out);
+  image_camera_kernel<<<grid_for((n + 3) / 4), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      points, n, fx, fy, cx, cy, flip_h, height, to_image, out, aligned_to(points, 16) && aligned_to(out, 16));
   DM_LAUNCHED();
   return DM_OK;
 }
@@ -235,8 +311,9 @@ extern "C" int dm_depth_to_points_f32(const float* depth, const uint8_t* valid_i
   const long long total = (long long)frames * H * W;
   if (total == 0) return DM_OK;
   if (!depth || !points || !valid_out) return DM_EINVAL;
-  depth_to_points_kernel<<<grid_for(total), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      depth, valid_in, total, H, W, fx, fy, cx, cy, flip_h, has_tmin, tmin, has_tmax, tmax, points, valid_out);
+  depth_to_points_kernel<<<grid_for((total + 3) / 4), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      depth, valid_in, total, H, W, fx, fy, cx, cy, flip_h, has_tmin, tmin, has_tmax, tmax, points, valid_out,
+      aligned_to(depth, 16) && aligned_to(points, 16) && aligned_to(valid_out, 4) && (!valid_in || aligned_to(valid_in, 4)));
   DM_LAUNCHED();
   return DM_OK;
 }
