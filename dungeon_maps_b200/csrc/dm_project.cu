@@ -60,6 +60,7 @@ struct ProjPlan {
   int ws_warps;          // warp-specialised kernel: consumer warps per CTA (tile = 128 px each)
   int ws_groups;         // ... channel groups a frame's value planes are staged in (each group re-reads the depth row)
   int ws_cg;             // ... value channels per group
+  int lean;              // C == 0: hmap_proj_kernel + hmap_resolve_kernel instead of the persistent kernel
   int ws_r2d;            // ... image rows per 2-D tile (tensor-map TMA), 0: tiles of 128 * ws_warps consecutive pixels
   size_t ws_stage_bytes; // warp-specialised kernel: one stage of 128 * ws_warps pixels
   size_t smem_ws;        // stage + barriers/item/sample block
@@ -83,7 +84,9 @@ static ProjPlan make_plan(const DmProjCfg& cfg, int b, int tile_rows = -1) {
   const size_t M = (size_t)cfg.Mh * cfg.Mw;
   p.slot_words = (M * p.CP + 3) & ~(size_t)3;
   size_t ring = kRingBudgetBytes / (p.slot_words * 4);
-  if (ring > (size_t)kMaxRing) ring = kMaxRing;
+  // height maps only (C == 0) take the two plain launches of the height-map path: a slot per frame, up to 64
+  p.lean = cfg.C == 0 && g_tile_rows != -3;
+  if (ring > (size_t)(p.lean ? 64 : kMaxRing)) ring = p.lean ? 64 : kMaxRing;
   if (ring > (size_t)(b > 0 ? b : 1)) ring = (size_t)(b > 0 ? b : 1);
   if (ring < 2) ring = 2;
   p.ring = (int)ring;
@@ -1210,6 +1213,110 @@ proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values
 }
 
 
+// ================= height maps only (C == 0): two plain launches ================================================
+// MapBuilder.plot and every caller that asks for a height map project depth alone: 5.2 MB of input and 0.8 MB of output
+// per 480 x 640 frame.  The persistent kernel's ticket machinery (913 tickets per frame, cross-CTA dependencies) costs
+// more than that work: 100 us per 32 frames where the traffic is worth 10 us (ncu r02h).  Here every frame of the call
+// has a key plane of its own (acc: nf x M words, zero between calls), so there is nothing to wait for:
+//   hmap_proj_kernel    a thread = 4 consecutive pixels (one 128-bit load): cells + heights with the device functions
+//                       of the persistent kernel (same bits), equal neighbours folded in-thread, one RED.MAX per run;
+//   hmap_resolve_kernel a thread = 4 cells: key -> value / mask (utils.py:472-491), the plane is zero again after.
+template <int FAST, bool IS_MIN>
+__global__ void __launch_bounds__(256)
+hmap_proj_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ valid,
+                 const DmProjSample* __restrict__ samples, const DmProjCfg cfg, int frame0, int vec,
+                 uint32_t* __restrict__ acc, unsigned long long slot_words) {
+  __shared__ DmProjSample sp;
+  const int slot = blockIdx.y, frame = frame0 + slot;
+  const int N = cfg.H * cfg.W;
+  if (threadIdx.x < (int)(sizeof(DmProjSample) / 4))
+    reinterpret_cast<uint32_t*>(&sp)[threadIdx.x] = reinterpret_cast<const uint32_t*>(samples + frame)[threadIdx.x];
+  __syncthreads();
+  const Rcps rcp{__frcp_rn(cfg.map_res), __frcp_rn(cfg.fx), __frcp_rn(cfg.fy)};
+  const float* dplane = depth + (size_t)frame * N;
+  const uint8_t* vplane = valid ? valid + (size_t)frame * N : nullptr;
+  uint32_t* plane = acc + (size_t)slot * slot_words;
+  const float fill = cfg.fill_value;
+  for (int n0 = (blockIdx.x * 256 + threadIdx.x) * 4; n0 < N; n0 += gridDim.x * 1024) {
+    int cl[4] = {-1, -1, -1, -1};
+    float y[4] = {0.f, 0.f, 0.f, 0.f};
+    if (vec) {  // W % 4 == 0, 16-byte aligned planes: the quad lies in one image row
+      const float4 z4 = ld_stream_f4(dplane + n0);
+      const float z[4] = {z4.x, z4.y, z4.z, z4.w};
+      uint32_t vm = 0x01010101u;
+      if (vplane) vm = *reinterpret_cast<const uint32_t*>(vplane + n0);
+      const int r = n0 / cfg.W, c = n0 - r * cfg.W;
+      if (FAST) {
+        const float yy = cfg.flip_h ? __fsub_rn((float)(cfg.H - 1), (float)r) : (float)r;
+        const float yn = div_by_rcp(__fsub_rn(yy, cfg.cy), cfg.fy, rcp.fy);
+        bool rowok = true;
+        const int kb = cfg.clip_border;
+        if (kb > 0) rowok = (r >= kb) && (r < cfg.H - kb);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float xn = div_by_rcp(__fsub_rn((float)(c + k), cfg.cx), cfg.fx, rcp.fx);
+          bool ok = rowok && (((vm >> (8 * k)) & 0xffu) != 0);
+          if (kb > 0) ok = ok && (c + k >= kb) && (c + k < cfg.W - kb);
+          cl[k] = pixel_cell_fast<FAST == 2, true>(cfg, sp, xn, yn, z[k], ok, &y[k], rcp.res);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          cl[k] = pixel_cell(cfg, sp, r, c + k, z[k], ((vm >> (8 * k)) & 0xffu) != 0, &y[k]);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int n = n0 + k;
+        if (n < N) {
+          const int r = n / cfg.W, c = n - r * cfg.W;
+          cl[k] = pixel_cell(cfg, sp, r, c, ld_stream_f1(dplane + n), vplane ? vplane[n] != 0 : true, &y[k]);
+        }
+      }
+    }
+    // runs of equal neighbouring cells fold in-thread; the last pixel of a run issues
+    const bool p01 = (cl[0] >= 0) && (cl[0] == cl[1]);
+    const bool p12 = (cl[1] >= 0) && (cl[1] == cl[2]);
+    const bool p23 = (cl[2] >= 0) && (cl[2] == cl[3]);
+    y[1] = p01 ? red2<IS_MIN>(y[0], y[1]) : y[1];
+    y[2] = p12 ? red2<IS_MIN>(y[1], y[2]) : y[2];
+    y[3] = p23 ? red2<IS_MIN>(y[2], y[3]) : y[3];
+    if (cl[0] >= 0 && !p01 && beats<IS_MIN>(y[0], fill)) red_max_u32(plane + cl[0], key_of<IS_MIN>(y[0]));
+    if (cl[1] >= 0 && !p12 && beats<IS_MIN>(y[1], fill)) red_max_u32(plane + cl[1], key_of<IS_MIN>(y[1]));
+    if (cl[2] >= 0 && !p23 && beats<IS_MIN>(y[2], fill)) red_max_u32(plane + cl[2], key_of<IS_MIN>(y[2]));
+    if (cl[3] >= 0 && beats<IS_MIN>(y[3], fill)) red_max_u32(plane + cl[3], key_of<IS_MIN>(y[3]));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+hmap_resolve_kernel(uint32_t* __restrict__ acc, unsigned long long slot_words, const DmProjCfg cfg, int frame0, int vec,
+                    float* __restrict__ topdown, uint8_t* __restrict__ mask) {
+  const int slot = blockIdx.y, frame = frame0 + slot;
+  const int M = cfg.Mh * cfg.Mw;
+  uint32_t* plane = acc + (size_t)slot * slot_words;
+  float* tp = topdown + (size_t)frame * M;
+  uint8_t* mp = mask + (size_t)frame * M;
+  const float fill = cfg.fill_value;
+  const int is_min = cfg.reduction;
+  for (int m0 = (blockIdx.x * 256 + threadIdx.x) * 4; m0 < M; m0 += gridDim.x * 1024) {
+    if (vec && m0 + 3 < M) {  // M % 4 == 0 and 16-byte aligned outputs
+      const uint4 k = __ldcg(reinterpret_cast<const uint4*>(plane + m0));
+      if (k.x | k.y | k.z | k.w) __stcg(reinterpret_cast<uint4*>(plane + m0), make_uint4(0u, 0u, 0u, 0u));
+      // utils.py:472-491: a key is only ever stored for a value that beats fill, so "key present" == "changed" == mask
+      st_stream_f4(tp + m0, make_float4(k.x ? dec_red(k.x, is_min) : fill, k.y ? dec_red(k.y, is_min) : fill,
+                                        k.z ? dec_red(k.z, is_min) : fill, k.w ? dec_red(k.w, is_min) : fill));
+      st_stream_u32(mp + m0, (k.x ? 1u : 0u) | (k.y ? 0x100u : 0u) | (k.z ? 0x10000u : 0u) | (k.w ? 0x1000000u : 0u));
+    } else {
+      for (int m = m0; m < min(m0 + 4, M); ++m) {
+        const uint32_t k = __ldcg(plane + m);
+        if (k) __stcg(plane + m, 0u);
+        st_stream_f1(tp + m, k ? dec_red(k, is_min) : fill);
+        st_stream_u8(mp + m, k ? 1 : 0);
+      }
+    }
+  }
+}
+
 static bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 struct DeviceInfo {
@@ -1299,6 +1406,27 @@ extern "C" int dm_orth_project_f32(const float* depth, const float* values, cons
     g_dev[dev].ready = true;
   }
   const int N = cfg->H * cfg->W, M = cfg->Mh * cfg->Mw;
+  if (p.lean) {
+    uint32_t* planes = reinterpret_cast<uint32_t*>(static_cast<char*>(workspace) + p.ctrl_bytes + p.flag_bytes);
+    const int pvec = (cfg->W % 4 == 0) && aligned(depth, 16) && (!valid || aligned(valid, 4));
+    const int rvec = (M % 4 == 0) && aligned(topdown, 16) && aligned(mask, 4);
+    void (*kern)(const float*, const uint8_t*, const DmProjSample*, DmProjCfg, int, int, uint32_t*, unsigned long long) = nullptr;
+    const bool mn = cfg->reduction != 0;
+    switch (cfg->fast_steps) {
+      case 1: kern = mn ? hmap_proj_kernel<1, true> : hmap_proj_kernel<1, false>; break;
+      case 2: kern = mn ? hmap_proj_kernel<2, true> : hmap_proj_kernel<2, false>; break;
+      default: kern = mn ? hmap_proj_kernel<0, true> : hmap_proj_kernel<0, false>; break;
+    }
+    for (int f0 = 0; f0 < b; f0 += p.ring) {
+      const int nf = (b - f0) < p.ring ? (b - f0) : p.ring;
+      dim3 gp((N + 1023) / 1024, nf), gr((M + 1023) / 1024, nf);
+      kern<<<gp, 256, 0, stream>>>(depth, valid, samples, *cfg, f0, pvec, planes, (unsigned long long)p.slot_words);
+      DM_LAUNCHED();
+      hmap_resolve_kernel<<<gr, 256, 0, stream>>>(planes, (unsigned long long)p.slot_words, *cfg, f0, rvec, topdown, mask);
+      DM_LAUNCHED();
+    }
+    return DM_OK;
+  }
   uint32_t* ctrl = static_cast<uint32_t*>(workspace);
   uint32_t* flags = reinterpret_cast<uint32_t*>(static_cast<char*>(workspace) + p.ctrl_bytes);
   uint32_t* acc = reinterpret_cast<uint32_t*>(static_cast<char*>(workspace) + p.ctrl_bytes + p.flag_bytes);
@@ -1326,7 +1454,7 @@ extern "C" int dm_orth_project_f32(const float* depth, const float* values, cons
                                   : (long long)((N + ws_tile - 1) / ws_tile)) * p.ws_groups;
   const int ws_rtiles = (M + 64 * p.ws_warps * kResK - 1) / (64 * p.ws_warps * kResK);
   const long long ws_total = (long long)(b + p.lag) * (ws_tiles + ws_rtiles);
-  const bool ws_ok = (N % 4 == 0) && (cfg->W % 4 == 0) && aligned(depth, 16) && (!values || aligned(values, 16)) &&
+  const bool ws_ok = g_tile_rows != -2 && (N % 4 == 0) && (cfg->W % 4 == 0) && aligned(depth, 16) && (!values || aligned(values, 16)) &&
                      (!valid || aligned(valid, 4)) && p.smem_ws <= 220 * 1024 && ws_total < (1ll << 31) &&
                      cfg->fast_steps >= 0 && cfg->fast_steps <= 2 && p.ws_cg <= 32 &&
                      (unsigned long long)p.ring * p.slot_words < (1ull << 31);
