@@ -104,6 +104,7 @@ _SIGNATURES = {
                                                 c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
   "dm_orth_project_labels_host_f32": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(DmProjCfg),
                                                      c_int32, c_void_p, c_void_p, c_void_p, c_int32]),
+  "dm_upload_params": (ctypes.c_int, [c_void_p, c_size_t, c_void_p, POINTER(c_void_p)]),
   "dm_device_status": (ctypes.c_int, [c_int32]),
   "dm_debug_set_wait_guard": (None, [ctypes.c_uint64, ctypes.c_uint32]),
   "dm_debug_set_host_chunk": (None, [c_int32]),

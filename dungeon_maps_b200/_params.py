@@ -281,79 +281,33 @@ def flow_samples(pose, pitch, cam_h, n_points: int) -> torch.Tensor:
                     local_to_camera(pitch, cam_h, n_points)), dim=1)
 
 
-class _PinnedRing:
-  """Pinned staging slots for the small per-call parameter blocks.  `tensor.to(device)` from pageable memory
-  synchronises the stream (torch waits for the copy, i.e. for everything queued before it), which would
-  serialise the host with the GPU once per call whenever a pose changes; a copy from a pinned slot is queued
-  like a kernel.  A slot is re-used `slots` uploads later, after waiting on the event recorded behind its copy."""
+class DeviceBlock:
+  """A parameter block uploaded by dm_upload_params: a raw device pointer into the library's ring of slots, valid for
+  the work queued on the current stream before the 64th upload after it (every caller hands it to the very next C
+  call).  Quacks like the tensor the callers used to get: data_ptr()."""
+  __slots__ = ("ptr", "nbytes")
 
-  def __init__(self, slots: int = 64, slot_bytes: int = 1 << 16):
-    self.slots, self.slot_bytes = slots, slot_bytes
-    self._bufs, self._events, self._next = {}, {}, {}
-    self._streams = {}
+  def __init__(self, ptr: int, nbytes: int):
+    self.ptr, self.nbytes = ptr, nbytes
 
-  def _stream(self, device: torch.device):
-    """torch Stream object of the current stream, looked up by its raw handle (torch.cuda.current_stream builds a
-    new object per call, ~10 us)."""
-    raw = nat.stream_ptr(device)
-    hit = self._streams.get((device.index, raw))
-    if hit is None:
-      hit = self._streams[(device.index, raw)] = torch.cuda.current_stream(device)
-    return hit
-
-  def to_device(self, host: torch.Tensor, device: torch.device) -> torch.Tensor:
-    nbytes = host.numel() * host.element_size()
-    if nbytes == 0 or nbytes > self.slot_bytes:
-      return host.to(device)
-    key = device.index if device.index is not None else torch.cuda.current_device()
-    if key not in self._bufs:
-      self._bufs[key] = [None] * self.slots
-      self._events[key] = [None] * self.slots
-      self._next[key] = 0
-    i = self._next[key]
-    self._next[key] = (i + 1) % self.slots
-    if self._bufs[key][i] is None:
-      self._bufs[key][i] = torch.empty(self.slot_bytes, dtype=torch.uint8).pin_memory()
-      self._events[key][i] = torch.cuda.Event()
-    else:
-      self._events[key][i].synchronize()  # the copy that last read this slot has run (it was queued long ago)
-    staged = self._bufs[key][i][:nbytes].view(host.dtype).view(host.shape)
-    staged.copy_(host)
-    dev = torch.empty(host.shape, dtype=host.dtype, device=device)
-    dev.copy_(staged, non_blocking=True)
-    self._events[key][i].record(self._stream(device))
-    return dev
+  def data_ptr(self) -> int:
+    return self.ptr
 
 
-_ring = _PinnedRing()
+_UPLOAD_MAX = 64 * 1024  # kUpSlotBytes of csrc/dm_api.cu
 
 
-class _DeviceCache:
-  """Small LRU of uploaded parameter blocks keyed by their bytes (MapProjector defaults
-  repeat call after call)."""
-
-  def __init__(self, capacity: int = 64):
-    self._d = OrderedDict()
-    self._cap = capacity
-
-  def get(self, host: torch.Tensor, device: torch.device) -> torch.Tensor:
-    host = host.contiguous()
-    key = (device.index, nat.stream_ptr(device), host.dtype, tuple(host.shape),
-           host.numpy().tobytes())
-    hit = self._d.get(key)
-    if hit is not None:
-      self._d.move_to_end(key)
-      return hit
-    dev = _ring.to_device(host, device)
-    self._d[key] = dev
-    if len(self._d) > self._cap:
-      self._d.popitem(last=False)
-    return dev
-
-
-_cache = _DeviceCache()
-
-
-def upload(host: torch.Tensor, device: torch.device) -> torch.Tensor:
-  """Device copy of a host parameter block, cached per (device, current stream, content)."""
-  return _cache.get(host, device)
+def upload(host: torch.Tensor, device: torch.device):
+  """Device copy of a host parameter block for the next call queued on the current stream: the library's pinned ring
+  and copy stream (dm_upload_params; a torch copy on the caller's stream put a copy-engine round trip between the
+  kernels of consecutive calls and cost ~50 us of host time).  Blocks above 64 KiB (thousands of samples) go through
+  torch.  Returns an object with data_ptr()."""
+  host = host.contiguous()
+  nbytes = host.numel() * host.element_size()
+  if nbytes == 0 or nbytes > _UPLOAD_MAX:
+    return host.to(device)
+  out = nat.c_void_p()
+  with torch.cuda.device(device):
+    rc = nat.lib().dm_upload_params(host.data_ptr(), nbytes, nat.stream_ptr(device), nat.ctypes.byref(out))
+  nat.check(rc, "dm_upload_params")
+  return DeviceBlock(out.value, nbytes)

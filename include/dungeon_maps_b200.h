@@ -147,6 +147,13 @@ int dm_orth_project_labels_host_f32(const float* depth, const uint8_t* labels, c
                                     const DmProjSample* samples, const DmProjCfg* cfg, int32_t b,
                                     float* topdown, uint8_t* mask, float* height, int32_t device);
 
+/* Uploads a small host-built parameter block (per-sample transforms, fuse sources, ...; at most 64 KiB) for the NEXT
+ * call queued on `stream` of the current device: copied through the library's ring of pinned slots on a copy stream of
+ * its own, `stream` waits for the copy.  *dev_ptr stays valid for the work queued on `stream` before the 64th upload
+ * after this one.  (What the Python layer used torch for: pinned staging + copy on the caller's stream, which put a
+ * copy-engine round trip between the kernels of consecutive calls.) */
+int dm_upload_params(const void* src, size_t nbytes, void* stream, void** dev_ptr);
+
 /* Device-side wait guard.  The projection kernels are persistent launches whose CTAs wait on one another's
  * per-frame completion counters; a wait that exceeds 4 s (a scheduling bug, never expected) does not hang the GPU:
  * the item is skipped, the launch re-zeroes its workspace before it ends, and DM_ETIMEOUT is reported ONCE by
