@@ -109,6 +109,7 @@ _SIGNATURES = {
   "dm_debug_set_wait_guard": (None, [ctypes.c_uint64, ctypes.c_uint32]),
   "dm_debug_set_host_chunk": (None, [c_int32]),
   "dm_debug_set_tile_rows": (None, [c_int32]),
+  "dm_debug_set_dense_shift": (None, [c_int32]),
   "dm_affine_grid_f32": (ctypes.c_int, [c_void_p, c_void_p, POINTER(DmFlowCfg), c_int32, c_void_p, c_void_p]),
   "dm_fuse_bbox_i64": (ctypes.c_int, [POINTER(DmFuseSource), c_int32, c_int32, c_int32, c_float, c_void_p, c_void_p]),
   "dm_fuse_scatter_f32": (ctypes.c_int, [POINTER(DmFuseSource), c_int32, c_int32, c_int32, POINTER(DmFuseTarget),

@@ -19,6 +19,7 @@ constexpr int kFuseThreads = 256;
 constexpr int kScanThreads = 128;
 constexpr int kMaxSources = 8;
 constexpr int kGroup = 16;  // mask bytes examined per work item (one 128-bit load)
+int g_dense_shift = 1;      // test hook (dm_debug_set_dense_shift): 0 keeps every plane on the per-cell path
 
 // Block-uniform state of the plane (one (sample, channel) image of one source) a block is scanning.
 struct PlaneCtx {
@@ -344,6 +345,55 @@ __device__ __forceinline__ void block_reduce_box(float& amin, float& amax, float
   }
 }
 
+// World map -> new world map (round 2).  A map in the global frame merged into a target in the global frame moves
+// every cell by the same whole number of columns and rows — give or take float rounding, which is why the reference's
+// per-cell arithmetic is what defines the result.  But that arithmetic is SEPARABLE without transform steps: the
+// target column is a function of the source column alone, the target row of the source row alone.  A block evaluates
+// both functions — the very float operations of source_point() and quantize_f() — over the plane's rectangle of valid
+// cells (a few hundred columns and rows) and accepts the plane when every column moved by one dx and every row by one
+// dz and all of them stay inside the canvas.  Then the rectangle is copied densely: whole rows of plain coalesced
+// stores (value where the cell is valid and beats the fill, the fill elsewhere) instead of one read-modify-write per
+// valid cell into lines of a 0.7 GB canvas the fill kernel has just pushed out of L2.  Only for the first source of a
+// call that filled the canvas itself (nothing else has written it yet); anything else takes the per-cell path.
+__device__ __forceinline__ bool plane_shift(const DmFuseSource& src, const PlaneCtx& ctx, const DmFuseTarget& tgt, int r0,
+                                            int r1, int c0, int c1, int* dx_out, int* dz_out) {
+  bool ok = ctx.step0.kind == DM_STEP_NONE && ctx.step1.kind == DM_STEP_NONE && r0 <= r1 && c0 <= c1;
+  auto col_of = [&](int c) {  // the x half of source_point + quantize_f
+    const float x = __fmul_rn(__fsub_rn((float)c, ctx.woff), src.map_res);
+    float xf, zf;
+    quantize_f(x, 0.0f, tgt.width_offset, tgt.height_offset, tgt.map_res, tgt.Mh, tgt.flip_h, &xf, &zf);
+    return xf;
+  };
+  auto row_of = [&](int r) {  // the z half
+    float zb = (float)r;
+    if (src.flip_h) zb = __fsub_rn((float)(src.h - 1), zb);
+    const float z = __fmul_rn(__fsub_rn(zb, ctx.hoff), src.map_res);
+    float xf, zf;
+    quantize_f(0.0f, z, tgt.width_offset, tgt.height_offset, tgt.map_res, tgt.Mh, tgt.flip_h, &xf, &zf);
+    return zf;
+  };
+  int dx = 0, dz = 0;
+  if (ok) {
+    const float x0 = col_of(c0), z0 = row_of(r0);
+    ok = x0 >= 0.0f && x0 < (float)tgt.Mw && z0 >= 0.0f && z0 < (float)tgt.Mh;
+    if (ok) {
+      dx = (int)x0 - c0;
+      dz = (int)z0 - r0;
+      for (int c = c0 + threadIdx.x; c <= c1 && ok; c += kScanThreads) {
+        const float xf = col_of(c);
+        ok = xf >= 0.0f && xf < (float)tgt.Mw && (int)xf - c == dx;
+      }
+      for (int r = r0 + threadIdx.x; r <= r1 && ok; r += kScanThreads) {
+        const float zf = row_of(r);
+        ok = zf >= 0.0f && zf < (float)tgt.Mh && (int)zf - r == dz;
+      }
+    }
+  }
+  *dx_out = dx;
+  *dz_out = dz;
+  return __syncthreads_and(ok) != 0;
+}
+
 __global__ void fuse_plane_box_init(int* box, int planes) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < planes; i += gridDim.x * blockDim.x) {
     box[4 * i + 0] = 0x7fffffff; box[4 * i + 1] = -1;  // rows:    min, max
@@ -359,7 +409,8 @@ __global__ void fuse_plane_box_init(int* box, int planes) {
 __global__ void __launch_bounds__(kScanThreads, 1024 / kScanThreads)
 fuse_scatter_kernel(const __grid_constant__ DmFuseSource src, int planes, int C, const DmFuseTarget tgt,
                     float* __restrict__ topdown, float* __restrict__ height, uint8_t* __restrict__ mask,
-                    int mask_inline, long long* __restrict__ next_bbox, int* __restrict__ next_plane_box) {
+                    int mask_inline, long long* __restrict__ next_bbox, int* __restrict__ next_plane_box,
+                    int fresh_canvas) {
   __shared__ PlaneCtx ctx;
   // next_bbox: what pass 1 of a FOLLOWING merge would find for the map written here, taken as a global-frame
   // source of the same resolution: min / max over its valid cells of quantize0(dequantize(cell)) (maps.py:1081-1086,
@@ -380,7 +431,58 @@ fuse_scatter_kernel(const __grid_constant__ DmFuseSource src, int planes, int C,
     float* oplane = height ? height + (long long)plane * M : nullptr;
     uint8_t* mplane = mask + (long long)plane * M;
     float pcmin = INFINITY, pcmax = -INFINITY, prmin = INFINITY, prmax = -INFINITY;  // this plane's marked cells
-    for_valid_cells(src, plane, [&](int cell, int r, int c) {
+    bool dense = false;
+    if (fresh_canvas && mask_inline && src.plane_box) {  // block-uniform
+      const int4 bx = __ldg(reinterpret_cast<const int4*>(src.plane_box) + plane);  // rmin, rmax, cmin, cmax
+      const int r0 = max(bx.x, 0), r1 = min(bx.y, src.h - 1), c0 = max(bx.z, 0), c1 = min(bx.w, src.w - 1);
+      int dx, dz;
+      dense = plane_shift(src, ctx, tgt, r0, r1, c0, c1, &dx, &dz);
+      if (dense) {
+        const uint8_t* smask = src.mask + (long long)plane * n;
+        const int wbox = c1 - c0 + 1;
+        // a block takes whole rows of the rectangle; a thread four cells of the row per round (their loads in flight
+        // together), consecutive lanes consecutive cells
+        for (int r = r0 + blockIdx.x; r <= r1; r += gridDim.x) {
+          const int srow = r * src.w + c0, trow = (r + dz) * tgt.Mw + (c0 + dx);
+          for (int cb = threadIdx.x; cb < wbox; cb += 4 * kScanThreads) {
+            uint8_t m[4];
+            float y[4], v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int ci = cb + k * kScanThreads;
+              m[k] = ci < wbox ? smask[srow + ci] : (uint8_t)0;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int ci = cb + k * kScanThreads;
+              y[k] = m[k] ? hplane[srow + ci] : 0.0f;
+              v[k] = (m[k] && vplane) ? vplane[srow + ci] : y[k];  // maps.py:2214-2216
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int ci = cb + k * kScanThreads;
+              if (ci >= wbox) continue;
+              float out = tgt.fill_value, hout = -INFINITY;
+              uint8_t mk = 0;
+              if (m[k]) {
+                if (v[k] == v[k] && better(v[k], tgt.fill_value, tgt.reduction)) {  // what the atomic leaves in a cell that held fill
+                  out = v[k];
+                  mk = 1;
+                  const float xf = (float)(c0 + ci + dx), zf = (float)(r + dz);
+                  pcmin = fminf(pcmin, xf); pcmax = fmaxf(pcmax, xf);
+                  prmin = fminf(prmin, zf); prmax = fmaxf(prmax, zf);
+                }
+                if (y[k] == y[k]) hout = fmaxf(hout, y[k]);  // maps.py:2258-2271: max against -inf
+              }
+              tplane[trow + ci] = out;
+              mplane[trow + ci] = mk;
+              if (oplane) oplane[trow + ci] = hout;
+            }
+          }
+        }
+      }
+    }
+    if (!dense) for_valid_cells(src, plane, [&](int cell, int r, int c) {
       const V3 p = source_point(src, ctx, hplane, cell, r, c);
       float xf, zf;  // maps.py:2232-2238
       quantize_f(p.x, p.z, tgt.width_offset, tgt.height_offset, tgt.map_res, tgt.Mh, tgt.flip_h, &xf, &zf);
@@ -537,12 +639,15 @@ static unsigned grid_for(long long items) {
   return (unsigned)blocks;
 }
 
+// fresh: the canvases hold nothing but what fuse_fill_kernel wrote (the caller filled them itself): the first source
+// may then write its cells with plain stores (plane_shift).
 static int launch_scatter(const DmFuseSource* sources, int n_sources, int b, int C, const DmFuseTarget& tgt,
                           float* topdown, uint8_t* mask, float* height, int mask_inline, cudaStream_t stream,
-                          long long* next_bbox = nullptr, int* next_plane_box = nullptr) {
+                          long long* next_bbox = nullptr, int* next_plane_box = nullptr, int fresh = 0) {
   for (int i = 0; i < n_sources; ++i) {
     fuse_scatter_kernel<<<plane_grid(sources[i], b * C), kScanThreads, 0, stream>>>(
-        sources[i], b * C, C, tgt, topdown, height, mask, mask_inline, next_bbox, next_plane_box);
+        sources[i], b * C, C, tgt, topdown, height, mask, mask_inline, next_bbox, next_plane_box,
+        (fresh && i == 0 && g_dense_shift) ? 1 : 0);
     DM_LAUNCHED();
   }
   return DM_OK;
@@ -551,6 +656,8 @@ static int launch_scatter(const DmFuseSource* sources, int n_sources, int b, int
 }  // namespace dm
 
 using namespace dm;
+
+extern "C" void dm_debug_set_dense_shift(int32_t on) { dm::g_dense_shift = on ? 1 : 0; }
 
 extern "C" int dm_fuse_bbox_i64(const DmFuseSource* sources, int32_t n_sources, int32_t b, int32_t C,
                                 float target_res, int64_t* out, void* stream_) {
@@ -615,7 +722,7 @@ extern "C" int dm_fuse_scatter_track_f32(const DmFuseSource* sources, int32_t n_
     }
   }
   const int rs = launch_scatter(sources, n_sources, b, C, *target, topdown, mask, height, mask_inline, stream,
-                                reinterpret_cast<long long*>(next_bbox), next_plane_box);
+                                reinterpret_cast<long long*>(next_bbox), next_plane_box, 1);
   if (rs != DM_OK) return rs;
   if (!mask_inline) {
     changed_mask_kernel<<<grid_for(n_out), kFuseThreads, 0, stream>>>(topdown, n_out, target->fill_value, mask);

@@ -171,6 +171,9 @@ void dm_debug_set_host_chunk(int32_t frames);
  * by one tensor-map TMA copy per tile (cp.async.bulk.tensor.3d; folds vertical runs before they leave the SM — fewer
  * REDs, more instructions: slower on the B200).  Every layout produces the same bits. */
 void dm_debug_set_tile_rows(int32_t rows);
+/* Test hook: 0 keeps the merge's first source on the per-cell scatter for every plane; 1 (default) lets planes whose
+ * cells all move by one whole (dx, dz) be copied densely (dm_fuse.cu: plane_shift).  Same bits either way. */
+void dm_debug_set_dense_shift(int32_t on);
 
 /* Per-sample parameters of camera_affine_grid (maps.py:353-460). */
 typedef struct DmFlowSample {

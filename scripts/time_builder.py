@@ -7,6 +7,8 @@ import torch
 import bench
 from dungeon_maps_b200 import _native as nat
 key = sys.argv[1]
+if os.environ.get("DM_DENSE") is not None:
+  nat.lib().dm_debug_set_dense_shift(int(os.environ["DM_DENSE"]))
 dev = torch.device("cuda", 0)
 args = types.SimpleNamespace(scene="room")
 frames = None

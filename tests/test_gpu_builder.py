@@ -162,3 +162,40 @@ def test_plane_boxes_equal_the_mask_extents_and_a_full_scan():
     nb.step(depth, cam_pose=poses[t], **kw)
   assert_same(npy(nb.world_map._tracked_box.plane_box), boxes, "native path plane boxes")
   assert_workspaces_clean()
+
+
+@pytest.mark.parametrize("native", [True, False])
+@pytest.mark.parametrize("fill,reduction,values", [(dmap.NINF, None, False), (None, None, False), (50., "min", False),
+                                                   (dmap.NINF, None, True)])
+def test_dense_world_copy_equals_the_per_cell_scatter(native, fill, reduction, values):
+  """A merge copies the old world map into the new canvas densely when every cell of a plane moves by one whole
+  (dx, dz) (dm_fuse.cu: plane_shift) and cell by cell otherwise: the same maps, offsets and tracked rectangles,
+  step after step (dm_debug_set_dense_shift switches the dense path off), and the oracle's bits."""
+  from dungeon_maps_b200 import _native as nat
+  if values and native:
+    pytest.skip("the C step covers height maps only")
+  b, T, H, W = 3, 7, 120, 160
+  poses = _walk(b, T, seed=11)
+  kw = dict(to_global=False, width_offset=60., height_offset=0., map_width=120, map_height=120)
+  runs = []
+  try:
+    for dense in (1, 0):
+      nat.lib().dm_debug_set_dense_shift(dense)
+      bld = _builder(native, fill=fill, reduction=reduction)
+      worlds = []
+      for t in range(T):
+        depth = synth.room_depth(b, H, W, HFOV, PITCH, 0.88, poses[t].cuda(), seed=11, half=6.0, device="cuda")
+        vm = synth.uniform((b, 2, H, W), 100 + t, -1., 1., device="cuda") if values else None
+        bld.step(depth, cam_pose=poses[t], value_map=vm, **kw)
+        wm = bld.world_map
+        tb = getattr(wm, "_tracked_box", None)
+        worlds.append((wm, None if tb is None or tb.plane_box is None else tb.plane_box.cpu().numpy().copy()))
+      runs.append(worlds)
+  finally:
+    nat.lib().dm_debug_set_dense_shift(1)
+  for t, ((wa, ba), (wb, bb)) in enumerate(zip(*runs)):
+    _same_map(wa, wb, f"step {t} world (dense vs per-cell)")
+    assert (ba is None) == (bb is None)
+    if ba is not None:
+      assert np.array_equal(ba, bb), f"step {t}: tracked rectangles differ"
+  assert_workspaces_clean()
