@@ -79,9 +79,13 @@ def _alloc_canvas(shape: Tuple[int, ...], dtype: torch.dtype, dev: torch.device)
   n = int(np.prod(shape))
   if n < (1 << 18):
     return torch.empty(shape, dtype=dtype, device=dev)
+  return torch.empty((_canvas_cap(n),), dtype=dtype, device=dev)[:n].view(shape)
+
+
+def _canvas_cap(n: int) -> int:
+  """Size class of a canvas of n elements: the next of {5/8, 6/8, 7/8, 8/8} of the power of two above n."""
   top = 1 << (n - 1).bit_length()          # smallest power of two >= n
-  cap = next(c for c in (top // 2 + k * (top // 8) for k in range(1, 5)) if c >= n)
-  return torch.empty((cap,), dtype=dtype, device=dev)[:n].view(shape)
+  return next(c for c in (top // 2 + k * (top // 8) for k in range(1, 5)) if c >= n)
 
 
 def release_workspaces() -> None:
@@ -1313,6 +1317,18 @@ class MapBuilder():
                             world.mask.shape[-1], float(world.proj.width_offset), float(world.proj.height_offset),
                             nat.ptr(box), nat.ptr(planes))
       shape = nat.DmMergeShape()
+      # Everything the merge needs that does not depend on the bounding box is set up BEFORE the call that waits for it:
+      # the GPU idles from the moment the box arrives until the merge kernels are queued.  The new canvas is as a rule
+      # in the size class of the old one (the map grows by a few cells per step), so canvases of that class are taken
+      # from the allocator ahead of the sync and only replaced when the box asks for more.
+      track = nb.fill == nb.fill
+      next_box = torch.empty((5,), dtype=torch.int64, device=dev) if track else None
+      next_planes = torch.empty((b, 4), dtype=torch.int32, device=dev) if track else None
+      spec_top = spec_mask = None
+      if have_world and world.mask.numel() >= (1 << 18):
+        cap = _canvas_cap(world.mask.numel())
+        spec_top = torch.empty((cap,), dtype=torch.float32, device=dev)
+        spec_mask = torch.empty((cap,), dtype=torch.bool, device=dev)
       nat.check(lib.dm_builder_plot(nb.handle, depth_map.data_ptr(), pose.data_ptr(), sin.data_ptr(), cos.data_ptr(),
                                     local_top.data_ptr(), local_mask.data_ptr(), wref, shape, stream),
                 "dm_builder_plot")
@@ -1321,11 +1337,14 @@ class MapBuilder():
                                      map_projector=target)
         return local
       mh, mw = shape.map_height, shape.map_width
-      topdown = _alloc_canvas((b, 1, mh, mw), torch.float32, dev)
-      mask = _alloc_canvas((b, 1, mh, mw), torch.bool, dev)
-      track = nb.fill == nb.fill
-      next_box = torch.empty((5,), dtype=torch.int64, device=dev) if track else None
-      next_planes = torch.empty((b, 4), dtype=torch.int32, device=dev) if track else None
+      n_new = b * mh * mw
+      if spec_top is not None and (1 << 18) <= n_new <= spec_top.numel():
+        topdown = spec_top[:n_new].view(b, 1, mh, mw)
+        mask = spec_mask[:n_new].view(b, 1, mh, mw)
+      else:
+        topdown = _alloc_canvas((b, 1, mh, mw), torch.float32, dev)
+        mask = _alloc_canvas((b, 1, mh, mw), torch.bool, dev)
+      spec_top = spec_mask = None
       out = nat.DmMapRef(topdown.data_ptr(), mask.data_ptr(), mh, mw, shape.width_offset, shape.height_offset,
                          nat.ptr(next_box), nat.ptr(next_planes))
       nat.check(lib.dm_builder_merge(nb.handle, out, stream), "dm_builder_merge")
