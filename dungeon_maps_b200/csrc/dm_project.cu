@@ -930,7 +930,9 @@ __device__ __forceinline__ bool ws_resolve_slice(uint32_t* __restrict__ acc_slot
 // the group's value planes and one for the depth plane; tmv / tmd are the tensor maps of `values` (W, H, b C) and
 // `depth` (W, H, b), encoded on the host per call.
 template <int FAST, bool IS_MIN, int WW, int R2D>
-__global__ void __launch_bounds__(32 * (WW + 1))
+// (the 4-row layout is held to 6 CTAs per SM, the shared-memory limit: left alone ptxas takes 88 registers for it and
+// 4 CTAs fit — 0.509 instead of 0.471 ms per config-2 step)
+__global__ void __launch_bounds__(32 * (WW + 1), (R2D == 4 && WW == 4) ? 6 : 1)
 proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values,
                const uint8_t* __restrict__ valid, const DmProjSample* __restrict__ samples,
                const DmProjCfg cfg, const ProjDims d, int b, uint32_t* __restrict__ ctrl,

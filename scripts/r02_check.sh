@@ -49,7 +49,15 @@ done
 NCU="ncu --metrics gpu__time_duration.sum --clock-control none --csv"
 timeout 300 $NCU -k regex:"proj_|resolve_" -c 40 --log-file gpurun_out/launches_labels_${TAG}.csv python bench.py --workload proj_labels --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 2 > gpurun_out/ncu_launches_labels_${TAG}.log 2>&1
 timeout 300 $NCU -k regex:"proj_|resolve_" -c 40 --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extra --e2e-steps 2 > gpurun_out/ncu_launches_${TAG}.log 2>&1
+timeout 600 $NCU -k regex:"proj_|resolve_|fuse_|changed_" -s 1200 -c 200 --log-file gpurun_out/launches_builder_${TAG}.csv python bench.py --workload builder --steps 100 --no-cpu-baseline --e2e-steps 2 > gpurun_out/ncu_launches_builder_${TAG}.log 2>&1
+timeout 300 $NCU -k regex:"flow_" -c 30 --log-file gpurun_out/launches_flow_${TAG}.csv python bench.py --workload flow --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 2 > gpurun_out/ncu_launches_flow_${TAG}.log 2>&1
 FULL="ncu --set full --clock-control none --import-source on -f"
+# the merge kernels + the height-map projection at the end of the config-4 walk
+timeout 600 $FULL -k regex:"fuse_scatter|fuse_fill|fuse_bbox_kernel|hmap_" -s 1500 -c 7 -o gpurun_out/prof_fuse_${TAG} python bench.py --workload builder --steps 100 --no-cpu-baseline --e2e-steps 2 > gpurun_out/ncu_full_fuse_${TAG}.log 2>&1
+tail -2 gpurun_out/ncu_full_fuse_${TAG}.log
+# the float kernel on 2-D tiles (tensor-map TMA): optional layout, for the record
+timeout 600 $FULL -k regex:"proj_ws" -s 5 -c 1 -o gpurun_out/prof_proj2d_${TAG} python scripts/time_proj.py --rows 4 --scene room --steps 3 > gpurun_out/ncu_full_proj2d_${TAG}.log 2>&1
+tail -2 gpurun_out/ncu_full_proj2d_${TAG}.log
 timeout 600 $FULL -k regex:"proj_lbl" -s 4 -c 1 -o gpurun_out/prof_labels_${TAG} python bench.py --workload proj_labels --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 2 > gpurun_out/ncu_full_labels_${TAG}.log 2>&1
 tail -2 gpurun_out/ncu_full_labels_${TAG}.log
 timeout 600 $FULL -k regex:"proj_ws" -s 4 -c 1 -o gpurun_out/prof_proj_${TAG} python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extra --e2e-steps 2 > gpurun_out/ncu_full_${TAG}.log 2>&1
