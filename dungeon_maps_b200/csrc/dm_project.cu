@@ -25,6 +25,7 @@
 //    — which is what keeps the dependency waits of a deep, many-tiles-in-flight schedule rare.
 //  * Shapes whose planes are not 16-byte aligned take the plain-load kernels (proj_kernel /
 //    resolve_kernel, chunked over the ring) — same device functions, same results.
+#include <cstdio>
 #include <cstdlib>
 
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link)
@@ -932,7 +933,10 @@ __device__ __forceinline__ bool ws_resolve_slice(uint32_t* __restrict__ acc_slot
 template <int FAST, bool IS_MIN, int WW, int R2D>
 // (the 4-row layout is held to 6 CTAs per SM, the shared-memory limit: left alone ptxas takes 88 registers for it and
 // 4 CTAs fit — 0.509 instead of 0.471 ms per config-2 step)
-__global__ void __launch_bounds__(32 * (WW + 1), (R2D == 4 && WW == 4) ? 6 : 1)
+#ifndef DM_WS_MINB
+#define DM_WS_MINB 0  // 0: no occupancy target, ptxas's own heuristics (a target of 1 lets it take 80+ registers: 4 CTAs per SM, 0.537 ms)
+#endif
+__global__ void __launch_bounds__(32 * (WW + 1), (R2D == 4 && WW == 4) ? 6 : DM_WS_MINB)
 proj_ws_kernel(const float* __restrict__ depth, const float* __restrict__ values,
                const uint8_t* __restrict__ valid, const DmProjSample* __restrict__ samples,
                const DmProjCfg cfg, const ProjDims d, int b, uint32_t* __restrict__ ctrl,
@@ -1484,6 +1488,9 @@ extern "C" int dm_orth_project_f32(const float* depth, const float* values, cons
     int per_sm = 0;
     DM_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ws_threads, p.smem_ws));
     if (per_sm < 1) return DM_EINVAL;
+#ifdef DM_EXPERIMENT_KNOBS
+    if (getenv("DM_DEBUG_PLAN")) fprintf(stderr, "proj_ws: per_sm %d sms %d smem %zu threads %d r2d %d\n", per_sm, g_dev[dev].sms, p.smem_ws, ws_threads, r2d);
+#endif
     long long grid = (long long)g_dev[dev].sms * per_sm;
     if (grid > ws_total) grid = ws_total;
     kern<<<(unsigned)grid, ws_threads, p.smem_ws, stream>>>(depth, values, valid, samples, *cfg, dw, b, ctrl, flags,
