@@ -372,9 +372,9 @@ class BuilderWorkload:
     self.fixed = key == "builder_fixed"
     self.metric = ("MapBuilder env-steps/sec (32 envs, 480x640 depth -> 400x400 local height map -> merged into "
                    + ("fixed 2400x2400 world maps in place)" if self.fixed else "the growing world map, reference semantics)"))
-    self.kernel = ("one MapBuilder.step = dm_builder_step_fixed: dm::proj_ws_kernel + dm::fuse_scatter_kernel (in place)"
+    self.kernel = ("one MapBuilder.step = dm_builder_step_fixed: dm::hmap_proj_kernel + dm::hmap_resolve_kernel + dm::fuse_scatter_kernel (in place)"
                    if self.fixed else
-                   "one MapBuilder.step = dm_builder_plot + dm_builder_merge: dm::proj_ws_kernel, fuse_bbox, [host sync], "
+                   "one MapBuilder.step = dm_builder_plot + dm_builder_merge: dm::hmap_proj_kernel, hmap_resolve, fuse_bbox, [host sync], "
                    "fuse_fill, fuse_scatter x2; roofline over the WHOLE step (host sync included)")
     self.name = ("BASELINE config 4: MapBuilder.step over 32 envs x 100-step walk, " +
                  ("fixed 2400x2400 canvases, in-place max-merge" if self.fixed else
