@@ -128,6 +128,10 @@ _SIGNATURES = {
   "dm_builder_destroy": (None, [c_void_p]),
   "dm_builder_plot": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      POINTER(DmMapRef), POINTER(DmMergeShape), c_void_p]),
+  "dm_builder_plot_prefill": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                             POINTER(DmMapRef), POINTER(DmMergeShape), c_void_p, c_void_p, c_int64,
+                                             c_void_p]),
+  "dm_builder_plot_wait": (ctypes.c_int, [c_void_p, POINTER(DmMergeShape)]),
   "dm_builder_merge": (ctypes.c_int, [c_void_p, POINTER(DmMapRef), c_void_p]),
   "dm_builder_step_fixed": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                            POINTER(DmMapRef), c_void_p]),

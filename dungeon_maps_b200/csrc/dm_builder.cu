@@ -43,6 +43,10 @@ struct DmBuilder {
   // what dm_builder_plot leaves for dm_builder_merge
   DmFuseSource src[2];
   int n_src = 0;
+  cudaEvent_t ev_bbox = nullptr;     // the bounding box has reached the host
+  float* prefilled_top = nullptr;    // canvases dm_builder_plot_prefill filled while the host waited for the box
+  uint8_t* prefilled_mask = nullptr;
+  int64_t prefilled_cells = 0;
 };
 
 static void builder_free(DmBuilder* h) {
@@ -52,6 +56,7 @@ static void builder_free(DmBuilder* h) {
     if (h->d_params[i]) cudaFree(h->d_params[i]);
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   }
+  if (h->ev_bbox) cudaEventDestroy(h->ev_bbox);
   if (h->d_bbox) cudaFree(h->d_bbox);
   if (h->h_bbox) cudaFreeHost(h->h_bbox);
   if (h->ws) cudaFree(h->ws);
@@ -87,6 +92,7 @@ extern "C" int dm_builder_create(const DmBuilderCfg* cfg, int32_t device, DmBuil
     DM_TRY(cudaHostAlloc(reinterpret_cast<void**>(&h->h_params[i]), h->param_bytes, cudaHostAllocDefault));
     DM_TRY(cudaMalloc(reinterpret_cast<void**>(&h->d_params[i]), h->param_bytes));
     DM_TRY(cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming));
+    if (!h->ev_bbox) DM_TRY(cudaEventCreateWithFlags(&h->ev_bbox, cudaEventDisableTiming));
   }
   DM_TRY(cudaMalloc(reinterpret_cast<void**>(&h->d_bbox), 5 * sizeof(int64_t)));
   DM_TRY(cudaHostAlloc(reinterpret_cast<void**>(&h->h_bbox), 5 * sizeof(int64_t), cudaHostAllocDefault));
@@ -183,7 +189,21 @@ static void make_sources(DmBuilder* h, char* d_base, float* local_topdown, uint8
 extern "C" int dm_builder_plot(DmBuilder* h, const float* depth, const float* pose, const float* sin_yaw,
                                const float* cos_yaw, float* local_topdown, uint8_t* local_mask, const DmMapRef* world,
                                DmMergeShape* shape, void* stream_) {
-  if (!h || !depth || !pose || !sin_yaw || !cos_yaw || !local_topdown || !local_mask || !shape) return DM_EINVAL;
+  return dm_builder_plot_prefill(h, depth, pose, sin_yaw, cos_yaw, local_topdown, local_mask, world, shape, nullptr,
+                                 nullptr, 0, stream_);
+}
+
+// dm_builder_plot + speculation: the GPU is idle from the moment the bounding box is on its way to the host until the
+// merge kernels are queued (copy latency, the host computing the canvas shape, five launches) — ~55 us of a 316 us step.
+// The canvas of the merge is as a rule in the size class of the old world map, so the caller hands canvases of that
+// class in BEFORE the box is known: the fill (the largest merge kernel, 115 us) is queued right behind the box's copy
+// and runs while the host waits for the box and prepares the scatter launches.  dm_builder_merge skips its fill when
+// `out` is what was prefilled (and large enough); anything else is filled as before.
+extern "C" int dm_builder_plot_prefill(DmBuilder* h, const float* depth, const float* pose, const float* sin_yaw,
+                                       const float* cos_yaw, float* local_topdown, uint8_t* local_mask,
+                                       const DmMapRef* world, DmMergeShape* shape, float* prefill_topdown,
+                                       uint8_t* prefill_mask, int64_t prefill_cells, void* stream_) {
+  if (!h || !depth || !pose || !sin_yaw || !cos_yaw || !local_topdown || !local_mask) return DM_EINVAL;
   if (world && (!world->topdown || !world->mask || world->h <= 0 || world->w <= 0)) return DM_EINVAL;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   char* d_base = nullptr;
@@ -204,7 +224,19 @@ extern "C" int dm_builder_plot(DmBuilder* h, const float* depth, const float* po
                                seeded ? world->box : nullptr, h->d_bbox, stream);
   if (rc != DM_OK) return rc;
   DM_CUDA_OK(cudaMemcpyAsync(h->h_bbox, h->d_bbox, 5 * sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
-  DM_CUDA_OK(cudaStreamSynchronize(stream));  // the reference's .item() sync (maps.py:2172-2173)
+  DM_CUDA_OK(cudaEventRecord(h->ev_bbox, stream));
+  h->prefilled_top = nullptr; h->prefilled_mask = nullptr; h->prefilled_cells = 0;
+  if (prefill_topdown && prefill_mask && prefill_cells > 0) {
+    rc = dm_fuse_canvas_init_f32(prefill_topdown, prefill_mask, nullptr, prefill_cells, h->cfg.merge_fill_value, stream);
+    if (rc != DM_OK) return rc;
+    h->prefilled_top = prefill_topdown; h->prefilled_mask = prefill_mask; h->prefilled_cells = prefill_cells;
+  }
+  return shape ? dm_builder_plot_wait(h, shape) : DM_OK;  // shape == NULL: the caller waits later (dm_builder_plot_wait)
+}
+
+extern "C" int dm_builder_plot_wait(DmBuilder* h, DmMergeShape* shape) {
+  if (!h || !shape) return DM_EINVAL;
+  DM_CUDA_OK(cudaEventSynchronize(h->ev_bbox));  // the reference's .item() sync (maps.py:2172-2173)
   const int64_t min_x = h->h_bbox[0], max_x = h->h_bbox[1], min_z = h->h_bbox[2], max_z = h->h_bbox[3];
   shape->n_valid = h->h_bbox[4];
   if (shape->n_valid == 0) return DM_OK;  // maps.py:2217-2225: the caller keeps the last map
@@ -225,8 +257,11 @@ extern "C" int dm_builder_merge(DmBuilder* h, const DmMapRef* out, void* stream_
   tgt.Mh = out->h; tgt.Mw = out->w; tgt.flip_h = c.proj.flip_h; tgt.map_res = c.proj.map_res;
   tgt.width_offset = out->width_offset; tgt.height_offset = out->height_offset;
   tgt.fill_value = c.merge_fill_value; tgt.reduction = c.merge_reduction;
-  const int rc = dm_fuse_scatter_track_f32(h->src, h->n_src, c.b, 1, &tgt, out->topdown, out->mask, nullptr, out->box,
-                                           out->plane_box, stream_);
+  const bool prefilled = out->topdown == h->prefilled_top && out->mask == h->prefilled_mask &&
+                         (int64_t)c.b * out->h * out->w <= h->prefilled_cells;
+  const int rc = fuse_scatter_track(h->src, h->n_src, c.b, 1, &tgt, out->topdown, out->mask, nullptr, out->box,
+                                    out->plane_box, prefilled ? 1 : 0, stream_);
+  h->prefilled_top = nullptr; h->prefilled_mask = nullptr; h->prefilled_cells = 0;
   h->n_src = 0;
   return rc;
 }

@@ -47,6 +47,11 @@ int ordered_reduce(unsigned long long* keys, const float* values, long long n, i
                    float* canvas, uint8_t* mask_or, cudaStream_t stream);
 int bits_for(unsigned long long max_key_exclusive);
 
+// dm_fuse_scatter_track_f32 with `prefilled`: the canvases already hold the fill (dm_fuse.cu; used by dm_builder.cu)
+int fuse_scatter_track(const DmFuseSource* sources, int32_t n_sources, int32_t b, int32_t C, const DmFuseTarget* target,
+                       float* topdown, uint8_t* mask, float* height, int64_t* next_bbox, int32_t* next_plane_box,
+                       int prefilled, void* stream);
+
 // ---- reference arithmetic ------------------------------------------------------
 struct V3 {
   float x, y, z;

@@ -694,6 +694,14 @@ extern "C" int dm_fuse_scatter_f32(const DmFuseSource* sources, int32_t n_source
 extern "C" int dm_fuse_scatter_track_f32(const DmFuseSource* sources, int32_t n_sources, int32_t b, int32_t C,
                                          const DmFuseTarget* target, float* topdown, uint8_t* mask, float* height,
                                          int64_t* next_bbox, int32_t* next_plane_box, void* stream_) {
+  return fuse_scatter_track(sources, n_sources, b, C, target, topdown, mask, height, next_bbox, next_plane_box, 0,
+                            stream_);
+}
+
+// prefilled: the canvases already hold what fuse_fill_kernel writes (dm_builder_plot_prefill queued it) — untouched since
+int dm::fuse_scatter_track(const DmFuseSource* sources, int32_t n_sources, int32_t b, int32_t C,
+                           const DmFuseTarget* target, float* topdown, uint8_t* mask, float* height,
+                           int64_t* next_bbox, int32_t* next_plane_box, int prefilled, void* stream_) {
   if (!target || !topdown || !mask || target->Mh <= 0 || target->Mw <= 0) return DM_EINVAL;
   if (target->reduction < 0 || target->reduction > 4) return DM_EINVAL;
   if (target->reduction >= 2 && (next_bbox || next_plane_box)) return DM_EINVAL;  // tracking assumes "mask = beats fill"
@@ -705,9 +713,11 @@ extern "C" int dm_fuse_scatter_track_f32(const DmFuseSource* sources, int32_t n_
   const int vec_ok = reinterpret_cast<uintptr_t>(topdown) % 16 == 0 && reinterpret_cast<uintptr_t>(mask) % 16 == 0 &&
                      (!height || reinterpret_cast<uintptr_t>(height) % 16 == 0);
   const int mask_inline = target->fill_value == target->fill_value;  // not NaN
-  fuse_fill_kernel<<<grid_for((n_out + 3) / 4), kFuseThreads, 0, stream>>>(topdown, height, mask, n_out,
-                                                                           target->fill_value, vec_ok);
-  DM_LAUNCHED();
+  if (!prefilled) {
+    fuse_fill_kernel<<<grid_for((n_out + 3) / 4), kFuseThreads, 0, stream>>>(topdown, height, mask, n_out,
+                                                                             target->fill_value, vec_ok);
+    DM_LAUNCHED();
+  }
   if (target->reduction >= 2)  // order-dependent reductions: the reference's point order, bit for bit
     return launch_ordered(sources, n_sources, b, C, *target, topdown, mask, height, stream);
   if (next_bbox || next_plane_box) {

@@ -1279,12 +1279,14 @@ class MapBuilder():
     local_mask = torch.empty((b, 1, Mh, Mw), dtype=torch.bool, device=dev)
     lib = nat.lib()
     stream = nat.stream_ptr(dev)
-    # the local map as plot() describes it (maps.py:2459-2469); offsets as compute_center_offsets returns them
-    local_kw = {k: v for k, v in kwargs.items() if k in _CTOR_ARGS}
-    local_kw["width_offset"] = torch.tensor([woff], dtype=torch.float32)
-    local_kw["height_offset"] = torch.tensor([hoff], dtype=torch.float32)
-    local = TopdownMap(topdown_map=local_top, mask=local_mask, height_map=local_top,
-                       map_projector=proj.clone(cam_pose=cam_pose, **local_kw), is_height_map=True)
+    def make_local():
+      """The local map as plot() describes it (maps.py:2459-2469); offsets as compute_center_offsets returns them.
+      Built AFTER the step's kernels are queued: host bookkeeping belongs behind GPU work, not in front of it."""
+      local_kw = {k: v for k, v in kwargs.items() if k in _CTOR_ARGS}
+      local_kw["width_offset"] = torch.tensor([woff], dtype=torch.float32)
+      local_kw["height_offset"] = torch.tensor([hoff], dtype=torch.float32)
+      return TopdownMap(topdown_map=local_top, mask=local_mask, height_map=local_top,
+                        map_projector=proj.clone(cam_pose=cam_pose, **local_kw), is_height_map=True)
     target = proj.clone(cam_pose=cam_pose)
     with torch.cuda.device(dev):
       if self._fixed is not None:
@@ -1304,7 +1306,7 @@ class MapBuilder():
           topdown_map=topdown, mask=mask, height_map=topdown, is_height_map=True,
           map_projector=target.clone(to_global=True, width_offset=Wc / 2., height_offset=Hc / 2., map_width=Wc,
                                      map_height=Hc))
-        return local
+        return make_local()
       wref = None
       if have_world:
         box = world._tracked_box.box if _tracked_box_valid(world, target, dev) else None
@@ -1329,9 +1331,14 @@ class MapBuilder():
         cap = _canvas_cap(world.mask.numel())
         spec_top = torch.empty((cap,), dtype=torch.float32, device=dev)
         spec_mask = torch.empty((cap,), dtype=torch.bool, device=dev)
-      nat.check(lib.dm_builder_plot(nb.handle, depth_map.data_ptr(), pose.data_ptr(), sin.data_ptr(), cos.data_ptr(),
-                                    local_top.data_ptr(), local_mask.data_ptr(), wref, shape, stream),
-                "dm_builder_plot")
+      # ... and their fill is queued behind the box's copy: it runs while the host waits for the box
+      nat.check(lib.dm_builder_plot_prefill(nb.handle, depth_map.data_ptr(), pose.data_ptr(), sin.data_ptr(),
+                                            cos.data_ptr(), local_top.data_ptr(), local_mask.data_ptr(), wref, None,
+                                            nat.ptr(spec_top), nat.ptr(spec_mask),
+                                            0 if spec_top is None else spec_top.numel(), stream),
+                "dm_builder_plot_prefill")
+      local = make_local()  # while the projection, the box reduction and the prefill run
+      nat.check(lib.dm_builder_plot_wait(nb.handle, shape), "dm_builder_plot_wait")
       if shape.n_valid == 0:  # maps.py:2217-2225
         self._world_map = TopdownMap(topdown_map=local.topdown_map, mask=local.mask, height_map=local.height_map,
                                      map_projector=target)

@@ -350,6 +350,17 @@ void dm_builder_destroy(DmBuilder* builder);
 int dm_builder_plot(DmBuilder* builder, const float* depth, const float* pose, const float* sin_yaw,
                     const float* cos_yaw, float* local_topdown, uint8_t* local_mask, const DmMapRef* world,
                     DmMergeShape* shape, void* stream);
+/* dm_builder_plot with speculation: prefill_topdown / prefill_mask (prefill_cells elements each; may be NULL / 0) are
+ * canvases the caller expects to merge into — as a rule the size class of the old world map.  Their fill is queued right
+ * behind the bounding box's copy and runs while the host waits for the box; dm_builder_merge skips its own fill when
+ * `out` points at them and fits.  Same results as dm_builder_plot + dm_builder_merge. */
+int dm_builder_plot_prefill(DmBuilder* builder, const float* depth, const float* pose, const float* sin_yaw,
+                            const float* cos_yaw, float* local_topdown, uint8_t* local_mask, const DmMapRef* world,
+                            DmMergeShape* shape, float* prefill_topdown, uint8_t* prefill_mask, int64_t prefill_cells,
+                            void* stream);
+/* shape may be NULL in dm_builder_plot_prefill: the call then only queues its work and dm_builder_plot_wait blocks
+ * for the bounding box later (the caller has ~100 us of GPU work to prepare its own bookkeeping behind). */
+int dm_builder_plot_wait(DmBuilder* builder, DmMergeShape* shape);
 /* Step, second half: fills `out` (shape->map_height x map_width, offsets from `shape`) and scatters the world map
  * and the local map of the preceding dm_builder_plot into it. */
 int dm_builder_merge(DmBuilder* builder, const DmMapRef* out, void* stream);
