@@ -19,6 +19,10 @@ constexpr int kFuseThreads = 256;
 constexpr int kScanThreads = 128;
 constexpr int kMaxSources = 8;
 constexpr int kGroup = 16;  // mask bytes examined per work item (one 128-bit load)
+#ifndef DM_FUSE_MIN_CELLS
+#define DM_FUSE_MIN_CELLS 8192
+#endif
+constexpr long long kMinCellsPerBlock = DM_FUSE_MIN_CELLS;  // plane_grid: at least this many cells of a plane per block
 int g_dense_shift = 1;      // test hook (dm_debug_set_dense_shift): 0 keeps every plane on the per-cell path
 
 // Block-uniform state of the plane (one (sample, channel) image of one source) a block is scanning.
@@ -625,7 +629,11 @@ static dim3 plane_grid(const DmFuseSource& s, int planes) {
   const long long groups = ((long long)s.h * s.w + 2 * kGroup - 1) / kGroup;
   const int gy = planes < max_gy ? planes : max_gy;
   long long gx = (((long long)sm_count() * 8 * waves + gy - 1) / gy) * (256 / kScanThreads);
-  const long long gx_max = (groups + kScanThreads - 1) / kScanThreads;
+  long long gx_max = (groups + kScanThreads - 1) / kScanThreads;
+  // ... and a block should have a few thousand cells to scan: its fixed costs (context load, box reductions, their
+  // barriers and atomics) are ~10 us, which for a 400 x 400 local map split 148 ways was most of the kernel
+  const long long by_work = ((long long)s.h * s.w + kMinCellsPerBlock - 1) / kMinCellsPerBlock;
+  if (gx_max > by_work) gx_max = by_work;
   if (gx > gx_max) gx = gx_max;
   if (gx < 1) gx = 1;
   return dim3((unsigned)gx, (unsigned)gy);
@@ -645,9 +653,17 @@ static int launch_scatter(const DmFuseSource* sources, int n_sources, int b, int
                           float* topdown, uint8_t* mask, float* height, int mask_inline, cudaStream_t stream,
                           long long* next_bbox = nullptr, int* next_plane_box = nullptr, int fresh = 0) {
   for (int i = 0; i < n_sources; ++i) {
-    fuse_scatter_kernel<<<plane_grid(sources[i], b * C), kScanThreads, 0, stream>>>(
-        sources[i], b * C, C, tgt, topdown, height, mask, mask_inline, next_bbox, next_plane_box,
-        (fresh && i == 0 && g_dense_shift) ? 1 : 0);
+    const int dense = (fresh && i == 0 && g_dense_shift) ? 1 : 0;
+    dim3 grid = plane_grid(sources[i], b * C);
+    // the dense copy moves a few hundred rows per plane: with ~150 blocks per plane a block copies 3 rows and spends
+    // its life in per-block fixed costs (context load, shift test, two box reductions: 4 waves of ~10 us); one wave of
+    // fatter blocks instead
+    if (dense && mask_inline && sources[i].plane_box) {
+      const unsigned per_plane = (unsigned)((sm_count() * 8 + grid.y - 1) / grid.y);
+      if (grid.x > per_plane) grid.x = per_plane > 0 ? per_plane : 1;
+    }
+    fuse_scatter_kernel<<<grid, kScanThreads, 0, stream>>>(
+        sources[i], b * C, C, tgt, topdown, height, mask, mask_inline, next_bbox, next_plane_box, dense);
     DM_LAUNCHED();
   }
   return DM_OK;
