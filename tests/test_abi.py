@@ -183,3 +183,35 @@ def test_tracked_box_guard_host_logic():
   assert M._tracked_box_valid(m, proj, cpu)
   mask[0, 0, 0, 0] = True                                                  # mask edited in place
   assert not M._tracked_box_valid(m, proj, cpu)
+
+
+def test_canvas_size_classes():
+  """World canvases are allocated in size classes (maps._canvas_cap) so that the caching allocator can reuse the block
+  of the slightly smaller previous map, and the MapBuilder step takes canvases of the OLD map's class before the
+  bounding box is known: a class must hold the map, waste at most a quarter, and never shrink as the map grows."""
+  from dungeon_maps_b200 import maps as dmaps
+  prev = 0
+  for n in list(range(1 << 18, (1 << 18) + 4096, 37)) + [10 ** 6, 32 * 2204 * 2204, 32 * 2205 * 2204, (1 << 28) - 1,
+                                                         1 << 28, (1 << 28) + 1]:
+    cap = dmaps._canvas_cap(n)
+    assert n <= cap <= n + n // 4 + 8, (n, cap)
+    top = 1 << (n - 1).bit_length()
+    assert cap in (top // 2 + k * (top // 8) for k in range(1, 5)), (n, cap)
+  for n in range(1 << 18, 1 << 20, 4099):
+    cap = dmaps._canvas_cap(n)
+    assert cap >= prev
+    prev = cap
+
+
+def test_workspace_of_the_height_map_path():
+  """Depth-only calls (C = 0) get a key plane per frame, up to 64 per launch (csrc/dm_project.cu: hmap_* kernels); the
+  workspace query says so without a device."""
+  lib = nat.lib()
+  cfg = nat.DmProjCfg(H=480, W=640, C=0, Mh=400, Mw=400)
+  plane = 400 * 400 * 4
+  one, many, more = (lib.dm_orth_project_workspace_bytes(ctypes.byref(cfg), b) for b in (1, 64, 200))
+  assert many - one >= 62 * plane, "a plane per frame"
+  assert 0 <= more - many < 4096, "at most 64 planes (longer batches are chunked); only the control block grows"
+  cfg.C = 16
+  assert lib.dm_orth_project_workspace_bytes(ctypes.byref(cfg), 64) < 11 * 400 * 400 * 17 * 4 + (8 << 20), \
+      "float planes keep the 10-slot ring"
