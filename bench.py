@@ -431,6 +431,9 @@ class BuilderWorkload:
   def step(self):
     t = self.t % self.EPISODE
     if t == 0:
+      # a new episode: the loop lets go of the last episode's world map before it builds the next one (held across the
+      # reset it keeps 0.9 GB of fixed canvases alive and the new episode's canvases cost a 75 ms cudaMalloc, once)
+      self.out = None
       self.builder.reset()
     before = self.builder.world_map
     cells = lambda m: 0 if m is None or m.is_empty else m.mask.numel()
@@ -720,11 +723,19 @@ def time_steps(wl, steps, barrier, max_over_ranks, world):
     wl.reset_counters()
   barrier()
   ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  trace = [] if os.environ.get("DM_BENCH_TRACE") else None
   ev0.record()
   for _ in range(steps):
+    t_ = time.perf_counter()
     wl.step()
+    if trace is not None:
+      trace.append(time.perf_counter() - t_)
   ev1.record()
   barrier()
+  if trace:  # where the host time of the timed steps went (diagnostics, stderr)
+    top = sorted(range(len(trace)), key=lambda i: -trace[i])[:5]
+    print(f"[trace] {type(wl).__name__}/{getattr(wl, 'key', '')}: host us/step median {1e6 * sorted(trace)[len(trace) // 2]:.0f}, "
+          f"slowest {[(i, round(1e6 * trace[i])) for i in top]}", file=sys.stderr)
   ms = max_over_ranks(ev0.elapsed_time(ev1))
   algo = wl.algo_bytes_total / steps if isinstance(wl, BuilderWorkload) else wl.algo_bytes_per_step
   return ms / steps, world * wl.units_per_step * steps / (ms * 1e-3), algo
