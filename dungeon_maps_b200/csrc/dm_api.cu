@@ -195,6 +195,7 @@ Uploader g_up[kMaxDevices];
 }  // namespace
 
 extern "C" int dm_upload_params(const void* src, size_t nbytes, void* stream_, void** dev_ptr) {
+  DM_TRACE();
   if (!src || !dev_ptr || nbytes == 0 || nbytes > kUpSlotBytes) return DM_EINVAL;
   int device = 0;
   DM_CUDA_OK(cudaGetDevice(&device));
@@ -403,6 +404,7 @@ int orth_project_host(const float* depth, const float* values, const uint8_t* la
 extern "C" int dm_orth_project_host_f32(const float* depth, const float* values, const uint8_t* valid,
                                         const DmProjSample* samples, const DmProjCfg* cfg, int32_t b,
                                         float* topdown, uint8_t* mask, float* height, int32_t device) {
+  DM_TRACE();
   if (cfg && cfg->C > 0 && !values) return DM_EINVAL;
   return orth_project_host(depth, values, nullptr, valid, samples, cfg, b, topdown, mask, height, device);
 }
@@ -410,6 +412,7 @@ extern "C" int dm_orth_project_host_f32(const float* depth, const float* values,
 extern "C" int dm_orth_project_labels_host_f32(const float* depth, const uint8_t* labels, const uint8_t* valid,
                                                const DmProjSample* samples, const DmProjCfg* cfg, int32_t b,
                                                float* topdown, uint8_t* mask, float* height, int32_t device) {
+  DM_TRACE();
   if (!cfg || cfg->C <= 0 || !labels) return DM_EINVAL;
   return orth_project_host(depth, nullptr, labels, valid, samples, cfg, b, topdown, mask, height, device);
 }

@@ -64,6 +64,7 @@ static void builder_free(DmBuilder* h) {
 }
 
 extern "C" int dm_builder_create(const DmBuilderCfg* cfg, int32_t device, DmBuilder** out) {
+  DM_TRACE();
   if (!cfg || !out || cfg->b <= 0 || cfg->proj.C != 0) return DM_EINVAL;
   if (cfg->proj.H <= 0 || cfg->proj.W <= 0 || cfg->proj.Mh <= 0 || cfg->proj.Mw <= 0) return DM_EINVAL;
   if (cfg->merge_reduction != 0 && cfg->merge_reduction != 1) return DM_EINVAL;
@@ -189,6 +190,7 @@ static void make_sources(DmBuilder* h, char* d_base, float* local_topdown, uint8
 extern "C" int dm_builder_plot(DmBuilder* h, const float* depth, const float* pose, const float* sin_yaw,
                                const float* cos_yaw, float* local_topdown, uint8_t* local_mask, const DmMapRef* world,
                                DmMergeShape* shape, void* stream_) {
+  DM_TRACE();
   return dm_builder_plot_prefill(h, depth, pose, sin_yaw, cos_yaw, local_topdown, local_mask, world, shape, nullptr,
                                  nullptr, 0, stream_);
 }
@@ -203,6 +205,7 @@ extern "C" int dm_builder_plot_prefill(DmBuilder* h, const float* depth, const f
                                        const float* cos_yaw, float* local_topdown, uint8_t* local_mask,
                                        const DmMapRef* world, DmMergeShape* shape, float* prefill_topdown,
                                        uint8_t* prefill_mask, int64_t prefill_cells, void* stream_) {
+  DM_TRACE();
   if (!h || !depth || !pose || !sin_yaw || !cos_yaw || !local_topdown || !local_mask) return DM_EINVAL;
   if (world && (!world->topdown || !world->mask || world->h <= 0 || world->w <= 0)) return DM_EINVAL;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -235,6 +238,7 @@ extern "C" int dm_builder_plot_prefill(DmBuilder* h, const float* depth, const f
 }
 
 extern "C" int dm_builder_plot_wait(DmBuilder* h, DmMergeShape* shape) {
+  DM_TRACE();
   if (!h || !shape) return DM_EINVAL;
   DM_CUDA_OK(cudaEventSynchronize(h->ev_bbox));  // the reference's .item() sync (maps.py:2172-2173)
   const int64_t min_x = h->h_bbox[0], max_x = h->h_bbox[1], min_z = h->h_bbox[2], max_z = h->h_bbox[3];
@@ -251,6 +255,7 @@ extern "C" int dm_builder_plot_wait(DmBuilder* h, DmMergeShape* shape) {
 }
 
 extern "C" int dm_builder_merge(DmBuilder* h, const DmMapRef* out, void* stream_) {
+  DM_TRACE();
   if (!h || !out || !out->topdown || !out->mask || out->h <= 0 || out->w <= 0 || h->n_src <= 0) return DM_EINVAL;
   const DmBuilderCfg& c = h->cfg;
   DmFuseTarget tgt;
@@ -269,6 +274,7 @@ extern "C" int dm_builder_merge(DmBuilder* h, const DmMapRef* out, void* stream_
 extern "C" int dm_builder_step_fixed(DmBuilder* h, const float* depth, const float* pose, const float* sin_yaw,
                                      const float* cos_yaw, float* local_topdown, uint8_t* local_mask,
                                      const DmMapRef* canvas, void* stream_) {
+  DM_TRACE();
   if (!h || !depth || !pose || !sin_yaw || !cos_yaw || !local_topdown || !local_mask) return DM_EINVAL;
   if (!canvas || !canvas->topdown || !canvas->mask || canvas->h <= 0 || canvas->w <= 0) return DM_EINVAL;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);

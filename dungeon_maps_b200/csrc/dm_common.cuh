@@ -14,6 +14,19 @@
 
 namespace dm {
 
+// ---- tracing: NVTX ranges around every C entry point ---------------------------------------------
+// NVTX v3 is header-only and resolves its injection library at run time: no link dependency, and a push / pop pair
+// costs a few nanoseconds when no tool is attached.  nsys / ncu --nvtx then show `dm_orth_project_f32`, `dm_builder_merge`
+// ... as ranges on the calling thread with the kernels they queued underneath.
+#include <nvtx3/nvToolsExt.h>
+struct DmRange {
+  explicit DmRange(const char* name) { nvtxRangePushA(name); }
+  ~DmRange() { nvtxRangePop(); }
+  DmRange(const DmRange&) = delete;
+  DmRange& operator=(const DmRange&) = delete;
+};
+#define DM_TRACE() ::DmRange dm_range_(__func__)
+
 // ---- launch accounting / error plumbing -------------------------------------
 extern int64_t g_launches;  // defined in dm_api.cu
 

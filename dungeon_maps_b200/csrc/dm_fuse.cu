@@ -677,11 +677,13 @@ extern "C" void dm_debug_set_dense_shift(int32_t on) { dm::g_dense_shift = on ? 
 
 extern "C" int dm_fuse_bbox_i64(const DmFuseSource* sources, int32_t n_sources, int32_t b, int32_t C,
                                 float target_res, int64_t* out, void* stream_) {
+  DM_TRACE();
   return dm_fuse_bbox_seeded_i64(sources, n_sources, b, C, target_res, nullptr, out, stream_);
 }
 
 extern "C" int dm_fuse_bbox_seeded_i64(const DmFuseSource* sources, int32_t n_sources, int32_t b, int32_t C,
                                        float target_res, const int64_t* seed, int64_t* out, void* stream_) {
+  DM_TRACE();
   if (!out) return DM_EINVAL;
   if (n_sources == 0 && !seed) return DM_EINVAL;
   if (n_sources != 0) {
@@ -704,12 +706,14 @@ extern "C" int dm_fuse_bbox_seeded_i64(const DmFuseSource* sources, int32_t n_so
 extern "C" int dm_fuse_scatter_f32(const DmFuseSource* sources, int32_t n_sources, int32_t b, int32_t C,
                                    const DmFuseTarget* target, float* topdown, uint8_t* mask, float* height,
                                    void* stream_) {
+  DM_TRACE();
   return dm_fuse_scatter_track_f32(sources, n_sources, b, C, target, topdown, mask, height, nullptr, nullptr, stream_);
 }
 
 extern "C" int dm_fuse_scatter_track_f32(const DmFuseSource* sources, int32_t n_sources, int32_t b, int32_t C,
                                          const DmFuseTarget* target, float* topdown, uint8_t* mask, float* height,
                                          int64_t* next_bbox, int32_t* next_plane_box, void* stream_) {
+  DM_TRACE();
   return fuse_scatter_track(sources, n_sources, b, C, target, topdown, mask, height, next_bbox, next_plane_box, 0,
                             stream_);
 }
@@ -764,6 +768,7 @@ int dm::fuse_scatter_track(const DmFuseSource* sources, int32_t n_sources, int32
 extern "C" int dm_fuse_inplace_f32(const DmFuseSource* sources, int32_t n_sources, int32_t b, int32_t C,
                                    const DmFuseTarget* target, float* topdown, uint8_t* mask, float* height,
                                    void* stream_) {
+  DM_TRACE();
   if (!target || !topdown || !mask || target->Mh <= 0 || target->Mw <= 0) return DM_EINVAL;
   if (target->reduction < 0 || target->reduction > 4) return DM_EINVAL;
   if (!(target->fill_value == target->fill_value)) return DM_EINVAL;  // NaN fill has no in-place mask rule
@@ -778,6 +783,7 @@ extern "C" int dm_fuse_inplace_f32(const DmFuseSource* sources, int32_t n_source
 /* Fills fresh world canvases for dm_fuse_inplace_f32: topdown = fill_value, height = -inf (may be NULL), mask = 0. */
 extern "C" int dm_fuse_canvas_init_f32(float* topdown, uint8_t* mask, float* height, int64_t n, float fill_value,
                                        void* stream_) {
+  DM_TRACE();
   if (!topdown || !mask || n < 0) return DM_EINVAL;
   if (n == 0) return DM_OK;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);

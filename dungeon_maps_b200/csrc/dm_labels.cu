@@ -630,6 +630,7 @@ extern "C" int dm_orth_project_labels_f32(const float* depth, const uint8_t* lab
                                           const DmProjSample* samples, const DmProjCfg* cfg, int32_t b,
                                           float* topdown, uint8_t* mask, float* height, void* workspace,
                                           size_t workspace_bytes, void* stream_) {
+  DM_TRACE();
   if (!cfg || b < 0) return DM_EINVAL;
   if (b == 0) return DM_OK;
   if (!depth || !labels || !samples || !topdown || !mask || !workspace) return DM_EINVAL;

@@ -282,6 +282,7 @@ using namespace dm;
 
 extern "C" int dm_transform_points_f32(const float* points, const DmStep* steps, int32_t n_steps, int32_t b,
                                        int64_t n, float* out, void* stream) {
+  DM_TRACE();
   if (b < 0 || n < 0 || n_steps < 0) return DM_EINVAL;
   const long long total = (long long)b * n;
   if (total == 0) return DM_OK;
@@ -294,6 +295,7 @@ extern "C" int dm_transform_points_f32(const float* points, const DmStep* steps,
 
 extern "C" int dm_image_camera_f32(const float* points, int64_t n, float fx, float fy, float cx, float cy,
                                    int32_t flip_h, int32_t height, int32_t to_image, float* out, void* stream) {
+  DM_TRACE();
   if (n < 0) return DM_EINVAL;
   if (n == 0) return DM_OK;
   if (!points || !out) return DM_EINVAL;
@@ -307,6 +309,7 @@ extern "C" int dm_depth_to_points_f32(const float* depth, const uint8_t* valid_i
                                       int32_t W, float fx, float fy, float cx, float cy, int32_t flip_h,
                                       int32_t has_tmin, float tmin, int32_t has_tmax, float tmax, float* points,
                                       uint8_t* valid_out, void* stream) {
+  DM_TRACE();
   if (frames < 0 || H <= 0 || W <= 0) return DM_EINVAL;
   const long long total = (long long)frames * H * W;
   if (total == 0) return DM_OK;
@@ -322,6 +325,7 @@ extern "C" int dm_map_quantize_f32(const float* x, const float* z, const float* 
                                    const float* height_offset, int32_t b, int64_t n, float map_res,
                                    int32_t map_height, int32_t flip_h, int64_t* x_bin, int64_t* z_bin,
                                    void* stream) {
+  DM_TRACE();
   if (b < 0 || n < 0) return DM_EINVAL;
   const long long total = (long long)b * n;
   if (total == 0) return DM_OK;
@@ -336,6 +340,7 @@ extern "C" int dm_map_quantize_f32(const float* x, const float* z, const float* 
 extern "C" int dm_map_dequantize_f32(const float* x_bin, const float* z_bin, const float* width_offset,
                                      const float* height_offset, int32_t b, int64_t n, float map_res,
                                      int32_t map_height, int32_t flip_h, float* x, float* z, void* stream) {
+  DM_TRACE();
   if (b < 0 || n < 0) return DM_EINVAL;
   const long long total = (long long)b * n;
   if (total == 0) return DM_OK;
@@ -350,6 +355,7 @@ extern "C" int dm_scatter_f32(const float* values, const int64_t* coords, const 
                               int64_t N, int32_t Mh, int32_t Mw, int32_t has_fill, float fill_value,
                               int32_t reduction, const float* canvas_in, float* canvas_out, uint8_t* mask,
                               void* stream_) {
+  DM_TRACE();
   if (B < 0 || N < 0 || Mh <= 0 || Mw <= 0 || reduction < 0 || reduction > 4) return DM_EINVAL;
   if (B == 0) return DM_OK;
   if (!canvas_out || !mask || (N > 0 && (!values || !coords))) return DM_EINVAL;
@@ -388,6 +394,7 @@ extern "C" int dm_scatter_f32(const float* values, const int64_t* coords, const 
 extern "C" int dm_crop_nearest_f32(const float* image, const float* center, int32_t b, int32_t c, int32_t h,
                                    int32_t w, int32_t crop_h, int32_t crop_w, int32_t border, float fill,
                                    float* out, void* stream) {
+  DM_TRACE();
   if (b < 0 || c < 0 || h <= 0 || w <= 0 || crop_h < 0 || crop_w < 0) return DM_EINVAL;
   const long long total = (long long)b * c * crop_h * crop_w;
   if (total == 0) return DM_OK;
@@ -400,6 +407,7 @@ extern "C" int dm_crop_nearest_f32(const float* image, const float* center, int3
 
 extern "C" int dm_crop_nearest_u8(const uint8_t* image, const float* center, int32_t b, int32_t c, int32_t h,
                                   int32_t w, int32_t crop_h, int32_t crop_w, uint8_t* out, void* stream) {
+  DM_TRACE();
   if (b < 0 || c < 0 || h <= 0 || w <= 0 || crop_h < 0 || crop_w < 0) return DM_EINVAL;
   const long long total = (long long)b * c * crop_h * crop_w;
   if (total == 0) return DM_OK;
