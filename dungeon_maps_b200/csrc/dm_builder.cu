@@ -216,16 +216,34 @@ extern "C" int dm_builder_plot_prefill(DmBuilder* h, const float* depth, const f
   DmProjCfg pc = h->cfg.proj;
   pc.fast_steps = fast;
   pc.want_height = 0;  // C == 0: the topdown map is the height map (maps.py:333-334)
-  rc = dm_orth_project_f32(depth, nullptr, nullptr, reinterpret_cast<const DmProjSample*>(d_base), &pc, h->cfg.b,
-                           local_topdown, local_mask, nullptr, h->ws, h->ws_bytes, stream);
-  if (rc != DM_OK) return rc;
   make_sources(h, d_base, local_topdown, local_mask, world);
   // pass 1 (maps.py:2146-2179): a world map that carries the box its own scatter pass tracked only seeds the reduction
   const bool seeded = world && world->box;
-  const DmFuseSource* scan = seeded ? &h->src[h->n_src - 1] : h->src;
-  rc = dm_fuse_bbox_seeded_i64(scan, seeded ? 1 : h->n_src, h->cfg.b, 1, h->cfg.proj.map_res,
-                               seeded ? world->box : nullptr, h->d_bbox, stream);
-  if (rc != DM_OK) return rc;
+  // the projection's resolve pass and pass 1 over the local map it writes are ONE kernel (dm_fuse.cu:
+  // hmap_resolve_bbox_kernel) whenever the depth-only projection can hand over its key planes
+  uint32_t* planes = nullptr;
+  unsigned long long slot_words = 0;
+  rc = hmap_project_keys(depth, nullptr, reinterpret_cast<const DmProjSample*>(d_base), &pc, h->cfg.b, h->ws, h->ws_bytes,
+                         stream, &planes, &slot_words);
+  if (rc == DM_OK) {
+    rc = hmap_resolve_with_bbox(planes, slot_words, &pc, h->cfg.b, local_topdown, local_mask, &h->src[h->n_src - 1],
+                                h->cfg.proj.map_res, seeded ? world->box : nullptr, h->d_bbox, stream);
+    if (rc != DM_OK) return rc;
+    if (world && !seeded) {  // an untracked world map is scanned as before
+      rc = fuse_bbox_accumulate(h->src, 1, h->cfg.b, 1, h->cfg.proj.map_res, h->d_bbox, stream);
+      if (rc != DM_OK) return rc;
+    }
+  } else if (rc == DM_EINVAL) {  // more than 64 frames, or the height-map path is switched off: the unfused sequence
+    rc = dm_orth_project_f32(depth, nullptr, nullptr, reinterpret_cast<const DmProjSample*>(d_base), &pc, h->cfg.b,
+                             local_topdown, local_mask, nullptr, h->ws, h->ws_bytes, stream);
+    if (rc != DM_OK) return rc;
+    const DmFuseSource* scan = seeded ? &h->src[h->n_src - 1] : h->src;
+    rc = dm_fuse_bbox_seeded_i64(scan, seeded ? 1 : h->n_src, h->cfg.b, 1, h->cfg.proj.map_res,
+                                 seeded ? world->box : nullptr, h->d_bbox, stream);
+    if (rc != DM_OK) return rc;
+  } else {
+    return rc;
+  }
   DM_CUDA_OK(cudaMemcpyAsync(h->h_bbox, h->d_bbox, 5 * sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
   DM_CUDA_OK(cudaEventRecord(h->ev_bbox, stream));
   h->prefilled_top = nullptr; h->prefilled_mask = nullptr; h->prefilled_cells = 0;

@@ -65,6 +65,20 @@ int fuse_scatter_track(const DmFuseSource* sources, int32_t n_sources, int32_t b
                        float* topdown, uint8_t* mask, float* height, int64_t* next_bbox, int32_t* next_plane_box,
                        int prefilled, void* stream);
 
+// MapBuilder.plot fused with pass 1 of the merge (dm_builder.cu): the depth-only projection writes its key planes
+// (dm_project.cu: hmap_project_keys, at most 64 frames, DM_EINVAL otherwise / when the height-map path is switched off),
+// and ONE kernel resolves them into the local map and reduces that map's contribution to the merge's bounding box
+// (dm_fuse.cu: hmap_resolve_with_bbox) — instead of resolve, bbox init and a bbox kernel that scans the mask just written.
+int hmap_project_keys(const float* depth, const uint8_t* valid, const DmProjSample* samples, const DmProjCfg* cfg,
+                      int32_t b, void* workspace, size_t workspace_bytes, cudaStream_t stream, uint32_t** planes,
+                      unsigned long long* slot_words);
+int hmap_resolve_with_bbox(uint32_t* planes, unsigned long long slot_words, const DmProjCfg* cfg, int32_t b,
+                           float* topdown, uint8_t* mask, const DmFuseSource* local, float target_res,
+                           const int64_t* seed, int64_t* bbox, cudaStream_t stream);
+// pass 1 over `sources` into an ALREADY initialised bbox (dm_fuse.cu)
+int fuse_bbox_accumulate(const DmFuseSource* sources, int32_t n_sources, int32_t b, int32_t C, float target_res,
+                         int64_t* bbox, cudaStream_t stream);
+
 // ---- reference arithmetic ------------------------------------------------------
 struct V3 {
   float x, y, z;

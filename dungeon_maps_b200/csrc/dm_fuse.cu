@@ -308,6 +308,95 @@ fuse_bbox_kernel(const __grid_constant__ DmFuseSource src, int planes, int C, fl
   }
 }
 
+// MapBuilder.plot's resolve pass (dm_project.cu: hmap_resolve_kernel — key -> value / mask, plane zero again) fused
+// with pass 1 of the merge over the map it writes: a cell that holds a key IS a valid cell of the local map, so its
+// point goes through source_point() and quantize_f() right here (the operations of fuse_bbox_kernel, same bits) and
+// the separate scan of the 5 MB of masks just written, its launch and the bbox init go away (20 + 4 us of a 292 us step).
+__global__ void __launch_bounds__(256)
+hmap_resolve_bbox_kernel(uint32_t* __restrict__ acc, unsigned long long slot_words, const DmProjCfg cfg, int vec,
+                         float* __restrict__ topdown, uint8_t* __restrict__ mask,
+                         const __grid_constant__ DmFuseSource src, float res, long long* __restrict__ out) {
+  __shared__ PlaneCtx ctx;
+  const int frame = blockIdx.y;
+  load_plane_ctx(src, frame, &ctx);
+  const int M = cfg.Mh * cfg.Mw;
+  uint32_t* plane = acc + (size_t)frame * slot_words;
+  float* tp = topdown + (size_t)frame * M;
+  uint8_t* mp = mask + (size_t)frame * M;
+  const float fill = cfg.fill_value;
+  const int is_min = cfg.reduction;
+  long long mnx = 0x7fffffffffffffffLL, mxx = (long long)0x8000000000000000ULL;
+  long long mnz = mnx, mxz = mxx;
+  unsigned long long cnt = 0;
+  auto visit = [&](int m, float v) {  // valid cell m of the local map holding height v
+    const int r = m / cfg.Mw, c = m - r * cfg.Mw;
+    // maps.py:1081-1086 map_dequantize + the source's steps, exactly as source_point()
+    float zb = (float)r;
+    if (src.flip_h) zb = __fsub_rn((float)(src.h - 1), zb);
+    V3 p;
+    p.z = __fmul_rn(__fsub_rn(zb, ctx.hoff), src.map_res);
+    p.x = __fmul_rn(__fsub_rn((float)c, ctx.woff), src.map_res);
+    p.y = v;
+    if (ctx.step0.kind != DM_STEP_NONE) p = apply_step(ctx.step0, p);
+    if (ctx.step1.kind != DM_STEP_NONE) p = apply_step(ctx.step1, p);
+    float xf, zf;  // maps.py:2159-2165: map_quantize(width_offset=0., height_offset=0., flip_h=False)
+    quantize_f(p.x, p.z, 0.0f, 0.0f, res, 0, 0, &xf, &zf);
+    const long long xi = f2i64(xf), zi = f2i64(zf);
+    mnx = xi < mnx ? xi : mnx; mxx = xi > mxx ? xi : mxx;
+    mnz = zi < mnz ? zi : mnz; mxz = zi > mxz ? zi : mxz;
+    ++cnt;
+  };
+  for (int m0 = (blockIdx.x * 256 + threadIdx.x) * 4; m0 < M; m0 += gridDim.x * 1024) {
+    if (vec && m0 + 3 < M) {
+      const uint4 k = __ldcg(reinterpret_cast<const uint4*>(plane + m0));
+      if (k.x | k.y | k.z | k.w) __stcg(reinterpret_cast<uint4*>(plane + m0), make_uint4(0u, 0u, 0u, 0u));
+      const float v0 = k.x ? dec_red(k.x, is_min) : fill, v1 = k.y ? dec_red(k.y, is_min) : fill;
+      const float v2 = k.z ? dec_red(k.z, is_min) : fill, v3 = k.w ? dec_red(k.w, is_min) : fill;
+      st_stream_f4(tp + m0, make_float4(v0, v1, v2, v3));
+      st_stream_u32(mp + m0, (k.x ? 1u : 0u) | (k.y ? 0x100u : 0u) | (k.z ? 0x10000u : 0u) | (k.w ? 0x1000000u : 0u));
+      if (k.x) visit(m0, v0);
+      if (k.y) visit(m0 + 1, v1);
+      if (k.z) visit(m0 + 2, v2);
+      if (k.w) visit(m0 + 3, v3);
+    } else {
+      for (int m = m0; m < min(m0 + 4, M); ++m) {
+        const uint32_t k = __ldcg(plane + m);
+        if (k) __stcg(plane + m, 0u);
+        const float v = k ? dec_red(k, is_min) : fill;
+        st_stream_f1(tp + m, v);
+        st_stream_u8(mp + m, k ? 1 : 0);
+        if (k) visit(m, v);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const long long a = __shfl_xor_sync(0xffffffffu, mnx, o), b2 = __shfl_xor_sync(0xffffffffu, mxx, o);
+    const long long c2 = __shfl_xor_sync(0xffffffffu, mnz, o), d2 = __shfl_xor_sync(0xffffffffu, mxz, o);
+    const unsigned long long e2 = __shfl_xor_sync(0xffffffffu, cnt, o);
+    mnx = a < mnx ? a : mnx; mxx = b2 > mxx ? b2 : mxx;
+    mnz = c2 < mnz ? c2 : mnz; mxz = d2 > mxz ? d2 : mxz;
+    cnt += e2;
+  }
+  __shared__ long long sm[8][4];
+  __shared__ unsigned long long sc[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sm[warp][0] = mnx; sm[warp][1] = mxx; sm[warp][2] = mnz; sm[warp][3] = mxz; sc[warp] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) {
+      mnx = sm[w][0] < mnx ? sm[w][0] : mnx; mxx = sm[w][1] > mxx ? sm[w][1] : mxx;
+      mnz = sm[w][2] < mnz ? sm[w][2] : mnz; mxz = sm[w][3] > mxz ? sm[w][3] : mxz;
+      cnt += sc[w];
+    }
+    if (cnt) {
+      atomicMin(out + 0, mnx); atomicMax(out + 1, mxx);
+      atomicMin(out + 2, mnz); atomicMax(out + 3, mxz);
+      atomicAdd(reinterpret_cast<unsigned long long*>(out + 4), cnt);
+    }
+  }
+}
+
 // Fresh canvases: topdown = fill (utils.py:472-473), height = -inf (maps.py:2268), mask = false.
 // Consecutive lanes store consecutive 16-byte words (a thread owning 64 contiguous bytes made every warp
 // store touch 32 different lines: 45 % of DRAM peak in ncu); unaligned bases / the tail take the scalar loop.
@@ -674,6 +763,39 @@ static int launch_scatter(const DmFuseSource* sources, int n_sources, int b, int
 using namespace dm;
 
 extern "C" void dm_debug_set_dense_shift(int32_t on) { dm::g_dense_shift = on ? 1 : 0; }
+
+int dm::fuse_bbox_accumulate(const DmFuseSource* sources, int32_t n_sources, int32_t b, int32_t C, float target_res,
+                             int64_t* bbox, cudaStream_t stream) {
+  if (!bbox) return DM_EINVAL;
+  const int rc = check_sources(sources, n_sources, b, C);
+  if (rc != DM_OK) return rc;
+  for (int i = 0; i < n_sources; ++i) {
+    fuse_bbox_kernel<<<plane_grid(sources[i], b * C), kScanThreads, 0, stream>>>(sources[i], b * C, C, target_res,
+                                                                               reinterpret_cast<long long*>(bbox));
+    DM_LAUNCHED();
+  }
+  return DM_OK;
+}
+
+int dm::hmap_resolve_with_bbox(uint32_t* planes, unsigned long long slot_words, const DmProjCfg* cfg, int32_t b,
+                               float* topdown, uint8_t* mask, const DmFuseSource* local, float target_res,
+                               const int64_t* seed, int64_t* bbox, cudaStream_t stream) {
+  if (!planes || !cfg || !topdown || !mask || !local || !bbox || b <= 0) return DM_EINVAL;
+  const int rc = check_sources(local, 1, b, 1);
+  if (rc != DM_OK) return rc;
+  if (local->h != cfg->Mh || local->w != cfg->Mw) return DM_EINVAL;
+  fuse_bbox_init<<<1, 1, 0, stream>>>(reinterpret_cast<long long*>(bbox), reinterpret_cast<const long long*>(seed));
+  DM_LAUNCHED();
+  const int M = cfg->Mh * cfg->Mw;
+  const int vec = (M % 4 == 0) && reinterpret_cast<uintptr_t>(topdown) % 16 == 0 && reinterpret_cast<uintptr_t>(mask) % 4 == 0;
+  // blocks of 4 x 1024 cells: few enough that their five same-address atomics stay cheap
+  const unsigned gx = (unsigned)((M + 4095) / 4096);
+  hmap_resolve_bbox_kernel<<<dim3(gx > 0 ? gx : 1, b), 256, 0, stream>>>(planes, slot_words, *cfg, vec, topdown, mask,
+                                                                         *local, target_res,
+                                                                         reinterpret_cast<long long*>(bbox));
+  DM_LAUNCHED();
+  return DM_OK;
+}
 
 extern "C" int dm_fuse_bbox_i64(const DmFuseSource* sources, int32_t n_sources, int32_t b, int32_t C,
                                 float target_res, int64_t* out, void* stream_) {

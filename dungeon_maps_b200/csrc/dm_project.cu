@@ -1368,6 +1368,34 @@ using namespace dm;
 
 extern "C" void dm_debug_set_tile_rows(int32_t rows) { dm::g_tile_rows = rows; }
 
+int dm::hmap_project_keys(const float* depth, const uint8_t* valid, const DmProjSample* samples, const DmProjCfg* cfg,
+                          int32_t b, void* workspace, size_t workspace_bytes, cudaStream_t stream, uint32_t** planes_out,
+                          unsigned long long* slot_words_out) {
+  if (!cfg || !depth || !samples || !workspace || !planes_out || !slot_words_out || b <= 0 || cfg->C != 0) return DM_EINVAL;
+  if (cfg->H <= 0 || cfg->W <= 0 || cfg->Mh <= 0 || cfg->Mw <= 0) return DM_EINVAL;
+  if ((long long)cfg->H * cfg->W >= (1ll << 31) || (long long)cfg->Mh * cfg->Mw >= (1ll << 30)) return DM_EINVAL;
+  if (cfg->reduction != 0 && cfg->reduction != 1) return DM_EINVAL;
+  const ProjPlan p = make_plan(*cfg, b);
+  if (!p.lean || b > p.ring) return DM_EINVAL;  // the caller falls back to dm_orth_project_f32
+  if (workspace_bytes < p.workspace_bytes() || !aligned(workspace, 256)) return DM_EWORKSPACE;
+  const int N = cfg->H * cfg->W;
+  uint32_t* planes = reinterpret_cast<uint32_t*>(static_cast<char*>(workspace) + p.ctrl_bytes + p.flag_bytes);
+  const int pvec = (cfg->W % 4 == 0) && aligned(depth, 16) && (!valid || aligned(valid, 4));
+  void (*kern)(const float*, const uint8_t*, const DmProjSample*, DmProjCfg, int, int, uint32_t*, unsigned long long) = nullptr;
+  const bool mn = cfg->reduction != 0;
+  switch (cfg->fast_steps) {
+    case 1: kern = mn ? hmap_proj_kernel<1, true> : hmap_proj_kernel<1, false>; break;
+    case 2: kern = mn ? hmap_proj_kernel<2, true> : hmap_proj_kernel<2, false>; break;
+    default: kern = mn ? hmap_proj_kernel<0, true> : hmap_proj_kernel<0, false>; break;
+  }
+  kern<<<dim3((N + 1023) / 1024, b), 256, 0, stream>>>(depth, valid, samples, *cfg, 0, pvec, planes,
+                                                       (unsigned long long)p.slot_words);
+  DM_LAUNCHED();
+  *planes_out = planes;
+  *slot_words_out = (unsigned long long)p.slot_words;
+  return DM_OK;
+}
+
 extern "C" size_t dm_orth_project_workspace_bytes(const DmProjCfg* cfg, int32_t b) {
   if (!cfg || b <= 0 || cfg->Mh <= 0 || cfg->Mw <= 0) return 0;
   const ProjPlan p = make_plan(*cfg, b);
