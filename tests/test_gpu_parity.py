@@ -681,3 +681,30 @@ def test_native_library_is_the_path():
   assert nat.launch_count() == before + 1
   maps = open("/proc/self/maps").read()
   assert "libdungeon_maps_b200.so" in maps
+
+
+def test_parameter_uploads_across_streams_and_many_calls():
+  """dm_upload_params recycles a ring of 64 device slots and fences their reuse with markers on the caller's stream:
+  more calls than slots, alternating between two streams, every call with poses of its own — each result must be the
+  one a fresh single-stream call gives."""
+  b, H, W, C = 3, 32, 40, 2
+  depth, values, _ = synth.frames("room", b, H, W, C, seed=3, device="cuda")
+  proj = dmap.MapProjector(width=W, height=H, hfov=HFOV, cam_pose=[0., 0., 0.], width_offset=25., height_offset=0.,
+                           cam_pitch=PITCH, cam_height=0.88, map_res=0.1, map_width=50, map_height=50,
+                           trunc_depth_min=0.15, trunc_depth_max=5.05, to_global=True, device="cuda")
+  poses = [synth.poses(b, 1000 + i) for i in range(150)]
+  want = []
+  for p in poses:
+    top, mask, _ = proj.orth_project(depth, values, cam_pose=p, get_height_map=True)
+    want.append((top.clone(), mask.clone(), proj.camera_affine_grid(depth, p * 0.1).clone()))
+  torch.cuda.synchronize()
+  streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+  got = []
+  for i, p in enumerate(poses):
+    with torch.cuda.stream(streams[i % 2]):
+      top, mask, _ = proj.orth_project(depth, values, cam_pose=p, get_height_map=True)
+      got.append((top, mask, proj.camera_affine_grid(depth, p * 0.1)))
+  torch.cuda.synchronize()
+  for i, (w, g) in enumerate(zip(want, got)):
+    assert torch.equal(w[0], g[0]) and torch.equal(w[1], g[1]), f"call {i}: maps differ"
+    assert torch.equal(w[2].nan_to_num(), g[2].nan_to_num()), f"call {i}: grids differ"
