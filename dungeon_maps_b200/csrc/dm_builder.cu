@@ -247,6 +247,7 @@ extern "C" int dm_builder_plot_prefill(DmBuilder* h, const float* depth, const f
   DM_CUDA_OK(cudaMemcpyAsync(h->h_bbox, h->d_bbox, 5 * sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
   DM_CUDA_OK(cudaEventRecord(h->ev_bbox, stream));
   h->prefilled_top = nullptr; h->prefilled_mask = nullptr; h->prefilled_cells = 0;
+  prefill_cells &= ~(int64_t)15;
   if (prefill_topdown && prefill_mask && prefill_cells > 0) {
     rc = dm_fuse_canvas_init_f32(prefill_topdown, prefill_mask, nullptr, prefill_cells, h->cfg.merge_fill_value, stream);
     if (rc != DM_OK) return rc;
@@ -280,8 +281,15 @@ extern "C" int dm_builder_merge(DmBuilder* h, const DmMapRef* out, void* stream_
   tgt.Mh = out->h; tgt.Mw = out->w; tgt.flip_h = c.proj.flip_h; tgt.map_res = c.proj.map_res;
   tgt.width_offset = out->width_offset; tgt.height_offset = out->height_offset;
   tgt.fill_value = c.merge_fill_value; tgt.reduction = c.merge_reduction;
-  const bool prefilled = out->topdown == h->prefilled_top && out->mask == h->prefilled_mask &&
-                         (int64_t)c.b * out->h * out->w <= h->prefilled_cells;
+  // the prefill covers the first prefilled_cells cells (a multiple of 16: the tail below starts 16-byte aligned) of the
+  // canvases the caller guessed; a map that outgrew the guess gets its tail filled here
+  const int64_t n_cells = (int64_t)c.b * out->h * out->w;
+  const bool prefilled = out->topdown == h->prefilled_top && out->mask == h->prefilled_mask && h->prefilled_cells > 0;
+  if (prefilled && n_cells > h->prefilled_cells) {
+    const int rf = dm_fuse_canvas_init_f32(out->topdown + h->prefilled_cells, out->mask + h->prefilled_cells, nullptr,
+                                           n_cells - h->prefilled_cells, c.merge_fill_value, stream_);
+    if (rf != DM_OK) return rf;
+  }
   const int rc = fuse_scatter_track(h->src, h->n_src, c.b, 1, &tgt, out->topdown, out->mask, nullptr, out->box,
                                     out->plane_box, prefilled ? 1 : 0, stream_);
   h->prefilled_top = nullptr; h->prefilled_mask = nullptr; h->prefilled_cells = 0;

@@ -1332,10 +1332,12 @@ class MapBuilder():
         spec_top = torch.empty((cap,), dtype=torch.float32, device=dev)
         spec_mask = torch.empty((cap,), dtype=torch.bool, device=dev)
       # ... and their fill is queued behind the box's copy: it runs while the host waits for the box
+      # (prefilled: the old map's cells + 2 % — the map grows by a row or a column now and then; dm_builder_merge fills
+      # whatever tail the new map has beyond that, and the rest of the size class stays untouched)
+      n_guess = 0 if spec_top is None else min(spec_top.numel(), world.mask.numel() + world.mask.numel() // 50 + 4096)
       nat.check(lib.dm_builder_plot_prefill(nb.handle, depth_map.data_ptr(), pose.data_ptr(), sin.data_ptr(),
                                             cos.data_ptr(), local_top.data_ptr(), local_mask.data_ptr(), wref, None,
-                                            nat.ptr(spec_top), nat.ptr(spec_mask),
-                                            0 if spec_top is None else spec_top.numel(), stream),
+                                            nat.ptr(spec_top), nat.ptr(spec_mask), n_guess, stream),
                 "dm_builder_plot_prefill")
       local = make_local()  # while the projection, the box reduction and the prefill run
       nat.check(lib.dm_builder_plot_wait(nb.handle, shape), "dm_builder_plot_wait")

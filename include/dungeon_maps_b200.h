@@ -352,8 +352,9 @@ int dm_builder_plot(DmBuilder* builder, const float* depth, const float* pose, c
                     DmMergeShape* shape, void* stream);
 /* dm_builder_plot with speculation: prefill_topdown / prefill_mask (prefill_cells elements each; may be NULL / 0) are
  * canvases the caller expects to merge into — as a rule the size class of the old world map.  Their fill is queued right
- * behind the bounding box's copy and runs while the host waits for the box; dm_builder_merge skips its own fill when
- * `out` points at them and fits.  Same results as dm_builder_plot + dm_builder_merge. */
+ * behind the bounding box's copy and runs while the host waits for the box; dm_builder_merge then only fills the cells of
+ * `out` beyond prefill_cells (rounded down to a multiple of 16) when `out` points at them.  Same results as
+ * dm_builder_plot + dm_builder_merge. */
 int dm_builder_plot_prefill(DmBuilder* builder, const float* depth, const float* pose, const float* sin_yaw,
                             const float* cos_yaw, float* local_topdown, uint8_t* local_mask, const DmMapRef* world,
                             DmMergeShape* shape, float* prefill_topdown, uint8_t* prefill_mask, int64_t prefill_cells,
