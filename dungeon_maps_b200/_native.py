@@ -12,7 +12,7 @@ import torch
 
 from . import build as _build
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class NativeError(RuntimeError):

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DM_ABI_VERSION 2
+#define DM_ABI_VERSION 3
 
 #define DM_OK 0
 #define DM_EINVAL (-1)     /* bad argument (null pointer, non-positive size, ...) */

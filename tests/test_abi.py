@@ -34,7 +34,7 @@ def test_library_loads_and_exports_every_declared_symbol():
   for name in _declared_functions():
     assert hasattr(handle, name), f"libdungeon_maps_b200.so does not export {name}"
   lib = nat.lib()
-  assert lib.dm_abi_version() == nat.ABI_VERSION == 2
+  assert lib.dm_abi_version() == nat.ABI_VERSION == 3
   assert b"sm_100a" in lib.dm_build_info()
   assert lib.dm_launch_count() >= 0
 
